@@ -1,0 +1,373 @@
+"""CPU oracle: a numpy/SciPy restatement of the reference's algorithm for the ASVGP hot path.
+
+TEST INFRASTRUCTURE ONLY.  Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / reference
+arm may import this module; nothing under `asvgp_b200/` does (the product path has no CPU fallback).
+
+Parity pinning: the reference ships no tests, one known answer (the Snelson notebook ELBO,
+experiments/snelson/example.ipynb cell 3 = -60.8356263428725).  This restatement is pinned (a) against that
+value and (b) against outputs of the *unmodified reference files run under numpy stand-ins* in the build
+container (`oracle/make_golden.py` -> tests/golden/*.npz; checked by tests/test_oracle_golden.py).
+
+Every function cites the reference file:line it follows (paths relative to /root/reference).  It deliberately
+shares no code with asvgp_b200/: basis pieces come from the Cox-de Boor recursion in x-units, Gram tables from
+Gauss-Legendre quadrature, the O(N) precompute uses the same SciPy sparse calls the reference makes.
+"""
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+SQRT3, SQRT5 = np.sqrt(3.0), np.sqrt(5.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a1: mesh  (asvgp/basis.py:13-18)
+# ---------------------------------------------------------------------------------------------------------------------
+def make_mesh(a, b, m, k, mesh_dtype="tf"):
+    """mesh = cast(tf.linspace(a, b, m-(k-1)), f64); delta = mesh[1]-mesh[0]  (basis.py:17-18).
+    'tf' emulates TF dtype inference: Python floats -> float32 linspace, ints -> float64."""
+    n = m - (k - 1)
+    if mesh_dtype == "tf":
+        mesh_dtype = "float64" if all(isinstance(v, (int, np.integer)) for v in (a, b)) else "float32"
+    if mesh_dtype == "float64":
+        mesh = np.linspace(float(a), float(b), n)
+    else:
+        f = np.float32
+        step = f(f(f(b) - f(a)) / f(n - 1))
+        mesh = np.empty(n, dtype=f)
+        mesh[0], mesh[-1] = f(a), f(b)
+        mesh[1:-1] = f(a) + step * np.arange(1, n - 1, dtype=f)
+        mesh = mesh.astype(np.float64)
+    return mesh, float(mesh[1] - mesh[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a2: basis evaluation  (asvgp/basis.py:51-80 and the per-order `_evaluate*`)
+# ---------------------------------------------------------------------------------------------------------------------
+def locate(mesh, x):
+    """idx = relu(searchsorted_left(mesh, x) - 1), u = mesh[idx]  (basis.py:58-59)."""
+    idx = np.maximum(np.searchsorted(mesh, x, side="left") - 1, 0).astype(np.int64)
+    return idx, mesh[idx]
+
+
+def pieces(k, s, delta, dx=0):
+    """Values of the dx-th x-derivative of the k+1 non-zero degree-k B-splines at offset s = x - u from the
+    left knot; row r of the result belongs to basis row idx + r.  Cox-de Boor on the uniform knots u + i*delta
+    (the reference's `_evaluate`, `_evaluate_grad`, ... are expanded forms of the same polynomials: its b_i is
+    row k+1-i here, basis.py:72)."""
+    s = np.asarray(s, dtype=np.float64)
+    # polynomial coefficient arrays in s for each piece, built by the recursion on polynomials
+    P = [np.poly1d([1.0])]                      # degree 0: one piece (the interval itself)
+    for d in range(1, k + 1):
+        new = []
+        for r in range(d + 1):
+            # function with support starting (d - r) intervals to the left of u: knots t_0 = -(d-r)*delta
+            t0 = -(d - r) * delta
+            acc = np.poly1d([0.0])
+            if r - 1 >= 0:                      # left parent (same support start), degree d-1
+                acc = acc + np.poly1d([1.0, -t0]) / (d * delta) * P[r - 1]
+            if r <= d - 1:                      # right parent (support start one interval later)
+                acc = acc + np.poly1d([-1.0, t0 + (d + 1) * delta]) / (d * delta) * P[r]
+            new.append(acc)
+        P = new
+    out = np.empty((k + 1,) + s.shape)
+    for r in range(k + 1):
+        p = P[r]
+        for _ in range(dx):
+            p = p.deriv()
+        out[r] = p(s)
+    return out
+
+
+def make_Kuf(mesh, delta, k, m, X, dx=0):
+    """Sparse (m, n) Kuf exactly as the reference assembles it (basis.py:72-76, inducing_features.py:47-48)."""
+    x = np.asarray(X, dtype=np.float64).reshape(-1)
+    n = x.shape[0]
+    idx, u = locate(mesh, x)
+    vals = pieces(k, x - u, delta, dx)
+    rows = (idx[None, :] + np.arange(k + 1)[:, None]).reshape(-1)
+    cols = np.tile(np.arange(n), k + 1)
+    return sp.csr_matrix((vals.reshape(-1), (rows, cols)), shape=(m, n))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a3/a4: static Gram and boundary bands  (asvgp/basis.py:31-45, 82-114 and the l2_*_inner_product tables)
+# ---------------------------------------------------------------------------------------------------------------------
+def gram_band(k, m, delta, q):
+    """Lower band (k+1, m) of int_a^b phi_i^(q) phi_j^(q) dx, band[d, j] = S[j+d, j]; truncated edge functions
+    (basis.py:31-45).  Gauss-Legendre with k+2 nodes per interval is exact for these polynomials."""
+    nodes, wts = np.polynomial.legendre.leggauss(k + 2)
+    s = 0.5 * (nodes + 1.0) * delta
+    V = pieces(k, s, delta, q)                                  # (k+1, nq)
+    W = (V * (0.5 * delta * wts)[None, :]) @ V.T               # per-interval Gram, rows/cols = local piece index
+    band = np.zeros((k + 1, m))
+    for c in range(m - k):                                      # interval c touches rows c..c+k
+        for r in range(k + 1):
+            for t in range(r + 1):
+                band[r - t, c + t] += W[r, t]
+    return band
+
+
+def boundary_band(k, m, delta, dx):
+    """make_boundary_conditions(dx) for dx=0,1,2 (basis.py:82-114): outer product of the first k boundary values
+    at x=a, d-th diagonal written at both ends of row d, last row zero.  dx=3,4 vanish for m>2k."""
+    band = np.zeros((k + 1, m))
+    if dx in (3, 4):
+        return band
+    v = pieces(k, np.array(0.0), delta, dx)[:k]
+    for d in range(k):
+        l = v[d:] * v[: k - d]
+        band[d, : k - d] = l
+        band[d, m - d - (k - d): m - d] = l
+    return band
+
+
+def static_bands(k, m, delta):
+    t = {n: gram_band(k, m, delta, q) for q, n in enumerate("ABCD") if q <= k}
+    t["BC"] = boundary_band(k, m, delta, 0)
+    t["BC_grad"] = boundary_band(k, m, delta, 1)
+    t["BC_ggrad"] = boundary_band(k, m, delta, 2)
+    return t
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a5: Kuu  (asvgp/inducing_features.py:12-44)
+# ---------------------------------------------------------------------------------------------------------------------
+def kuu_coefficients(kind, ell, var):
+    """{table name: coefficient} with Kuu = sum coeff * table  (inducing_features.py:16-44)."""
+    if kind == "Matern12":
+        return {"A": 1 / (2 * ell * var), "B": ell / (2 * var), "BC": 1 / (2 * var)}
+    if kind == "Matern32":
+        return {"A": SQRT3 / (4 * ell * var), "B": ell / (2 * SQRT3 * var), "C": ell**3 / (12 * SQRT3 * var),
+                "BC": 1 / (2 * var), "BC_grad": ell**2 / (2 * var)}
+    if kind == "Matern52":
+        return {"A": 3 * SQRT5 / (16 * ell * var), "B": 9 * ell / (16 * SQRT5 * var),
+                "C": 9 * ell**3 / (80 * SQRT5 * var), "D": 3 * ell**5 / (400 * SQRT5 * var),
+                "BC": 9 / (16 * var), "BC_grad": 3 * ell**2 / (10 * var), "BC_ggrad": 9 * ell**4 / (400 * var)}
+    raise ValueError(kind)
+
+
+def make_Kuu(kind, ell, var, tables):
+    return sum(c * tables[n] for n, c in kuu_coefficients(kind, ell, var).items())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a7: O(N) precompute  (asvgp/gpr.py:39-44, asvgp/utils.py:24-30)
+# ---------------------------------------------------------------------------------------------------------------------
+def sparse_to_band(K_sparse, bw):
+    m = K_sparse.shape[0]
+    band = np.zeros((bw + 1, m))
+    for d in range(bw + 1):
+        band[d, : m - d] = K_sparse.diagonal(k=-d)
+    return band
+
+
+def precompute_1d(mesh, delta, k, m, X, y):
+    """Kuf_y = Kuf@y, KufKfu = band(Kuf@Kuf.T), tr_yTy = sum(y^2) with the reference's own SciPy sparse calls
+    (gpr.py:40-44).  This function is also the 1-thread CPU baseline of bench.py."""
+    Kuf = make_Kuf(mesh, delta, k, m, X)
+    y = np.asarray(y, dtype=np.float64).reshape(Kuf.shape[1], -1)
+    Kuf_y = Kuf @ y
+    G = sparse_to_band(Kuf @ Kuf.T, k)
+    return G, Kuf_y, float(np.sum(np.square(y)))
+
+
+def precompute_1d_chunked(mesh, delta, k, m, X, y, chunk=1 << 20):
+    """Same sums accumulated chunk by chunk (bounded memory) — used for large-N parity checks."""
+    x = np.asarray(X, dtype=np.float64).reshape(-1)
+    y = np.asarray(y, dtype=np.float64).reshape(x.shape[0], -1)
+    G = np.zeros((k + 1, m))
+    b = np.zeros((m, y.shape[1]))
+    yy = 0.0
+    for s in range(0, x.shape[0], chunk):
+        g, bb, t = precompute_1d(mesh, delta, k, m, x[s:s + chunk], y[s:s + chunk])
+        G += g
+        b += bb
+        yy += t
+    return G, b, yy
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# banded helpers (stand for banded_matrices ops at gpr.py:56-75)
+# ---------------------------------------------------------------------------------------------------------------------
+def band_to_dense_sym(band):
+    k, m = band.shape[0] - 1, band.shape[1]
+    A = np.zeros((m, m))
+    for d in range(k + 1):
+        i = np.arange(m - d)
+        A[i + d, i] = band[d, : m - d]
+        A[i, i + d] = band[d, : m - d]
+    return A
+
+
+def takahashi_band(L):
+    """Lower band of (L L^T)^-1 from the lower band of L (banded.inverse_from_cholesky_band, gpr.py:59)."""
+    k, m = L.shape[0] - 1, L.shape[1]
+    S = np.zeros((k + 1, m))
+    for j in range(m - 1, -1, -1):
+        ljj = L[0, j]
+        hi = min(m - 1, j + k)
+        for i in range(hi, j - 1, -1):
+            acc = 0.0
+            for r in range(j + 1, hi + 1):
+                a, c = (r, i) if r >= i else (i, r)
+                acc += L[r - j, j] * S[a - c, c]
+            S[i - j, j] = (1.0 / ljj**2 if i == j else 0.0) - acc / ljj
+    return S
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a8: collapsed ELBO  (asvgp/gpr.py:49-89)
+# ---------------------------------------------------------------------------------------------------------------------
+def elbo_1d(Kuu, G, Kuf_y, tr_yTy, n, var, sigma2, return_terms=False):
+    """The 7-term bound of gpr.py:81-87 from lower bands (SciPy LAPACK band routines)."""
+    k = Kuu.shape[0] - 1
+    D = Kuf_y.shape[1]
+    L_Kuu = sla.cholesky_banded(Kuu, lower=True)                     # gpr.py:56
+    log_det_Kuu = np.sum(np.log(np.square(L_Kuu[0])))                # gpr.py:57
+    Kuu_inv = takahashi_band(L_Kuu)                                  # gpr.py:59
+    w = np.full((k + 1, 1), 2.0)
+    w[0] = 1.0
+    trace_term = np.sum(w * Kuu_inv * G)                             # gpr.py:60-70 (diag of band x band product)
+    P = G / sigma2 + Kuu                                             # gpr.py:72
+    L_P = sla.cholesky_banded(P, lower=True)                         # gpr.py:73
+    log_det_P = np.sum(np.log(np.square(L_P[0])))                    # gpr.py:74
+    c = sla.solve_banded((k, 0), L_P, Kuf_y) / sigma2                # gpr.py:75
+    ND = float(n * D)
+    elbo = -0.5 * ND * np.log(2 * np.pi * sigma2)                    # gpr.py:81
+    elbo -= 0.5 * D * log_det_P
+    elbo += 0.5 * D * log_det_Kuu
+    elbo -= 0.5 * tr_yTy / sigma2
+    elbo += 0.5 * np.sum(np.square(c))
+    elbo -= 0.5 * n * var / sigma2                                   # gpr.py:86 (K_diag = var per point)
+    elbo += 0.5 * trace_term / sigma2
+    if return_terms:
+        return elbo, dict(log_det_Kuu=log_det_Kuu, log_det_P=log_det_P, trace=trace_term, quad=np.sum(np.square(c)))
+    return elbo
+
+
+def elbo_grad_1d_dense(kind, tables, G, Kuf_y, tr_yTy, n, var, ell, sigma2):
+    """ELBO and d/d(var, ell, sigma2) by torch-fp64 autograd through a dense restatement of gpr.py:49-89 — the
+    gradient oracle (the reference gets these from TF reverse mode through the banded ops)."""
+    import torch
+
+    th = torch.tensor([var, ell, sigma2], dtype=torch.float64, requires_grad=True)
+    v, l, s2 = th[0], th[1], th[2]
+    dense = {nme: torch.from_numpy(band_to_dense_sym(t)) for nme, t in tables.items()}
+    r3, r5 = float(SQRT3), float(SQRT5)
+    if kind == "Matern12":
+        co = {"A": 1 / (2 * l * v), "B": l / (2 * v), "BC": 1 / (2 * v)}
+    elif kind == "Matern32":
+        co = {"A": r3 / (4 * l * v), "B": l / (2 * r3 * v), "C": l**3 / (12 * r3 * v), "BC": 1 / (2 * v),
+              "BC_grad": l**2 / (2 * v)}
+    else:
+        co = {"A": 3 * r5 / (16 * l * v), "B": 9 * l / (16 * r5 * v), "C": 9 * l**3 / (80 * r5 * v),
+              "D": 3 * l**5 / (400 * r5 * v), "BC": 9 / (16 * v), "BC_grad": 3 * l**2 / (10 * v),
+              "BC_ggrad": 9 * l**4 / (400 * v)}
+    Kuu = sum(c * dense[nme] for nme, c in co.items())
+    Gd = torch.from_numpy(band_to_dense_sym(G))
+    b = torch.from_numpy(np.asarray(Kuf_y, dtype=np.float64))
+    D = b.shape[1]
+    LK = torch.linalg.cholesky(Kuu)
+    P = Kuu + Gd / s2
+    LP = torch.linalg.cholesky(P)
+    c = torch.linalg.solve_triangular(LP, b, upper=False) / s2
+    elbo = (-0.5 * n * D * torch.log(2 * np.pi * s2) - D * torch.log(torch.diagonal(LP)).sum()
+            + D * torch.log(torch.diagonal(LK)).sum() - 0.5 * tr_yTy / s2 + 0.5 * (c**2).sum()
+            - 0.5 * n * v / s2 + 0.5 * torch.trace(torch.cholesky_solve(Gd, LK)) / s2)
+    elbo.backward()
+    return float(elbo.detach()), th.grad.numpy().copy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a10: 1-D predictor  (asvgp/gpr.py:91-136)
+# ---------------------------------------------------------------------------------------------------------------------
+def predict_1d(mesh, delta, k, m, Kuu, G, Kuf_y, var, sigma2, Xnew):
+    """mean = Kus^T P^-1 Kuf_y / sigma2, var = v + diag(Kus^T P^-1 Kus) - diag(Kus^T Kuu^-1 Kus)
+    (gpr.py:96-118; CHOLMOD calls replaced by LAPACK band solves)."""
+    P = G / sigma2 + Kuu
+    cP = sla.cholesky_banded(P, lower=True)
+    cK = sla.cholesky_banded(Kuu, lower=True)
+    alpha = sla.cho_solve_banded((cP, True), Kuf_y) / sigma2
+    Kus = make_Kuf(mesh, delta, k, m, Xnew)
+    mean = Kus.T @ alpha
+    Kd = Kus.toarray()
+    v = var + np.sum(Kd * sla.cho_solve_banded((cP, True), Kd), axis=0) \
+        - np.sum(Kd * sla.cho_solve_banded((cK, True), Kd), axis=0)
+    return mean, v.reshape(-1, 1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a11-a15: Kronecker model  (asvgp/kronecker.py:7-33, asvgp/gpr.py:240-359, asvgp/utils.py:45-57)
+# ---------------------------------------------------------------------------------------------------------------------
+def khatri_rao_rows(A, B):
+    """Kuf[i1*m2+i2, n] = A[i1,n]*B[i2,n] (kronecker.py:24-33: sparse_repeats x sparse_tile, elementwise)."""
+    A, B = sp.csc_matrix(A), sp.csc_matrix(B)
+    m1, m2, n = A.shape[0], B.shape[0], A.shape[1]
+    rows, cols, data = [], [], []
+    for j in range(n):
+        a_r, a_v = A.indices[A.indptr[j]:A.indptr[j + 1]], A.data[A.indptr[j]:A.indptr[j + 1]]
+        b_r, b_v = B.indices[B.indptr[j]:B.indptr[j + 1]], B.data[B.indptr[j]:B.indptr[j + 1]]
+        rows.append((a_r[:, None] * m2 + b_r[None, :]).reshape(-1))
+        data.append((a_v[:, None] * b_v[None, :]).reshape(-1))
+        cols.append(np.full(rows[-1].shape, j))
+    return sp.csr_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(m1 * m2, n))
+
+
+def precompute_kron(meshes, deltas, k, ms, X, y, chunk=200000):
+    """Kuf_y and sparse KufKfu of GPR_kron.__init__ (gpr.py:268-274), accumulated in chunks."""
+    X = np.asarray(X, dtype=np.float64)
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    M = ms[0] * ms[1]
+    G = sp.csr_matrix((M, M))
+    b = np.zeros((M, 1))
+    for s in range(0, X.shape[0], chunk):
+        K1 = make_Kuf(meshes[0], deltas[0], k, ms[0], X[s:s + chunk, 0])
+        K2 = make_Kuf(meshes[1], deltas[1], k, ms[1], X[s:s + chunk, 1])
+        # vectorised Khatri-Rao (every column has exactly (k+1) non-zeros per factor)
+        n = K1.shape[1]
+        K1c, K2c = K1.tocsc(), K2.tocsc()
+        K1c.sort_indices(); K2c.sort_indices()
+        r1 = K1c.indices.reshape(n, k + 1); v1 = K1c.data.reshape(n, k + 1)
+        r2 = K2c.indices.reshape(n, k + 1); v2 = K2c.data.reshape(n, k + 1)
+        rows = (r1[:, :, None].astype(np.int64) * ms[1] + r2[:, None, :]).reshape(-1)
+        data = (v1[:, :, None] * v2[:, None, :]).reshape(-1)
+        cols = np.repeat(np.arange(n), (k + 1) ** 2)
+        Kuf = sp.csr_matrix((data, (rows, cols)), shape=(M, n))
+        G = G + Kuf @ Kuf.T
+        b += Kuf @ y[s:s + chunk]
+    return G.tocsr(), b, float(np.sum(np.square(y)))
+
+
+def elbo_kron_dense(Kuu_bands, G_sparse, Kuf_y, tr_yTy, n, variances, sigma2):
+    """GPR_kron.elbo (gpr.py:282-308) with dense M^2 x M^2 algebra — small sizes only."""
+    Ks = [band_to_dense_sym(b) for b in Kuu_bands]
+    Kuu = np.kron(Ks[0], Ks[1])                                   # utils.py:45-51
+    L_Kuu = np.kron(np.linalg.cholesky(Ks[0]), np.linalg.cholesky(Ks[1]))
+    Gd = G_sparse.toarray()
+    P = Kuu + Gd / sigma2
+    L_P = np.linalg.cholesky(P)
+    c = sla.solve_triangular(L_P, Kuf_y, lower=True) / sigma2
+    elbo = -0.5 * n * np.log(2 * np.pi * sigma2)
+    elbo -= np.sum(np.log(np.diag(L_P)))
+    elbo += np.sum(np.log(np.diag(L_Kuu)))
+    elbo -= 0.5 * tr_yTy / sigma2
+    elbo += 0.5 * np.sum(np.square(c))
+    elbo -= 0.5 * n * np.prod(variances) / sigma2
+    elbo += 0.5 * np.trace(sla.cho_solve((L_Kuu, True), Gd)) / sigma2
+    return elbo
+
+
+def predict_kron_dense(meshes, deltas, k, ms, Kuu_bands, G_sparse, Kuf_y, variances, sigma2, Xnew):
+    """GPR_kron.predict_f (gpr.py:310-334), dense."""
+    Ks = [band_to_dense_sym(b) for b in Kuu_bands]
+    Kuu = np.kron(Ks[0], Ks[1])
+    P = Kuu + G_sparse.toarray() / sigma2
+    K1 = make_Kuf(meshes[0], deltas[0], k, ms[0], Xnew[:, 0]).toarray()
+    K2 = make_Kuf(meshes[1], deltas[1], k, ms[1], Xnew[:, 1]).toarray()
+    Kus = (K1[:, None, :] * K2[None, :, :]).reshape(ms[0] * ms[1], -1)
+    cP = sla.cho_factor(P, lower=True)
+    alpha = sla.cho_solve(cP, Kuf_y) / sigma2
+    mean = Kus.T @ alpha
+    var = np.prod(variances) + np.sum(Kus * sla.cho_solve(cP, Kus), axis=0) \
+        - np.sum(Kus * np.linalg.solve(Kuu, Kus), axis=0)
+    return mean, var.reshape(-1, 1)
