@@ -1,0 +1,56 @@
+"""ctypes loader of libasvgp_sm100a.so (the C ABI declared in include/asvgp_b200.h).
+
+There is deliberately no CPU fallback: if the library has not been built, or a call fails, this raises."""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libasvgp_sm100a.so")
+
+_c_double_p = ctypes.c_void_p
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_dbl = ctypes.c_double
+_vp = ctypes.c_void_p
+
+# name -> argtypes; every function returns int except the two runtime queries.  Kept in sync with
+# include/asvgp_b200.h by tests/test_c_abi.py.
+SIGNATURES = {
+    "asvgp_basis_eval_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "asvgp_accum_1d": [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp],
+    "asvgp_predict_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+class AsvgpNativeError(RuntimeError):
+    pass
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AsvgpNativeError(
+            "libasvgp_sm100a.so not found at %s — build it with `python -m asvgp_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.asvgp_abi_version.restype = ctypes.c_int
+    lib.asvgp_abi_version.argtypes = []
+    lib.asvgp_last_error.restype = ctypes.c_char_p
+    lib.asvgp_last_error.argtypes = []
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise AsvgpNativeError("%s failed (%d): %s" % (name, rc, lib.asvgp_last_error().decode()))

@@ -1,0 +1,116 @@
+// Shared device/host helpers of libasvgp_sm100a: error reporting, knot-interval location, B-spline pieces.
+//
+// Everything numeric here is `ASVGP_HD` (host + device) so that tests/host_harness.cpp can compile the very same
+// templates with g++ and check them against numpy on a machine without a GPU.  That harness is test
+// infrastructure; the product entry points (the extern "C" functions) only ever launch the CUDA kernels.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cmath>
+
+#if defined(__CUDACC__)
+#define ASVGP_HD __host__ __device__ __forceinline__
+#else
+#define ASVGP_HD inline
+#endif
+
+namespace asvgp {
+
+constexpr int kMaxOrder = 6;
+
+// ---- status codes returned by every C-ABI entry point (0 = ok, <0 = bad argument / CUDA error) ----------------
+enum Status : int {
+    kOk = 0,
+    kBadArgument = -1,
+    kCudaError = -2,
+    kUnsupported = -3,
+};
+
+void set_last_error(const char* fmt, ...);
+
+#if defined(__CUDACC__)
+#define ASVGP_CUDA_OK(expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t err__ = (expr);                                                                 \
+        if (err__ != cudaSuccess) {                                                                 \
+            ::asvgp::set_last_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__),      \
+                                    __FILE__, __LINE__);                                            \
+            return ::asvgp::kCudaError;                                                             \
+        }                                                                                           \
+    } while (0)
+#endif
+
+#define ASVGP_REQUIRE(cond, ...)                      \
+    do {                                              \
+        if (!(cond)) {                                \
+            ::asvgp::set_last_error(__VA_ARGS__);     \
+            return ::asvgp::kBadArgument;             \
+        }                                             \
+    } while (0)
+
+// ---- knot mesh ------------------------------------------------------------------------------------------------
+// The kernels take the mesh *array* (not just a, delta): the reference gathers the left knot u from the mesh and
+// uses delta = mesh[1]-mesh[0] for every interval (basis.py:18,58-59), and a TF-built float32 mesh has slightly
+// uneven gaps.
+struct Mesh {
+    const double* knots;   // [n_knots], ascending
+    int n_knots;           // m - k + 1
+    double x0;             // knots[0]
+    double inv_delta;      // 1 / (knots[1] - knots[0])
+};
+
+template <class LoadFn>
+ASVGP_HD int locate_interval(const Mesh& mesh, double x, LoadFn load) {
+    // Reference semantics (basis.py:58): idx = max(searchsorted_left(mesh, x) - 1, 0), i.e. the largest idx with
+    // mesh[idx] < x (a point exactly on a knot belongs to the interval on its LEFT, quirk Q2); clamped to the
+    // last interval for x >= b (the reference would index one row past the matrix there, quirk Q4).
+    int hi = mesh.n_knots - 2;
+    double g = floor((x - mesh.x0) * mesh.inv_delta);
+    int idx = g < 0.0 ? 0 : (g > (double)hi ? hi : (int)g);
+    while (idx > 0 && !(load(mesh.knots + idx) < x)) --idx;
+    while (idx < hi && load(mesh.knots + idx + 1) < x) ++idx;
+    return idx;
+}
+
+// ---- B-spline pieces --------------------------------------------------------------------------------------------
+// w[r], r = 0..K : value at t = (x-u)/delta of basis row idx + r on interval idx (reference b_{K+1-r},
+// basis.py:72,133-136,188-192,274-280,...).  Cox-de Boor on uniform knots, all in registers:
+//   piece^d_r(t) = ((t + d - r)/d) piece^{d-1}_{r-1}(t) + ((1 - t + r)/d) piece^{d-1}_r(t).
+template <int K>
+ASVGP_HD void bspline_pieces(double t, double (&w)[K + 1]) {
+    w[0] = 1.0;
+#pragma unroll
+    for (int d = 1; d <= K; ++d) {
+        const double inv_d = 1.0 / (double)d;
+        double prev = 0.0;   // piece^{d-1}_{r-1}
+#pragma unroll
+        for (int r = 0; r <= d; ++r) {
+            const double cur = (r <= d - 1) ? w[r] : 0.0;            // piece^{d-1}_r
+            const double left = (t + (double)(d - r)) * inv_d;       // multiplies piece^{d-1}_{r-1}
+            const double right = ((1.0 - t) + (double)r) * inv_d;    // multiplies piece^{d-1}_r
+            w[r] = left * prev + right * cur;
+            prev = cur;
+        }
+    }
+}
+
+// dx-th derivative pieces by Horner on the exact piece coefficients (host-provided, (K+1)x(K+1) row-major,
+// ascending powers of t), scaled by delta^-dx.  Only used by the API-parity entry point asvgp_basis_eval_1d.
+template <int K>
+ASVGP_HD void bspline_pieces_coef(double t, const double* coef, double scale, double (&w)[K + 1]) {
+#pragma unroll
+    for (int r = 0; r <= K; ++r) {
+        double acc = coef[r * (K + 1) + K];
+#pragma unroll
+        for (int p = K - 1; p >= 0; --p) acc = acc * t + coef[r * (K + 1) + p];
+        w[r] = acc * scale;
+    }
+}
+
+ASVGP_HD constexpr int tri_index(int r, int s) { return r * (r + 1) / 2 + s; }   // r >= s
+template <int K> struct Counts {
+    static constexpr int kPairs = (K + 1) * (K + 2) / 2;   // unique entries of w w^T
+    static constexpr int kAcc = kPairs + (K + 1);          // + projections w*y
+};
+
+}  // namespace asvgp

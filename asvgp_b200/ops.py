@@ -1,0 +1,101 @@
+"""Thin Python faces of the C-ABI entry points.  torch is used for device memory and streams only; every
+operator below runs a hand-written sm_100a kernel through ctypes (no torch math on the hot path, no CPU
+fallback).  Inputs may be numpy arrays, torch tensors or any object exporting `__dlpack__`."""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise _lib.AsvgpNativeError("asvgp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(a, dtype=F64):
+    """numpy / torch / DLPack object -> contiguous CUDA tensor of `dtype` on the current device."""
+    if isinstance(a, torch.Tensor):
+        t = a
+    elif isinstance(a, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    elif hasattr(a, "__dlpack__"):
+        t = torch.from_dlpack(a)
+    else:
+        t = torch.as_tensor(np.asarray(a))
+    return t.to(device=device(), dtype=dtype).contiguous()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def device_mesh(basis):
+    """The basis' knot mesh as a CUDA tensor (cached on the basis object per device)."""
+    dev = device()
+    cache = basis.__dict__.setdefault("_dev_mesh", {})
+    if dev not in cache:
+        cache[dev] = torch.from_numpy(np.ascontiguousarray(basis.mesh, dtype=np.float64)).to(dev)
+    return cache[dev]
+
+
+def basis_eval_1d(X, basis, dx=0):
+    """(idx[n] int64, vals[(k+1), n]) as numpy arrays — rows idx+r of Kuf (reference basis.py:51-80)."""
+    x = to_device(X).reshape(-1)
+    n, k = x.numel(), basis.order
+    mesh = device_mesh(basis)
+    idx = torch.empty(n, dtype=torch.int64, device=x.device)
+    vals = torch.empty((k + 1, n), dtype=F64, device=x.device)
+    coef = to_device(basis.piece_coefficients(dx)) if dx > 0 else None
+    _lib.call("asvgp_basis_eval_1d", _p(x), n, _p(mesh), mesh.numel(), k, int(dx), _p(coef), _p(idx), _p(vals),
+              _stream())
+    return idx.cpu().numpy(), vals.cpu().numpy()
+
+
+def accum_size_1d(basis):
+    return (basis.order + 2) * basis.m + 2
+
+
+def accum_1d(x, y, basis, acc=None):
+    """Adds sum_n w_n w_n^T (lower band), sum_n w_n y_n, sum y^2 and the count of the points (x, y) into the
+    packed accumulator [G_band | b | sum(y^2) | count] (allocated zeroed if None).  Reference gpr.py:39-44."""
+    x = to_device(x).reshape(-1)
+    y = to_device(y).reshape(-1)
+    if x.numel() != y.numel():
+        raise ValueError("x and y must have the same number of points")
+    mesh = device_mesh(basis)
+    if acc is None:
+        acc = torch.zeros(accum_size_1d(basis), dtype=F64, device=x.device)
+    _lib.call("asvgp_accum_1d", _p(x), _p(y), x.numel(), _p(mesh), mesh.numel(), basis.order, _p(acc), _stream())
+    return acc
+
+
+def split_accum_1d(acc, basis):
+    """Views (G_band (k+1, M), b (M,), scal (2,)) into the packed accumulator."""
+    k, m = basis.order, basis.m
+    return acc[: (k + 1) * m].view(k + 1, m), acc[(k + 1) * m: (k + 2) * m], acc[(k + 2) * m:]
+
+
+def predict_1d(xnew, basis, alpha, S_band, variance, mean=None, var=None):
+    """Posterior mean/variance at xnew from alpha = P^-1 b / sigma2 and S = band(P^-1) - band(Kuu^-1)
+    (reference gpr.py:91-136)."""
+    x = to_device(xnew).reshape(-1)
+    n = x.numel()
+    mesh = device_mesh(basis)
+    alpha = to_device(alpha).reshape(-1)
+    S_band = to_device(S_band)
+    if mean is None:
+        mean = torch.empty(n, dtype=F64, device=x.device)
+    if var is None:
+        var = torch.empty(n, dtype=F64, device=x.device)
+    _lib.call("asvgp_predict_1d", _p(x), n, _p(mesh), mesh.numel(), basis.order, _p(alpha), _p(S_band),
+              float(variance), _p(mean), _p(var), _stream())
+    return mean, var
