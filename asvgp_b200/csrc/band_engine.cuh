@@ -1,0 +1,454 @@
+// Partitioned banded SPD engine: Cholesky / log-determinant / solve / Takahashi selected inverse of a symmetric
+// positive definite matrix of bandwidth K, with the length-M dependency chain cut into P independent chunks.
+//
+// Stands for the banded_matrices ops the reference calls once per optimiser step (reference gpr.py:56-75):
+// cholesky_band, the log-det from its first band row, solve_triang_mat, inverse_from_cholesky_band — and for the
+// CHOLMOD factorisations/solves of predict_f (gpr.py:96-108).  Everything the ELBO, its gradients and the
+// predictor need (log-dets, b^T P^-1 b, alpha = P^-1 b, band(A^-1)) is invariant to the elimination order, so the
+// order used here differs from the reference's left-to-right sweep (SURVEY §7 hard part 1):
+//
+//   indices:  [ I_0 | S_0 | I_1 | S_1 | ... | S_{P-2} | I_{P-1} ]     S_q = K-wide separators
+//
+//   phase 1 (one thread per chunk, lock-step):  right-looking elimination of the columns of I_p.  The band rows
+//            that reach into S_p are a natural continuation of the band; the coupling to S_{p-1} is carried as K
+//            extra "spike" rows.  Leaves the Schur complement pieces D_p, E_p and the reduced right-hand side.
+//   phase 2 (one thread):  the reduced system on the separators is itself SPD banded, of size (P-1)K and bandwidth
+//            2K-1, and goes through the same serial routine (no spikes).
+//   phase 3 (one thread per chunk):  back-substitution and/or the Takahashi recursion inside each chunk, seeded
+//            with the separator values from phase 2.
+//
+// The serial dependency chain is ~M/P + (2K-1)/K*(P-1)K columns instead of M.  Every routine is templated on the
+// scalar (double or Dual<1>) so the same sweep yields the hyper-parameter derivative, and is ASVGP_HD so that
+// tests/host_harness.cpp can run it on the CPU against dense numpy (test infrastructure; the product only
+// launches it from banded_1d.cu).
+#pragma once
+#include "common.cuh"
+#include "dual.cuh"
+
+namespace asvgp {
+
+// ---- index layout ----------------------------------------------------------------------------------------------
+struct ChunkLayout {
+    int M, K, P;
+    int base, rem;     // interior sizes: base+1 for p < rem, base otherwise
+    ASVGP_HD int size(int p) const { return base + (p < rem ? 1 : 0); }
+    ASVGP_HD int start(int p) const { return p * (base + K) + (p < rem ? p : rem); }   // first interior index
+    ASVGP_HD int sep_start(int q) const { return start(q) + size(q); }                  // first index of S_q
+    ASVGP_HD int max_size() const { return base + (rem > 0 ? 1 : 0); }
+    ASVGP_HD int n_reduced() const { return (P - 1) * K; }
+};
+
+inline ChunkLayout make_layout(int M, int K, int P) {
+    ChunkLayout L;
+    L.M = M; L.K = K;
+    // every interior needs at least K+1 columns so that no band entry couples two different separators
+    while (P > 1 && (M - (P - 1) * K) / P < K + 1) --P;
+    L.P = P;
+    const int interior = M - (P - 1) * K;
+    L.base = interior / P;
+    L.rem = interior % P;
+    return L;
+}
+
+// Heuristic chunk count: balance the chunk sweep (M/P columns) against the reduced sweep ((P-1)K columns of a
+// matrix 2K-1 wide, ~1.5x the work per column).
+inline int default_chunks(int M, int K) {
+    if (M < 64 * (K + 1)) return 1;
+    int P = (int)(sqrt((double)M / (1.5 * K)) + 0.5);
+    if (P > 128) P = 128;
+    if (P < 1) P = 1;
+    return P;
+}
+
+// ---- per-column record kept for the backward passes ----------------------------------------------------------------
+// Stored "column-step major" so that the P lanes working in lock-step touch consecutive addresses:
+//   rec[(field * n_steps + j) * P + p],  fields: 0 = 1/pivot, 1..K = L[j+a, j], K+1..2K = spike X[rho, j], 2K+1 = y_j
+template <class T, int K>
+struct ColumnStore {
+    T* rec;
+    int n_steps, P;
+    static constexpr int kFields = 2 * K + 2;
+    ASVGP_HD T& at(int field, int j, int p) const { return rec[((size_t)field * n_steps + j) * P + p]; }
+    static size_t count(int n_steps, int P) { return (size_t)kFields * n_steps * P; }
+};
+
+template <class T, int K>
+struct ChunkSchur {          // what phase 1 leaves behind for chunk p
+    T logdet, quad;
+    T Dend[K][K];            // lower triangle: updated block (S_p, S_p), original entries included
+    T rend[K];               // updated right-hand side on S_p
+    T E[K][K];               // E[a][rho] = coupling (S_p row a, S_{p-1} col rho)
+    T SLL[K][K];             // lower triangle: sum_j X[rho,j] X[rho',j]   (to subtract from block (S_{p-1}, S_{p-1}))
+    T rhsL[K];               // sum_j X[rho,j] y_j                          (to subtract from rhs on S_{p-1})
+    int info;                // 0 or 1 + global index of the first non-positive pivot
+};
+
+// ---- phase 1 / phase 2 forward: right-looking elimination of n columns starting at global column g0 -----------
+// A(d, j) -> T : entry A[j+d, j] of the lower band (must return 0 when j+d >= size or j >= size or j < 0)
+// rhs(j)  -> T : right-hand side (0 outside)
+// SPIKE: carry the K spike rows coupling to the K indices just before g0.
+template <class T, int K, bool SPIKE, bool STORE, class MatFn, class RhsFn>
+ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, const ColumnStore<T, K>& store,
+                                int p, ChunkSchur<T, K>& out) {
+    T W[K + 1][K + 1];       // lower triangle of the active window, rows/cols g .. g+K
+    T r[K + 1];
+    T c[SPIKE ? K : 1][K + 1];
+#pragma unroll
+    for (int a = 0; a <= K; ++a) {
+#pragma unroll
+        for (int b = 0; b <= a; ++b) W[a][b] = A(a - b, g0 + b);
+        r[a] = rhs(g0 + a);
+    }
+    if (SPIKE) {
+#pragma unroll
+        for (int rho = 0; rho < K; ++rho)
+#pragma unroll
+            for (int a = 0; a <= K; ++a)
+                c[rho][a] = (a <= rho) ? A(a + K - rho, g0 - K + rho) : zero_of<T>();
+    }
+    T logdet = zero_of<T>(), quad = zero_of<T>();
+    T SLL[K][K], rhsL[K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        rhsL[a] = zero_of<T>();
+#pragma unroll
+        for (int b = 0; b < K; ++b) SLL[a][b] = zero_of<T>();
+    }
+    int info = 0;
+
+    for (int j = 0; j < n_steps; ++j) {
+        if (j < n) {
+            const int g = g0 + j;
+            if (!(value_of(W[0][0]) > 0.0) && info == 0) info = g + 1;
+            logdet += log_of(W[0][0]);
+            const T ip = recip_of(sqrt_of(W[0][0]));
+            T l[K + 1];
+#pragma unroll
+            for (int a = 1; a <= K; ++a) l[a] = W[a][0] * ip;
+            const T yj = r[0] * ip;
+            quad += yj * yj;
+            T X[SPIKE ? K : 1];
+            if (SPIKE) {
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) {
+                    X[rho] = c[rho][0] * ip;
+                    rhsL[rho] += X[rho] * yj;
+#pragma unroll
+                    for (int r2 = 0; r2 <= rho; ++r2) SLL[rho][r2] += X[rho] * X[r2];
+                }
+            }
+            if (STORE) {
+                store.at(0, j, p) = ip;
+#pragma unroll
+                for (int a = 1; a <= K; ++a) store.at(a, j, p) = l[a];
+                if (SPIKE) {
+#pragma unroll
+                    for (int rho = 0; rho < K; ++rho) store.at(K + 1 + rho, j, p) = X[rho];
+                }
+                store.at(2 * K + 1, j, p) = yj;
+            }
+            // trailing update and window shift
+#pragma unroll
+            for (int a = 1; a <= K; ++a) {
+#pragma unroll
+                for (int b = 1; b <= a; ++b) W[a - 1][b - 1] = W[a][b] - l[a] * l[b];
+                r[a - 1] = r[a] - l[a] * yj;
+                if (SPIKE) {
+#pragma unroll
+                    for (int rho = 0; rho < K; ++rho) c[rho][a - 1] = c[rho][a] - l[a] * X[rho];
+                }
+            }
+#pragma unroll
+            for (int b = 0; b <= K; ++b) W[K][b] = A(K - b, g + 1 + b);
+            r[K] = rhs(g + 1 + K);
+            if (SPIKE) {
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) c[rho][K] = zero_of<T>();
+            }
+        }
+    }
+    out.logdet = logdet;
+    out.quad = quad;
+    out.info = info;
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        out.rend[a] = r[a];
+        out.rhsL[a] = rhsL[a];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            out.Dend[a][b] = (b <= a) ? W[a][b] : zero_of<T>();
+            out.SLL[a][b] = SLL[a][b];
+            out.E[a][b] = SPIKE ? c[b][a] : zero_of<T>();
+        }
+    }
+}
+
+// ---- serial back-substitution L^T x = y on stored columns (used for the reduced system) -----------------------------
+template <class T, int K>
+ASVGP_HD void backsolve_serial(int n, const ColumnStore<T, K>& store, T* x) {
+    T xw[K + 1];
+#pragma unroll
+    for (int a = 0; a <= K; ++a) xw[a] = zero_of<T>();
+    for (int j = n - 1; j >= 0; --j) {
+        T acc = store.at(2 * K + 1, j, 0);
+#pragma unroll
+        for (int a = 1; a <= K; ++a) acc -= store.at(a, j, 0) * xw[a];
+        const T xj = acc * store.at(0, j, 0);
+#pragma unroll
+        for (int a = K; a >= 2; --a) xw[a] = xw[a - 1];
+        xw[1] = xj;
+        x[j] = xj;
+    }
+}
+
+// ---- serial Takahashi recursion on stored columns: lower band of (L L^T)^-1, sig[d * n + j] ---------------------------
+template <class T, int K>
+ASVGP_HD void selinv_serial(int n, const ColumnStore<T, K>& store, T* sig) {
+    T Z[K][K];     // Sigma[g+1+a, g+1+b] of the columns already done (symmetric, full storage)
+#pragma unroll
+    for (int a = 0; a < K; ++a)
+#pragma unroll
+        for (int b = 0; b < K; ++b) Z[a][b] = zero_of<T>();
+    for (int j = n - 1; j >= 0; --j) {
+        const T ip = store.at(0, j, 0);
+        T l[K], w[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) l[a] = store.at(a + 1, j, 0);
+        T dot = zero_of<T>();
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            T acc = zero_of<T>();
+#pragma unroll
+            for (int b = 0; b < K; ++b) acc += Z[a][b] * l[b];
+            w[a] = acc;
+            dot += l[a] * acc;
+        }
+        const T ip2 = ip * ip;
+        const T sjj = ip2 + dot * ip2;
+        sig[j] = sjj;
+        T col[K];
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            col[a] = -(w[a] * ip);
+            if (j + 1 + a < n) sig[(size_t)(a + 1) * n + j] = col[a];
+        }
+        // shift: new neighbour set is {j, j+1, .., j+K-1}
+#pragma unroll
+        for (int a = K - 1; a >= 1; --a)
+#pragma unroll
+            for (int b = K - 1; b >= 1; --b) Z[a][b] = Z[a - 1][b - 1];
+        Z[0][0] = sjj;
+#pragma unroll
+        for (int a = 1; a < K; ++a) { Z[a][0] = col[a - 1]; Z[0][a] = col[a - 1]; }
+    }
+}
+
+// ---- phase 3: backward sweep inside chunk p (solve and/or selected inverse) --------------------------------------------
+// x_red / sig_red: solution and selected-inverse band ((2K) x n_red, row-major) of the reduced system (may be null
+// when the corresponding output is not requested).  x_out[M]; sig_out[(K+1) x M] lower band of A^-1.
+template <class T, int K, bool SOLVE, bool SELINV>
+ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const ColumnStore<T, K>& store,
+                             const T* x_red, const T* sig_red, T* x_out, T* sig_out) {
+    constexpr int KR = 2 * K - 1;
+    const int n = lay.size(p), s = lay.start(p), M = lay.M, nred = lay.n_reduced();
+    const bool has_left = p > 0, has_right = p < lay.P - 1;
+    (void)KR;
+    T xw[K + 1], xL[K];
+    T Z[2 * K][2 * K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        xw[a + 1] = (SOLVE && has_right) ? x_red[p * K + a] : zero_of<T>();
+        xL[a] = (SOLVE && has_left) ? x_red[(p - 1) * K + a] : zero_of<T>();
+    }
+    xw[0] = zero_of<T>();
+    if (SELINV) {
+#pragma unroll
+        for (int a = 0; a < 2 * K; ++a)
+#pragma unroll
+            for (int b = 0; b < 2 * K; ++b) Z[a][b] = zero_of<T>();
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+#pragma unroll
+            for (int b = 0; b <= a; ++b) {
+                if (has_right) { Z[a][b] = sig_red[(size_t)(a - b) * nred + p * K + b]; Z[b][a] = Z[a][b]; }
+                if (has_left) {
+                    Z[K + a][K + b] = sig_red[(size_t)(a - b) * nred + (p - 1) * K + b];
+                    Z[K + b][K + a] = Z[K + a][K + b];
+                }
+            }
+#pragma unroll
+            for (int rho = 0; rho < K; ++rho) {
+                if (has_left && has_right) {
+                    Z[a][K + rho] = sig_red[(size_t)(K + a - rho) * nred + (p - 1) * K + rho];
+                    Z[K + rho][a] = Z[a][K + rho];
+                }
+            }
+        }
+    }
+    for (int j = n_steps - 1; j >= 0; --j) {
+        if (j < n) {
+            const int g = s + j;
+            const T ip = store.at(0, j, p);
+            T lv[2 * K];
+#pragma unroll
+            for (int a = 0; a < K; ++a) {
+                lv[a] = store.at(a + 1, j, p);
+                lv[K + a] = store.at(K + 1 + a, j, p);
+            }
+            if (SOLVE) {
+                T acc = store.at(2 * K + 1, j, p);
+#pragma unroll
+                for (int a = 0; a < K; ++a) { acc -= lv[a] * xw[a + 1]; acc -= lv[K + a] * xL[a]; }
+                const T xj = acc * ip;
+#pragma unroll
+                for (int a = K; a >= 2; --a) xw[a] = xw[a - 1];
+                xw[1] = xj;
+                x_out[g] = xj;
+            }
+            if (SELINV) {
+                T w[2 * K];
+                T dot = zero_of<T>();
+#pragma unroll
+                for (int a = 0; a < 2 * K; ++a) {
+                    T acc = zero_of<T>();
+#pragma unroll
+                    for (int b = 0; b < 2 * K; ++b) acc += Z[a][b] * lv[b];
+                    w[a] = acc;
+                    dot += lv[a] * acc;
+                }
+                const T ip2 = ip * ip;
+                const T sjj = ip2 + dot * ip2;
+                sig_out[g] = sjj;
+                T col[2 * K];
+#pragma unroll
+                for (int a = 0; a < 2 * K; ++a) col[a] = -(w[a] * ip);
+#pragma unroll
+                for (int a = 0; a < K; ++a) {
+                    if (g + 1 + a < M) sig_out[(size_t)(a + 1) * M + g] = col[a];            // rows below, same band
+                    // (row g, column S_{p-1}[rho]) lies inside the band iff j <= rho
+                    if (has_left && j <= a) sig_out[(size_t)(j + K - a) * M + (s - K + a)] = col[K + a];
+                }
+                // shift the band part of Z; the separator part stays
+#pragma unroll
+                for (int a = K - 1; a >= 1; --a) {
+#pragma unroll
+                    for (int b = K - 1; b >= 1; --b) Z[a][b] = Z[a - 1][b - 1];
+#pragma unroll
+                    for (int rho = 0; rho < K; ++rho) { Z[a][K + rho] = Z[a - 1][K + rho]; Z[K + rho][a] = Z[a][K + rho]; }
+                }
+                Z[0][0] = sjj;
+#pragma unroll
+                for (int a = 1; a < K; ++a) { Z[a][0] = col[a - 1]; Z[0][a] = col[a - 1]; }
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) { Z[0][K + rho] = col[K + rho]; Z[K + rho][0] = col[K + rho]; }
+            }
+        }
+    }
+}
+
+}  // namespace asvgp
+
+// =====================================================================================================================
+// Phase drivers shared by the CUDA kernels (banded_1d.cu) and the CPU test harness (tests/host_harness.cpp)
+// =====================================================================================================================
+namespace asvgp {
+
+template <class T, int K>
+struct ChainWork {                      // caller-provided scratch, all device (or host) memory
+    ColumnStore<T, K> cols;             // chunk columns: kFields x n_steps x P
+    ChunkSchur<T, K>* schur;            // [P]
+    T* red_band;                        // (2K) x n_red   reduced lower band (bandwidth 2K-1)
+    T* red_rhs;                         // n_red
+    ColumnStore<T, 2 * K - 1> red_cols; // reduced columns: (4K) x n_red x 1
+    T* x_red;                           // n_red
+    T* sig_red;                         // (2K) x n_red
+};
+
+template <class T, int K>
+struct ChainTotals { T logdet, quad; int info; };
+
+template <class T, int K, bool STORE, class MatFn, class RhsFn>
+ASVGP_HD void chain_phase1(const ChunkLayout& lay, int p, MatFn A, RhsFn rhs, const ChainWork<T, K>& w) {
+    const int n_steps = lay.max_size();
+    if (lay.P == 1) eliminate_columns<T, K, false, STORE>(0, lay.M, n_steps, A, rhs, w.cols, 0, w.schur[0]);
+    else eliminate_columns<T, K, true, STORE>(lay.start(p), lay.size(p), n_steps, A, rhs, w.cols, p, w.schur[p]);
+}
+
+template <class T, int KR>
+struct RedMat {
+    const T* band; int n;
+    ASVGP_HD T operator()(int d, int j) const {
+        return (j >= 0 && j < n && j + d < n) ? band[(size_t)d * n + j] : zero_of<T>();
+    }
+};
+template <class T>
+struct RedRhs {
+    const T* v; int n;
+    ASVGP_HD T operator()(int j) const { return (j >= 0 && j < n) ? v[j] : zero_of<T>(); }
+};
+
+// Executed by ONE thread.  Assembles the reduced (separator) system from the chunk Schur pieces, eliminates it,
+// and (optionally) back-substitutes / runs the Takahashi recursion on it.
+template <class T, int K, bool SOLVE, bool SELINV>
+ASVGP_HD ChainTotals<T, K> chain_phase2(const ChunkLayout& lay, const ChainWork<T, K>& w) {
+    constexpr int KR = 2 * K - 1;
+    ChainTotals<T, K> tot;
+    tot.logdet = zero_of<T>();
+    tot.quad = zero_of<T>();
+    tot.info = 0;
+    for (int p = 0; p < lay.P; ++p) {
+        tot.logdet += w.schur[p].logdet;
+        tot.quad += w.schur[p].quad;
+        if (w.schur[p].info != 0 && (tot.info == 0 || w.schur[p].info < tot.info)) tot.info = w.schur[p].info;
+    }
+    const int nred = lay.n_reduced();
+    if (nred == 0) return tot;
+    for (int i = 0; i < (KR + 1) * nred; ++i) w.red_band[i] = zero_of<T>();
+    for (int q = 0; q < lay.P - 1; ++q) {
+        const ChunkSchur<T, K>& left = w.schur[q];        // chunk q ends at S_q
+        const ChunkSchur<T, K>& right = w.schur[q + 1];   // chunk q+1 starts after S_q
+        for (int a = 0; a < K; ++a) {
+            w.red_rhs[q * K + a] = left.rend[a] - right.rhsL[a];
+            for (int b = 0; b <= a; ++b)
+                w.red_band[(size_t)(a - b) * nred + q * K + b] = left.Dend[a][b] - right.SLL[a][b];
+            if (q + 1 < lay.P - 1) {
+                // rows of S_{q+1}, columns of S_q: produced by chunk q+1 (its E)
+                for (int rho = 0; rho < K; ++rho)
+                    w.red_band[(size_t)(K + a - rho) * nred + q * K + rho] = right.E[a][rho];
+            }
+        }
+    }
+    ChunkSchur<T, KR> red_out;
+    RedMat<T, KR> RA{w.red_band, nred};
+    RedRhs<T> Rb{w.red_rhs, nred};
+    eliminate_columns<T, KR, false, (SOLVE || SELINV)>(0, nred, nred, RA, Rb, w.red_cols, 0, red_out);
+    tot.logdet += red_out.logdet;
+    tot.quad += red_out.quad;
+    if (red_out.info != 0 && tot.info == 0) tot.info = lay.M + red_out.info;   // failure inside the separator system
+    if (SOLVE) backsolve_serial<T, KR>(nred, w.red_cols, w.x_red);
+    if (SELINV) selinv_serial<T, KR>(nred, w.red_cols, w.sig_red);
+    return tot;
+}
+
+template <class T, int K, bool SOLVE, bool SELINV>
+ASVGP_HD void chain_phase3(const ChunkLayout& lay, int p, const ChainWork<T, K>& w, T* x_out, T* sig_out) {
+    const int n_steps = lay.max_size();
+    if (lay.P == 1) {
+        if (SOLVE) backsolve_serial<T, K>(lay.M, w.cols, x_out);
+        if (SELINV) selinv_serial<T, K>(lay.M, w.cols, sig_out);
+        return;
+    }
+    const int nred = lay.n_reduced();
+    if (p < lay.P - 1) {                 // separator S_p: copy from the reduced solution
+        const int g = lay.sep_start(p);
+        for (int a = 0; a < K; ++a) {
+            if (SOLVE) x_out[g + a] = w.x_red[p * K + a];
+            if (SELINV)
+                for (int b = 0; b <= a; ++b)
+                    sig_out[(size_t)(a - b) * lay.M + g + b] = w.sig_red[(size_t)(a - b) * nred + p * K + b];
+        }
+    }
+    chunk_backward<T, K, SOLVE, SELINV>(lay, p, n_steps, w.cols, w.x_red, w.sig_red, x_out, sig_out);
+}
+
+}  // namespace asvgp

@@ -225,13 +225,13 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
             } else {
                 // interval crossing (or unsorted input)
                 int where[VEC];
-                bool pending = false;
+                bool pending = false, added_old = false;
                 int cand = -1;
 #pragma unroll
                 for (int e = 0; e < VEC; ++e) {
                     where[e] = -1;
                     if (valid[e]) {
-                        if (in[e]) wa.add(mesh, xs[j][e], ys[j][e]);
+                        if (in[e]) { wa.add(mesh, xs[j][e], ys[j][e]); added_old = true; }
                         else {
                             where[e] = locate_interval(mesh, xs[j][e], LdgLoader());
                             pending = true;
@@ -239,7 +239,8 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
                         }
                     }
                 }
-                wa.dirty = true;
+                // (cur == -1 before the first point: nothing accumulated yet, nothing to flush)
+                wa.dirty = wa.dirty || __any_sync(0xffffffffu, added_old);
                 wa.flush(G, b, M, lane);
                 const unsigned pend = __ballot_sync(0xffffffffu, pending);   // non-zero here
                 const int src = 31 - __clz(pend);

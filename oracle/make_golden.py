@@ -98,6 +98,7 @@ def synth_1d(ns):
             if k < need:
                 continue
             kern = getattr(ns.gpflow.kernels, kind)()
+            last_kind = kind
             model = ns.gpr.GPR_1d((x.reshape(-1, 1), y.reshape(-1, 1)), kern, basis)
             for tag, (v, l, s2) in (("a", (1.0, 1.0, 0.1)), ("b", (1.3, 2.5, 0.7))):
                 set_hypers(ns, model, [kern], [(v, l)], s2)
@@ -109,7 +110,7 @@ def synth_1d(ns):
         mu, var = model.predict_f(xs)
         out[key + "_xs"], out[key + "_mean"], out[key + "_var"] = xs, np.asarray(mu), np.asarray(var)
         out[key + "_pred_hypers"] = np.array([1.3, 2.5, 0.7])
-        out[key + "_pred_kind"] = kind
+        out[key + "_pred_kind"] = last_kind
     np.savez_compressed(os.path.join(OUT, "synth_1d.npz"), **out)
     print("synth_1d:", len(out), "arrays")
 
