@@ -19,6 +19,13 @@ SIGNATURES = {
     "asvgp_basis_eval_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "asvgp_accum_1d": [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp],
     "asvgp_predict_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp],
+    "asvgp_kuu_assemble": [_vp, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
+    "asvgp_elbo_grad_1d": [_vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp],
+    "asvgp_posterior_1d": [_vp, _vp, _c_int, _c_int, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
+}
+# functions whose return value is not a status code
+VALUE_FUNCTIONS = {
+    "asvgp_workspace_bytes_1d": (_c_i64, [_c_int, _c_int, _c_int]),
 }
 
 _lib = None
@@ -44,6 +51,10 @@ def load():
     for name, argtypes in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
+        fn.argtypes = argtypes
+    for name, (restype, argtypes) in VALUE_FUNCTIONS.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
         fn.argtypes = argtypes
     _lib = lib
     return lib

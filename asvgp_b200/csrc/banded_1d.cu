@@ -1,0 +1,414 @@
+// Latency-bound banded kernels of the 1-D model: Kuu assembly, collapsed ELBO + hyper-parameter gradients,
+// posterior weights for the predictor.
+//
+//   asvgp_kuu_assemble   <- SplineFeatures1D.make_Kuu                    (reference asvgp/inducing_features.py:12-44)
+//   asvgp_elbo_grad_1d   <- GPR_1d.elbo + its TF-autodiff gradient       (reference asvgp/gpr.py:49-89, example.py:31-32)
+//   asvgp_posterior_1d   <- the factorisations/solves of GPR_1d.predict_f (reference asvgp/gpr.py:96-108)
+//
+// Design.  The work is O(M k^2) flops — nothing — but a length-M dependency chain of
+// sqrt/div/FMA.  Each "chain" (one SPD banded matrix) runs in ONE CTA through the partitioned engine of
+// band_engine.cuh: P lanes eliminate P chunks in lock-step, lane 0 eliminates the (P-1)k separator system, the lanes
+// sweep back.  Independent chains run in different CTAs of the same launch:
+//   ELBO+grad : [Kuu, d/dl] with Takahashi + trace,  [P, d/dl] forward only,  [P, d/dsigma2] forward only
+//   posterior : [Kuu] Takahashi,  [P] solve + Takahashi
+// Derivatives ride along as Dual<1> tangents; the variance derivative follows analytically from the sigma2 one
+// because Kuu is proportional to 1/variance (see elbo_finalize_kernel).
+#include <cuda_runtime.h>
+
+#include "band_engine.cuh"
+#include "../../include/asvgp_b200.h"
+
+namespace asvgp {
+
+constexpr int kChainThreads = 128;          // >= max chunk count P
+constexpr int kMaxTerms = 12;
+
+// ------------------------------------------------------------------------------------------------------------------
+// Kuu assembly
+// ------------------------------------------------------------------------------------------------------------------
+struct KuuTerms {
+    int n_terms;
+    double coef[kMaxTerms];
+    double dcoef[kMaxTerms];
+};
+
+__global__ void __launch_bounds__(256) kuu_assemble_kernel(const double* __restrict__ tables, KuuTerms terms,
+                                                           int64_t band_elems, double* __restrict__ Kuu,
+                                                           double* __restrict__ dKuu) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < band_elems;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0, dv = 0.0;
+        for (int t = 0; t < terms.n_terms; ++t) {
+            const double s = __ldg(tables + (int64_t)t * band_elems + i);
+            v = fma(terms.coef[t], s, v);
+            dv = fma(terms.dcoef[t], s, dv);
+        }
+        Kuu[i] = v;
+        if (dKuu != nullptr) dKuu[i] = dv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// matrix / right-hand-side functors fed to the engine
+// ------------------------------------------------------------------------------------------------------------------
+template <class T> struct BandMat;      // A = alpha*Kuu + beta*G  with tangent  ta*dKuu + tb*G
+template <> struct BandMat<Dual<1>> {
+    const double* Kuu; const double* dKuu; const double* G;
+    double beta, tb; int use_dK; int M;
+    __device__ __forceinline__ Dual<1> operator()(int d, int j) const {
+        Dual<1> r; r.v = 0.0; r.d[0] = 0.0;
+        if (j >= 0 && j < M && j + d < M) {
+            const size_t i = (size_t)d * M + j;
+            const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
+            r.v = fma(beta, g, __ldg(Kuu + i));
+            r.d[0] = (use_dK ? __ldg(dKuu + i) : 0.0) + tb * g;
+        }
+        return r;
+    }
+};
+template <> struct BandMat<double> {
+    const double* Kuu; const double* dKuu; const double* G;
+    double beta, tb; int use_dK; int M;
+    __device__ __forceinline__ double operator()(int d, int j) const {
+        if (j >= 0 && j < M && j + d < M) {
+            const size_t i = (size_t)d * M + j;
+            const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
+            return fma(beta, g, __ldg(Kuu + i));
+        }
+        return 0.0;
+    }
+};
+template <class T> struct VecRhs {
+    const double* b; int M;
+    __device__ __forceinline__ T operator()(int j) const {
+        return make_scalar<T>((b != nullptr && j >= 0 && j < M) ? __ldg(b + j) : 0.0, 0.0);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// workspace carving (host) — one ChainWork per chain out of a caller-provided buffer
+// ------------------------------------------------------------------------------------------------------------------
+template <class T, int K>
+struct ChainPlan {
+    static size_t bytes(const ChunkLayout& lay) {
+        constexpr int KR = 2 * K - 1;
+        const size_t nred = (size_t)lay.n_reduced() + 1;
+        size_t n = 0;
+        n += ColumnStore<T, K>::count(lay.max_size(), lay.P) * sizeof(T);
+        n += (size_t)lay.P * sizeof(ChunkSchur<T, K>);
+        n += (size_t)(KR + 1) * nred * sizeof(T) * 2;            // red_band, sig_red
+        n += nred * sizeof(T) * 2;                               // red_rhs, x_red
+        n += ColumnStore<T, KR>::count((int)nred, 1) * sizeof(T);
+        return (n + 255) & ~(size_t)255;
+    }
+    static ChainWork<T, K> carve(const ChunkLayout& lay, char* base) {
+        constexpr int KR = 2 * K - 1;
+        const size_t nred = (size_t)lay.n_reduced() + 1;
+        ChainWork<T, K> w;
+        char* p = base;
+        w.cols = ColumnStore<T, K>{reinterpret_cast<T*>(p), lay.max_size(), lay.P};
+        p += ColumnStore<T, K>::count(lay.max_size(), lay.P) * sizeof(T);
+        w.red_band = reinterpret_cast<T*>(p); p += (size_t)(KR + 1) * nred * sizeof(T);
+        w.sig_red = reinterpret_cast<T*>(p); p += (size_t)(KR + 1) * nred * sizeof(T);
+        w.red_rhs = reinterpret_cast<T*>(p); p += nred * sizeof(T);
+        w.x_red = reinterpret_cast<T*>(p); p += nred * sizeof(T);
+        w.red_cols = ColumnStore<T, KR>{reinterpret_cast<T*>(p), lay.n_reduced(), 1};
+        p += ColumnStore<T, KR>::count((int)nred, 1) * sizeof(T);
+        w.schur = reinterpret_cast<ChunkSchur<T, K>*>(p);
+        return w;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// ELBO + gradient
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+struct ElboArgs {
+    ChunkLayout lay;
+    ChainWork<Dual<1>, K> work[3];
+    const double* Kuu; const double* dKuu; const double* G; const double* b;
+    double sigma2;
+    Dual<1>* sigK;          // (K+1) x M   band(Kuu^-1) with d/dl tangent
+    double* partial;        // [3 chains][8]: logdet, dlogdet, quad, dquad, trace, dtrace, info
+};
+
+template <int K>
+__global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> a) {
+    using T = Dual<1>;
+    const int chain = blockIdx.x, p = threadIdx.x;
+    const ChunkLayout lay = a.lay;
+    const ChainWork<T, K>& w = a.work[chain];
+    const int M = lay.M;
+    __shared__ ChainTotals<T, K> tot;
+    __shared__ double s_red[2][kChainThreads / 32];
+    double* out = a.partial + chain * 8;
+
+    if (chain == 0) {
+        BandMat<T> A{a.Kuu, a.dKuu, nullptr, 0.0, 0.0, 1, M};
+        VecRhs<T> rhs{nullptr, M};
+        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
+        __syncthreads();
+        if (p == 0) tot = chain_phase2<T, K, false, true>(lay, w);
+        __syncthreads();
+        if (p < lay.P) chain_phase3<T, K, false, true>(lay, p, w, static_cast<T*>(nullptr), a.sigK);
+        __syncthreads();
+        // trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G), off-diagonals twice (reference gpr.py:60-70)
+        double tr = 0.0, dtr = 0.0;
+        for (int i = p; i < (K + 1) * M; i += kChainThreads) {
+            const double wgt = (i < M) ? 1.0 : 2.0;
+            const double g = wgt * __ldg(a.G + i);
+            const T s = a.sigK[i];
+            tr = fma(s.v, g, tr);
+            dtr = fma(s.d[0], g, dtr);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            tr += __shfl_xor_sync(0xffffffffu, tr, o);
+            dtr += __shfl_xor_sync(0xffffffffu, dtr, o);
+        }
+        if ((p & 31) == 0) { s_red[0][p >> 5] = tr; s_red[1][p >> 5] = dtr; }
+        __syncthreads();
+        if (p == 0) {
+            tr = 0.0; dtr = 0.0;
+            for (int i = 0; i < kChainThreads / 32; ++i) { tr += s_red[0][i]; dtr += s_red[1][i]; }
+            out[4] = tr; out[5] = dtr;
+        }
+    } else {
+        const double inv_s2 = 1.0 / a.sigma2;
+        // chain 1: tangent d/dl (dKuu);  chain 2: tangent d/dsigma2 (-G/sigma2^2)
+        BandMat<T> A{a.Kuu, a.dKuu, a.G, inv_s2, chain == 1 ? 0.0 : -inv_s2 * inv_s2, chain == 1 ? 1 : 0, M};
+        VecRhs<T> rhs{a.b, M};
+        if (p < lay.P) chain_phase1<T, K, false>(lay, p, A, rhs, w);
+        __syncthreads();
+        if (p == 0) tot = chain_phase2<T, K, false, false>(lay, w);
+        __syncthreads();
+    }
+    if (p == 0) {
+        out[0] = tot.logdet.v; out[1] = tot.logdet.d[0];
+        out[2] = tot.quad.v;   out[3] = tot.quad.d[0];
+        out[6] = (double)tot.info;
+    }
+}
+
+// Collapsed bound of reference gpr.py:81-87 and its derivatives.  With Q = b^T P^-1 b (so that
+// sum(c^2) = Q / sigma2^2, gpr.py:75,85), tr = trace(Kuu^-1 G):
+//   ELBO = -N/2 log(2 pi s2) - 1/2 log|P| + 1/2 log|Kuu| - yy/(2 s2) + Q/(2 s2^2) - N v/(2 s2) + tr/(2 s2)
+// Kuu = Kt(l)/v  =>  P = (Kt + (v/s2) G)/v, hence d/dv of log|P| and Q follow from d/ds2:
+//   dlog|P|/dv = -M/v - (s2/v) dlog|P|/ds2,   dQ/dv = Q/v - (s2/v) dQ/ds2,   dlog|Kuu|/dv = -M/v,   dtr/dv = tr/v.
+__global__ void elbo_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ scal, int M,
+                                     double variance, double sigma2, double* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double* cK = partial;          // Kuu chain (d/dl)
+    const double* cL = partial + 8;      // P chain (d/dl)
+    const double* cS = partial + 16;     // P chain (d/dsigma2)
+    const double yy = scal[0], N = scal[1];
+    const double v = variance, s2 = sigma2;
+    const double logdetK = cK[0], dlogdetK_dl = cK[1], tr = cK[4], dtr_dl = cK[5];
+    const double logdetP = cL[0], dlogdetP_dl = cL[1], Q = cL[2], dQ_dl = cL[3];
+    const double dlogdetP_ds = cS[1], dQ_ds = cS[3];
+    const double two_pi = 6.283185307179586476925286766559;
+    const double elbo = -0.5 * N * log(two_pi * s2) - 0.5 * logdetP + 0.5 * logdetK - 0.5 * yy / s2
+                        + 0.5 * Q / (s2 * s2) - 0.5 * N * v / s2 + 0.5 * tr / s2;
+    const double d_l = -0.5 * dlogdetP_dl + 0.5 * dlogdetK_dl + 0.5 * dQ_dl / (s2 * s2) + 0.5 * dtr_dl / s2;
+    const double d_s = -0.5 * N / s2 - 0.5 * dlogdetP_ds + 0.5 * yy / (s2 * s2) + 0.5 * dQ_ds / (s2 * s2)
+                       - Q / (s2 * s2 * s2) + 0.5 * N * v / (s2 * s2) - 0.5 * tr / (s2 * s2);
+    const double dlogdetP_dv = -(double)M / v - (s2 / v) * dlogdetP_ds;
+    const double dQ_dv = Q / v - (s2 / v) * dQ_ds;
+    const double d_v = -0.5 * dlogdetP_dv - 0.5 * (double)M / v + 0.5 * dQ_dv / (s2 * s2) - 0.5 * N / s2
+                       + 0.5 * tr / (v * s2);
+    out[0] = elbo; out[1] = d_v; out[2] = d_l; out[3] = d_s;
+    out[4] = logdetK; out[5] = logdetP; out[6] = Q; out[7] = tr;
+    double info = cK[6];
+    if (info == 0.0) info = cL[6];
+    if (info == 0.0) info = cS[6];
+    out[8] = info;
+    out[9] = dlogdetK_dl; out[10] = dlogdetP_dl; out[11] = dQ_dl; out[12] = dtr_dl; out[13] = dlogdetP_ds;
+    out[14] = dQ_ds; out[15] = cL[0] - cS[0];      // consistency of the two P chains (must be ~0)
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// posterior weights
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+struct PosteriorArgs {
+    ChunkLayout lay;
+    ChainWork<double, K> work[2];
+    const double* Kuu; const double* G; const double* b;
+    double sigma2;
+    double* sigK; double* sigP; double* x;       // (K+1) x M, (K+1) x M, M
+    double* info;                                // [2]
+};
+
+template <int K>
+__global__ void __launch_bounds__(kChainThreads) posterior_chains_kernel(PosteriorArgs<K> a) {
+    using T = double;
+    const int chain = blockIdx.x, p = threadIdx.x;
+    const ChunkLayout lay = a.lay;
+    const ChainWork<T, K>& w = a.work[chain];
+    const int M = lay.M;
+    __shared__ ChainTotals<T, K> tot;
+    if (chain == 0) {
+        BandMat<T> A{a.Kuu, nullptr, nullptr, 0.0, 0.0, 0, M};
+        VecRhs<T> rhs{nullptr, M};
+        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
+        __syncthreads();
+        if (p == 0) tot = chain_phase2<T, K, false, true>(lay, w);
+        __syncthreads();
+        if (p < lay.P) chain_phase3<T, K, false, true>(lay, p, w, static_cast<T*>(nullptr), a.sigK);
+    } else {
+        BandMat<T> A{a.Kuu, nullptr, a.G, 1.0 / a.sigma2, 0.0, 0, M};
+        VecRhs<T> rhs{a.b, M};
+        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
+        __syncthreads();
+        if (p == 0) tot = chain_phase2<T, K, true, true>(lay, w);
+        __syncthreads();
+        if (p < lay.P) chain_phase3<T, K, true, true>(lay, p, w, a.x, a.sigP);
+    }
+    __syncthreads();
+    if (p == 0) a.info[chain] = (double)tot.info;
+}
+
+__global__ void __launch_bounds__(256) posterior_combine_kernel(const double* __restrict__ sigK,
+                                                                const double* __restrict__ sigP,
+                                                                const double* __restrict__ x, double inv_s2, int M,
+                                                                int band_elems, double* __restrict__ alpha,
+                                                                double* __restrict__ S) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < band_elems; i += gridDim.x * blockDim.x) {
+        S[i] = sigP[i] - sigK[i];
+        if (i < M) alpha[i] = x[i] * inv_s2;
+    }
+}
+
+template <int K>
+static size_t elbo_work_bytes(const ChunkLayout& lay) {
+    return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
+           + 256;
+}
+template <int K>
+static size_t posterior_work_bytes(const ChunkLayout& lay) {
+    return 2 * ChainPlan<double, K>::bytes(lay) + 3 * ((((size_t)(K + 1) * lay.M * sizeof(double)) + 255) & ~(size_t)255)
+           + 256;
+}
+
+template <int K>
+static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* dKuu, const double* acc,
+                       double variance, double sigma2, double* out, char* work, cudaStream_t st) {
+    ElboArgs<K> a;
+    a.lay = lay;
+    char* p = work;
+    for (int c = 0; c < 3; ++c) { a.work[c] = ChainPlan<Dual<1>, K>::carve(lay, p); p += ChainPlan<Dual<1>, K>::bytes(lay); }
+    a.sigK = reinterpret_cast<Dual<1>*>(p);
+    p += ((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255;
+    a.partial = reinterpret_cast<double*>(p);
+    const int M = lay.M;
+    a.Kuu = Kuu; a.dKuu = dKuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
+    a.sigma2 = sigma2;
+    elbo_chains_kernel<K><<<3, kChainThreads, 0, st>>>(a);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    elbo_finalize_kernel<<<1, 32, 0, st>>>(a.partial, acc + (size_t)(K + 2) * M, M, variance, sigma2, out);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <int K>
+static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const double* acc, double sigma2,
+                            double* alpha, double* S, double* info, char* work, cudaStream_t st) {
+    PosteriorArgs<K> a;
+    a.lay = lay;
+    char* p = work;
+    for (int c = 0; c < 2; ++c) { a.work[c] = ChainPlan<double, K>::carve(lay, p); p += ChainPlan<double, K>::bytes(lay); }
+    const int M = lay.M;
+    const size_t band_bytes = (((size_t)(K + 1) * M * sizeof(double)) + 255) & ~(size_t)255;
+    a.sigK = reinterpret_cast<double*>(p); p += band_bytes;
+    a.sigP = reinterpret_cast<double*>(p); p += band_bytes;
+    a.x = reinterpret_cast<double*>(p);
+    a.Kuu = Kuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
+    a.sigma2 = sigma2;
+    a.info = info;
+    ASVGP_CUDA_OK(cudaMemsetAsync(a.sigK, 0, 2 * band_bytes, st));
+    posterior_chains_kernel<K><<<2, kChainThreads, 0, st>>>(a);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    const int band_elems = (K + 1) * M;
+    posterior_combine_kernel<<<(band_elems + 255) / 256, 256, 0, st>>>(a.sigK, a.sigP, a.x, 1.0 / sigma2, M, band_elems,
+                                                                      alpha, S);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+static ChunkLayout pick_layout(int M, int K, int chunks) {
+    int P = chunks > 0 ? chunks : default_chunks(M, K);
+    if (P > kChainThreads) P = kChainThreads;
+    return make_layout(M, K, P);
+}
+
+}  // namespace asvgp
+
+using namespace asvgp;
+
+#define ASVGP_DISPATCH_ORDER(order, CALL)                         \
+    switch (order) {                                              \
+        case 1: { constexpr int K = 1; CALL; } break;             \
+        case 2: { constexpr int K = 2; CALL; } break;             \
+        case 3: { constexpr int K = 3; CALL; } break;             \
+        case 4: { constexpr int K = 4; CALL; } break;             \
+        case 5: { constexpr int K = 5; CALL; } break;             \
+        case 6: { constexpr int K = 6; CALL; } break;             \
+        default:                                                  \
+            set_last_error("spline order %d not in 1..6", order); \
+            return kBadArgument;                                  \
+    }
+
+extern "C" int asvgp_kuu_assemble(const double* tables, int n_terms, const double* h_coef, const double* h_dcoef,
+                                  int M, int order, double* Kuu, double* dKuu, void* stream) {
+    ASVGP_REQUIRE(n_terms >= 1 && n_terms <= kMaxTerms, "kuu_assemble: n_terms=%d not in 1..%d", n_terms, kMaxTerms);
+    ASVGP_REQUIRE(M > 0 && order >= 1 && order <= kMaxOrder, "kuu_assemble: M=%d order=%d", M, order);
+    KuuTerms t;
+    t.n_terms = n_terms;
+    for (int i = 0; i < n_terms; ++i) { t.coef[i] = h_coef[i]; t.dcoef[i] = h_dcoef ? h_dcoef[i] : 0.0; }
+    const int64_t elems = (int64_t)(order + 1) * M;
+    const int blocks = (int)((elems + 255) / 256);
+    kuu_assemble_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(tables, t, elems, Kuu, dKuu);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+extern "C" int64_t asvgp_workspace_bytes_1d(int M, int order, int chunks) {
+    if (M <= 0 || order < 1 || order > kMaxOrder) return -1;
+    const ChunkLayout lay = pick_layout(M, order, chunks);
+    size_t e = 0, p = 0;
+    switch (order) {
+        case 1: e = elbo_work_bytes<1>(lay); p = posterior_work_bytes<1>(lay); break;
+        case 2: e = elbo_work_bytes<2>(lay); p = posterior_work_bytes<2>(lay); break;
+        case 3: e = elbo_work_bytes<3>(lay); p = posterior_work_bytes<3>(lay); break;
+        case 4: e = elbo_work_bytes<4>(lay); p = posterior_work_bytes<4>(lay); break;
+        case 5: e = elbo_work_bytes<5>(lay); p = posterior_work_bytes<5>(lay); break;
+        case 6: e = elbo_work_bytes<6>(lay); p = posterior_work_bytes<6>(lay); break;
+    }
+    return (int64_t)(e > p ? e : p);
+}
+
+extern "C" int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const double* acc, int M, int order,
+                                  double variance, double sigma2, int chunks, double* out, void* work,
+                                  int64_t work_bytes, void* stream) {
+    ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "elbo_grad_1d: M=%d order=%d", M, order);
+    ASVGP_REQUIRE(variance > 0.0 && sigma2 > 0.0, "elbo_grad_1d: variance=%g sigma2=%g must be positive", variance, sigma2);
+    ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "elbo_grad_1d: workspace too small");
+    const ChunkLayout lay = pick_layout(M, order, chunks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_elbo<K>(lay, Kuu, dKuu, acc, variance, sigma2, out,
+                                                              static_cast<char*>(work), st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_posterior_1d(const double* Kuu, const double* acc, int M, int order, double sigma2, int chunks,
+                                  double* alpha, double* S_band, double* info, void* work, int64_t work_bytes,
+                                  void* stream) {
+    ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "posterior_1d: M=%d order=%d", M, order);
+    ASVGP_REQUIRE(sigma2 > 0.0, "posterior_1d: sigma2=%g must be positive", sigma2);
+    ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "posterior_1d: workspace too small");
+    const ChunkLayout lay = pick_layout(M, order, chunks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_posterior<K>(lay, Kuu, acc, sigma2, alpha, S_band, info,
+                                                                   static_cast<char*>(work), st)) return rc; });
+    return kOk;
+}

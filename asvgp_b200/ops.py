@@ -99,3 +99,69 @@ def predict_1d(xnew, basis, alpha, S_band, variance, mean=None, var=None):
     _lib.call("asvgp_predict_1d", _p(x), n, _p(mesh), mesh.numel(), basis.order, _p(alpha), _p(S_band),
               float(variance), _p(mean), _p(var), _stream())
     return mean, var
+
+
+# ---- banded (latency-bound) operators ----------------------------------------------------------------------------------
+def workspace_1d(m, order, chunks=0):
+    """Scratch tensor for elbo_grad_1d / posterior_1d (cached per (device, m, order, chunks))."""
+    dev = device()
+    key = (dev, m, order, chunks)
+    ws = _WORKSPACES.get(key)
+    if ws is None:
+        nbytes = _lib.load().asvgp_workspace_bytes_1d(m, order, chunks)
+        if nbytes < 0:
+            raise _lib.AsvgpNativeError("asvgp_workspace_bytes_1d rejected m=%d order=%d" % (m, order))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+_WORKSPACES = {}
+
+
+def device_tables(basis, names):
+    """The named static bands of the basis stacked as one CUDA tensor [len(names), k+1, m] (cached)."""
+    dev = device()
+    cache = basis.__dict__.setdefault("_dev_tables", {})
+    key = (dev, tuple(names))
+    if key not in cache:
+        stack = np.stack([np.asarray(getattr(basis, n), dtype=np.float64) for n in names])
+        cache[key] = torch.from_numpy(np.ascontiguousarray(stack)).to(dev)
+    return cache[key]
+
+
+def kuu_assemble(basis, names, coef, dcoef=None, want_grad=True):
+    """Kuu = sum coef[n] * basis.<n> (and its lengthscale derivative) as CUDA bands (reference
+    inducing_features.py:12-44)."""
+    tables = device_tables(basis, names)
+    k, m = basis.order, basis.m
+    Kuu = torch.empty((k + 1, m), dtype=F64, device=tables.device)
+    dKuu = torch.empty_like(Kuu) if want_grad else None
+    c = (ctypes.c_double * len(names))(*[float(v) for v in coef])
+    dc = (ctypes.c_double * len(names))(*[float(v) for v in (dcoef if dcoef is not None else [0.0] * len(names))])
+    _lib.call("asvgp_kuu_assemble", _p(tables), len(names), ctypes.cast(c, ctypes.c_void_p),
+              ctypes.cast(dc, ctypes.c_void_p), m, k, _p(Kuu), _p(dKuu), _stream())
+    return Kuu, dKuu
+
+
+def elbo_grad_1d(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None):
+    """Launches the ELBO+gradient kernels; returns the 16-slot device result (see include/asvgp_b200.h)."""
+    k, m = basis.order, basis.m
+    ws = workspace_1d(m, k, chunks)
+    if out is None:
+        out = torch.empty(16, dtype=F64, device=acc.device)
+    _lib.call("asvgp_elbo_grad_1d", _p(Kuu), _p(dKuu), _p(acc), m, k, float(variance), float(sigma2), int(chunks),
+              _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
+def posterior_1d(Kuu, acc, basis, sigma2, chunks=0):
+    """alpha = P^-1 b / sigma2 and S = band(P^-1) - band(Kuu^-1) on the device (reference gpr.py:96-108)."""
+    k, m = basis.order, basis.m
+    ws = workspace_1d(m, k, chunks)
+    alpha = torch.empty(m, dtype=F64, device=acc.device)
+    S = torch.empty((k + 1, m), dtype=F64, device=acc.device)
+    info = torch.zeros(2, dtype=F64, device=acc.device)
+    _lib.call("asvgp_posterior_1d", _p(Kuu), _p(acc), m, k, float(sigma2), int(chunks), _p(alpha), _p(S), _p(info),
+              _p(ws), ws.numel(), _stream())
+    return alpha, S, info

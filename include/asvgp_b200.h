@@ -65,6 +65,37 @@ ASVGP_API int asvgp_accum_1d(const double* x, const double* y, int64_t n, const 
 ASVGP_API int asvgp_predict_1d(const double* xnew, int64_t n, const double* mesh, int n_knots, int order, const double* alpha,
                      const double* S_band, double variance, double* mean, double* var, void* stream);
 
+/* ---- a5: Kuu assembly ----------------------------------------------------------------------------------------------------
+ * Replaces SplineFeatures1D.make_Kuu (inducing_features.py:12-44): Kuu = sum_t coef[t] * tables[t] over the static
+ * bands A, B, C, D, BC, BC_grad, BC_ggrad of the basis (basis.py:31-45,82-114), each (order+1) x M, stacked
+ * contiguously in `tables`.  `h_coef` / `h_dcoef` are HOST arrays of the Matern coefficients and of their
+ * derivatives w.r.t. the lengthscale; dKuu (may be NULL) receives sum_t dcoef[t] * tables[t]. */
+ASVGP_API int asvgp_kuu_assemble(const double* tables, int n_terms, const double* h_coef, const double* h_dcoef, int M,
+                                 int order, double* Kuu, double* dKuu, void* stream);
+
+/* Scratch bytes needed by asvgp_elbo_grad_1d / asvgp_posterior_1d (chunks = 0: library default). */
+ASVGP_API int64_t asvgp_workspace_bytes_1d(int M, int order, int chunks);
+
+/* ---- a8 + a9: collapsed ELBO and its hyper-parameter gradients ------------------------------------------------------------
+ * Replaces GPR_1d.elbo (gpr.py:49-89: cholesky_band x2, inverse_from_cholesky_band, product_band_band,
+ * solve_triang_mat) and the TF reverse-mode gradient the optimiser asks for (example.py:31-32).
+ * `acc` is the packed accumulator of asvgp_accum_1d (after any all-reduce).  `chunks`: number of partitions of the
+ * banded sweeps (0 = default).  out[16] (device):
+ *   [0] ELBO  [1] dELBO/dvariance  [2] dELBO/dlengthscale  [3] dELBO/dsigma2
+ *   [4] log|Kuu|  [5] log|P|  [6] b^T P^-1 b  [7] trace(Kuu^-1 G)  [8] info (0 ok, j+1 first non-positive pivot)
+ *   [9..15] diagnostics (individual derivatives). */
+ASVGP_API int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const double* acc, int M, int order,
+                                 double variance, double sigma2, int chunks, double* out, void* work,
+                                 int64_t work_bytes, void* stream);
+
+/* ---- a10 (factorisation half): posterior weights -------------------------------------------------------------------------
+ * Replaces the CHOLMOD factorisations and solves of GPR_1d.predict_f (gpr.py:96-108):
+ * alpha = P^-1 Kuf_y / sigma2 and S = band(P^-1) - band(Kuu^-1), P = Kuu + G / sigma2.  info[2] (device): failing
+ * pivot of the Kuu / P factorisation or 0. */
+ASVGP_API int asvgp_posterior_1d(const double* Kuu, const double* acc, int M, int order, double sigma2, int chunks,
+                                 double* alpha, double* S_band, double* info, void* work, int64_t work_bytes,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

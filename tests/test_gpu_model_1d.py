@@ -1,0 +1,119 @@
+"""GPU parity of the 1-D model through the reference-shaped API: ELBO vs golden (reference-under-shim) at rel 1e-10,
+gradients vs the torch-autograd oracle at 1e-8, predictions at 1e-9 abs, the notebook known answer after L-BFGS."""
+import numpy as np
+import pytest
+
+from oracle import asvgp_oracle as O
+
+pytestmark = pytest.mark.gpu
+KINDS = ("Matern12", "Matern32", "Matern52")
+
+
+def _model(X, y, kind, k, a, b, m, hyp=None, **kw):
+    from asvgp_b200 import basis as B, kernels as Kn
+    from asvgp_b200.gpr import GPR_1d
+
+    basis = getattr(B, "B%dSpline" % k)(a, b, m)
+    kern = getattr(Kn, kind)()
+    model = GPR_1d((X.reshape(-1, 1), y.reshape(-1, 1)), kern, basis, **kw)
+    if hyp is not None:
+        kern.variance.assign(hyp[0]); kern.lengthscales.assign(hyp[1]); model.likelihood.variance.assign(hyp[2])
+    return model
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_snelson_elbo_golden(cuda, golden, kind):
+    g = golden("snelson")
+    model = _model(g["X"], g["y"], kind, 3, -3.5, 10.5, 100)
+    np.testing.assert_allclose(model.inducing_features.make_Kuu(model.kernel), g["Kuu111_" + kind], rtol=1e-12, atol=1e-13)
+    assert abs(model.elbo() - float(g["elbo111_" + kind])) <= 1e-10 * abs(float(g["elbo111_" + kind]))
+    model = _model(g["X"], g["y"], kind, 3, -3.5, 10.5, 100, hyp=(0.8, 1.03, 0.08))
+    assert abs(model.elbo() - float(g["elbo_b_" + kind])) <= 1e-10 * abs(float(g["elbo_b_" + kind]))
+
+
+@pytest.mark.parametrize("chunks", [1, 2, 3, 7])
+def test_snelson_chunking_invariance(cuda, golden, chunks):
+    g = golden("snelson")
+    model = _model(g["X"], g["y"], "Matern32", 3, -3.5, 10.5, 100, hyp=(0.8, 1.03, 0.08), chunks=chunks)
+    assert abs(model.elbo() - float(g["elbo_b_Matern32"])) <= 1e-10 * abs(float(g["elbo_b_Matern32"]))
+
+
+def test_snelson_predict_golden(cuda, golden):
+    g = golden("snelson")
+    model = _model(g["X"], g["y"], "Matern32", 3, -3.5, 10.5, 100, hyp=tuple(g["opt_hypers"]))
+    assert abs(model.elbo() - float(g["elbo_opt"])) <= 1e-10 * abs(float(g["elbo_opt"]))
+    mean, var = model.predict_f(g["Xtest"])
+    np.testing.assert_allclose(mean, g["pred_mean"], atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, g["pred_var"], atol=1e-9, rtol=0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_synth_elbo_and_predict_golden(cuda, golden, k):
+    g = golden("synth_1d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    for kind in KINDS:
+        for tag, hyp in (("a", (1.0, 1.0, 0.1)), ("b", (1.3, 2.5, 0.7))):
+            name = "%s_%s_elbo_%s" % (key, kind, tag)
+            if name not in g.files:
+                continue
+            model = _model(g[key + "_x"], g[key + "_y"], kind, k, -1, m + 1, m, hyp=hyp)
+            want = float(g[name])
+            assert abs(model.elbo() - want) <= 1e-10 * abs(want), (kind, tag)
+    kind = str(g[key + "_pred_kind"])
+    model = _model(g[key + "_x"], g[key + "_y"], kind, k, -1, m + 1, m, hyp=tuple(g[key + "_pred_hypers"]))
+    mean, var = model.predict_f(g[key + "_xs"])
+    np.testing.assert_allclose(mean, g[key + "_mean"], atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, g[key + "_var"], atol=1e-9, rtol=0)
+
+
+@pytest.mark.parametrize("kind,k", [("Matern12", 1), ("Matern12", 3), ("Matern32", 2), ("Matern32", 3),
+                                    ("Matern52", 3), ("Matern32", 4), ("Matern52", 5)])
+@pytest.mark.parametrize("chunks", [0, 5])
+def test_gradients_match_autograd_oracle(cuda, golden, kind, k, chunks):
+    g = golden("synth_1d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    hyp = (1.3, 2.5, 0.7)
+    model = _model(g[key + "_x"], g[key + "_y"], kind, k, -1, m + 1, m, hyp=hyp, chunks=chunks)
+    elbo, grads = model.elbo_and_grad()
+    tables = O.static_bands(k, m, model.basis.delta)
+    e0, g0 = O.elbo_grad_1d_dense(kind, tables, g[key + "_G"], g[key + "_Kuf_y"], float(g[key + "_tr_yTy"]),
+                                  g[key + "_x"].shape[0], hyp[0], hyp[1], hyp[2])
+    assert abs(elbo - e0) <= 1e-10 * abs(e0)
+    got = np.array([grads[id(model.kernel.variance)], grads[id(model.kernel.lengthscales)],
+                    grads[id(model.likelihood.variance)]])
+    np.testing.assert_allclose(got, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
+
+
+def test_medium_m_partitioned_vs_oracle(cuda):
+    """C2 shape (N=1e6, M=1000): default chunking (P>1) against the SciPy banded oracle."""
+    rng = np.random.default_rng(1997)
+    n, m, k = 1_000_000, 1000, 3
+    x = np.sort(rng.uniform(0.0, m, n))
+    y = np.sin(2 * np.pi * x / 37) + 0.5 * np.sin(2 * np.pi * x / 3.1) + 0.3 * rng.standard_normal(n)
+    y = (y - y.mean()) / y.std()
+    for kind, hyp in (("Matern32", (1.0, 1.0, 0.1)), ("Matern52", (1.0, 1.0, 1.0)), ("Matern32", (1.0, 10.0, 0.1))):
+        model = _model(x, y, kind, k, -1, m + 1, m, hyp=hyp)
+        tables = O.static_bands(k, m, model.basis.delta)
+        G0, b0, yy0 = O.precompute_1d_chunked(model.basis.mesh, model.basis.delta, k, m, x, y)
+        Kuu = O.make_Kuu(kind, hyp[1], hyp[0], tables)
+        want = O.elbo_1d(Kuu, G0, b0, yy0, n, hyp[0], hyp[2])
+        assert abs(model.elbo() - want) <= 1e-10 * abs(want), (kind, hyp)
+        xs = rng.uniform(1.0, m - 1.0, 500)
+        mean, var = model.predict_f(xs.reshape(-1, 1))
+        mean0, var0 = O.predict_1d(model.basis.mesh, model.basis.delta, k, m, Kuu, G0, b0, hyp[0], hyp[2], xs)
+        np.testing.assert_allclose(mean, mean0, atol=1e-9, rtol=0)
+        np.testing.assert_allclose(var, var0, atol=1e-9, rtol=0)
+
+
+def test_snelson_notebook_known_answer(cuda, golden):
+    """L-BFGS-B from GPflow's defaults must land on the reference notebook's stored ELBO (example.ipynb cell 3)."""
+    from asvgp_b200.optimizers import Scipy
+
+    g = golden("snelson")
+    model = _model(g["X"], g["y"], "Matern32", 3, -3.5, 10.5, 100)
+    Scipy().minimize(model.training_loss, model.trainable_variables)
+    elbo = model.elbo()
+    assert abs(elbo - float(g["notebook_elbo"])) < 1e-6
+    assert elbo < float(g["notebook_exact_gp"])
