@@ -62,12 +62,11 @@ class GPR_1d(_ModelBase):
         if y.shape[1] != 1:
             raise NotImplementedError("multi-output y (D > 1) is not implemented yet")
         self.X, self.y = X, y
-        self._x = ops.to_device(X).reshape(-1)
-        self._y = ops.to_device(y).reshape(-1)
-        if check_inputs and self._x.numel():
-            lo, hi = torch.aminmax(self._x)
-            assert lo.item() > basis.a
-            assert hi.item() < basis.b
+        on_device = isinstance(X, torch.Tensor) and X.is_cuda
+        if check_inputs and X.shape[0]:
+            lo, hi = (torch.aminmax(X) if isinstance(X, torch.Tensor) else (X.min(), X.max()))
+            assert float(lo) > basis.a
+            assert float(hi) < basis.b
 
         # Init model (reference gpr.py:29-34)
         self.kernel = kernel
@@ -81,7 +80,10 @@ class GPR_1d(_ModelBase):
 
         # Precompute static quantities (reference gpr.py:39-44): one fused pass over this rank's points,
         # then (multi-GPU) one all-reduce of the packed buffer.
-        self._acc = ops.accum_1d(self._x, self._y, basis)
+        if on_device:
+            self._acc = ops.accum_1d(X.reshape(-1), y.reshape(-1), basis)
+        else:                       # host data: streamed through pinned staging buffers, never fully resident
+            self._acc = ops.accum_1d_host(X, y, basis)
         self._distributed = _dist.is_distributed(distributed)
         if self._distributed:
             _dist.allreduce_packed(self._acc)

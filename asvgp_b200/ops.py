@@ -165,3 +165,70 @@ def posterior_1d(Kuu, acc, basis, sigma2, chunks=0):
     _lib.call("asvgp_posterior_1d", _p(Kuu), _p(acc), m, k, float(sigma2), int(chunks), _p(alpha), _p(S), _p(info),
               _p(ws), ws.numel(), _stream())
     return alpha, S, info
+
+
+# ---- host-resident data: stream it through pinned staging buffers ------------------------------------------------------
+_STAGING = {}
+
+
+def _staging(dev, chunk):
+    key = (dev, chunk)
+    st = _STAGING.get(key)
+    if st is None:
+        st = dict(
+            host=[torch.empty((2, chunk), dtype=F64).pin_memory() for _ in range(2)],
+            dev=[torch.empty((2, chunk), dtype=F64, device=dev) for _ in range(2)],
+            copy_stream=torch.cuda.Stream(device=dev),
+            filled=[torch.cuda.Event() for _ in range(2)],
+            drained=[torch.cuda.Event() for _ in range(2)],
+            staged=[torch.cuda.Event() for _ in range(2)],
+        )
+        _STAGING[key] = st
+    return st
+
+
+def accum_1d_host(x, y, basis, acc=None, chunk=1 << 23):
+    """accum_1d for HOST arrays (numpy or CPU tensors): the points are streamed to the GPU in `chunk`-point pieces,
+    host->pinned staging (unless already pinned), async H2D on a copy stream, double-buffered against the accumulate
+    kernel — the device never holds more than two chunks."""
+    dev = device()
+    xt = torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x, dtype=F64).reshape(-1)
+    yt = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y, dtype=F64).reshape(-1)
+    n = xt.numel()
+    if yt.numel() != n:
+        raise ValueError("x and y must have the same number of points")
+    mesh = device_mesh(basis)
+    if acc is None:
+        acc = torch.zeros(accum_size_1d(basis), dtype=F64, device=dev)
+    if n == 0:
+        return acc
+    chunk = min(chunk, n + (n & 1))
+    st = _staging(dev, chunk)
+    pinned = xt.is_pinned() and yt.is_pinned()
+    main = torch.cuda.current_stream()
+    cs = st["copy_stream"]
+    n_chunks = -(-n // chunk)
+    for c in range(n_chunks):
+        lo, hi = c * chunk, min((c + 1) * chunk, n)
+        s = c & 1
+        dbuf = st["dev"][s]
+        if c >= 2:
+            cs.wait_event(st["drained"][s])            # kernel that read dbuf two chunks ago has finished
+        with torch.cuda.stream(cs):
+            if pinned:
+                dbuf[0, : hi - lo].copy_(xt[lo:hi], non_blocking=True)
+                dbuf[1, : hi - lo].copy_(yt[lo:hi], non_blocking=True)
+            else:
+                hbuf = st["host"][s]
+                if c >= 2:
+                    st["staged"][s].synchronize()      # previous H2D out of this pinned buffer has completed
+                hbuf[0, : hi - lo].copy_(xt[lo:hi])
+                hbuf[1, : hi - lo].copy_(yt[lo:hi])
+                dbuf[:, : hi - lo].copy_(hbuf[:, : hi - lo], non_blocking=True)
+                st["staged"][s].record(cs)
+            st["filled"][s].record(cs)
+        main.wait_event(st["filled"][s])
+        _lib.call("asvgp_accum_1d", _p(dbuf[0]), _p(dbuf[1]), hi - lo, _p(mesh), mesh.numel(), basis.order, _p(acc),
+                  ctypes.c_void_p(main.cuda_stream))
+        st["drained"][s].record(main)
+    return acc

@@ -1,0 +1,160 @@
+"""Pins the CPU oracle (oracle/asvgp_oracle.py) to the golden vectors produced by the UNMODIFIED reference run
+under numpy stand-ins (oracle/make_golden.py), and to the reference's own stored known answer."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import asvgp_oracle as O
+
+KINDS = ("Matern12", "Matern32", "Matern52")
+
+
+def test_snelson_tables_precompute_and_elbo(golden):
+    g = golden("snelson")
+    mesh, delta = O.make_mesh(-3.5, 10.5, 100, 3)
+    np.testing.assert_array_equal(mesh, g["mesh"])
+    assert delta == float(g["delta"])
+    T = O.static_bands(3, 100, delta)
+    for name in ("A", "B", "C", "D", "BC", "BC_grad", "BC_ggrad"):
+        np.testing.assert_allclose(T[name], g["tab_" + name], rtol=1e-13, atol=1e-13 * np.abs(g["tab_" + name]).max())
+    assert not g["tab_BC_ggrad_none"].any() and not g["tab_BC_none_ggrad"].any()
+    G, b, yy = O.precompute_1d(mesh, delta, 3, 100, g["X"], g["y"])
+    np.testing.assert_allclose(G, g["G"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(b, g["Kuf_y"], rtol=1e-12, atol=1e-14)
+    assert abs(yy - float(g["tr_yTy"])) < 1e-12
+    for kind in KINDS:
+        Kuu = O.make_Kuu(kind, 1.0, 1.0, T)
+        np.testing.assert_allclose(Kuu, g["Kuu111_" + kind], rtol=1e-12, atol=1e-12)
+        e = O.elbo_1d(Kuu, G, b, yy, 200, 1.0, 1.0)
+        assert abs(e - float(g["elbo111_" + kind])) <= 1e-10 * abs(e)
+        e = O.elbo_1d(O.make_Kuu(kind, 1.03, 0.8, T), G, b, yy, 200, 0.8, 0.08)
+        assert abs(e - float(g["elbo_b_" + kind])) <= 1e-10 * abs(e)
+
+
+def test_snelson_known_answer_and_predictions(golden):
+    g = golden("snelson")
+    mesh, delta = O.make_mesh(-3.5, 10.5, 100, 3)
+    T = O.static_bands(3, 100, delta)
+    G, b, yy = O.precompute_1d(mesh, delta, 3, 100, g["X"], g["y"])
+    v, l, s2 = g["opt_hypers"]
+    Kuu = O.make_Kuu("Matern32", l, v, T)
+    e = O.elbo_1d(Kuu, G, b, yy, 200, v, s2)
+    # at the (10-digit) stored optimum the ELBO equals the reference notebook's printed value to ~1e-8
+    assert abs(e - float(g["notebook_elbo"])) < 5e-8
+    assert abs(e - float(g["elbo_opt"])) <= 1e-10 * abs(e)
+    assert e < float(g["notebook_exact_gp"])
+    mean, var = O.predict_1d(mesh, delta, 3, 100, Kuu, G, b, v, s2, g["Xtest"])
+    np.testing.assert_allclose(mean, g["pred_mean"], atol=1e-9)
+    np.testing.assert_allclose(var, g["pred_var"], atol=1e-9)
+
+
+def test_snelson_optimum_is_stationary(golden):
+    g = golden("snelson")
+    mesh, delta = O.make_mesh(-3.5, 10.5, 100, 3)
+    T = O.static_bands(3, 100, delta)
+    G, b, yy = O.precompute_1d(mesh, delta, 3, 100, g["X"], g["y"])
+    v, l, s2 = g["opt_hypers"]
+    _, grad = O.elbo_grad_1d_dense("Matern32", T, G, b, yy, 200, v, l, s2)
+    assert np.abs(grad).max() < 5e-2          # constrained-space gradient at the 10-digit stored optimum
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+def test_basis_eval_golden(golden, k):
+    g = golden("basis_eval")
+    for tag, a, b in (("f32", -3.5, 10.5), ("f64", -1, 41)):
+        key = "k%d_%s" % (k, tag)
+        mesh, delta = O.make_mesh(a, b, 40, k)
+        np.testing.assert_array_equal(mesh, g[key + "_mesh"])
+        for dx in range(4):
+            name = key + "_dx%d" % dx
+            if name in g.files:
+                got = O.make_Kuf(mesh, delta, k, 40, g[key + "_x"], dx).toarray()
+                np.testing.assert_allclose(got, g[name], rtol=1e-12, atol=1e-12 * np.abs(g[name]).max())
+        T = O.static_bands(k, 40, delta)
+        for name in ("A", "B", "C", "D", "BC", "BC_grad", "BC_ggrad"):
+            if key + "_" + name in g.files:
+                want = g[key + "_" + name]
+                np.testing.assert_allclose(T[name], want, rtol=1e-12, atol=1e-12 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_synth_1d_golden(golden, k):
+    g = golden("synth_1d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    mesh, delta = O.make_mesh(-1, m + 1, m, k)
+    T = O.static_bands(k, m, delta)
+    x, y = g[key + "_x"], g[key + "_y"]
+    G, b, yy = O.precompute_1d(mesh, delta, k, m, x, y)
+    np.testing.assert_allclose(G, g[key + "_G"], rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(b, g[key + "_Kuf_y"], rtol=1e-12, atol=1e-12)
+    G2, b2, yy2 = O.precompute_1d_chunked(mesh, delta, k, m, x, y, chunk=3000)
+    np.testing.assert_allclose(G2, G, rtol=1e-12, atol=1e-12)
+    for kind in KINDS:
+        for tag, (v, l, s2) in (("a", (1.0, 1.0, 0.1)), ("b", (1.3, 2.5, 0.7))):
+            name = "%s_%s_elbo_%s" % (key, kind, tag)
+            if name in g.files:
+                e = O.elbo_1d(O.make_Kuu(kind, l, v, T), G, b, yy, x.shape[0], v, s2)
+                assert abs(e - float(g[name])) <= 1e-10 * abs(e), name
+    v, l, s2 = g[key + "_pred_hypers"]
+    Kuu = O.make_Kuu(str(g[key + "_pred_kind"]), l, v, T)
+    mean, var = O.predict_1d(mesh, delta, k, m, Kuu, G, b, v, s2, g[key + "_xs"])
+    np.testing.assert_allclose(mean, g[key + "_mean"], atol=1e-9)
+    np.testing.assert_allclose(var, g[key + "_var"], atol=1e-9)
+
+
+def test_autograd_oracle_matches_finite_differences(golden):
+    g = golden("synth_1d")
+    m = int(g["k3_m"])
+    mesh, delta = O.make_mesh(-1, m + 1, m, 3)
+    T = O.static_bands(3, m, delta)
+    G, b, yy, n = g["k3_G"], g["k3_Kuf_y"], float(g["k3_tr_yTy"]), g["k3_x"].shape[0]
+    th = np.array([1.3, 2.5, 0.7])
+    _, grad = O.elbo_grad_1d_dense("Matern52", T, G, b, yy, n, *th)
+
+    def f(t):
+        return O.elbo_1d(O.make_Kuu("Matern52", t[1], t[0], T), G, b, yy, n, t[0], t[2])
+
+    for i in range(3):
+        h = 1e-4 * th[i]
+        e = np.zeros(3); e[i] = h
+        fd = (-f(th + 2 * e) + 8 * f(th + e) - 8 * f(th - e) + f(th - 2 * e)) / (12 * h)
+        assert abs(fd - grad[i]) <= 1e-6 * max(1.0, abs(grad[i]))
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_kron_golden(golden, k):
+    g = golden("kron_2d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    X, y = g["X"], g["y"]
+    meshes, deltas = zip(*[O.make_mesh(0, 1, m, k), O.make_mesh(0, 2, m, k)])
+    G, b, yy = O.precompute_kron(meshes, deltas, k, [m, m], X, y, chunk=1000)
+    Gref = sp.coo_matrix((g[key + "_G_val"], (g[key + "_G_row"], g[key + "_G_col"])), shape=(m * m, m * m)).toarray()
+    np.testing.assert_allclose(G.toarray(), Gref, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(b, g[key + "_Kuf_y"], rtol=1e-11, atol=1e-13)
+    T = [O.static_bands(k, m, d) for d in deltas]
+    Ks = [O.make_Kuu("Matern32", .3, .7, T[0]), O.make_Kuu("Matern32", .5, 1.3, T[1])]
+    e = O.elbo_kron_dense(Ks, G, b, yy, X.shape[0], [.7, 1.3], .05)
+    assert abs(e - float(g[key + "_elbo"])) <= 1e-10 * abs(e)
+    assert int(g[key + "_bandwidth"]) == k * (m + 1)
+    mean, var = O.predict_kron_dense(meshes, deltas, k, [m, m], Ks, G, b, [.7, 1.3], .05, g[key + "_Xs"])
+    np.testing.assert_allclose(mean, g[key + "_mean"], atol=1e-9)
+    np.testing.assert_allclose(var, g[key + "_var"], atol=1e-9)
+    if key + "_elbo_m52_m12" in g.files:
+        Ks = [O.make_Kuu("Matern52", .4, .9, T[0]), O.make_Kuu("Matern12", .6, 1.1, T[1])]
+        e = O.elbo_kron_dense(Ks, G, b, yy, X.shape[0], [.9, 1.1], .2)
+        assert abs(e - float(g[key + "_elbo_m52_m12"])) <= 1e-10 * abs(e)
+
+
+def test_oracle_matches_live_reference_when_present(golden):
+    """In the build container the reference itself is importable under the shim: re-check one value live."""
+    from oracle import ref_under_shim
+
+    if not ref_under_shim.available():
+        pytest.skip("/root/reference is not present on this machine")
+    ns = ref_under_shim.load()
+    g = golden("snelson")
+    basis = ns.basis.B3Spline(-3.5, 10.5, 100)
+    model = ns.gpr.GPR_1d((g["X"], g["y"]), ns.gpflow.kernels.Matern52(), basis)
+    assert abs(float(model.elbo()) - float(g["elbo111_Matern52"])) < 1e-9
