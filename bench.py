@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""Benchmark of the ASVGP hot path on B200: ELBO + gradient datapoints/s at N = 1e8, M = 1e4 (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload 1d|1d-random|...]
+
+One "step" = one pass of the hot path over one batch of synthetic points:
+    accumulate (asvgp_accum_1d, O(N))  ->  [N>1: one NCCL all-reduce of the packed band]  ->  Kuu assembly +
+    ELBO + 3 hyper-parameter gradients (asvgp_elbo_grad_1d, O(M k^2), replicated per rank).
+`value` is whole-job datapoints/s with inputs resident in HBM; `e2e` is the same metric through the public API
+(`GPR_1d((X, y), kernel, basis)` + `training_loss_and_gradients()`) with HOST buffers, host->device copies inside the
+timed region.  Weak scaling: every rank owns N points.  `--impl reference` times the CPU port of the reference's own
+algorithm (oracle/asvgp_oracle.py: the same SciPy sparse calls as reference gpr.py:39-44 + LAPACK band routines) on
+all host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N per rank, M, spline order, kernel, sorted?)
+    "1d": (100_000_000, 10_000, 3, "Matern52", True),
+    "1d-m32": (100_000_000, 10_000, 3, "Matern32", True),
+    "1d-random": (100_000_000, 10_000, 3, "Matern52", False),
+    "1d-c2": (1_000_000, 1_000, 3, "Matern32", True),
+}
+HYPERS = (1.0, 1.0, 0.1)          # variance, lengthscale, sigma^2
+BYTES_PER_POINT_ACCUM = 16         # x and y read once
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="1d", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=float, default=None, help="override points per rank (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi, in the background, during the timed region)
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# synthetic data: x ~ U(0, M) on domain (-1, M+1) so delta ~ 1; smooth signal + noise, standardised
+# ---------------------------------------------------------------------------------------------------------------------
+def make_data(torch, n, m, rank, world, is_sorted, seed=1997):
+    gen = torch.Generator(device="cuda").manual_seed(seed + rank)
+    lo, hi = (m * rank / world, m * (rank + 1) / world) if is_sorted else (0.0, float(m))
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) * (hi - lo) + lo
+    x.clamp_(1e-9, m - 1e-9)
+    if is_sorted:
+        x = torch.sort(x).values
+    y = torch.sin(x * (2 * 3.141592653589793 / 37.0)) + 0.5 * torch.sin(x * (2 * 3.141592653589793 / 3.1))
+    y += 0.3 * torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    y = (y - y.mean()) / y.std()
+    return x, y
+
+
+def cpu_sample(n, m, seed=1997):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    x = np.sort(rng.uniform(1e-9, m - 1e-9, n))
+    y = np.sin(x * (2 * np.pi / 37.0)) + 0.5 * np.sin(x * (2 * np.pi / 3.1)) + 0.3 * rng.standard_normal(n)
+    return x, (y - y.mean()) / y.std()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's algorithm
+# ---------------------------------------------------------------------------------------------------------------------
+_CPU_SHARED = {}
+
+
+def _cpu_chunk(span):
+    from oracle import asvgp_oracle as O
+
+    d = _CPU_SHARED          # inherited by fork: no pickling of the point arrays
+    return O.precompute_1d(d["mesh"], d["delta"], d["k"], d["m"], d["x"][span[0]:span[1]], d["y"][span[0]:span[1]])
+
+
+def cpu_step(pool, cores, mesh, delta, k, m, kind, tables, x, y):
+    """One reference-style step on the CPU: S1 precompute (gpr.py:39-44) over `cores` processes, then the ELBO
+    (gpr.py:49-89) and its three derivatives by central differences of the banded ELBO (the reference gets them from
+    TF reverse mode, which costs about two more banded passes — 6 extra O(M) evaluations are the same order)."""
+    import numpy as np
+
+    from oracle import asvgp_oracle as O
+
+    n = x.shape[0]
+    if pool is None:
+        parts = [O.precompute_1d(mesh, delta, k, m, x, y)]
+    else:
+        cuts = np.linspace(0, n, cores + 1).astype(np.int64)
+        parts = pool.map(_cpu_chunk, [(int(a), int(b)) for a, b in zip(cuts, cuts[1:])])
+    G = sum(p[0] for p in parts)
+    b = sum(p[1] for p in parts)
+    yy = sum(p[2] for p in parts)
+    v, l, s2 = HYPERS
+
+    def f(v, l, s2):
+        return O.elbo_1d(O.make_Kuu(kind, l, v, tables), G, b, yy, n, v, s2)
+
+    e = f(v, l, s2)
+    h = 1e-5
+    grad = [(f(v + h, l, s2) - f(v - h, l, s2)) / (2 * h), (f(v, l + h, s2) - f(v, l - h, s2)) / (2 * h),
+            (f(v, l, s2 + h) - f(v, l, s2 - h)) / (2 * h)]
+    return e, grad
+
+
+def run_cpu(n_sample, m, k, kind, steps, warmup, cores):
+    import multiprocessing as mp
+
+    from oracle import asvgp_oracle as O
+
+    mesh, delta = O.make_mesh(-1, m + 1, m, k)
+    tables = O.static_bands(k, m, delta)
+    x, y = cpu_sample(n_sample, m)
+    _CPU_SHARED.update(mesh=mesh, delta=delta, k=k, m=m, x=x, y=y)
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    try:
+        for _ in range(warmup):
+            cpu_step(pool, cores, mesh, delta, k, m, kind, tables, x, y)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_step(pool, cores, mesh, delta, k, m, kind, tables, x, y)
+        dt = (time.perf_counter() - t0) / steps
+    finally:
+        if pool is not None:
+            pool.close()
+    return n_sample / dt, dt
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, m, k, kind, is_sorted = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    n_sample = int(min(n, 2_000_000 * cores))            # ~1 s of work per core per step
+    value, dt = run_cpu(n_sample, m, k, kind, args.steps, max(args.warmup, 1), cores)
+    sample = "first %d of the %d points per step, %d processes (SciPy sparsetools/LAPACK are single-threaded)" % (
+        n_sample, n, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, n, m, k, kind, is_sorted),
+        "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(name, n, m, k, kind, is_sorted):
+    return {"workload": "1-D collapsed ELBO + (variance, lengthscale, sigma2) gradients, N=%d points per GPU, M=%d "
+                        "B%d-spline features, %s, x %s" % (n, m, k, kind, "sorted ascending" if is_sorted else "in random order"),
+            "name": name, "n_per_gpu": n, "m": m, "order": k, "kernel": kind, "hypers": list(HYPERS),
+            "l2_policy": "inputs (16 B/pt x N = %.1f GB) are larger than the 126 MB L2" % (16 * n / 1e9)}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from asvgp_b200 import basis as B, kernels as Kn, ops
+    from asvgp_b200.gpr import GPR_1d
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m, k, kind, is_sorted = WORKLOADS[args.workload]
+    if args.n:
+        n = int(args.n)
+    basis = getattr(B, "B%dSpline" % k)(-1, m + 1, m)
+    kern = getattr(Kn, kind)(variance=HYPERS[0], lengthscales=HYPERS[1])
+    x, y = make_data(torch, n, m, rank, world, is_sorted)
+
+    from asvgp_b200.inducing_features import SplineFeatures1D
+
+    feats = SplineFeatures1D(kern, basis)
+    acc = torch.zeros(ops.accum_size_1d(basis), dtype=torch.float64, device="cuda")
+    out = torch.empty(16, dtype=torch.float64, device="cuda")
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+
+    def step(timers=None):
+        acc.zero_()
+        if timers: timers[0].record()
+        ops.accum_1d(x, y, basis, acc=acc)
+        if timers: timers[1].record()
+        if world > 1:
+            dist.all_reduce(acc)
+        if timers: timers[2].record()
+        Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
+        ops.elbo_grad_1d(Kuu, dKuu, acc, basis, HYPERS[0], HYPERS[2], out=out)
+        if timers: timers[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    res0 = out.cpu().numpy().copy()
+    assert res0[8] == 0 and np.isfinite(res0[:4]).all(), "ELBO evaluation failed: %r" % (res0,)
+
+    # ---- timed region: exactly K steps, CUDA events, max over ranks ------------------------------------------------
+    phase_ev = [[ev() for _ in range(4)] for _ in range(args.steps)]
+    t0, t1 = ev(), ev()
+    with ClockSampler(local) as clocks:
+        barrier()
+        t0.record()
+        for i in range(args.steps):
+            step(phase_ev[i])
+        t1.record()
+        barrier()
+    total_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+    accum_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in phase_ev]))
+    allred_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in phase_ev]))
+    elbo_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in phase_ev]))
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with host buffers ---------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(n, dtype=torch.float64).pin_memory(); xh.copy_(x)
+        yh = torch.empty(n, dtype=torch.float64).pin_memory(); yh.copy_(y)
+
+        def e2e_step():
+            model = GPR_1d((xh.view(-1, 1), yh.view(-1, 1)), kern, basis, check_inputs=False)
+            model.likelihood.variance.assign(HYPERS[2])
+            return model.training_loss_and_gradients()        # reads loss + gradient back to the host
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        k_e2e = max(3, min(args.steps, 10))
+        w0 = time.perf_counter()
+        for _ in range(k_e2e):
+            loss, grad = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - w0) / k_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert abs(-loss - res0[0]) <= 1e-9 * abs(res0[0]), "e2e ELBO differs from the device-resident one"
+        e2e = {"value": world * n / dt.item(), "unit": "datapoints/s", "h2d_bytes_per_step": 16 * n,
+               "d2h_bytes_per_step": 16 * 8, "ms_per_step": dt.item() * 1e3, "steps": k_e2e,
+               "api": "GPR_1d((X_host, y_host), kernel, basis).training_loss_and_gradients()"}
+        del xh, yh
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = measured_peaks()
+    achieved = BYTES_PER_POINT_ACCUM * n / (accum_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "accum_1d_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    line = {
+        "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.workload, n, m, k, kind, is_sorted),
+        "phases_ms": {"accumulate": accum_ms, "allreduce": allred_ms, "kuu_elbo_grad": elbo_ms},
+        "elbo": float(res0[0]), "grad": [float(v) for v in res0[1:4]],
+        "roofline": {"kernel": "accum_1d_kernel<%d,2>" % k, "bound": "hbm", "achieved": achieved,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM * n, "launch_ms": accum_ms, "traffic": traffic},
+        "clocks": clocks.summary(),
+        "gpu_launches": args.steps * 4,          # accum_1d + kuu_assemble + elbo_chains + elbo_finalize per step
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu_baseline:
+        n_sample = min(n, 20_000_000)
+        v1, dt1 = run_cpu(n_sample, m, k, kind, 1, 0, 1)
+        line["cpu_baseline"] = {"value": v1, "unit": "datapoints/s", "cores": 1, "kind": "port",
+                                "sample": "one step on the first %d sorted points of the workload (%.1f s), single "
+                                          "thread like the reference's SciPy/LAPACK path" % (n_sample, dt1)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

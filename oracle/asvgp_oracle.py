@@ -199,10 +199,33 @@ def band_to_dense_sym(band):
     return A
 
 
+def _c_oracle():
+    """oracle/_build/liboracle.so (plain C, built by oracle/Makefile) if present, else None."""
+    global _C_LIB
+    if _C_LIB is False:
+        import ctypes
+        import os
+
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liboracle.so")
+        _C_LIB = ctypes.CDLL(path) if os.path.exists(path) else None
+    return _C_LIB
+
+
+_C_LIB = False
+
+
 def takahashi_band(L):
-    """Lower band of (L L^T)^-1 from the lower band of L (banded.inverse_from_cholesky_band, gpr.py:59)."""
+    """Lower band of (L L^T)^-1 from the lower band of L (banded.inverse_from_cholesky_band, gpr.py:59).
+    Uses the plain-C twin (oracle/band_ref.c) when built, else the same recursion in Python."""
     k, m = L.shape[0] - 1, L.shape[1]
     S = np.zeros((k + 1, m))
+    lib = _c_oracle()
+    if lib is not None:
+        import ctypes
+
+        Lc = np.ascontiguousarray(L, dtype=np.float64)
+        lib.takahashi_band(Lc.ctypes.data_as(ctypes.c_void_p), k, m, S.ctypes.data_as(ctypes.c_void_p))
+        return S
     for j in range(m - 1, -1, -1):
         ljj = L[0, j]
         hi = min(m - 1, j + k)
