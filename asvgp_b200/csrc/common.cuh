@@ -74,23 +74,54 @@ ASVGP_HD int locate_interval(const Mesh& mesh, double x, LoadFn load) {
 
 // ---- B-spline pieces --------------------------------------------------------------------------------------------
 // w[r], r = 0..K : value at t = (x-u)/delta of basis row idx + r on interval idx (reference b_{K+1-r},
-// basis.py:72,133-136,188-192,274-280,...).  Cox-de Boor on uniform knots, all in registers:
-//   piece^d_r(t) = ((t + d - r)/d) piece^{d-1}_{r-1}(t) + ((1 - t + r)/d) piece^{d-1}_r(t).
+// basis.py:72,133-136,188-192,274-280,...): piece_r(t) = N_K(t + K - r), N_K the cardinal B-spline.
+//
+// The piece polynomials are generated at COMPILE time: K! * N_K(s + t) has integer coefficients, built by the
+// Cox-de Boor recursion  d! N_d(s+t) = (t+s) (d-1)! N_{d-1}(s+t) + (d+1-s-t) (d-1)! N_{d-1}(s-1+t)  in integer
+// arithmetic, so every coefficient c/K! is a correctly rounded double and each piece costs K FMAs (Horner) —
+// K(K+1) fp64 instructions per point instead of ~5x that for the recursion evaluated at run time (the accumulate
+// kernel was fp64-pipe bound with the latter: profiles/r01_accum_1d_v1.md).
+template <int K>
+struct PieceTable {
+    long long c[K + 1][K + 1];   // c[r][p]: coefficient of t^p in K! * piece_r(t)
+    long long fact;              // K!
+};
+
+template <int K>
+constexpr PieceTable<K> make_piece_table() {
+    long long prev[K + 1][K + 2] = {};
+    long long cur[K + 1][K + 2] = {};
+    prev[0][0] = 1;
+    long long fact = 1;
+    for (int d = 1; d <= K; ++d) {
+        fact *= d;
+        for (int s = 0; s <= d; ++s)
+            for (int p = 0; p <= K + 1; ++p) cur[s][p] = 0;
+        for (int s = 0; s <= d; ++s) {
+            if (s <= d - 1)
+                for (int p = 0; p <= d - 1; ++p) { cur[s][p] += s * prev[s][p]; cur[s][p + 1] += prev[s][p]; }
+            if (s >= 1)
+                for (int p = 0; p <= d - 1; ++p) { cur[s][p] += (d + 1 - s) * prev[s - 1][p]; cur[s][p + 1] -= prev[s - 1][p]; }
+        }
+        for (int s = 0; s <= d; ++s)
+            for (int p = 0; p <= K + 1; ++p) prev[s][p] = cur[s][p];
+    }
+    PieceTable<K> t{};
+    t.fact = fact;
+    for (int r = 0; r <= K; ++r)
+        for (int p = 0; p <= K; ++p) t.c[r][p] = prev[K - r][p];
+    return t;
+}
+
 template <int K>
 ASVGP_HD void bspline_pieces(double t, double (&w)[K + 1]) {
-    w[0] = 1.0;
+    constexpr PieceTable<K> tab = make_piece_table<K>();
 #pragma unroll
-    for (int d = 1; d <= K; ++d) {
-        const double inv_d = 1.0 / (double)d;
-        double prev = 0.0;   // piece^{d-1}_{r-1}
+    for (int r = 0; r <= K; ++r) {
+        double acc = (double)tab.c[r][K] / (double)tab.fact;
 #pragma unroll
-        for (int r = 0; r <= d; ++r) {
-            const double cur = (r <= d - 1) ? w[r] : 0.0;            // piece^{d-1}_r
-            const double left = (t + (double)(d - r)) * inv_d;       // multiplies piece^{d-1}_{r-1}
-            const double right = ((1.0 - t) + (double)r) * inv_d;    // multiplies piece^{d-1}_r
-            w[r] = left * prev + right * cur;
-            prev = cur;
-        }
+        for (int p = K - 1; p >= 0; --p) acc = fma(acc, t, (double)tab.c[r][p] / (double)tab.fact);
+        w[r] = acc;
     }
 }
 
