@@ -62,14 +62,15 @@ inline int default_chunks(int M, int K) {
 
 // ---- per-column record kept for the backward passes ----------------------------------------------------------------
 // Stored "column-step major" so that the P lanes working in lock-step touch consecutive addresses:
-//   rec[(field * n_steps + j) * P + p],  fields: 0 = 1/pivot, 1..K = L[j+a, j], K+1..2K = spike X[rho, j], 2K+1 = y_j
-template <class T, int K>
+//   rec[(field * n_steps + j) * P + p],  fields: 0 = 1/pivot, 1..K = L[j+a, j], [K+1..2K = spike X[rho, j],] last = y_j
+template <class T, int K, bool SPIKE = true>
 struct ColumnStore {
     T* rec;
     int n_steps, P;
-    static constexpr int kFields = 2 * K + 2;
+    static constexpr int kFields = SPIKE ? 2 * K + 2 : K + 2;
+    static constexpr int kY = kFields - 1;
     ASVGP_HD T& at(int field, int j, int p) const { return rec[((size_t)field * n_steps + j) * P + p]; }
-    static size_t count(int n_steps, int P) { return (size_t)kFields * n_steps * P; }
+    ASVGP_HD static size_t count(int n_steps, int P) { return (size_t)kFields * n_steps * P; }
 };
 
 template <class T, int K>
@@ -87,8 +88,21 @@ struct ChunkSchur {          // what phase 1 leaves behind for chunk p
 // A(d, j) -> T : entry A[j+d, j] of the lower band (must return 0 when j+d >= size or j >= size or j < 0)
 // rhs(j)  -> T : right-hand side (0 outside)
 // SPIKE: carry the K spike rows coupling to the K indices just before g0.
-template <class T, int K, bool SPIKE, bool STORE, class MatFn, class RhsFn>
-ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, const ColumnStore<T, K>& store,
+template <class T, int K>
+struct WindowRow {           // what enters the active window after eliminating column g: row g+1+K and its rhs
+    T a[K + 1];
+    T r;
+};
+
+template <class T, int K, class MatFn, class RhsFn>
+ASVGP_HD void fetch_row(MatFn& A, RhsFn& rhs, int g, WindowRow<T, K>& row) {
+#pragma unroll
+    for (int b = 0; b <= K; ++b) row.a[b] = A(K - b, g + 1 + b);
+    row.r = rhs(g + 1 + K);
+}
+
+template <class T, int K, bool SPIKE, bool STORE, class MatFn, class RhsFn, class Store>
+ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, const Store& store,
                                 int p, ChunkSchur<T, K>& out) {
     T W[K + 1][K + 1];       // lower triangle of the active window, rows/cols g .. g+K
     T r[K + 1];
@@ -106,7 +120,9 @@ ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, 
             for (int a = 0; a <= K; ++a)
                 c[rho][a] = (a <= rho) ? A(a + K - rho, g0 - K + rho) : zero_of<T>();
     }
-    T logdet = zero_of<T>(), quad = zero_of<T>();
+    LogAccum<T> logdet;
+    logdet.init();
+    T quad = zero_of<T>();
     T SLL[K][K], rhsL[K];
 #pragma unroll
     for (int a = 0; a < K; ++a) {
@@ -116,58 +132,73 @@ ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, 
     }
     int info = 0;
 
-    for (int j = 0; j < n_steps; ++j) {
-        if (j < n) {
-            const int g = g0 + j;
-            if (!(value_of(W[0][0]) > 0.0) && info == 0) info = g + 1;
-            logdet += log_of(W[0][0]);
-            const T ip = recip_of(sqrt_of(W[0][0]));
-            T l[K + 1];
+    // The rows entering the window are fetched two columns ahead of their use so that their memory latency hides
+    // behind the rsqrt/FMA chain of the columns in between (the accessors are branch-free, so the K+2 loads of a
+    // row issue back to back).
+    WindowRow<T, K> rowA, rowB;
+    fetch_row<T, K>(A, rhs, g0, rowA);
+    fetch_row<T, K>(A, rhs, g0 + 1, rowB);
+
+    auto step = [&](int j, const WindowRow<T, K>& row) {
+        const int g = g0 + j;
+        if (!(value_of(W[0][0]) > 0.0) && info == 0) info = g + 1;
+        const T ip = rsqrt_of(W[0][0]);
+        logdet.add(W[0][0], ip);
+        T l[K + 1];
 #pragma unroll
-            for (int a = 1; a <= K; ++a) l[a] = W[a][0] * ip;
-            const T yj = r[0] * ip;
-            quad += yj * yj;
-            T X[SPIKE ? K : 1];
-            if (SPIKE) {
+        for (int a = 1; a <= K; ++a) l[a] = W[a][0] * ip;
+        const T yj = r[0] * ip;
+        quad += yj * yj;
+        T X[SPIKE ? K : 1];
+        if (SPIKE) {
 #pragma unroll
-                for (int rho = 0; rho < K; ++rho) {
-                    X[rho] = c[rho][0] * ip;
-                    rhsL[rho] += X[rho] * yj;
+            for (int rho = 0; rho < K; ++rho) {
+                X[rho] = c[rho][0] * ip;
+                rhsL[rho] += X[rho] * yj;
 #pragma unroll
-                    for (int r2 = 0; r2 <= rho; ++r2) SLL[rho][r2] += X[rho] * X[r2];
-                }
-            }
-            if (STORE) {
-                store.at(0, j, p) = ip;
-#pragma unroll
-                for (int a = 1; a <= K; ++a) store.at(a, j, p) = l[a];
-                if (SPIKE) {
-#pragma unroll
-                    for (int rho = 0; rho < K; ++rho) store.at(K + 1 + rho, j, p) = X[rho];
-                }
-                store.at(2 * K + 1, j, p) = yj;
-            }
-            // trailing update and window shift
-#pragma unroll
-            for (int a = 1; a <= K; ++a) {
-#pragma unroll
-                for (int b = 1; b <= a; ++b) W[a - 1][b - 1] = W[a][b] - l[a] * l[b];
-                r[a - 1] = r[a] - l[a] * yj;
-                if (SPIKE) {
-#pragma unroll
-                    for (int rho = 0; rho < K; ++rho) c[rho][a - 1] = c[rho][a] - l[a] * X[rho];
-                }
-            }
-#pragma unroll
-            for (int b = 0; b <= K; ++b) W[K][b] = A(K - b, g + 1 + b);
-            r[K] = rhs(g + 1 + K);
-            if (SPIKE) {
-#pragma unroll
-                for (int rho = 0; rho < K; ++rho) c[rho][K] = zero_of<T>();
+                for (int r2 = 0; r2 <= rho; ++r2) SLL[rho][r2] += X[rho] * X[r2];
             }
         }
+        if (STORE) {
+            store.at(0, j, p) = ip;
+#pragma unroll
+            for (int a = 1; a <= K; ++a) store.at(a, j, p) = l[a];
+            if (SPIKE) {
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) store.at(K + 1 + rho, j, p) = X[rho];
+            }
+            store.at(Store::kY, j, p) = yj;
+        }
+        // trailing update and window shift
+#pragma unroll
+        for (int a = 1; a <= K; ++a) {
+#pragma unroll
+            for (int b = 1; b <= a; ++b) W[a - 1][b - 1] = W[a][b] - l[a] * l[b];
+            r[a - 1] = r[a] - l[a] * yj;
+            if (SPIKE) {
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) c[rho][a - 1] = c[rho][a] - l[a] * X[rho];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b <= K; ++b) W[K][b] = row.a[b];
+        r[K] = row.r;
+        if (SPIKE) {
+#pragma unroll
+            for (int rho = 0; rho < K; ++rho) c[rho][K] = zero_of<T>();
+        }
+    };
+
+    for (int j = 0; j < n_steps; j += 2) {
+        WindowRow<T, K> nextA, nextB;
+        fetch_row<T, K>(A, rhs, g0 + j + 2, nextA);
+        if (j < n) step(j, rowA);
+        fetch_row<T, K>(A, rhs, g0 + j + 3, nextB);
+        if (j + 1 < n) step(j + 1, rowB);
+        rowA = nextA;
+        rowB = nextB;
     }
-    out.logdet = logdet;
+    out.logdet = logdet.result();
     out.quad = quad;
     out.info = info;
 #pragma unroll
@@ -184,13 +215,13 @@ ASVGP_HD void eliminate_columns(int g0, int n, int n_steps, MatFn A, RhsFn rhs, 
 }
 
 // ---- serial back-substitution L^T x = y on stored columns (used for the reduced system) -----------------------------
-template <class T, int K>
-ASVGP_HD void backsolve_serial(int n, const ColumnStore<T, K>& store, T* x) {
+template <class T, int K, class Store>
+ASVGP_HD void backsolve_serial(int n, const Store& store, T* x) {
     T xw[K + 1];
 #pragma unroll
     for (int a = 0; a <= K; ++a) xw[a] = zero_of<T>();
     for (int j = n - 1; j >= 0; --j) {
-        T acc = store.at(2 * K + 1, j, 0);
+        T acc = store.at(Store::kY, j, 0);
 #pragma unroll
         for (int a = 1; a <= K; ++a) acc -= store.at(a, j, 0) * xw[a];
         const T xj = acc * store.at(0, j, 0);
@@ -202,8 +233,8 @@ ASVGP_HD void backsolve_serial(int n, const ColumnStore<T, K>& store, T* x) {
 }
 
 // ---- serial Takahashi recursion on stored columns: lower band of (L L^T)^-1, sig[d * n + j] ---------------------------
-template <class T, int K>
-ASVGP_HD void selinv_serial(int n, const ColumnStore<T, K>& store, T* sig) {
+template <class T, int K, class Store>
+ASVGP_HD void selinv_serial(int n, const Store& store, T* sig) {
     T Z[K][K];     // Sigma[g+1+a, g+1+b] of the columns already done (symmetric, full storage)
 #pragma unroll
     for (int a = 0; a < K; ++a)
@@ -247,7 +278,7 @@ ASVGP_HD void selinv_serial(int n, const ColumnStore<T, K>& store, T* sig) {
 // x_red / sig_red: solution and selected-inverse band ((2K) x n_red, row-major) of the reduced system (may be null
 // when the corresponding output is not requested).  x_out[M]; sig_out[(K+1) x M] lower band of A^-1.
 template <class T, int K, bool SOLVE, bool SELINV>
-ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const ColumnStore<T, K>& store,
+ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const ColumnStore<T, K, true>& store,
                              const T* x_red, const T* sig_red, T* x_out, T* sig_out) {
     constexpr int KR = 2 * K - 1;
     const int n = lay.size(p), s = lay.start(p), M = lay.M, nred = lay.n_reduced();
@@ -285,64 +316,81 @@ ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const C
             }
         }
     }
-    for (int j = n_steps - 1; j >= 0; --j) {
-        if (j < n) {
-            const int g = s + j;
-            const T ip = store.at(0, j, p);
-            T lv[2 * K];
+    // column records are fetched two columns ahead of their use (they sit in L2: written by phase 1)
+    struct Rec { T ip; T lv[2 * K]; T y; };
+    auto fetch = [&](int j, Rec& rec) {
+        const int jj = j < 0 ? 0 : (j >= n_steps ? n_steps - 1 : j);     // clamped: out-of-range records are never used
+        rec.ip = store.at(0, jj, p);
+#pragma unroll
+        for (int a = 0; a < K; ++a) {
+            rec.lv[a] = store.at(a + 1, jj, p);
+            rec.lv[K + a] = store.at(K + 1 + a, jj, p);
+        }
+        rec.y = store.at(ColumnStore<T, K, true>::kY, jj, p);
+    };
+    auto step = [&](int j, const Rec& rec) {
+        const int g = s + j;
+        const T ip = rec.ip;
+        if (SOLVE) {
+            T acc = rec.y;
+#pragma unroll
+            for (int a = 0; a < K; ++a) { acc -= rec.lv[a] * xw[a + 1]; acc -= rec.lv[K + a] * xL[a]; }
+            const T xj = acc * ip;
+#pragma unroll
+            for (int a = K; a >= 2; --a) xw[a] = xw[a - 1];
+            xw[1] = xj;
+            x_out[g] = xj;
+        }
+        if (SELINV) {
+            T w[2 * K];
+            T dot = zero_of<T>();
+#pragma unroll
+            for (int a = 0; a < 2 * K; ++a) {
+                T acc = zero_of<T>();
+#pragma unroll
+                for (int b = 0; b < 2 * K; ++b) acc += Z[a][b] * rec.lv[b];
+                w[a] = acc;
+                dot += rec.lv[a] * acc;
+            }
+            const T ip2 = ip * ip;
+            const T sjj = ip2 + dot * ip2;
+            sig_out[g] = sjj;
+            T col[2 * K];
+#pragma unroll
+            for (int a = 0; a < 2 * K; ++a) col[a] = -(w[a] * ip);
 #pragma unroll
             for (int a = 0; a < K; ++a) {
-                lv[a] = store.at(a + 1, j, p);
-                lv[K + a] = store.at(K + 1 + a, j, p);
+                if (g + 1 + a < M) sig_out[(size_t)(a + 1) * M + g] = col[a];            // rows below, same band
+                // (row g, column S_{p-1}[rho]) lies inside the band iff j <= rho
+                if (has_left && j <= a) sig_out[(size_t)(j + K - a) * M + (s - K + a)] = col[K + a];
             }
-            if (SOLVE) {
-                T acc = store.at(2 * K + 1, j, p);
+            // shift the band part of Z; the separator part stays
 #pragma unroll
-                for (int a = 0; a < K; ++a) { acc -= lv[a] * xw[a + 1]; acc -= lv[K + a] * xL[a]; }
-                const T xj = acc * ip;
+            for (int a = K - 1; a >= 1; --a) {
 #pragma unroll
-                for (int a = K; a >= 2; --a) xw[a] = xw[a - 1];
-                xw[1] = xj;
-                x_out[g] = xj;
+                for (int b = K - 1; b >= 1; --b) Z[a][b] = Z[a - 1][b - 1];
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho) { Z[a][K + rho] = Z[a - 1][K + rho]; Z[K + rho][a] = Z[a][K + rho]; }
             }
-            if (SELINV) {
-                T w[2 * K];
-                T dot = zero_of<T>();
+            Z[0][0] = sjj;
 #pragma unroll
-                for (int a = 0; a < 2 * K; ++a) {
-                    T acc = zero_of<T>();
+            for (int a = 1; a < K; ++a) { Z[a][0] = col[a - 1]; Z[0][a] = col[a - 1]; }
 #pragma unroll
-                    for (int b = 0; b < 2 * K; ++b) acc += Z[a][b] * lv[b];
-                    w[a] = acc;
-                    dot += lv[a] * acc;
-                }
-                const T ip2 = ip * ip;
-                const T sjj = ip2 + dot * ip2;
-                sig_out[g] = sjj;
-                T col[2 * K];
-#pragma unroll
-                for (int a = 0; a < 2 * K; ++a) col[a] = -(w[a] * ip);
-#pragma unroll
-                for (int a = 0; a < K; ++a) {
-                    if (g + 1 + a < M) sig_out[(size_t)(a + 1) * M + g] = col[a];            // rows below, same band
-                    // (row g, column S_{p-1}[rho]) lies inside the band iff j <= rho
-                    if (has_left && j <= a) sig_out[(size_t)(j + K - a) * M + (s - K + a)] = col[K + a];
-                }
-                // shift the band part of Z; the separator part stays
-#pragma unroll
-                for (int a = K - 1; a >= 1; --a) {
-#pragma unroll
-                    for (int b = K - 1; b >= 1; --b) Z[a][b] = Z[a - 1][b - 1];
-#pragma unroll
-                    for (int rho = 0; rho < K; ++rho) { Z[a][K + rho] = Z[a - 1][K + rho]; Z[K + rho][a] = Z[a][K + rho]; }
-                }
-                Z[0][0] = sjj;
-#pragma unroll
-                for (int a = 1; a < K; ++a) { Z[a][0] = col[a - 1]; Z[0][a] = col[a - 1]; }
-#pragma unroll
-                for (int rho = 0; rho < K; ++rho) { Z[0][K + rho] = col[K + rho]; Z[K + rho][0] = col[K + rho]; }
-            }
+            for (int rho = 0; rho < K; ++rho) { Z[0][K + rho] = col[K + rho]; Z[K + rho][0] = col[K + rho]; }
         }
+    };
+    Rec recA, recB;
+    const int top = ((n_steps + 1) & ~1) - 1;        // odd index >= n_steps - 1: steps are taken in pairs (j, j-1)
+    fetch(top, recA);
+    fetch(top - 1, recB);
+    for (int j = top; j >= 0; j -= 2) {
+        Rec nextA, nextB;
+        fetch(j - 2, nextA);
+        if (j < n) step(j, recA);
+        fetch(j - 3, nextB);
+        if (j - 1 < n && j - 1 >= 0) step(j - 1, recB);
+        recA = nextA;
+        recB = nextB;
     }
 }
 
@@ -354,14 +402,37 @@ ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const C
 namespace asvgp {
 
 template <class T, int K>
-struct ChainWork {                      // caller-provided scratch, all device (or host) memory
-    ColumnStore<T, K> cols;             // chunk columns: kFields x n_steps x P
-    ChunkSchur<T, K>* schur;            // [P]
-    T* red_band;                        // (2K) x n_red   reduced lower band (bandwidth 2K-1)
-    T* red_rhs;                         // n_red
-    ColumnStore<T, 2 * K - 1> red_cols; // reduced columns: (4K) x n_red x 1
-    T* x_red;                           // n_red
-    T* sig_red;                         // (2K) x n_red
+struct ChainWork {
+    ColumnStore<T, K, true> cols;              // chunk columns (global memory): kFields x n_steps x P
+    // everything below is small and lives in shared memory inside the kernels (host memory in the test harness)
+    ChunkSchur<T, K>* schur;                   // [P]
+    T* red_band;                               // (2K) x n_red   reduced lower band (bandwidth 2K-1)
+    T* red_rhs;                                // n_red
+    ColumnStore<T, 2 * K - 1, false> red_cols; // reduced columns: (2K+1) x n_red x 1
+    T* x_red;                                  // n_red
+    T* sig_red;                                // (2K) x n_red
+};
+
+// bytes of the small (shared-memory) part of a ChainWork and its carving; the same code sizes the host harness
+template <class T, int K>
+struct ChainSmall {
+    static constexpr int KR = 2 * K - 1;
+    ASVGP_HD static size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
+    ASVGP_HD static size_t bytes(int P) {
+        const size_t nred = (size_t)(P - 1) * K + 1;
+        return align16((size_t)P * sizeof(ChunkSchur<T, K>)) + 2 * align16((size_t)(KR + 1) * nred * sizeof(T))
+               + 2 * align16(nred * sizeof(T)) + align16(ColumnStore<T, KR, false>::count((int)nred, 1) * sizeof(T));
+    }
+    ASVGP_HD static void carve(int P, char* base, ChainWork<T, K>& w) {
+        const size_t nred = (size_t)(P - 1) * K + 1;
+        char* p = base;
+        w.schur = reinterpret_cast<ChunkSchur<T, K>*>(p); p += align16((size_t)P * sizeof(ChunkSchur<T, K>));
+        w.red_band = reinterpret_cast<T*>(p); p += align16((size_t)(KR + 1) * nred * sizeof(T));
+        w.sig_red = reinterpret_cast<T*>(p); p += align16((size_t)(KR + 1) * nred * sizeof(T));
+        w.red_rhs = reinterpret_cast<T*>(p); p += align16(nred * sizeof(T));
+        w.x_red = reinterpret_cast<T*>(p); p += align16(nred * sizeof(T));
+        w.red_cols = ColumnStore<T, KR, false>{reinterpret_cast<T*>(p), (int)(nred - 1), 1};
+    }
 };
 
 template <class T, int K>
@@ -378,19 +449,54 @@ template <class T, int KR>
 struct RedMat {
     const T* band; int n;
     ASVGP_HD T operator()(int d, int j) const {
-        return (j >= 0 && j < n && j + d < n) ? band[(size_t)d * n + j] : zero_of<T>();
+        const bool ok = (j >= 0) & (j + d < n);
+        const T v = band[ok ? (size_t)d * n + j : 0];      // branch-free: the load always issues
+        return ok ? v : zero_of<T>();
     }
 };
 template <class T>
 struct RedRhs {
     const T* v; int n;
-    ASVGP_HD T operator()(int j) const { return (j >= 0 && j < n) ? v[j] : zero_of<T>(); }
+    ASVGP_HD T operator()(int j) const {
+        const bool ok = (j >= 0) & (j < n);
+        const T x = v[ok ? j : 0];
+        return ok ? x : zero_of<T>();
+    }
 };
 
-// Executed by ONE thread.  Assembles the reduced (separator) system from the chunk Schur pieces, eliminates it,
-// and (optionally) back-substitutes / runs the Takahashi recursion on it.
+// Phase 2a, executed by thread t of n_threads: zero the reduced band (strided).  Barrier afterwards.
+template <class T, int K>
+ASVGP_HD void chain_phase2_zero(const ChunkLayout& lay, int t, int n_threads, const ChainWork<T, K>& w) {
+    const int total = 2 * K * lay.n_reduced();
+    for (int i = t; i < total; i += n_threads) w.red_band[i] = zero_of<T>();
+}
+
+// Phase 2b, executed by thread q < P-1: block row q of the reduced (separator) system from the Schur pieces of the
+// chunks on either side of S_q.  Barrier afterwards.
+template <class T, int K>
+ASVGP_HD void chain_phase2_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
+    const int nred = lay.n_reduced();
+    const ChunkSchur<T, K>& left = w.schur[q];        // chunk q ends at S_q
+    const ChunkSchur<T, K>& right = w.schur[q + 1];   // chunk q+1 starts after S_q
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        w.red_rhs[q * K + a] = left.rend[a] - right.rhsL[a];
+#pragma unroll
+        for (int b = 0; b <= a; ++b)
+            w.red_band[(size_t)(a - b) * nred + q * K + b] = left.Dend[a][b] - right.SLL[a][b];
+        if (q >= 1) {
+            // rows of S_q, columns of S_{q-1}: produced by chunk q (its E)
+#pragma unroll
+            for (int rho = 0; rho < K; ++rho)
+                w.red_band[(size_t)(K + a - rho) * nred + (q - 1) * K + rho] = left.E[a][rho];
+        }
+    }
+}
+
+// Phase 2c, executed by ONE thread: eliminate the reduced system and (optionally) back-substitute / run the
+// Takahashi recursion on it; also sums the per-chunk log-determinants and quadratic forms.
 template <class T, int K, bool SOLVE, bool SELINV>
-ASVGP_HD ChainTotals<T, K> chain_phase2(const ChunkLayout& lay, const ChainWork<T, K>& w) {
+ASVGP_HD ChainTotals<T, K> chain_phase2_solve(const ChunkLayout& lay, const ChainWork<T, K>& w) {
     constexpr int KR = 2 * K - 1;
     ChainTotals<T, K> tot;
     tot.logdet = zero_of<T>();
@@ -403,21 +509,6 @@ ASVGP_HD ChainTotals<T, K> chain_phase2(const ChunkLayout& lay, const ChainWork<
     }
     const int nred = lay.n_reduced();
     if (nred == 0) return tot;
-    for (int i = 0; i < (KR + 1) * nred; ++i) w.red_band[i] = zero_of<T>();
-    for (int q = 0; q < lay.P - 1; ++q) {
-        const ChunkSchur<T, K>& left = w.schur[q];        // chunk q ends at S_q
-        const ChunkSchur<T, K>& right = w.schur[q + 1];   // chunk q+1 starts after S_q
-        for (int a = 0; a < K; ++a) {
-            w.red_rhs[q * K + a] = left.rend[a] - right.rhsL[a];
-            for (int b = 0; b <= a; ++b)
-                w.red_band[(size_t)(a - b) * nred + q * K + b] = left.Dend[a][b] - right.SLL[a][b];
-            if (q + 1 < lay.P - 1) {
-                // rows of S_{q+1}, columns of S_q: produced by chunk q+1 (its E)
-                for (int rho = 0; rho < K; ++rho)
-                    w.red_band[(size_t)(K + a - rho) * nred + q * K + rho] = right.E[a][rho];
-            }
-        }
-    }
     ChunkSchur<T, KR> red_out;
     RedMat<T, KR> RA{w.red_band, nred};
     RedRhs<T> Rb{w.red_rhs, nred};

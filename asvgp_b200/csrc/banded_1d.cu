@@ -51,18 +51,21 @@ __global__ void __launch_bounds__(256) kuu_assemble_kernel(const double* __restr
 // ------------------------------------------------------------------------------------------------------------------
 // matrix / right-hand-side functors fed to the engine
 // ------------------------------------------------------------------------------------------------------------------
-template <class T> struct BandMat;      // A = alpha*Kuu + beta*G  with tangent  ta*dKuu + tb*G
+// All accessors are branch-free (clamped index + select) so that the loads of one window row issue back to back
+// and can be hoisted two columns ahead of their use.
+template <class T> struct BandMat;      // A = Kuu + beta*G  with tangent  use_dK*dKuu + tb*G
 template <> struct BandMat<Dual<1>> {
     const double* Kuu; const double* dKuu; const double* G;
     double beta, tb; int use_dK; int M;
     __device__ __forceinline__ Dual<1> operator()(int d, int j) const {
-        Dual<1> r; r.v = 0.0; r.d[0] = 0.0;
-        if (j >= 0 && j < M && j + d < M) {
-            const size_t i = (size_t)d * M + j;
-            const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
-            r.v = fma(beta, g, __ldg(Kuu + i));
-            r.d[0] = (use_dK ? __ldg(dKuu + i) : 0.0) + tb * g;
-        }
+        const bool ok = (j >= 0) & (j + d < M);
+        const size_t i = ok ? (size_t)d * M + j : 0;
+        const double kv = __ldg(Kuu + i);
+        const double dk = use_dK ? __ldg(dKuu + i) : 0.0;
+        const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
+        Dual<1> r;
+        r.v = ok ? fma(beta, g, kv) : 0.0;
+        r.d[0] = ok ? fma(tb, g, dk) : 0.0;
         return r;
     }
 };
@@ -70,18 +73,19 @@ template <> struct BandMat<double> {
     const double* Kuu; const double* dKuu; const double* G;
     double beta, tb; int use_dK; int M;
     __device__ __forceinline__ double operator()(int d, int j) const {
-        if (j >= 0 && j < M && j + d < M) {
-            const size_t i = (size_t)d * M + j;
-            const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
-            return fma(beta, g, __ldg(Kuu + i));
-        }
-        return 0.0;
+        const bool ok = (j >= 0) & (j + d < M);
+        const size_t i = ok ? (size_t)d * M + j : 0;
+        const double kv = __ldg(Kuu + i);
+        const double g = (G != nullptr) ? __ldg(G + i) : 0.0;
+        return ok ? fma(beta, g, kv) : 0.0;
     }
 };
-template <class T> struct VecRhs {
-    const double* b; int M;
+template <class T> struct VecRhs {      // use == 0: zero right-hand side (b must still be a readable pointer)
+    const double* b; int M; int use;
     __device__ __forceinline__ T operator()(int j) const {
-        return make_scalar<T>((b != nullptr && j >= 0 && j < M) ? __ldg(b + j) : 0.0, 0.0);
+        const bool ok = (use != 0) & (j >= 0) & (j < M);
+        const double v = __ldg(b + (ok ? j : 0));
+        return make_scalar<T>(ok ? v : 0.0, 0.0);
     }
 };
 
@@ -91,33 +95,41 @@ template <class T> struct VecRhs {
 template <class T, int K>
 struct ChainPlan {
     static size_t bytes(const ChunkLayout& lay) {
-        constexpr int KR = 2 * K - 1;
-        const size_t nred = (size_t)lay.n_reduced() + 1;
-        size_t n = 0;
-        n += ColumnStore<T, K>::count(lay.max_size(), lay.P) * sizeof(T);
-        n += (size_t)lay.P * sizeof(ChunkSchur<T, K>);
-        n += (size_t)(KR + 1) * nred * sizeof(T) * 2;            // red_band, sig_red
-        n += nred * sizeof(T) * 2;                               // red_rhs, x_red
-        n += ColumnStore<T, KR>::count((int)nred, 1) * sizeof(T);
+        const size_t n = ColumnStore<T, K, true>::count(lay.max_size(), lay.P) * sizeof(T);
         return (n + 255) & ~(size_t)255;
     }
-    static ChainWork<T, K> carve(const ChunkLayout& lay, char* base) {
-        constexpr int KR = 2 * K - 1;
-        const size_t nred = (size_t)lay.n_reduced() + 1;
-        ChainWork<T, K> w;
-        char* p = base;
-        w.cols = ColumnStore<T, K>{reinterpret_cast<T*>(p), lay.max_size(), lay.P};
-        p += ColumnStore<T, K>::count(lay.max_size(), lay.P) * sizeof(T);
-        w.red_band = reinterpret_cast<T*>(p); p += (size_t)(KR + 1) * nred * sizeof(T);
-        w.sig_red = reinterpret_cast<T*>(p); p += (size_t)(KR + 1) * nred * sizeof(T);
-        w.red_rhs = reinterpret_cast<T*>(p); p += nred * sizeof(T);
-        w.x_red = reinterpret_cast<T*>(p); p += nred * sizeof(T);
-        w.red_cols = ColumnStore<T, KR>{reinterpret_cast<T*>(p), lay.n_reduced(), 1};
-        p += ColumnStore<T, KR>::count((int)nred, 1) * sizeof(T);
-        w.schur = reinterpret_cast<ChunkSchur<T, K>*>(p);
-        return w;
+    static ColumnStore<T, K, true> carve(const ChunkLayout& lay, char* base) {
+        return ColumnStore<T, K, true>{reinterpret_cast<T*>(base), lay.max_size(), lay.P};
     }
 };
+
+// Shared-memory budget: the separator system, its factor and the per-chunk Schur pieces live in dynamic shared
+// memory (they are touched by the single-thread phase, where global-memory latency would be fully exposed).
+constexpr size_t kChainSmemLimit = 200 * 1024;
+
+// One CTA = one chain.  `Mat`/`Rhs` feed the matrix; logdet/quad totals go to `tot`.
+template <class T, int K, bool STORE, bool SOLVE, bool SELINV, class Mat, class Rhs>
+__device__ __forceinline__ void run_chain(const ChunkLayout& lay, const ColumnStore<T, K, true>& cols, char* smem,
+                                          Mat A, Rhs rhs, T* x_out, T* sig_out, ChainTotals<T, K>* tot,
+                                          long long* clk) {
+    const int p = threadIdx.x;
+    ChainWork<T, K> w;
+    w.cols = cols;
+    ChainSmall<T, K>::carve(lay.P, smem, w);
+    if (p == 0 && clk) clk[0] = clock64();
+    if (lay.P > 1) chain_phase2_zero<T, K>(lay, p, blockDim.x, w);
+    if (p < lay.P) chain_phase1<T, K, STORE>(lay, p, A, rhs, w);
+    __syncthreads();
+    if (p == 0 && clk) clk[1] = clock64();
+    if (p < lay.P - 1) chain_phase2_assemble<T, K>(lay, p, w);
+    __syncthreads();
+    if (p == 0) *tot = chain_phase2_solve<T, K, SOLVE, SELINV>(lay, w);
+    __syncthreads();
+    if (p == 0 && clk) clk[2] = clock64();
+    if ((SOLVE || SELINV) && p < lay.P) chain_phase3<T, K, SOLVE, SELINV>(lay, p, w, x_out, sig_out);
+    __syncthreads();
+    if (p == 0 && clk) clk[3] = clock64();
+}
 
 // ------------------------------------------------------------------------------------------------------------------
 // ELBO + gradient
@@ -125,33 +137,29 @@ struct ChainPlan {
 template <int K>
 struct ElboArgs {
     ChunkLayout lay;
-    ChainWork<Dual<1>, K> work[3];
+    ColumnStore<Dual<1>, K, true> cols[3];
     const double* Kuu; const double* dKuu; const double* G; const double* b;
     double sigma2;
     Dual<1>* sigK;          // (K+1) x M   band(Kuu^-1) with d/dl tangent
-    double* partial;        // [3 chains][8]: logdet, dlogdet, quad, dquad, trace, dtrace, info
+    double* partial;        // [3 chains][16]: logdet, dlogdet, quad, dquad, trace, dtrace, info, -, clocks[4]
 };
 
 template <int K>
 __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> a) {
     using T = Dual<1>;
+    extern __shared__ __align__(16) char smem[];
     const int chain = blockIdx.x, p = threadIdx.x;
     const ChunkLayout lay = a.lay;
-    const ChainWork<T, K>& w = a.work[chain];
     const int M = lay.M;
     __shared__ ChainTotals<T, K> tot;
     __shared__ double s_red[2][kChainThreads / 32];
-    double* out = a.partial + chain * 8;
+    __shared__ long long clk[4];
+    double* out = a.partial + chain * 16;
 
     if (chain == 0) {
         BandMat<T> A{a.Kuu, a.dKuu, nullptr, 0.0, 0.0, 1, M};
-        VecRhs<T> rhs{nullptr, M};
-        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
-        __syncthreads();
-        if (p == 0) tot = chain_phase2<T, K, false, true>(lay, w);
-        __syncthreads();
-        if (p < lay.P) chain_phase3<T, K, false, true>(lay, p, w, static_cast<T*>(nullptr), a.sigK);
-        __syncthreads();
+        VecRhs<T> rhs{a.Kuu, M, 0};
+        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, clk);
         // trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G), off-diagonals twice (reference gpr.py:60-70)
         double tr = 0.0, dtr = 0.0;
         for (int i = p; i < (K + 1) * M; i += kChainThreads) {
@@ -177,16 +185,17 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
         const double inv_s2 = 1.0 / a.sigma2;
         // chain 1: tangent d/dl (dKuu);  chain 2: tangent d/dsigma2 (-G/sigma2^2)
         BandMat<T> A{a.Kuu, a.dKuu, a.G, inv_s2, chain == 1 ? 0.0 : -inv_s2 * inv_s2, chain == 1 ? 1 : 0, M};
-        VecRhs<T> rhs{a.b, M};
-        if (p < lay.P) chain_phase1<T, K, false>(lay, p, A, rhs, w);
-        __syncthreads();
-        if (p == 0) tot = chain_phase2<T, K, false, false>(lay, w);
-        __syncthreads();
+        VecRhs<T> rhs{a.b, M, 1};
+        run_chain<T, K, false, false, false>(lay, a.cols[chain], smem, A, rhs, static_cast<T*>(nullptr),
+                                             static_cast<T*>(nullptr), &tot, clk);
     }
     if (p == 0) {
         out[0] = tot.logdet.v; out[1] = tot.logdet.d[0];
         out[2] = tot.quad.v;   out[3] = tot.quad.d[0];
         out[6] = (double)tot.info;
+        const long long t_end = clock64();
+        out[8] = (double)(clk[1] - clk[0]); out[9] = (double)(clk[2] - clk[1]);
+        out[10] = (double)(clk[3] - clk[2]); out[11] = (double)(t_end - clk[3]);
     }
 }
 
@@ -199,8 +208,8 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ partial, const d
                                      double variance, double sigma2, double* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const double* cK = partial;          // Kuu chain (d/dl)
-    const double* cL = partial + 8;      // P chain (d/dl)
-    const double* cS = partial + 16;     // P chain (d/dsigma2)
+    const double* cL = partial + 16;     // P chain (d/dl)
+    const double* cS = partial + 32;     // P chain (d/dsigma2)
     const double yy = scal[0], N = scal[1];
     const double v = variance, s2 = sigma2;
     const double logdetK = cK[0], dlogdetK_dl = cK[1], tr = cK[4], dtr_dl = cK[5];
@@ -222,8 +231,10 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ partial, const d
     if (info == 0.0) info = cL[6];
     if (info == 0.0) info = cS[6];
     out[8] = info;
-    out[9] = dlogdetK_dl; out[10] = dlogdetP_dl; out[11] = dQ_dl; out[12] = dtr_dl; out[13] = dlogdetP_ds;
-    out[14] = dQ_ds; out[15] = cL[0] - cS[0];      // consistency of the two P chains (must be ~0)
+    // diagnostics: SM cycles of the Kuu chain's phases (chunk sweep, separator system, back sweep, trace)
+    out[9] = cK[8]; out[10] = cK[9]; out[11] = cK[10]; out[12] = cK[11];
+    out[13] = cL[8]; out[14] = cL[9];
+    out[15] = cL[0] - cS[0];      // consistency of the two P chains (must be ~0)
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -232,7 +243,7 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ partial, const d
 template <int K>
 struct PosteriorArgs {
     ChunkLayout lay;
-    ChainWork<double, K> work[2];
+    ColumnStore<double, K, true> cols[2];
     const double* Kuu; const double* G; const double* b;
     double sigma2;
     double* sigK; double* sigP; double* x;       // (K+1) x M, (K+1) x M, M
@@ -242,29 +253,20 @@ struct PosteriorArgs {
 template <int K>
 __global__ void __launch_bounds__(kChainThreads) posterior_chains_kernel(PosteriorArgs<K> a) {
     using T = double;
+    extern __shared__ __align__(16) char smem[];
     const int chain = blockIdx.x, p = threadIdx.x;
     const ChunkLayout lay = a.lay;
-    const ChainWork<T, K>& w = a.work[chain];
     const int M = lay.M;
     __shared__ ChainTotals<T, K> tot;
     if (chain == 0) {
         BandMat<T> A{a.Kuu, nullptr, nullptr, 0.0, 0.0, 0, M};
-        VecRhs<T> rhs{nullptr, M};
-        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
-        __syncthreads();
-        if (p == 0) tot = chain_phase2<T, K, false, true>(lay, w);
-        __syncthreads();
-        if (p < lay.P) chain_phase3<T, K, false, true>(lay, p, w, static_cast<T*>(nullptr), a.sigK);
+        VecRhs<T> rhs{a.Kuu, M, 0};
+        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, nullptr);
     } else {
         BandMat<T> A{a.Kuu, nullptr, a.G, 1.0 / a.sigma2, 0.0, 0, M};
-        VecRhs<T> rhs{a.b, M};
-        if (p < lay.P) chain_phase1<T, K, true>(lay, p, A, rhs, w);
-        __syncthreads();
-        if (p == 0) tot = chain_phase2<T, K, true, true>(lay, w);
-        __syncthreads();
-        if (p < lay.P) chain_phase3<T, K, true, true>(lay, p, w, a.x, a.sigP);
+        VecRhs<T> rhs{a.b, M, 1};
+        run_chain<T, K, true, true, true>(lay, a.cols[1], smem, A, rhs, a.x, a.sigP, &tot, nullptr);
     }
-    __syncthreads();
     if (p == 0) a.info[chain] = (double)tot.info;
 }
 
@@ -282,7 +284,7 @@ __global__ void __launch_bounds__(256) posterior_combine_kernel(const double* __
 template <int K>
 static size_t elbo_work_bytes(const ChunkLayout& lay) {
     return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
-           + 256;
+           + 512;
 }
 template <int K>
 static size_t posterior_work_bytes(const ChunkLayout& lay) {
@@ -296,14 +298,16 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
     ElboArgs<K> a;
     a.lay = lay;
     char* p = work;
-    for (int c = 0; c < 3; ++c) { a.work[c] = ChainPlan<Dual<1>, K>::carve(lay, p); p += ChainPlan<Dual<1>, K>::bytes(lay); }
+    for (int c = 0; c < 3; ++c) { a.cols[c] = ChainPlan<Dual<1>, K>::carve(lay, p); p += ChainPlan<Dual<1>, K>::bytes(lay); }
     a.sigK = reinterpret_cast<Dual<1>*>(p);
     p += ((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255;
     a.partial = reinterpret_cast<double*>(p);
     const int M = lay.M;
     a.Kuu = Kuu; a.dKuu = dKuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
     a.sigma2 = sigma2;
-    elbo_chains_kernel<K><<<3, kChainThreads, 0, st>>>(a);
+    const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(elbo_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    elbo_chains_kernel<K><<<3, kChainThreads, smem, st>>>(a);
     ASVGP_CUDA_OK(cudaGetLastError());
     elbo_finalize_kernel<<<1, 32, 0, st>>>(a.partial, acc + (size_t)(K + 2) * M, M, variance, sigma2, out);
     ASVGP_CUDA_OK(cudaGetLastError());
@@ -316,7 +320,7 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
     PosteriorArgs<K> a;
     a.lay = lay;
     char* p = work;
-    for (int c = 0; c < 2; ++c) { a.work[c] = ChainPlan<double, K>::carve(lay, p); p += ChainPlan<double, K>::bytes(lay); }
+    for (int c = 0; c < 2; ++c) { a.cols[c] = ChainPlan<double, K>::carve(lay, p); p += ChainPlan<double, K>::bytes(lay); }
     const int M = lay.M;
     const size_t band_bytes = (((size_t)(K + 1) * M * sizeof(double)) + 255) & ~(size_t)255;
     a.sigK = reinterpret_cast<double*>(p); p += band_bytes;
@@ -326,7 +330,9 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
     a.sigma2 = sigma2;
     a.info = info;
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sigK, 0, 2 * band_bytes, st));
-    posterior_chains_kernel<K><<<2, kChainThreads, 0, st>>>(a);
+    const size_t smem = ChainSmall<double, K>::bytes(lay.P);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(posterior_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    posterior_chains_kernel<K><<<2, kChainThreads, smem, st>>>(a);
     ASVGP_CUDA_OK(cudaGetLastError());
     const int band_elems = (K + 1) * M;
     posterior_combine_kernel<<<(band_elems + 255) / 256, 256, 0, st>>>(a.sigK, a.sigP, a.x, 1.0 / sigma2, M, band_elems,
@@ -335,9 +341,25 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
     return kOk;
 }
 
+template <int K>
+static int max_chunks_for_smem() {
+    int P = kChainThreads;
+    while (P > 1 && ChainSmall<Dual<1>, K>::bytes(P) > kChainSmemLimit) --P;
+    return P;
+}
+
 static ChunkLayout pick_layout(int M, int K, int chunks) {
     int P = chunks > 0 ? chunks : default_chunks(M, K);
-    if (P > kChainThreads) P = kChainThreads;
+    int cap = kChainThreads;
+    switch (K) {
+        case 1: cap = max_chunks_for_smem<1>(); break;
+        case 2: cap = max_chunks_for_smem<2>(); break;
+        case 3: cap = max_chunks_for_smem<3>(); break;
+        case 4: cap = max_chunks_for_smem<4>(); break;
+        case 5: cap = max_chunks_for_smem<5>(); break;
+        case 6: cap = max_chunks_for_smem<6>(); break;
+    }
+    if (P > cap) P = cap;
     return make_layout(M, K, P);
 }
 

@@ -30,22 +30,19 @@ template <class T> struct HostRhs {
 template <class T, int K>
 static int run_chain(int M, int P, const double* band, const double* dband, const double* rhs, double* scal,
                      double* x, double* sig) {
-    constexpr int KR = 2 * K - 1;
     ChunkLayout lay = make_layout(M, K, P);
-    const int ns = lay.max_size(), nred = lay.n_reduced();
-    std::vector<T> cols(ColumnStore<T, K>::count(ns, lay.P)), red_band((size_t)(KR + 1) * (nred + 1)), red_rhs(nred + 1),
-        red_cols(ColumnStore<T, KR>::count(nred + 1, 1)), x_red(nred + 1), sig_red((size_t)(KR + 1) * (nred + 1));
-    std::vector<ChunkSchur<T, K>> schur(lay.P);
+    const int ns = lay.max_size();
+    std::vector<T> cols(ColumnStore<T, K, true>::count(ns, lay.P));
+    std::vector<char> small(ChainSmall<T, K>::bytes(lay.P) + 64);
     ChainWork<T, K> w;
-    w.cols = ColumnStore<T, K>{cols.data(), ns, lay.P};
-    w.schur = schur.data();
-    w.red_band = red_band.data(); w.red_rhs = red_rhs.data();
-    w.red_cols = ColumnStore<T, KR>{red_cols.data(), nred, 1};
-    w.x_red = x_red.data(); w.sig_red = sig_red.data();
+    w.cols = ColumnStore<T, K, true>{cols.data(), ns, lay.P};
+    ChainSmall<T, K>::carve(lay.P, small.data(), w);
     HostMat<T> A{band, dband, M};
     HostRhs<T> b{rhs, M};
     for (int p = 0; p < lay.P; ++p) chain_phase1<T, K, true>(lay, p, A, b, w);
-    ChainTotals<T, K> tot = chain_phase2<T, K, true, true>(lay, w);
+    for (int t = 0; t < 7; ++t) chain_phase2_zero<T, K>(lay, t, 7, w);
+    for (int q = 0; q + 1 < lay.P; ++q) chain_phase2_assemble<T, K>(lay, q, w);
+    ChainTotals<T, K> tot = chain_phase2_solve<T, K, true, true>(lay, w);
     std::vector<T> xo(M), so((size_t)(K + 1) * M, zero_of<T>());
     for (int p = 0; p < lay.P; ++p) chain_phase3<T, K, true, true>(lay, p, w, xo.data(), so.data());
     const int nt = sizeof(T) / sizeof(double);
