@@ -125,3 +125,51 @@ def boundary_band(k, m, dx, delta):
         band[d, :n] = diag
         band[d, m - d - n: m - d] = diag
     return band
+
+
+# ---- Bernstein-type expansions used by the 2-D accumulate kernel -------------------------------------------------------
+def _comb(n, k):
+    from math import comb
+
+    return comb(n, k)
+
+
+def _to_bernstein(poly, n):
+    """Coefficients c_p with poly(t) = sum_p c_p t^p (1-t)^(n-p), from ascending monomial coefficients
+    (t^k = t^k (t + (1-t))^(n-k))."""
+    out = [Fraction(0)] * (n + 1)
+    for k, a in enumerate(poly):
+        if a == 0:
+            continue
+        for j in range(n - k + 1):
+            out[k + j] += a * _comb(n - k, j)
+    return out
+
+
+@lru_cache(maxsize=None)
+def product_bernstein(k):
+    """C[r][s][p] (exact): piece_r(t) piece_s(t) = sum_p C[r][s][p] t^p (1-t)^(2k-p).  All entries are >= 0 (uniform
+    B-spline pieces have non-negative Bezier coefficients), so expanding per-cell moments of t^p (1-t)^(2k-p) back
+    into the Gram stencil involves no cancellation."""
+    P = piece_coeffs(k, 0)
+    out = tuple(tuple(tuple(_to_bernstein(_poly_mul(list(P[r]), list(P[s])), 2 * k)) for s in range(k + 1))
+                for r in range(k + 1))
+    assert all(c >= 0 for a in out for b in a for c in b)
+    return out
+
+
+@lru_cache(maxsize=None)
+def piece_bernstein(k):
+    """D[r][p] (exact): piece_r(t) = sum_p D[r][p] t^p (1-t)^(k-p), all >= 0."""
+    P = piece_coeffs(k, 0)
+    out = tuple(tuple(_to_bernstein(list(P[r]), k)) for r in range(k + 1))
+    assert all(c >= 0 for a in out for c in a)
+    return out
+
+
+def product_bernstein_float(k):
+    return np.array([[[float(c) for c in s] for s in r] for r in product_bernstein(k)], dtype=np.float64)
+
+
+def piece_bernstein_float(k):
+    return np.array([[float(c) for c in r] for r in piece_bernstein(k)], dtype=np.float64)

@@ -281,6 +281,61 @@ __global__ void __launch_bounds__(256) posterior_combine_kernel(const double* __
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// band(A^-1) and log|A| of one SPD band matrix with one tangent — used for the per-dimension factors K1, K2 of the
+// Kronecker model (log|K1 (x) K2| = m2 log|K1| + m1 log|K2| and trace((K1 (x) K2)^-1 G) only need the bands of the
+// factor inverses, reference gpr.py:288-289,307)
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+struct BandInvArgs {
+    ChunkLayout lay;
+    ColumnStore<Dual<1>, K, true> cols;
+    const double* A; const double* dA;
+    Dual<1>* sig;             // scratch (K+1) x M duals
+    double* sig_val; double* sig_tan;
+    double* scal;             // [4]: log|A|, d log|A|, info, -
+};
+
+template <int K>
+__global__ void __launch_bounds__(kChainThreads) band_inverse_kernel(BandInvArgs<K> a) {
+    using T = Dual<1>;
+    extern __shared__ __align__(16) char smem[];
+    const int p = threadIdx.x;
+    const ChunkLayout lay = a.lay;
+    const int M = lay.M;
+    __shared__ ChainTotals<T, K> tot;
+    BandMat<T> A{a.A, a.dA, nullptr, 0.0, 0.0, 1, M};
+    VecRhs<T> rhs{a.A, M, 0};
+    run_chain<T, K, true, false, true>(lay, a.cols, smem, A, rhs, static_cast<T*>(nullptr), a.sig, &tot, nullptr);
+    for (int i = p; i < (K + 1) * M; i += kChainThreads) {
+        const T s = a.sig[i];
+        a.sig_val[i] = s.v;
+        a.sig_tan[i] = s.d[0];
+    }
+    if (p == 0) {
+        a.scal[0] = tot.logdet.v; a.scal[1] = tot.logdet.d[0]; a.scal[2] = (double)tot.info; a.scal[3] = 0.0;
+    }
+}
+
+template <int K>
+static int launch_band_inverse(const ChunkLayout& lay, const double* A, const double* dA, double* sig_val,
+                               double* sig_tan, double* scal, char* work, cudaStream_t st) {
+    BandInvArgs<K> a;
+    a.lay = lay;
+    char* p = work;
+    a.cols = ChainPlan<Dual<1>, K>::carve(lay, p);
+    p += ChainPlan<Dual<1>, K>::bytes(lay);
+    a.sig = reinterpret_cast<Dual<1>*>(p);
+    a.A = A; a.dA = dA; a.sig_val = sig_val; a.sig_tan = sig_tan; a.scal = scal;
+    ASVGP_CUDA_OK(cudaMemsetAsync(a.sig, 0, (size_t)(K + 1) * lay.M * sizeof(Dual<1>), st));
+    const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(band_inverse_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    band_inverse_kernel<K><<<1, kChainThreads, smem, st>>>(a);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 template <int K>
 static size_t elbo_work_bytes(const ChunkLayout& lay) {
     return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
@@ -432,5 +487,16 @@ extern "C" int asvgp_posterior_1d(const double* Kuu, const double* acc, int M, i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_posterior<K>(lay, Kuu, acc, sigma2, alpha, S_band, info,
                                                                    static_cast<char*>(work), st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_band_inverse_1d(const double* A, const double* dA, int M, int order, int chunks, double* sig_val,
+                                     double* sig_tan, double* scal, void* work, int64_t work_bytes, void* stream) {
+    ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "band_inverse_1d: M=%d order=%d", M, order);
+    ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "band_inverse_1d: workspace too small");
+    const ChunkLayout lay = pick_layout(M, order, chunks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_band_inverse<K>(lay, A, dA, sig_val, sig_tan, scal,
+                                                                      static_cast<char*>(work), st)) return rc; });
     return kOk;
 }

@@ -1,0 +1,408 @@
+// Streaming 2-D (Kronecker) kernels: fused Gram/projection accumulation and posterior predictor.
+//
+//   asvgp_accum_2d   <- GPR_kron.__init__ precompute: per-dimension make_Kuf, kron.make_kvs_sparse (row-wise
+//                       Khatri-Rao), Kuf @ y, Kuf @ Kuf.T           (reference asvgp/gpr.py:268-274, kronecker.py:7-33)
+//   asvgp_predict_2d <- GPR_kron.predict_f / predict_f_sparse       (reference asvgp/gpr.py:310-359)
+//
+// accum_2d design.  A point in cell (c1, c2) adds w w^T with w = a (x) b, a = pieces(t1),
+// b = pieces(t2): (k+1)^2 ((k+1)^2 + 1)/2 = 136 products for k = 3 — too many accumulators for one thread, and the
+// kernel would sit far above the fp64 ridge.  But every product a_r a_s b_u b_v is a polynomial of degree 2k in t1 and
+// in t2, so all of them live in the (2k+1)^2-dimensional span of
+//        beta_p(t1) beta_q(t2),   beta_p(t) = t^p (1-t)^(2k-p),
+// and expand in it with NON-NEGATIVE coefficients (B-spline pieces have non-negative Bezier coefficients), i.e. without
+// cancellation.  So each thread keeps (2k+1)^2 + (k+1)^2 = 65 moment sums (k = 3) in registers for the cell it is in,
+// one FMA per moment per point, and flushes them to a per-cell moment table (fp64 RED, L2 resident) when its points
+// move to another cell.  A second, tiny kernel expands the moment table into the Gram stencil and the projection.
+// Every thread walks its own contiguous slice of the points, so raster-ordered data (x1 slow) gives runs of
+// ~n2/(m2-k) points per flush; any order gives the right answer.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "../../include/asvgp_b200.h"
+
+namespace asvgp {
+
+struct LdgLoader2 {
+    __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); }
+};
+
+__device__ __forceinline__ Mesh load_mesh2(const double* knots, int n_knots) {
+    Mesh m;
+    m.knots = knots;
+    m.n_knots = n_knots;
+    m.x0 = __ldg(knots);
+    m.inv_delta = 1.0 / (__ldg(knots + 1) - m.x0);
+    return m;
+}
+
+struct Interval {            // cached knot interval of one dimension
+    int idx;
+    double u, lo, hi;
+    __device__ __forceinline__ void reset() { idx = -1; u = 0.0; lo = INFINITY; hi = -INFINITY; }
+    __device__ __forceinline__ bool inside(double x) const { return x > lo && x <= hi; }
+    __device__ __forceinline__ void set(const Mesh& mesh, int i) {
+        idx = i;
+        u = __ldg(mesh.knots + i);
+        lo = (i == 0) ? -INFINITY : u;
+        hi = (i == mesh.n_knots - 2) ? INFINITY : __ldg(mesh.knots + i + 1);
+    }
+};
+
+template <int K> struct Moments {
+    static constexpr int NB = 2 * K + 1;            // Bernstein-type functions per dimension for the Gram part
+    static constexpr int NY = K + 1;                // ... for the projection part
+    static constexpr int kGram = NB * NB;
+    static constexpr int kProj = NY * NY;
+    static constexpr int kAll = kGram + kProj;      // doubles per cell in the moment table
+};
+
+// powers t^0..t^N and (1-t)^0..(1-t)^N
+template <int N>
+__device__ __forceinline__ void powers(double t, double (&tp)[N + 1], double (&up)[N + 1]) {
+    const double u = 1.0 - t;
+    tp[0] = 1.0; up[0] = 1.0;
+#pragma unroll
+    for (int i = 1; i <= N; ++i) { tp[i] = tp[i - 1] * t; up[i] = up[i - 1] * u; }
+}
+
+// Thread-private accumulation over a contiguous slice of points.  [P0, P1) is the range of the dim-1 moment index
+// this launch handles (register budget: one launch for k <= 3, split launches for k >= 4); WITH_Y: also the
+// projection moments, sum y^2 and the count.
+template <int K, int P0, int P1, bool WITH_Y>
+__global__ void __launch_bounds__(256, 1)
+accum_2d_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
+                const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
+                double* __restrict__ cellmom, double* __restrict__ scal) {
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY;
+    constexpr int NP = P1 - P0;
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int nc2 = nk2 - 1;
+
+    const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (n + n_threads - 1) / n_threads;
+    per = (per + 1) & ~(int64_t)1;                                  // even: y is read two points at a time
+    const int64_t begin = tid * per < n ? tid * per : n;
+    const int64_t end = begin + per < n ? begin + per : n;
+
+    double acc[NP * NB];
+    double accy[WITH_Y ? NY * NY : 1];
+#pragma unroll
+    for (int i = 0; i < NP * NB; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < (WITH_Y ? NY * NY : 1); ++i) accy[i] = 0.0;
+    double yy = 0.0;
+    Interval i1, i2;
+    i1.reset(); i2.reset();
+    bool dirty = false;
+
+    auto flush = [&]() {
+        if (dirty) {
+            double* dst = cellmom + ((int64_t)i1.idx * nc2 + i2.idx) * Mo::kAll;
+#pragma unroll
+            for (int p = 0; p < NP; ++p)
+#pragma unroll
+                for (int q = 0; q < NB; ++q) {
+                    atomicAdd(dst + (P0 + p) * NB + q, acc[p * NB + q]);
+                    acc[p * NB + q] = 0.0;
+                }
+            if (WITH_Y) {
+#pragma unroll
+                for (int i = 0; i < NY * NY; ++i) { atomicAdd(dst + Mo::kGram + i, accy[i]); accy[i] = 0.0; }
+            }
+            dirty = false;
+        }
+    };
+    auto add = [&](double x1, double x2, double yv) {
+        if (!(i1.inside(x1) && i2.inside(x2))) {
+            flush();
+            if (!i1.inside(x1)) i1.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+            if (!i2.inside(x2)) i2.set(mesh2, locate_interval(mesh2, x2, LdgLoader2()));
+        }
+        const double t1 = (x1 - i1.u) * mesh1.inv_delta, t2 = (x2 - i2.u) * mesh2.inv_delta;
+        double tp1[2 * K + 1], up1[2 * K + 1], tp2[2 * K + 1], up2[2 * K + 1];
+        powers<2 * K>(t1, tp1, up1);
+        powers<2 * K>(t2, tp2, up2);
+        double b2[NB];
+#pragma unroll
+        for (int q = 0; q < NB; ++q) b2[q] = tp2[q] * up2[2 * K - q];
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const double b1 = tp1[P0 + p] * up1[2 * K - (P0 + p)];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) acc[p * NB + q] = fma(b1, b2[q], acc[p * NB + q]);
+        }
+        if (WITH_Y) {
+            double g2[NY];
+#pragma unroll
+            for (int q = 0; q < NY; ++q) g2[q] = tp2[q] * up2[K - q];
+#pragma unroll
+            for (int p = 0; p < NY; ++p) {
+                const double g1 = yv * (tp1[p] * up1[K - p]);
+#pragma unroll
+                for (int q = 0; q < NY; ++q) accy[p * NY + q] = fma(g1, g2[q], accy[p * NY + q]);
+            }
+            yy = fma(yv, yv, yy);
+        }
+        dirty = true;
+    };
+
+    // X is row-major [n, 2]: one 16-byte load per point; begin is even so y pairs are 16-byte aligned too
+    const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
+    int64_t i = begin;
+    for (; i + 4 <= end; i += 4) {
+        const double2 pa = __ldg(X2 + i), pb = __ldg(X2 + i + 1), pc = __ldg(X2 + i + 2), pd = __ldg(X2 + i + 3);
+        double2 ya = make_double2(0.0, 0.0), yb = ya;
+        if (WITH_Y) {
+            ya = __ldg(reinterpret_cast<const double2*>(y + i));
+            yb = __ldg(reinterpret_cast<const double2*>(y + i + 2));
+        }
+        add(pa.x, pa.y, ya.x);
+        add(pb.x, pb.y, ya.y);
+        add(pc.x, pc.y, yb.x);
+        add(pd.x, pd.y, yb.y);
+    }
+    for (; i < end; ++i) {
+        const double2 pa = __ldg(X2 + i);
+        add(pa.x, pa.y, WITH_Y ? __ldg(y + i) : 0.0);
+    }
+    flush();
+
+    if (WITH_Y) {
+        __shared__ double s_yy[8];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+        if ((threadIdx.x & 31) == 0) s_yy[threadIdx.x >> 5] = yy;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_yy[w];
+            atomicAdd(scal, tot);
+            if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+        }
+    }
+}
+
+// Expands the per-cell moments into the Gram stencil and the projection:
+//   G[(c1+r1, c2+r2), (c1+s1, c2+s2)] += sum_pq C[r1][s1][p] C[r2][s2][q] mom[p][q]      (lower part only)
+//   b[(c1+r1, c2+r2)]                 += sum_pq D[r1][p] D[r2][q] ymom[p][q]
+// One CTA per cell; thread = one (r1, s1, r2, s2) combination (or one (r1, r2) for b).
+// Stencil layout: Gs[e * M + j], e = d1 * (2k+1) + (d2 + k), d1 = i1 - j1 in [0, k], d2 = i2 - j2 in [-k, k],
+// j = j1 * m2 + j2; stored for (d1 > 0) or (d1 == 0 and d2 >= 0).
+template <int K>
+__global__ void __launch_bounds__(256) expand_moments_2d_kernel(const double* __restrict__ cellmom,
+                                                               const double* __restrict__ Cprod,
+                                                               const double* __restrict__ Dy, int nc1, int nc2, int m2,
+                                                               int64_t M, double* __restrict__ Gs,
+                                                               double* __restrict__ b) {
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY, K1 = K + 1;
+    __shared__ double s_mom[Mo::kAll];
+    __shared__ double s_C[K1 * K1 * NB];
+    __shared__ double s_D[K1 * NY];
+    const int cell = blockIdx.x;
+    const int c1 = cell / nc2, c2 = cell % nc2;
+    for (int i = threadIdx.x; i < Mo::kAll; i += blockDim.x) s_mom[i] = cellmom[(int64_t)cell * Mo::kAll + i];
+    for (int i = threadIdx.x; i < K1 * K1 * NB; i += blockDim.x) s_C[i] = Cprod[i];
+    for (int i = threadIdx.x; i < K1 * NY; i += blockDim.x) s_D[i] = Dy[i];
+    __syncthreads();
+    for (int o = threadIdx.x; o < K1 * K1 * K1 * K1; o += blockDim.x) {
+        const int s2 = o % K1, r2 = (o / K1) % K1, s1 = (o / (K1 * K1)) % K1, r1 = o / (K1 * K1 * K1);
+        const int d1 = r1 - s1, d2 = r2 - s2;
+        if (d1 < 0 || (d1 == 0 && d2 < 0)) continue;
+        double v = 0.0;
+#pragma unroll
+        for (int p = 0; p < NB; ++p) {
+            double inner = 0.0;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) inner = fma(s_C[(r2 * K1 + s2) * NB + q], s_mom[p * NB + q], inner);
+            v = fma(s_C[(r1 * K1 + s1) * NB + p], inner, v);
+        }
+        const int e = d1 * (2 * K + 1) + (d2 + K);
+        const int64_t j = (int64_t)(c1 + s1) * m2 + (c2 + s2);
+        atomicAdd(Gs + (int64_t)e * M + j, v);
+    }
+    for (int o = threadIdx.x; o < K1 * K1; o += blockDim.x) {
+        const int r2 = o % K1, r1 = o / K1;
+        double v = 0.0;
+#pragma unroll
+        for (int p = 0; p < NY; ++p) {
+            double inner = 0.0;
+#pragma unroll
+            for (int q = 0; q < NY; ++q) inner = fma(s_D[r2 * NY + q], s_mom[Mo::kGram + p * NY + q], inner);
+            v = fma(s_D[r1 * NY + p], inner, v);
+        }
+        atomicAdd(b + (int64_t)(c1 + r1) * m2 + (c2 + r2), v);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// predictor: mean = w^T alpha, var = v1 v2 + w^T Sigma_P w - (a^T S1 a)(b^T S2 b),  w = a (x) b
+// (reference gpr.py:321-332).  Only the stencil entries of P^-1 and the bands of K1^-1, K2^-1 are needed.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256) predict_2d_kernel(const double* __restrict__ X, int64_t n,
+                                                         const double* __restrict__ knots1, int nk1,
+                                                         const double* __restrict__ knots2, int nk2, int m1, int m2,
+                                                         const double* __restrict__ alpha,
+                                                         const double* __restrict__ SigP,      // stencil layout
+                                                         const double* __restrict__ S1,        // (K+1) x m1 lower band
+                                                         const double* __restrict__ S2,        // (K+1) x m2 lower band
+                                                         double prior_var, double* __restrict__ mean,
+                                                         double* __restrict__ var) {
+    constexpr int K1 = K + 1, NS = 2 * K + 1;
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int64_t M = (int64_t)m1 * m2;
+    const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double2 pt = __ldg(X2 + i);
+        const int c1 = locate_interval(mesh1, pt.x, LdgLoader2());
+        const int c2 = locate_interval(mesh2, pt.y, LdgLoader2());
+        double a[K1], bb[K1];
+        bspline_pieces<K>((pt.x - __ldg(knots1 + c1)) * mesh1.inv_delta, a);
+        bspline_pieces<K>((pt.y - __ldg(knots2 + c2)) * mesh2.inv_delta, bb);
+        double mu = 0.0, q = 0.0;
+#pragma unroll
+        for (int r1 = 0; r1 < K1; ++r1) {
+#pragma unroll
+            for (int r2 = 0; r2 < K1; ++r2) {
+                const double wr = a[r1] * bb[r2];
+                const int64_t irow = (int64_t)(c1 + r1) * m2 + (c2 + r2);
+                mu = fma(wr, __ldg(alpha + irow), mu);
+                // row (r1, r2) against all columns (s1, s2) <= (r1, r2) in the stencil's lower part
+                double rowsum = 0.5 * wr * __ldg(SigP + (int64_t)(0 * NS + K) * M + irow);
+#pragma unroll
+                for (int s1 = 0; s1 <= r1; ++s1) {
+#pragma unroll
+                    for (int s2 = 0; s2 < K1; ++s2) {
+                        const int d1 = r1 - s1, d2 = r2 - s2;
+                        if (d1 == 0 && d2 <= 0) continue;
+                        const int64_t j = (int64_t)(c1 + s1) * m2 + (c2 + s2);
+                        rowsum = fma(a[s1] * bb[s2], __ldg(SigP + (int64_t)(d1 * NS + d2 + K) * M + j), rowsum);
+                    }
+                }
+                q = fma(wr, rowsum, q);
+            }
+        }
+        double q1 = 0.0, q2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < K1; ++r) {
+            double row1 = 0.5 * a[r] * __ldg(S1 + c1 + r), row2 = 0.5 * bb[r] * __ldg(S2 + c2 + r);
+#pragma unroll
+            for (int s = 0; s < r; ++s) {
+                row1 = fma(a[s], __ldg(S1 + (int64_t)(r - s) * m1 + c1 + s), row1);
+                row2 = fma(bb[s], __ldg(S2 + (int64_t)(r - s) * m2 + c2 + s), row2);
+            }
+            q1 = fma(a[r], row1, q1);
+            q2 = fma(bb[r], row2, q2);
+        }
+        mean[i] = mu;
+        var[i] = prior_var + 2.0 * q - (2.0 * q1) * (2.0 * q2);
+    }
+}
+
+static int sm_count2() {
+    static int cached = 0;
+    if (cached == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) cached = 148;
+    }
+    return cached;
+}
+
+template <int K, int P0, int P1, bool WITH_Y>
+static int launch_accum_part(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2,
+                             int nk2, double* cellmom, double* scal, cudaStream_t st) {
+    const int64_t want = (n + 511) / 512;          // at least ~2 points per thread; at most one CTA per SM
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, sm_count2()));
+    accum_2d_kernel<K, P0, P1, WITH_Y><<<blocks, 256, 0, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <int K>
+static int launch_accum_2d(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2,
+                           int nk2, double* cellmom, double* scal, cudaStream_t st);
+
+#define ASVGP_ACC2D(K_, ...)                                                                                          \
+    template <>                                                                                                       \
+    int launch_accum_2d<K_>(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2, \
+                            int nk2, double* cellmom, double* scal, cudaStream_t st) {                                \
+        int rc = kOk;                                                                                                 \
+        __VA_ARGS__                                                                                                   \
+        return rc;                                                                                                    \
+    }
+#define PART(K_, P0_, P1_, Y_) \
+    if (rc == kOk) rc = launch_accum_part<K_, P0_, P1_, Y_>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, st);
+// moment index ranges per launch: <= ~70 register-resident sums per thread
+ASVGP_ACC2D(1, PART(1, 0, 3, true))
+ASVGP_ACC2D(2, PART(2, 0, 5, true))
+ASVGP_ACC2D(3, PART(3, 0, 7, true))
+ASVGP_ACC2D(4, PART(4, 0, 5, true) PART(4, 5, 9, false))
+ASVGP_ACC2D(5, PART(5, 0, 3, true) PART(5, 3, 8, false) PART(5, 8, 11, false))
+ASVGP_ACC2D(6, PART(6, 0, 2, true) PART(6, 2, 6, false) PART(6, 6, 10, false) PART(6, 10, 13, false))
+
+}  // namespace asvgp
+
+using namespace asvgp;
+
+#define ASVGP_DISPATCH_ORDER(order, CALL)                         \
+    switch (order) {                                              \
+        case 1: { constexpr int K = 1; CALL; } break;             \
+        case 2: { constexpr int K = 2; CALL; } break;             \
+        case 3: { constexpr int K = 3; CALL; } break;             \
+        case 4: { constexpr int K = 4; CALL; } break;             \
+        case 5: { constexpr int K = 5; CALL; } break;             \
+        case 6: { constexpr int K = 6; CALL; } break;             \
+        default:                                                  \
+            set_last_error("spline order %d not in 1..6", order); \
+            return kBadArgument;                                  \
+    }
+
+extern "C" int64_t asvgp_accum_2d_moment_doubles(int n_knots1, int n_knots2, int order) {
+    if (order < 1 || order > kMaxOrder || n_knots1 < 2 || n_knots2 < 2) return -1;
+    const int64_t per = (int64_t)(2 * order + 1) * (2 * order + 1) + (int64_t)(order + 1) * (order + 1);
+    return per * (n_knots1 - 1) * (n_knots2 - 1);
+}
+
+extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const double* mesh1, int n_knots1,
+                              const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
+                              void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "accum_2d: n=%lld knots=%d,%d", (long long)n, n_knots1, n_knots2);
+    ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
+                  "accum_2d: X and y must be 16-byte aligned");
+    if (n == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_expand_moments_2d(const double* cellmom, const double* Cprod, const double* Dy, int n_knots1,
+                                       int n_knots2, int order, double* Gs, double* b, void* stream) {
+    ASVGP_REQUIRE(n_knots1 >= 2 && n_knots2 >= 2, "expand_moments_2d: knots=%d,%d", n_knots1, n_knots2);
+    const int nc1 = n_knots1 - 1, nc2 = n_knots2 - 1;
+    const int m2 = n_knots2 + order - 1;
+    const int64_t M = (int64_t)(n_knots1 + order - 1) * m2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, (expand_moments_2d_kernel<K><<<nc1 * nc2, 256, 0, st>>>(cellmom, Cprod, Dy, nc1, nc2, m2, M, Gs, b)));
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+extern "C" int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
+                                int n_knots2, int order, const double* alpha, const double* SigP, const double* S1,
+                                const double* S2, double prior_var, double* mean, double* var, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "predict_2d: n=%lld", (long long)n);
+    ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(Xnew) & 15u) == 0, "predict_2d: Xnew must be 16-byte aligned");
+    if (n == 0) return kOk;
+    const int m1 = n_knots1 + order - 1, m2 = n_knots2 + order - 1;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count2() * 8);
+    ASVGP_DISPATCH_ORDER(order, (predict_2d_kernel<K><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, n_knots1, mesh2, n_knots2, m1, m2, alpha, SigP, S1, S2, prior_var, mean, var)));
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}

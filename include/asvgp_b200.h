@@ -96,6 +96,65 @@ ASVGP_API int asvgp_posterior_1d(const double* Kuu, const double* acc, int M, in
                                  double* alpha, double* S_band, double* info, void* work, int64_t work_bytes,
                                  void* stream);
 
+/* ---- band(A^-1) and log|A| with one tangent ------------------------------------------------------------------------------
+ * Replaces banded.cholesky_band + banded.inverse_from_cholesky_band (gpr.py:56-59) and their TF gradients for ONE banded
+ * SPD matrix A (lower band (order+1) x M) with tangent dA: sig_val = band(A^-1), sig_tan = band(-A^-1 dA A^-1),
+ * scal[4] = { log|A|, d log|A|, info, 0 }.  Used per dimension by the Kronecker model (gpr.py:287-289,307). */
+ASVGP_API int asvgp_band_inverse_1d(const double* A, const double* dA, int M, int order, int chunks, double* sig_val,
+                                    double* sig_tan, double* scal, void* work, int64_t work_bytes, void* stream);
+
+/* ==== 2-D (Kronecker) model =================================================================================================
+ * Basis index (i1, i2) -> i1*m2 + i2 (kronecker.py:7-30), M = m1*m2.  Block-banded matrices travel in STENCIL layout:
+ * S[e*M + j], e = d1*(2*order+1) + (d2+order), holding A[(j1+d1, j2+d2), (j1, j2)] for d1 in [0,order],
+ * d2 in [-order,order], stored for d1 > 0 or (d1 == 0 and d2 >= 0); everything else is zero. */
+
+/* Doubles of the per-cell moment table used by asvgp_accum_2d ((2o+1)^2 + (o+1)^2 per cell). */
+ASVGP_API int64_t asvgp_accum_2d_moment_doubles(int n_knots1, int n_knots2, int order);
+
+/* ---- a11 + a12: O(N) accumulation for the Kronecker model -----------------------------------------------------------------
+ * Replaces GPR_kron.__init__'s per-dimension make_Kuf, kron.make_kvs_sparse (row-wise Khatri-Rao, kronecker.py:7-33),
+ * `Kuf @ y` and `Kuf @ Kuf.T` (gpr.py:268-274).  X is row-major [n, 2].  Adds (does not zero) per-cell moments into
+ * `cellmom` and { sum y^2, count } into scal[2]; both can be all-reduced across ranks before expansion. */
+ASVGP_API int asvgp_accum_2d(const double* X, const double* y, int64_t n, const double* mesh1, int n_knots1,
+                             const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
+                             void* stream);
+
+/* Expands the moment table into the Gram stencil Gs[(o+1)(2o+1) x M] and the projection b[M] (both must be zeroed by
+ * the caller).  Cprod[(o+1)(o+1)(2o+1)], Dy[(o+1)(o+1)]: exact Bernstein-type expansion tables (host-computed). */
+ASVGP_API int asvgp_expand_moments_2d(const double* cellmom, const double* Cprod, const double* Dy, int n_knots1,
+                                      int n_knots2, int order, double* Gs, double* b, void* stream);
+
+/* ---- a13 + a14: block-band factorisation of P = K1 (x) K2 + G / sigma2 -------------------------------------------------------
+ * Replaces utils.bands_to_kron_cholesky (utils.py:45-51), tf.linalg.cholesky(P), its log-det and
+ * triangular_solve(L_P, Kuf_y) (gpr.py:287-295) with a banded factorisation of scalar bandwidth order*(m2+1).
+ * band: asvgp_kron_band_doubles doubles (receives the factor); rhs_io[Mpad + ld]: in Kuf_y zero padded, out L^-1 Kuf_y;
+ * scal[3] = { log|P|, ||L^-1 Kuf_y||^2, info }. */
+ASVGP_API int64_t asvgp_kron_band_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kron_work_doubles(int m1, int m2, int order);
+ASVGP_API int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
+                                double sigma2, double* band, double* rhs_io, double* scal, void* stream);
+
+/* Selected inverse on the stencil pattern (blocked Takahashi recursion) and back-substitution: sigma_stencil = entries
+ * of P^-1 in stencil layout, x_io: in L^-1 b, out P^-1 b.  This is what the reference's dense cholesky_solve /
+ * TF reverse mode extract from P^-1 (gpr.py:293-307, 319-326). */
+ASVGP_API int asvgp_kron_selinv(const double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+                                double* sigma_stencil, double* work, void* stream);
+
+/* Scalar contractions for the ELBO gradient and the Kronecker trace term; out[11] (device):
+ *   [0..3]  sum P^-1 .* Op,  [4..7]  x^T Op x   for Op = G, dK1(x)K2, K1(x)dK2, K1(x)K2
+ *   [8..10] sum G .* (T1 (x) T2) for (T1,T2) = (S1,S2), (dS1,S2), (S1,dS2), S_i = band(K_i^-1). */
+ASVGP_API int asvgp_kron_terms(const double* SigP, const double* Gs, const double* x, const double* K1,
+                               const double* dK1, const double* K2, const double* dK2, const double* S1,
+                               const double* dS1, const double* S2, const double* dS2, int m1, int m2, int order,
+                               double* out, void* stream);
+
+/* ---- a15: 2-D posterior mean / variance ----------------------------------------------------------------------------------------
+ * Replaces GPR_kron.predict_f / predict_f_sparse (gpr.py:310-359): mean = w^T alpha, var = prior_var + w^T P^-1 w -
+ * (a^T K1^-1 a)(b^T K2^-1 b), w = a (x) b.  SigP in stencil layout, S1/S2 lower bands of K1^-1/K2^-1. */
+ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
+                               int n_knots2, int order, const double* alpha, const double* SigP, const double* S1,
+                               const double* S2, double prior_var, double* mean, double* var, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
