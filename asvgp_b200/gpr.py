@@ -171,3 +171,204 @@ class GPR_1d(_ModelBase):
         if isinstance(Xnew, torch.Tensor) and Xnew.is_cuda:
             return mean, var
         return mean.cpu().numpy(), var.cpu().numpy()
+
+
+class GPR_kron(_ModelBase):
+    """Collapsed-bound sparse GP regression on 2-D inputs with Kronecker-structured B-spline inducing features
+    (reference gpr.py:239-359).  Same constructor, attributes and methods; what differs is only *how*:
+
+      * the reference materialises the Khatri-Rao Kuf ((k+1)^2 N non-zeros), KufKfu as a DENSE M x M matrix and
+        factorises P densely (gpr.py:268-272, 293) — infeasible at M = 200 x 200.  Here the O(N) pass accumulates
+        per-cell polynomial moments (asvgp_accum_2d) that expand into the (k+1)(2k+1)-row stencil of KufKfu, P is
+        factorised as a band of scalar bandwidth k (m2 + 1) = `self.bandwidth` (gpr.py:262), and everything else
+        the bound, its gradients and the predictor need from P^-1 / Kuu^-1 are entries on the stencil pattern and
+        the bands of K1^-1, K2^-1 (SURVEY §8(a) a14, a15);
+      * `elbo_and_grad()` returns the five hyper-parameter derivatives with the bound (the reference gets them from
+        TF reverse mode through the dense factorisations);
+      * with torch.distributed initialised the data passed in are this rank's shard: the packed accumulator
+        [G stencil | Kuf_y | sum y^2 | N] is all-reduced once, the factorisation is replicated.
+    """
+
+    def __init__(self, data, kernels, bases, distributed="auto", check_inputs=True):
+        X, y = data
+        self.X, self.y = X, y
+        self.n = X.shape[0]
+        self.d = X.shape[1]
+
+        # Check dimensionality of inputs / valid kernels (reference gpr.py:247-252)
+        assert len(kernels) == len(bases) == self.d
+        if y.ndim == 1:
+            y = y.reshape(-1, 1)
+        assert y.shape[1] == 1
+        self._kinds = [kernel_kind(k) for k in kernels]
+        if self.d != 2:
+            raise NotImplementedError("GPR_kron is implemented for d = 2 (as reference utils.py:57)")
+        if check_inputs and self.n:
+            for i, basis in enumerate(bases):
+                col = X[:, i]
+                lo, hi = (torch.aminmax(col) if isinstance(col, torch.Tensor) else (col.min(), col.max()))
+                assert float(lo) > basis.a and float(hi) < basis.b, "inputs must lie strictly inside the basis domain"
+
+        self.kernel = kernels[-1]               # the reference hands the last loop kernel to GPModel (SURVEY Q8)
+        self.likelihood = Gaussian()
+        self.mean_function = None
+        self.num_latent_gps = 1
+        self.bases = list(bases)
+        self.kernels = list(kernels)
+
+        # Bandwidth (reference gpr.py:260-262; equals order * (m2 + 1) for d = 2)
+        self.m = self.bases[0].m
+        self.order = self.bases[0].order
+        self.bandwidth = self.order * (self.bases[1].m + 1)
+
+        self.inducing_features = [SplineFeatures1D(self.kernels[i], self.bases[i]) for i in range(self.d)]
+
+        # Precompute static quantities (reference gpr.py:268-274): one fused pass over this rank's points
+        dev = ops.device()
+        self._acc = torch.zeros(ops.accum_size_2d(self.bases), dtype=torch.float64, device=dev)
+        _, _, scal = ops.split_accum_2d(self._acc, self.bases)
+        cellmom = ops.moment_table_2d(self.bases)
+        if isinstance(X, torch.Tensor) and X.is_cuda:
+            ops.accum_2d(X, y.reshape(-1), self.bases, cellmom, scal)
+        else:
+            ops.accum_2d_host(X, y, self.bases, cellmom, scal)
+        ops.expand_moments_2d(cellmom, self.bases, self._acc)
+        del cellmom
+        self._distributed = _dist.is_distributed(distributed)
+        if self._distributed:
+            _dist.allreduce_packed(self._acc)
+        self._Gs, self._b, self._scal = ops.split_accum_2d(self._acc, self.bases)
+        self._host = None
+
+    # -- the reference's cached attributes (host copies, fetched lazily) --------------------------------------
+    def _host_stats(self):
+        if self._host is None:
+            self._host = (self._Gs.cpu().numpy(), self._b.cpu().numpy().reshape(-1, 1), self._scal.cpu().numpy())
+        return self._host
+
+    @property
+    def Kuf_y(self):
+        return self._host_stats()[1]
+
+    @property
+    def tr_yTy(self):
+        return float(self._host_stats()[2][0])
+
+    @property
+    def num_data(self):
+        return int(self._host_stats()[2][1])
+
+    @property
+    def KufKfu_sparse(self):
+        """Full symmetric KufKfu as a SciPy CSR matrix (reference gpr.py:271)."""
+        from . import utils
+
+        return utils.stencil_to_sparse(self._host_stats()[0], self.bases[0].m, self.bases[1].m, self.order)
+
+    @property
+    def KufKfu_band(self):
+        from . import utils
+
+        return utils.sparse_to_band(self.KufKfu_sparse, self.bandwidth)
+
+    @property
+    def trainable_variables(self):
+        out = []
+        for k in self.kernels:
+            out += [k.variance, k.lengthscales]
+        return out + [self.likelihood.variance]
+
+    # -- objective ---------------------------------------------------------------------------------------------
+    def _factors(self, want_grad):
+        """Per-dimension Kuu factors, their lengthscale derivatives, and the bands of their inverses."""
+        Ks, dKs, Ss, dSs, scals = [], [], [], [], []
+        for feat, kern, basis in zip(self.inducing_features, self.kernels, self.bases):
+            K, dK = feat.make_Kuu_device(kern, want_grad=True)
+            S, dS, sc = ops.band_inverse_1d(K, dK, basis)
+            Ks.append(K); dKs.append(dK); Ss.append(S); dSs.append(dS); scals.append(sc)
+        return Ks, dKs, Ss, dSs, scals
+
+    def _evaluate(self, want_grad):
+        s2 = hyper_value(self.likelihood.variance)
+        v = [hyper_value(k.variance) for k in self.kernels]
+        m1, m2 = self.bases[0].m, self.bases[1].m
+        ws = ops.kron_workspace(m1, m2, self.order)
+        Ks, dKs, Ss, dSs, scals = self._factors(want_grad)
+        ops.kron_factor(Ks[0], Ks[1], self._acc, self.bases, s2, ws)
+        if want_grad:
+            SigP, x = ops.kron_selinv(self.bases, ws)
+        else:
+            ws.sigma_stencil.zero_()
+            SigP, x = ws.sigma_stencil, ws.rhs[: ws.M]            # x unused for the value (multiplied by nothing read)
+        ops.kron_terms(SigP, self._acc, x, Ks[0], dKs[0], Ks[1], dKs[1], Ss[0], dSs[0], Ss[1], dSs[1], self.bases,
+                       ws.terms)
+        packed = torch.cat([scals[0], scals[1], ws.scal, ws.terms, self._scal]).cpu().numpy()   # one D2H read
+        sc1, sc2, scP, T, (yy, N) = packed[0:4], packed[4:8], packed[8:11], packed[11:22], packed[22:24]
+        info = scP[2] or sc1[2] or sc2[2]
+        if info != 0:
+            raise np.linalg.LinAlgError("Cholesky failed: non-positive pivot %d" % int(info))
+        M = m1 * m2
+        logdetK = m2 * sc1[0] + m1 * sc2[0]                       # log|K1 (x) K2|
+        logdetP, Q, tr = scP[0], scP[1], T[8]
+        v12 = v[0] * v[1]
+        elbo = (-0.5 * N * np.log(2 * np.pi * s2) - 0.5 * logdetP + 0.5 * logdetK - 0.5 * yy / s2
+                + 0.5 * Q / s2**2 - 0.5 * N * v12 / s2 + 0.5 * tr / s2)
+        self.last_terms = dict(log_det_Kuu=logdetK, log_det_P=logdetP, quad=Q, trace=tr)
+        if not want_grad:
+            return float(elbo), None
+        trPG, trPdK1, trPdK2, trPK = T[0:4]
+        xGx, xdK1x, xdK2x, xKx = T[4:8]
+        d_l1 = -0.5 * trPdK1 + 0.5 * m2 * sc1[1] - 0.5 * xdK1x / s2**2 + 0.5 * T[9] / s2
+        d_l2 = -0.5 * trPdK2 + 0.5 * m1 * sc2[1] - 0.5 * xdK2x / s2**2 + 0.5 * T[10] / s2
+        # Kuu is proportional to 1 / (v1 v2): dKuu/dv_i = -Kuu / v_i
+        common = 0.5 * trPK - 0.5 * M + 0.5 * xKx / s2**2 + 0.5 * tr / s2
+        d_v1 = common / v[0] - 0.5 * N * v[1] / s2
+        d_v2 = common / v[1] - 0.5 * N * v[0] / s2
+        d_s2 = (-0.5 * N / s2 + 0.5 * trPG / s2**2 + 0.5 * yy / s2**2 + 0.5 * xGx / s2**4 - Q / s2**3
+                + 0.5 * N * v12 / s2**2 - 0.5 * tr / s2**2)
+        grads = {id(self.kernels[0].variance): d_v1, id(self.kernels[0].lengthscales): d_l1,
+                 id(self.kernels[1].variance): d_v2, id(self.kernels[1].lengthscales): d_l2,
+                 id(self.likelihood.variance): d_s2}
+        return float(elbo), grads
+
+    def elbo_and_grad(self):
+        """ELBO (reference gpr.py:282-308) and {id(param): dELBO/dparam} for (v1, l1, v2, l2, sigma^2)."""
+        return self._evaluate(True)
+
+    def elbo(self):
+        """Variational bound on the log marginal likelihood (reference gpr.py:282-308)."""
+        return np.float64(self._evaluate(False)[0])
+
+    def maximum_log_likelihood_objective(self):
+        return self.elbo()
+
+    # -- prediction ----------------------------------------------------------------------------------------------
+    def posterior_weights(self):
+        """(alpha, SigP stencil, S1, S2) on the device: alpha = P^-1 Kuf_y / sigma2, SigP = stencil entries of P^-1,
+        S_i = band(K_i^-1)."""
+        s2 = hyper_value(self.likelihood.variance)
+        ws = ops.kron_workspace(self.bases[0].m, self.bases[1].m, self.order)
+        Ks, _, Ss, _, scals = self._factors(False)
+        ops.kron_factor(Ks[0], Ks[1], self._acc, self.bases, s2, ws)
+        SigP, x = ops.kron_selinv(self.bases, ws)
+        info = torch.stack([ws.scal[2], scals[0][2], scals[1][2]])
+        return x / s2, SigP, Ss[0], Ss[1], info
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        """Posterior mean and variance at Xnew[n*, 2], each (n*, 1) (reference gpr.py:310-334)."""
+        assert not full_output_cov
+        if full_cov:
+            raise NotImplementedError
+        alpha, SigP, S1, S2, info = self.posterior_weights()
+        prior = hyper_value(self.kernels[0].variance) * hyper_value(self.kernels[1].variance)
+        mean, var = ops.predict_2d(Xnew, self.bases, alpha, SigP, S1, S2, prior)
+        if info.any().item():
+            raise np.linalg.LinAlgError("Cholesky failed in predict_f")
+        mean, var = mean.view(-1, 1), var.view(-1, 1)
+        if isinstance(Xnew, torch.Tensor) and Xnew.is_cuda:
+            return mean, var
+        return mean.cpu().numpy(), var.cpu().numpy()
+
+    def predict_f_sparse(self, Xnew, full_cov=False, full_output_cov=False):
+        """Same numbers as predict_f (reference gpr.py:336-359 is its CHOLMOD twin)."""
+        return self.predict_f(Xnew, full_cov=full_cov, full_output_cov=full_output_cov)

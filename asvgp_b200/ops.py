@@ -232,3 +232,225 @@ def accum_1d_host(x, y, basis, acc=None, chunk=1 << 23):
                   ctypes.c_void_p(main.cuda_stream))
         st["drained"][s].record(main)
     return acc
+
+
+# =====================================================================================================================
+# 2-D (Kronecker) operators
+# =====================================================================================================================
+def _check_bases_2d(bases):
+    if len(bases) != 2:
+        raise NotImplementedError("the Kronecker kernels are written for d = 2 (as reference utils.py:57)")
+    if bases[0].order != bases[1].order:
+        raise ValueError("all bases of a Kronecker model must have the same order (reference gpr.py:260-262)")
+    return bases[0].order, bases[0].m, bases[1].m
+
+
+def stencil_rows(order):
+    """Rows of the stencil layout: offsets d1 in [0, k], d2 in [-k, k]."""
+    return (order + 1) * (2 * order + 1)
+
+
+def accum_size_2d(bases):
+    """Doubles of the packed 2-D accumulator [G stencil (n_e x M) | b (M) | sum y^2 | count]."""
+    k, m1, m2 = _check_bases_2d(bases)
+    return (stencil_rows(k) + 1) * m1 * m2 + 2
+
+
+def split_accum_2d(acc, bases):
+    k, m1, m2 = _check_bases_2d(bases)
+    M, ne = m1 * m2, stencil_rows(k)
+    return acc[: ne * M].view(ne, M), acc[ne * M: (ne + 1) * M], acc[(ne + 1) * M:]
+
+
+def moment_table_2d(bases):
+    """Zeroed per-cell moment table for accum_2d."""
+    k, _, _ = _check_bases_2d(bases)
+    n = _lib.load().asvgp_accum_2d_moment_doubles(bases[0].mesh.shape[0], bases[1].mesh.shape[0], k)
+    return torch.zeros(n, dtype=F64, device=device())
+
+
+def accum_2d(X, y, bases, cellmom, scal):
+    """Adds the per-cell moments of the points (X[n,2], y[n]) into `cellmom` and (sum y^2, n) into `scal`
+    (reference gpr.py:268-274 without materialising the Khatri-Rao Kuf)."""
+    k, _, _ = _check_bases_2d(bases)
+    X = to_device(X)
+    y = to_device(y).reshape(-1)
+    if X.dim() != 2 or X.shape[1] != 2 or X.shape[0] != y.numel():
+        raise ValueError("X must be [n, 2] and y [n]")
+    if X.data_ptr() % 16:            # the kernel reads one point (16 B) / two targets per load
+        X = X.clone()
+    if y.data_ptr() % 16:
+        y = y.clone()
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    _lib.call("asvgp_accum_2d", _p(X), _p(y), X.shape[0], _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
+              _p(cellmom), _p(scal), _stream())
+    return cellmom, scal
+
+
+def _expansion_tables(order, dev):
+    key = (dev, order)
+    t = _EXPANSION.get(key)
+    if t is None:
+        from . import _spline_tables as tab
+
+        t = (torch.from_numpy(np.ascontiguousarray(tab.product_bernstein_float(order))).to(dev),
+             torch.from_numpy(np.ascontiguousarray(tab.piece_bernstein_float(order))).to(dev))
+        _EXPANSION[key] = t
+    return t
+
+
+_EXPANSION = {}
+
+
+def expand_moments_2d(cellmom, bases, acc):
+    """Adds the Gram stencil and the projection implied by the moment table into the packed accumulator."""
+    k, _, _ = _check_bases_2d(bases)
+    Gs, b, _ = split_accum_2d(acc, bases)
+    Cprod, Dy = _expansion_tables(k, acc.device)
+    _lib.call("asvgp_expand_moments_2d", _p(cellmom), _p(Cprod), _p(Dy), bases[0].mesh.shape[0],
+              bases[1].mesh.shape[0], k, _p(Gs), _p(b), _stream())
+    return acc
+
+
+def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22):
+    """accum_2d for HOST arrays: streamed through pinned staging buffers, double-buffered against the kernel."""
+    dev = device()
+    Xt = torch.as_tensor(np.asarray(X) if not isinstance(X, torch.Tensor) else X, dtype=F64)
+    yt = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y, dtype=F64).reshape(-1)
+    n = Xt.shape[0]
+    if Xt.dim() != 2 or Xt.shape[1] != 2 or yt.numel() != n:
+        raise ValueError("X must be [n, 2] and y [n]")
+    Xt = Xt.contiguous()
+    if n == 0:
+        return cellmom, scal
+    k, _, _ = _check_bases_2d(bases)
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    chunk = min(chunk, n + (n & 1))
+    key = (dev, "2d", chunk)
+    st = _STAGING.get(key)
+    if st is None:
+        st = dict(host=[torch.empty(3 * chunk, dtype=F64).pin_memory() for _ in range(2)],
+                  dev=[torch.empty(3 * chunk, dtype=F64, device=dev) for _ in range(2)],
+                  copy_stream=torch.cuda.Stream(device=dev),
+                  filled=[torch.cuda.Event() for _ in range(2)], drained=[torch.cuda.Event() for _ in range(2)],
+                  staged=[torch.cuda.Event() for _ in range(2)])
+        _STAGING[key] = st
+    pinned = Xt.is_pinned() and yt.is_pinned()
+    main, cs = torch.cuda.current_stream(), st["copy_stream"]
+    for c in range(-(-n // chunk)):
+        lo, hi = c * chunk, min((c + 1) * chunk, n)
+        cnt, s = hi - lo, c & 1
+        dbuf = st["dev"][s]
+        dX, dy = dbuf[: 2 * cnt].view(cnt, 2), dbuf[2 * chunk: 2 * chunk + cnt]
+        if c >= 2:
+            cs.wait_event(st["drained"][s])
+        with torch.cuda.stream(cs):
+            if pinned:
+                dX.copy_(Xt[lo:hi], non_blocking=True)
+                dy.copy_(yt[lo:hi], non_blocking=True)
+            else:
+                hbuf = st["host"][s]
+                if c >= 2:
+                    st["staged"][s].synchronize()
+                hbuf[: 2 * cnt].view(cnt, 2).copy_(Xt[lo:hi])
+                hbuf[2 * chunk: 2 * chunk + cnt].copy_(yt[lo:hi])
+                dbuf[: 2 * cnt].copy_(hbuf[: 2 * cnt], non_blocking=True)
+                dy.copy_(hbuf[2 * chunk: 2 * chunk + cnt], non_blocking=True)
+                st["staged"][s].record(cs)
+            st["filled"][s].record(cs)
+        main.wait_event(st["filled"][s])
+        _lib.call("asvgp_accum_2d", _p(dX), _p(dy), cnt, _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
+                  _p(cellmom), _p(scal), ctypes.c_void_p(main.cuda_stream))
+        st["drained"][s].record(main)
+    return cellmom, scal
+
+
+def band_inverse_1d(A, dA, basis, chunks=0):
+    """(band(A^-1), band(-A^-1 dA A^-1), scal[4] = {log|A|, dlog|A|, info, -}) of one banded SPD factor."""
+    k, m = basis.order, basis.m
+    ws = workspace_1d(m, k, chunks)
+    sig = torch.empty((k + 1, m), dtype=F64, device=A.device)
+    dsig = torch.empty_like(sig)
+    scal = torch.empty(4, dtype=F64, device=A.device)
+    _lib.call("asvgp_band_inverse_1d", _p(A), _p(dA if dA is not None else A), m, k, int(chunks), _p(sig), _p(dsig),
+              _p(scal), _p(ws), ws.numel(), _stream())
+    return sig, dsig, scal
+
+
+class KronWorkspace:
+    """Device buffers of the block-band factorisation of P = K1 (x) K2 + G / sigma2 (cached per (device, m1, m2, k))."""
+
+    def __init__(self, m1, m2, order):
+        lib = _lib.load()
+        dev = device()
+        self.m1, self.m2, self.order = m1, m2, order
+        self.M = m1 * m2
+        nb = lib.asvgp_kron_band_doubles(m1, m2, order)
+        nw = lib.asvgp_kron_work_doubles(m1, m2, order)
+        if nb < 0 or nw < 0:
+            raise _lib.AsvgpNativeError("kron workspace query rejected m=%d,%d order=%d" % (m1, m2, order))
+        self.band = torch.empty(nb, dtype=F64, device=dev)
+        self.sig_band = None                     # allocated on first selected inverse
+        self.nb = nb
+        self.work = torch.empty(nw, dtype=F64, device=dev)
+        self.w = order * m2 + order
+        self.Mpad = -(-self.M // 64) * 64
+        self.rhs = torch.zeros(self.Mpad + self.w + 64, dtype=F64, device=dev)
+        self.scal = torch.zeros(3, dtype=F64, device=dev)
+        self.sigma_stencil = torch.zeros((stencil_rows(order), self.M), dtype=F64, device=dev)
+        self.terms = torch.zeros(11, dtype=F64, device=dev)
+
+
+_KRON_WS = {}
+
+
+def kron_workspace(m1, m2, order):
+    key = (device(), m1, m2, order)
+    ws = _KRON_WS.get(key)
+    if ws is None:
+        ws = _KRON_WS[key] = KronWorkspace(m1, m2, order)
+    return ws
+
+
+def kron_factor(K1, K2, acc, bases, sigma2, ws):
+    """Block-band Cholesky of P, forward substitution of Kuf_y; ws.scal = {log|P|, ||L^-1 b||^2, info}."""
+    k, m1, m2 = _check_bases_2d(bases)
+    Gs, b, _ = split_accum_2d(acc, bases)
+    ws.rhs.zero_()
+    ws.rhs[: ws.M].copy_(b)
+    _lib.call("asvgp_kron_factor", _p(K1), _p(K2), _p(Gs), m1, m2, k, float(sigma2), _p(ws.band), _p(ws.rhs),
+              _p(ws.scal), _stream())
+    return ws
+
+
+def kron_selinv(bases, ws):
+    """Selected inverse of P on the stencil pattern (ws.sigma_stencil) and x = P^-1 Kuf_y (ws.rhs[:M])."""
+    k, m1, m2 = _check_bases_2d(bases)
+    if ws.sig_band is None:
+        ws.sig_band = torch.empty(ws.nb, dtype=F64, device=ws.band.device)
+    _lib.call("asvgp_kron_selinv", _p(ws.band), m1, m2, k, _p(ws.sig_band), _p(ws.rhs), _p(ws.sigma_stencil),
+              _p(ws.work), _stream())
+    return ws.sigma_stencil, ws.rhs[: ws.M]
+
+
+def kron_terms(SigP, acc, x, K1, dK1, K2, dK2, S1, dS1, S2, dS2, bases, out):
+    k, m1, m2 = _check_bases_2d(bases)
+    Gs, _, _ = split_accum_2d(acc, bases)
+    _lib.call("asvgp_kron_terms", _p(SigP), _p(Gs), _p(x), _p(K1), _p(dK1), _p(K2), _p(dK2), _p(S1), _p(dS1), _p(S2),
+              _p(dS2), m1, m2, k, _p(out), _stream())
+    return out
+
+
+def predict_2d(Xnew, bases, alpha, SigP, S1, S2, prior_var):
+    """Posterior mean / variance of the Kronecker model at Xnew[n, 2] (reference gpr.py:310-359)."""
+    k, _, _ = _check_bases_2d(bases)
+    X = to_device(Xnew)
+    if X.dim() != 2 or X.shape[1] != 2:
+        raise ValueError("Xnew must be [n, 2]")
+    n = X.shape[0]
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    mean = torch.empty(n, dtype=F64, device=X.device)
+    var = torch.empty(n, dtype=F64, device=X.device)
+    _lib.call("asvgp_predict_2d", _p(X), n, _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k, _p(alpha),
+              _p(SigP), _p(S1), _p(S2), float(prior_var), _p(mean), _p(var), _stream())
+    return mean, var

@@ -47,3 +47,25 @@ def bands_to_sparse(K_bands, mat_bandwidth):
     """Sparse Kronecker product of two banded factors (reference utils.py:53-57, d = 2 only)."""
     Ks = [sparse.csc_matrix(band_to_dense(k)) for k in K_bands]
     return sparse.kron(Ks[0], Ks[1])
+
+
+def stencil_to_sparse(Gs, m1, m2, order):
+    """Full symmetric sparse matrix from the stencil layout of the Kronecker kernels: Gs[e, j] with
+    e = d1*(2k+1) + (d2+k) holds A[(j1+d1, j2+d2), (j1, j2)], j = j1*m2 + j2 (include/asvgp_b200.h)."""
+    Gs = np.asarray(Gs)
+    k, M = order, m1 * m2
+    j = np.arange(M)
+    j1, j2 = j // m2, j % m2
+    rows, cols, vals = [], [], []
+    for d1 in range(k + 1):
+        for d2 in range(-k, k + 1):
+            if d1 == 0 and d2 < 0:
+                continue
+            ok = (j1 + d1 < m1) & (j2 + d2 >= 0) & (j2 + d2 < m2)
+            i = (j1 + d1) * m2 + (j2 + d2)
+            v = Gs[d1 * (2 * k + 1) + d2 + k]
+            rows.append(i[ok]); cols.append(j[ok]); vals.append(v[ok])
+            if d1 or d2:
+                rows.append(j[ok]); cols.append(i[ok]); vals.append(v[ok])
+    A = sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(M, M))
+    return A.tocsr()

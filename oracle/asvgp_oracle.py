@@ -394,3 +394,85 @@ def predict_kron_dense(meshes, deltas, k, ms, Kuu_bands, G_sparse, Kuf_y, varian
     var = np.prod(variances) + np.sum(Kus * sla.cho_solve(cP, Kus), axis=0) \
         - np.sum(Kus * np.linalg.solve(Kuu, Kus), axis=0)
     return mean, var.reshape(-1, 1)
+
+
+def _kuu_coefficients_torch(kind, l, v):
+    r3, r5 = float(SQRT3), float(SQRT5)
+    if kind == "Matern12":
+        return {"A": 1 / (2 * l * v), "B": l / (2 * v), "BC": 1 / (2 * v)}
+    if kind == "Matern32":
+        return {"A": r3 / (4 * l * v), "B": l / (2 * r3 * v), "C": l**3 / (12 * r3 * v), "BC": 1 / (2 * v),
+                "BC_grad": l**2 / (2 * v)}
+    return {"A": 3 * r5 / (16 * l * v), "B": 9 * l / (16 * r5 * v), "C": 9 * l**3 / (80 * r5 * v),
+            "D": 3 * l**5 / (400 * r5 * v), "BC": 9 / (16 * v), "BC_grad": 3 * l**2 / (10 * v),
+            "BC_ggrad": 9 * l**4 / (400 * v)}
+
+
+def elbo_grad_kron_dense(kinds, tables, G_sparse, Kuf_y, tr_yTy, n, hypers, sigma2):
+    """GPR_kron.elbo (gpr.py:282-308) and d/d(v1, l1, v2, l2, sigma2) by torch-fp64 autograd through the dense
+    algebra the reference itself uses (the reference gets them from TF reverse mode).  hypers = [(v1, l1), (v2, l2)].
+    Small sizes only."""
+    import torch
+
+    th = torch.tensor([hypers[0][0], hypers[0][1], hypers[1][0], hypers[1][1], sigma2], dtype=torch.float64,
+                      requires_grad=True)
+    Ks = []
+    for i in range(2):
+        v, l = th[2 * i], th[2 * i + 1]
+        dense = {nme: torch.from_numpy(band_to_dense_sym(t)) for nme, t in tables[i].items()}
+        Ks.append(sum(c * dense[nme] for nme, c in _kuu_coefficients_torch(kinds[i], l, v).items()))
+    s2 = th[4]
+    Kuu = torch.kron(Ks[0], Ks[1])                                           # utils.py:45-51
+    L_Kuu = torch.kron(torch.linalg.cholesky(Ks[0]), torch.linalg.cholesky(Ks[1]))
+    Gd = torch.from_numpy(np.asarray(G_sparse.toarray(), dtype=np.float64))
+    b = torch.from_numpy(np.asarray(Kuf_y, dtype=np.float64).reshape(-1, 1))
+    L_P = torch.linalg.cholesky(Kuu + Gd / s2)
+    c = torch.linalg.solve_triangular(L_P, b, upper=False) / s2
+    elbo = (-0.5 * n * torch.log(2 * np.pi * s2) - torch.log(torch.diagonal(L_P)).sum()
+            + torch.log(torch.diagonal(L_Kuu)).sum() - 0.5 * tr_yTy / s2 + 0.5 * (c**2).sum()
+            - 0.5 * n * th[0] * th[2] / s2 + 0.5 * torch.trace(torch.cholesky_solve(Gd, L_Kuu)) / s2)
+    elbo.backward()
+    return float(elbo.detach()), th.grad.numpy().copy()
+
+
+def kron_band(Kuu_bands, G_sparse, sigma2, k, ms):
+    """Lower band (bw+1, M) of P = K1 (x) K2 + G / sigma2 with bw = k (m2 + 1) (gpr.py:262, 292)."""
+    Ks = [sp.csr_matrix(band_to_dense_sym(b)) for b in Kuu_bands]
+    P = (sp.kron(Ks[0], Ks[1]) + G_sparse / sigma2).tocsr()
+    return sparse_to_band(P, k * (ms[1] + 1))
+
+
+def elbo_kron_banded(Kuu_bands, G_sparse, Kuf_y, tr_yTy, n, variances, sigma2, k, ms):
+    """Same bound as elbo_kron_dense with LAPACK band routines on the scalar band of P and the Kronecker identities
+    log|K1 (x) K2| = m2 log|K1| + m1 log|K2|, trace((K1 (x) K2)^-1 G) = sum G .* (K1^-1 (x) K2^-1) —
+    for sizes where the dense M x M algebra of the reference is too slow.  Validated against elbo_kron_dense."""
+    m1, m2 = ms
+    Pb = kron_band(Kuu_bands, G_sparse, sigma2, k, ms)
+    L_P = sla.cholesky_banded(Pb, lower=True)
+    log_det_P = 2.0 * np.sum(np.log(L_P[0]))
+    c = sla.solve_banded((Pb.shape[0] - 1, 0), L_P, np.asarray(Kuf_y).reshape(-1, 1)) / sigma2
+    cK = [sla.cholesky_banded(b, lower=True) for b in Kuu_bands]
+    log_det_Kuu = m2 * 2.0 * np.sum(np.log(cK[0][0])) + m1 * 2.0 * np.sum(np.log(cK[1][0]))
+    Kinv = [sla.cho_solve_banded((c_, True), np.eye(c_.shape[1])) for c_ in cK]
+    G = sp.coo_matrix(G_sparse)
+    tr = np.sum(G.data * Kinv[0][G.row // m2, G.col // m2] * Kinv[1][G.row % m2, G.col % m2])
+    elbo = -0.5 * n * np.log(2 * np.pi * sigma2) - 0.5 * log_det_P + 0.5 * log_det_Kuu - 0.5 * tr_yTy / sigma2
+    elbo += 0.5 * np.sum(np.square(c)) - 0.5 * n * np.prod(variances) / sigma2 + 0.5 * tr / sigma2
+    return elbo
+
+
+def predict_kron_banded(meshes, deltas, k, ms, Kuu_bands, G_sparse, Kuf_y, variances, sigma2, Xnew):
+    """GPR_kron.predict_f_sparse (gpr.py:336-359) with LAPACK band solves instead of CHOLMOD."""
+    m1, m2 = ms
+    Pb = kron_band(Kuu_bands, G_sparse, sigma2, k, ms)
+    cP = sla.cholesky_banded(Pb, lower=True)
+    alpha = sla.cho_solve_banded((cP, True), np.asarray(Kuf_y).reshape(-1, 1)) / sigma2
+    K1 = make_Kuf(meshes[0], deltas[0], k, m1, Xnew[:, 0]).toarray()
+    K2 = make_Kuf(meshes[1], deltas[1], k, m2, Xnew[:, 1]).toarray()
+    Kus = (K1[:, None, :] * K2[None, :, :]).reshape(m1 * m2, -1)
+    mean = Kus.T @ alpha
+    cK = [sla.cholesky_banded(b, lower=True) for b in Kuu_bands]
+    q1 = np.sum(K1 * sla.cho_solve_banded((cK[0], True), K1), axis=0)
+    q2 = np.sum(K2 * sla.cho_solve_banded((cK[1], True), K2), axis=0)
+    var = np.prod(variances) + np.sum(Kus * sla.cho_solve_banded((cP, True), Kus), axis=0) - q1 * q2
+    return mean, var.reshape(-1, 1)

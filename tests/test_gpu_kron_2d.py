@@ -1,0 +1,206 @@
+"""GPU parity of the 2-D Kronecker model through the reference-shaped API (GPR_kron): Gram stencil / projection vs
+the golden vectors produced by the unmodified reference under the shim (rel 1e-10), ELBO vs golden (rel 1e-10),
+gradients vs the torch-autograd dense oracle (1e-8), predictions vs golden (1e-9 abs), plus a mid-size case against
+the LAPACK-band oracle and size-independent properties (order invariance, additivity over shards)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import asvgp_oracle as O
+
+pytestmark = pytest.mark.gpu
+DOMAINS = ((0, 1), (0, 2))
+
+
+def _model(X, y, k, ms, kinds=("Matern32", "Matern32"), hyp=None, sigma2=None, domains=DOMAINS, **kw):
+    from asvgp_b200 import basis as B, kernels as Kn
+    from asvgp_b200.gpr import GPR_kron
+
+    cls = getattr(B, "B%dSpline" % k)
+    bases = [cls(domains[0][0], domains[0][1], ms[0]), cls(domains[1][0], domains[1][1], ms[1])]
+    kerns = [getattr(Kn, kind)() for kind in kinds]
+    model = GPR_kron((X, y.reshape(-1, 1)), kerns, bases, **kw)
+    if hyp is not None:
+        for kern, (v, l) in zip(kerns, hyp):
+            kern.variance.assign(v); kern.lengthscales.assign(l)
+    if sigma2 is not None:
+        model.likelihood.variance.assign(sigma2)
+    return model
+
+
+def _golden_G(g, key, m):
+    return sp.coo_matrix((g[key + "_G_val"], (g[key + "_G_row"], g[key + "_G_col"])), shape=(m * m, m * m)).toarray()
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_accumulate_matches_reference(cuda, golden, k):
+    g = golden("kron_2d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    model = _model(g["X"], g["y"], k, (m, m))
+    Gref = _golden_G(g, key, m)
+    scale = np.abs(Gref).max()
+    np.testing.assert_allclose(model.KufKfu_sparse.toarray(), Gref, rtol=1e-10, atol=1e-10 * scale)
+    np.testing.assert_allclose(model.Kuf_y, g[key + "_Kuf_y"], rtol=1e-10, atol=1e-10 * np.abs(g[key + "_Kuf_y"]).max())
+    assert abs(model.tr_yTy - float(g[key + "_tr_yTy"])) <= 1e-12 * float(g[key + "_tr_yTy"])
+    assert model.num_data == g["X"].shape[0]
+    assert model.bandwidth == int(g[key + "_bandwidth"])
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_elbo_golden(cuda, golden, k):
+    g = golden("kron_2d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    model = _model(g["X"], g["y"], k, (m, m), hyp=[(.7, .3), (1.3, .5)], sigma2=.05)
+    want = float(g[key + "_elbo"])
+    assert abs(model.elbo() - want) <= 1e-10 * abs(want)
+    e, _ = model.elbo_and_grad()
+    assert abs(e - want) <= 1e-10 * abs(want)
+    if key + "_elbo_m52_m12" in g.files:
+        model = _model(g["X"], g["y"], k, (m, m), kinds=("Matern52", "Matern12"), hyp=[(.9, .4), (1.1, .6)], sigma2=.2)
+        want = float(g[key + "_elbo_m52_m12"])
+        assert abs(model.elbo() - want) <= 1e-10 * abs(want)
+
+
+@pytest.mark.parametrize("k", [2, 3, 4])
+def test_predict_golden(cuda, golden, k):
+    g = golden("kron_2d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    model = _model(g["X"], g["y"], k, (m, m), hyp=[(.7, .3), (1.3, .5)], sigma2=.05)
+    mean, var = model.predict_f(g[key + "_Xs"])
+    np.testing.assert_allclose(mean, g[key + "_mean"], atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, g[key + "_var"], atol=1e-9, rtol=0)
+    mean2, var2 = model.predict_f_sparse(g[key + "_Xs"])
+    np.testing.assert_array_equal(mean, mean2)
+
+
+@pytest.mark.parametrize("k,kinds", [(3, ("Matern32", "Matern32")), (3, ("Matern52", "Matern12")),
+                                     (4, ("Matern32", "Matern52")), (2, ("Matern12", "Matern32"))])
+def test_gradients_match_autograd_oracle(cuda, golden, k, kinds):
+    g = golden("kron_2d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    hyp, s2 = [(.7, .3), (1.3, .5)], .05
+    model = _model(g["X"], g["y"], k, (m, m), kinds=kinds, hyp=hyp, sigma2=s2)
+    elbo, grads = model.elbo_and_grad()
+    deltas = [b.delta for b in model.bases]
+    T = [O.static_bands(k, m, d) for d in deltas]
+    G = sp.coo_matrix((g[key + "_G_val"], (g[key + "_G_row"], g[key + "_G_col"])), shape=(m * m, m * m)).tocsr()
+    e0, g0 = O.elbo_grad_kron_dense(kinds, T, G, g[key + "_Kuf_y"], float(g[key + "_tr_yTy"]), g["X"].shape[0], hyp, s2)
+    assert abs(elbo - e0) <= 1e-10 * abs(e0)
+    got = np.array([grads[id(p)] for p in model.trainable_variables])
+    np.testing.assert_allclose(got, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
+
+
+def _raster(n1, n2, rng, domains=((-80, -25), (15, 55)), inner=((-75, -30), (20, 50))):
+    x1 = np.linspace(inner[0][0], inner[0][1], n1)
+    x2 = np.linspace(inner[1][0], inner[1][1], n2)
+    X = np.stack(np.meshgrid(x1, x2, indexing="ij"), -1).reshape(-1, 2)          # x1 slow (raster order)
+    y = np.sin(X[:, 0] / 4.0) * np.cos(X[:, 1] / 3.0) + 0.05 * rng.standard_normal(X.shape[0])
+    return X, y
+
+
+def test_midsize_rectangular_vs_banded_oracle(cuda):
+    """eNATL60-shaped raster (x1 slow), m1 != m2, several block columns and row tiles in the band factorisation."""
+    rng = np.random.default_rng(5)
+    k, ms = 3, (40, 36)
+    domains = ((-80, -25), (15, 55))
+    X, y = _raster(500, 400, rng)
+    hyp, s2 = [(1.0, 6.0), (0.8, 5.0)], 0.01
+    model = _model(X, y, k, ms, hyp=hyp, sigma2=s2, domains=domains)
+    meshes = [b.mesh for b in model.bases]
+    deltas = [b.delta for b in model.bases]
+    G0, b0, yy0 = O.precompute_kron(meshes, deltas, k, list(ms), X, y)
+    scale = abs(G0).max()
+    assert abs(model.KufKfu_sparse - G0).max() <= 1e-10 * scale
+    np.testing.assert_allclose(model.Kuf_y, b0, rtol=1e-10, atol=1e-10 * np.abs(b0).max())
+    T = [O.static_bands(k, m, d) for m, d in zip(ms, deltas)]
+    Ks = [O.make_Kuu("Matern32", l, v, t) for (v, l), t in zip(hyp, T)]
+    want = O.elbo_kron_banded(Ks, G0, b0, yy0, X.shape[0], [h[0] for h in hyp], s2, k, list(ms))
+    assert abs(model.elbo() - want) <= 1e-10 * abs(want)
+    e, grads = model.elbo_and_grad()
+    assert abs(e - want) <= 1e-10 * abs(want)
+    # gradient vs central differences of the banded oracle (the dense autograd oracle is too slow at M = 1440)
+    params = model.trainable_variables
+    got = np.array([grads[id(p)] for p in params])
+    th0 = np.array([hyp[0][0], hyp[0][1], hyp[1][0], hyp[1][1], s2])
+
+    def f(th):
+        Ks = [O.make_Kuu("Matern32", th[1], th[0], T[0]), O.make_Kuu("Matern32", th[3], th[2], T[1])]
+        return O.elbo_kron_banded(Ks, G0, b0, yy0, X.shape[0], [th[0], th[2]], th[4], k, list(ms))
+
+    for i in range(5):
+        h = 1e-4 * th0[i]
+        e_ = np.zeros(5); e_[i] = h
+        fd = (-f(th0 + 2 * e_) + 8 * f(th0 + e_) - 8 * f(th0 - e_) + f(th0 - 2 * e_)) / (12 * h)
+        assert abs(fd - got[i]) <= 1e-6 * max(1.0, abs(got[i])), (i, fd, got[i])
+    Xs = np.stack([rng.uniform(-74, -31, 300), rng.uniform(21, 49, 300)], 1)
+    mean, var = model.predict_f(Xs)
+    mean0, var0 = O.predict_kron_banded(meshes, deltas, k, list(ms), Ks, G0, b0, [h[0] for h in hyp], s2, Xs)
+    np.testing.assert_allclose(mean, mean0, atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, var0, atol=1e-9, rtol=0)
+
+
+def test_accumulate_order_invariance_and_shard_additivity(cuda):
+    import torch
+
+    from asvgp_b200 import basis as B, ops
+
+    rng = np.random.default_rng(11)
+    X, y = _raster(700, 300, rng)
+    bases = [B.B3Spline(-80, -25, 30), B.B3Spline(15, 55, 24)]
+
+    def run(parts):
+        acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+        cm = ops.moment_table_2d(bases)
+        for Xp, yp in parts:
+            ops.accum_2d(Xp, yp, bases, cm, ops.split_accum_2d(acc, bases)[2])
+        ops.expand_moments_2d(cm, bases, acc)
+        return acc.cpu().numpy()
+
+    full = run([(X, y)])
+    perm = rng.permutation(X.shape[0])
+    shuffled = run([(X[perm], y[perm])])
+    cut = 123457
+    sharded = run([(X[:cut], y[:cut]), (X[cut:], y[cut:])])
+    scale = np.abs(full).max()
+    np.testing.assert_allclose(shuffled, full, rtol=0, atol=1e-11 * scale)
+    np.testing.assert_allclose(sharded, full, rtol=0, atol=1e-11 * scale)
+    assert full[-1] == X.shape[0]
+    # partition of unity: sum of all entries of Kuf Kuf^T = N, sum of Kuf y = sum y
+    Gs, b, _ = (t for t in np.split(full, [ops.stencil_rows(3) * 30 * 24, (ops.stencil_rows(3) + 1) * 30 * 24]))
+    Gs = Gs.reshape(ops.stencil_rows(3), -1)
+    diag = Gs[3].sum()
+    assert abs(2 * Gs.sum() - diag - X.shape[0]) <= 1e-9 * X.shape[0]
+    assert abs(b.sum() - y.sum()) <= 1e-9 * np.abs(y).sum()
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 1025])
+def test_accumulate_ragged_sizes(cuda, n):
+    import torch
+
+    from asvgp_b200 import basis as B, ops
+
+    rng = np.random.default_rng(n)
+    bases = [B.B3Spline(0, 1, 12), B.B3Spline(0, 2, 13)]
+    X = np.stack([rng.uniform(.01, .99, n), rng.uniform(.01, 1.99, n)], 1).reshape(n, 2)
+    y = rng.standard_normal(n)
+    acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+    cm = ops.moment_table_2d(bases)
+    ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2])
+    ops.expand_moments_2d(cm, bases, acc)
+    Gs, b, scal = [t.cpu().numpy() for t in ops.split_accum_2d(acc, bases)]
+    assert scal[1] == n
+    if n == 0:
+        assert not Gs.any() and not b.any()
+        return
+    from asvgp_b200 import utils
+
+    meshes = [bb.mesh for bb in bases]
+    deltas = [bb.delta for bb in bases]
+    G0, b0, yy0 = O.precompute_kron(meshes, deltas, 3, [12, 13], X, y)
+    assert abs(utils.stencil_to_sparse(Gs, 12, 13, 3) - G0).max() <= 1e-12
+    np.testing.assert_allclose(b, b0.ravel(), atol=1e-12)
+    assert abs(scal[0] - yy0) <= 1e-12 * max(yy0, 1.0)
