@@ -30,6 +30,14 @@ WORKLOADS = {
     "1d-random": (100_000_000, 10_000, 3, "Matern52", False),
     "1d-c2": (1_000_000, 1_000, 3, "Matern32", True),
 }
+WORKLOADS_2D = {
+    # name: (raster n1 x n2 per rank, m per dimension, spline order)   — BASELINE.json configs[3] (eNATL60-shaped)
+    "2d": (10_000, 10_000, 200, 3),
+    "2d-k4": (10_000, 10_000, 100, 4),          # what experiments/eNATL60/eNATL60.py:84 itself uses (B4, m = 100)
+    "2d-small": (2_000, 2_000, 60, 3),
+}
+HYPERS_2D = ((1.0, 5.0), (1.0, 4.0), 0.01)      # (v1, l1), (v2, l2), sigma^2: lengthscales ~ 18 knot spacings
+BYTES_PER_POINT_ACCUM_2D = 24                   # X[n,2] and y read once
 HYPERS = (1.0, 1.0, 0.1)          # variance, lengthscale, sigma^2
 BYTES_PER_POINT_ACCUM = 16         # x and y read once
 
@@ -40,7 +48,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="1d", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="1d", choices=sorted(WORKLOADS) + sorted(WORKLOADS_2D))
+    ap.add_argument("--no-2d", action="store_true", help="skip the 2-D Kronecker summary appended to the 1-D line")
     ap.add_argument("--n", type=float, default=None, help="override points per rank (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -190,8 +199,23 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n, m, k, kind, is_sorted = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
+    if args.workload in WORKLOADS_2D:
+        n1, n2, m, k = WORKLOADS_2D[args.workload]
+        value, dt, n_sample, t_acc, t_fac = run_cpu_2d(args.workload, max(1, min(args.steps, 3)), 0, cores)
+        sample = ("O(N) precompute timed on the first %d raster points over %d processes (%.2f s) and extrapolated "
+                  "linearly to N=%d, plus one LAPACK banded ELBO evaluation at full M (%.2f s); no gradients"
+                  % (n_sample, cores, t_acc, n1 * n2, t_fac))
+        print(json.dumps({
+            "impl": "reference", "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config_2d(args.workload, n1, n2, m, k),
+            "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+    n, m, k, kind, is_sorted = WORKLOADS[args.workload]
     n_sample = int(min(n, 2_000_000 * cores))            # ~1 s of work per core per step
     value, dt = run_cpu(n_sample, m, k, kind, args.steps, max(args.warmup, 1), cores)
     sample = "first %d of the %d points per step, %d processes (SciPy sparsetools/LAPACK are single-threaded)" % (
@@ -212,6 +236,254 @@ def workload_config(name, n, m, k, kind, is_sorted):
             "name": name, "n_per_gpu": n, "m": m, "order": k, "kernel": kind, "hypers": list(HYPERS),
             "l2_policy": "inputs (16 B/pt x N = %.1f GB) are larger than the 126 MB L2" % (16 * n / 1e9)}
 
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D Kronecker workload (BASELINE.json configs[3]): eNATL60-shaped raster, x1 slow, flat X[N, 2]
+# ---------------------------------------------------------------------------------------------------------------------
+DOM_2D = ((-80, -25), (15, 55))            # basis domains (experiments/eNATL60/eNATL60.py:84)
+INNER_2D = ((-75.0, -30.0), (20.0, 50.0))  # data extent (eNATL60.py:43-46)
+
+
+def make_data_2d(torch, n1, n2, rank, world, seed=1997):
+    lo = INNER_2D[0][0] + (INNER_2D[0][1] - INNER_2D[0][0]) * rank / world
+    hi = INNER_2D[0][0] + (INNER_2D[0][1] - INNER_2D[0][0]) * (rank + 1) / world
+    x1 = torch.linspace(lo, hi, n1 + 2, dtype=torch.float64, device="cuda")[1:-1]
+    x2 = torch.linspace(INNER_2D[1][0], INNER_2D[1][1], n2, dtype=torch.float64, device="cuda")
+    X = torch.stack([x1[:, None].expand(n1, n2), x2[None, :].expand(n1, n2)], -1).reshape(-1, 2).contiguous()
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    y = torch.zeros(n1 * n2, dtype=torch.float64, device="cuda")
+    for _ in range(8):                                    # smooth field: 8 random 2-D sinusoids
+        f1, f2, ph = (torch.rand(3, generator=gen, dtype=torch.float64) * torch.tensor([0.6, 0.8, 6.28])).tolist()
+        y += torch.sin(X[:, 0] * f1 + X[:, 1] * f2 + ph)
+    g2 = torch.Generator(device="cuda").manual_seed(seed + 17 + rank)
+    y += 0.05 * torch.randn(n1 * n2, dtype=torch.float64, device="cuda", generator=g2)
+    y = (y - 0.0) / 2.0
+    return X, y
+
+
+def workload_config_2d(name, n1, n2, m, k):
+    n = n1 * n2
+    return {"workload": "2-D Kronecker collapsed ELBO + (v1, l1, v2, l2, sigma2) gradients, N=%d raster points "
+                        "(%d x %d, x1 slow) per GPU, M=%d x %d B%d-spline features, Matern32 x Matern32"
+                        % (n, n1, n2, m, m, k),
+            "name": name, "n_per_gpu": n, "m": [m, m], "order": k, "kernel": "Matern32xMatern32",
+            "hypers": [list(HYPERS_2D[0]), list(HYPERS_2D[1]), HYPERS_2D[2]],
+            "l2_policy": "inputs (24 B/pt x N = %.1f GB) are larger than the 126 MB L2" % (24 * n / 1e9)}
+
+
+def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
+    """Times the 2-D path; returns the summary dict (rank 0) — used as the main line for --workload 2d* and as the
+    `kron_2d` appendix of the default 1-D line."""
+    import numpy as np
+
+    from asvgp_b200 import basis as B, kernels as Kn, ops
+    from asvgp_b200.gpr import GPR_kron
+    from asvgp_b200.inducing_features import SplineFeatures1D
+
+    n1, n2, m, k = WORKLOADS_2D[name]
+    if args.n:
+        n1 = n2 = int(round(float(args.n) ** 0.5))
+    n = n1 * n2
+    cls = getattr(B, "B%dSpline" % k)
+    bases = [cls(DOM_2D[0][0], DOM_2D[0][1], m), cls(DOM_2D[1][0], DOM_2D[1][1], m)]
+    kerns = [Kn.Matern32(variance=HYPERS_2D[0][0], lengthscales=HYPERS_2D[0][1]),
+             Kn.Matern32(variance=HYPERS_2D[1][0], lengthscales=HYPERS_2D[1][1])]
+    X, y = make_data_2d(torch, n1, n2, rank, world)
+
+    # the model object without its constructor's accumulate pass: the timed step does that pass itself
+    model = GPR_kron.__new__(GPR_kron)
+    model.kernels, model.bases, model.order, model.d = kerns, bases, k, 2
+    model.likelihood = Kn.Gaussian(HYPERS_2D[2])
+    model.inducing_features = [SplineFeatures1D(kerns[i], bases[i]) for i in range(2)]
+    model._acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+    model._Gs, model._b, model._scal = ops.split_accum_2d(model._acc, bases)
+    cellmom = ops.moment_table_2d(bases)
+    ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
+    result = {}
+
+    def step(timers=None):
+        model._acc.zero_(); cellmom.zero_()
+        if timers: timers[0].record()
+        ops.accum_2d(X, y, bases, cellmom, model._scal)
+        if timers: timers[1].record()
+        ops.expand_moments_2d(cellmom, bases, model._acc)
+        if world > 1:
+            dist.all_reduce(model._acc)
+        if timers: timers[2].record()
+        result["elbo"], result["grads"] = model.elbo_and_grad()        # factor + selected inverse + one D2H read
+        if timers: timers[3].record()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(warmup, 3)):
+        step()
+    barrier()
+    elbo0 = result["elbo"]
+    grad0 = [float(result["grads"][id(p)]) for p in model.trainable_variables]
+    assert np.isfinite(elbo0) and np.isfinite(grad0).all()
+
+    phase_ev = [[ev() for _ in range(4)] for _ in range(steps)]
+    t0, t1 = ev(), ev()
+    with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
+        barrier()
+        t0.record()
+        for i in range(steps):
+            step(phase_ev[i])
+        t1.record()
+        barrier()
+    total_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    ms_per_step = total_ms.item() / steps
+    accum_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in phase_ev]))
+    red_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in phase_ev]))
+    fact_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in phase_ev]))
+
+    e2e = None
+    if with_e2e:
+        Xh = torch.empty((n, 2), dtype=torch.float64).pin_memory(); Xh.copy_(X)
+        yh = torch.empty(n, dtype=torch.float64).pin_memory(); yh.copy_(y)
+
+        def e2e_step():
+            mdl = GPR_kron((Xh, yh.view(-1, 1)), kerns, bases, check_inputs=False)
+            mdl.likelihood.variance.assign(HYPERS_2D[2])
+            return mdl.training_loss_and_gradients()
+
+        e2e_step()
+        barrier()
+        k_e2e = max(2, min(steps, 5))
+        w0 = time.perf_counter()
+        for _ in range(k_e2e):
+            loss, _g = e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - w0) / k_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert abs(-loss - elbo0) <= 1e-9 * abs(elbo0), "e2e ELBO differs from the device-resident one"
+        e2e = {"value": world * n / dt.item(), "unit": "datapoints/s", "h2d_bytes_per_step": 24 * n,
+               "d2h_bytes_per_step": 24 * 8, "ms_per_step": dt.item() * 1e3, "steps": k_e2e,
+               "api": "GPR_kron((X_host, y_host), kernels, bases).training_loss_and_gradients()"}
+        del Xh, yh
+
+    # predictor on the same raster (BASELINE.json configs[4]): sharded over ranks, no collective
+    alpha, SigP, S1, S2, _info = model.posterior_weights()
+    for _ in range(2):
+        ops.predict_2d(X, bases, alpha, SigP, S1, S2, 1.0)
+    p0, p1 = ev(), ev()
+    barrier()
+    p0.record()
+    for _ in range(3):
+        ops.predict_2d(X, bases, alpha, SigP, S1, S2, 1.0)
+    p1.record()
+    barrier()
+    pred_ms = torch.tensor([p0.elapsed_time(p1) / 3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(pred_ms, op=dist.ReduceOp.MAX)
+    pred_ms = pred_ms.item()
+
+    peaks, peak_kind = measured_peaks()
+    achieved = BYTES_PER_POINT_ACCUM_2D * n / (accum_ms * 1e-3) / 1e9
+    M, w = m * m, k * (m + 1)
+    flops = float(M) * w * w                       # Cholesky of the band; the selected inverse is ~2x that again
+    n_blk = -(-M // 64)
+    return {
+        "metric": "elbo_grad_datapoints_per_s", "value": world * n / (ms_per_step * 1e-3), "unit": "datapoints/s",
+        "n_gpus": world, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config_2d(name, n1, n2, m, k),
+        "phases_ms": {"accumulate": accum_ms, "expand_allreduce": red_ms, "factor_selinv_grad": fact_ms,
+                      "predict_same_raster": pred_ms},
+        "predict_points_per_s": world * n / (pred_ms * 1e-3),
+        "elbo": elbo0, "grad": grad0,
+        "roofline": {"kernel": "accum_2d_kernel<%d,...>" % k, "bound": "hbm", "achieved": achieved,
+                     "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                     "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
+                     "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM_2D * n, "launch_ms": accum_ms,
+                     "traffic": _traffic("accum_2d")},
+        "fp64_phase": {"what": "block-band Cholesky of P (bandwidth %d) + selected inverse + contractions" % w,
+                       "cholesky_flop": flops, "ms": fact_ms,
+                       "note": "latency-bound chain of %d block columns; flop rate vs the ~37 TF/s fp64 pipe is "
+                               "reported for orientation only" % n_blk,
+                       "cholesky_equiv_tflops": 3 * flops / (fact_ms * 1e-3) / 1e12},
+        "clocks": clocks.summary(),
+        # per step: accum + expand + 2 kuu_assemble + 2 band_inverse + assemble + 3 per block column (potrf, trsm,
+        # syrk) + trinv + 2 per block column (selected inverse) + stencil extract + contractions
+        "gpu_launches": steps * (10 + 5 * n_blk),
+        "e2e": e2e,
+    }
+
+
+def _traffic(kernel):
+    tpath = os.path.join(ROOT, "profiles", "%s_traffic.json" % kernel)
+    if os.path.exists(tpath):
+        return json.load(open(tpath)).get("dram_bytes_per_launch")
+    return None
+
+
+def run_cpu_2d(name, steps, warmup, cores):
+    """CPU arm of the 2-D workload: the port's O(N) precompute (same SciPy sparse calls as reference gpr.py:268-271)
+    on a bounded sample over `cores` processes + ONE banded ELBO evaluation at full M (LAPACK dpbtrf; the reference's
+    dense tf.linalg.cholesky of the M x M matrix is infeasible at 200 x 200).  Gradients are NOT included, which
+    favours this arm."""
+    import multiprocessing as mp
+
+    import numpy as np
+
+    from oracle import asvgp_oracle as O
+
+    n1, n2, m, k = WORKLOADS_2D[name]
+    n = n1 * n2
+    meshes, deltas = zip(*[O.make_mesh(DOM_2D[i][0], DOM_2D[i][1], m, k) for i in range(2)])
+    n_sample = int(min(n, 400_000 * cores))
+    rows = max(1, n_sample // n2)
+    x1 = np.linspace(INNER_2D[0][0], INNER_2D[0][1], n1 + 2)[1:-1][:rows]
+    x2 = np.linspace(INNER_2D[1][0], INNER_2D[1][1], n2)
+    X = np.stack(np.meshgrid(x1, x2, indexing="ij"), -1).reshape(-1, 2)
+    rng = np.random.default_rng(0)
+    y = np.sin(X[:, 0] / 4) * np.cos(X[:, 1] / 3) + 0.05 * rng.standard_normal(X.shape[0])
+    n_sample = X.shape[0]
+    _CPU_SHARED.update(meshes=meshes, deltas=deltas, k=k, ms=[m, m], X=X, y=y)
+    T = [O.static_bands(k, m, d) for d in deltas]
+    Ks = [O.make_Kuu("Matern32", HYPERS_2D[i][1], HYPERS_2D[i][0], T[i]) for i in range(2)]
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    cuts = np.linspace(0, n_sample, cores + 1).astype(np.int64)
+    spans = [(int(a), int(b)) for a, b in zip(cuts, cuts[1:])]
+
+    def one():
+        t0 = time.perf_counter()
+        parts = pool.map(_cpu_chunk_2d, spans) if pool else [_cpu_chunk_2d(spans[0])]
+        G = sum(p[0] for p in parts); b = sum(p[1] for p in parts); yy = sum(p[2] for p in parts)
+        t1 = time.perf_counter()
+        # regularise the sample's Gram as the full data set would (every cell populated): scale to N
+        e = O.elbo_kron_banded(Ks, G * (n / n_sample), b * (n / n_sample), yy * (n / n_sample), n,
+                               [HYPERS_2D[0][0], HYPERS_2D[1][0]], HYPERS_2D[2], k, [m, m])
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1, e
+
+    try:
+        for _ in range(warmup):
+            one()
+        ta, tf = [], []
+        for _ in range(steps):
+            a, f, _e = one()
+            ta.append(a); tf.append(f)
+    finally:
+        if pool is not None:
+            pool.close()
+    t_acc, t_fac = float(np.mean(ta)), float(np.mean(tf))
+    full_step = n / (n_sample / t_acc) + t_fac
+    return n / full_step, full_step, n_sample, t_acc, t_fac
+
+
+def _cpu_chunk_2d(span):
+    from oracle import asvgp_oracle as O
+
+    d = _CPU_SHARED
+    return O.precompute_kron(d["meshes"], d["deltas"], d["k"], d["ms"], d["X"][span[0]:span[1]], d["y"][span[0]:span[1]])
 
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
@@ -235,6 +507,19 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.workload in WORKLOADS_2D:
+        line = run_2d(args, args.workload, torch, dist, world, rank, args.steps, args.warmup, with_e2e=not args.no_e2e)
+        if rank == 0:
+            if world == 1 and not args.no_cpu_baseline:
+                v, dt, n_sample, t_acc, t_fac = run_cpu_2d(args.workload, 1, 0, 1)
+                line["cpu_baseline"] = {
+                    "value": v, "unit": "datapoints/s", "cores": 1, "kind": "port",
+                    "sample": "precompute on the first %d raster points (%.1f s, extrapolated linearly to N) + one "
+                              "LAPACK banded ELBO at full M (%.1f s), no gradients, single thread" % (n_sample, t_acc, t_fac)}
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n, m, k, kind, is_sorted = WORKLOADS[args.workload]
     if args.n:
         n = int(args.n)
@@ -319,6 +604,15 @@ def main():
                "api": "GPR_1d((X_host, y_host), kernel, basis).training_loss_and_gradients()"}
         del xh, yh
 
+    kron = None
+    if args.workload == "1d" and not args.no_2d and not args.n:
+        del x, y
+        torch.cuda.empty_cache()
+        try:
+            kron = run_2d(args, "2d", torch, dist, world, rank, max(3, min(args.steps, 5)), 3, with_e2e=not args.no_e2e)
+        except Exception as exc:            # the appendix must never take the headline line down with it
+            kron = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -326,10 +620,7 @@ def main():
 
     peaks, peak_kind = measured_peaks()
     achieved = BYTES_PER_POINT_ACCUM * n / (accum_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "accum_1d_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    traffic = _traffic("accum_1d")
     line = {
         "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -346,6 +637,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if kron is not None:
+        line["kron_2d"] = kron
     if world == 1 and not args.no_cpu_baseline:
         n_sample = min(n, 20_000_000)
         v1, dt1 = run_cpu(n_sample, m, k, kind, 1, 0, 1)
