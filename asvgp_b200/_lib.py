@@ -36,6 +36,8 @@ VALUE_FUNCTIONS = {
     "asvgp_accum_2d_moment_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_band_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kron_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kron_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
 }
 
 _lib = None

@@ -1,0 +1,846 @@
+// Block-band kernels of the 2-D (Kronecker) model as persistent tile-DAG kernels.
+//
+// P = K1 (x) K2 + G / sigma^2 is block banded with scalar bandwidth w = k (m2 + 1) (reference gpr.py:262); the
+// reference factorises it as a DENSE m1 m2 x m1 m2 matrix (tf.linalg.cholesky, gpr.py:293), infeasible at 200 x 200.
+//
+//   asvgp_kron_factor  <- utils.bands_to_kron_cholesky's Kronecker product, `Kuu + KufKfu / sigma2`,
+//                         tf.linalg.cholesky(P), its log-det, triangular_solve(L_P, Kuf_y)     (gpr.py:287-295)
+//   asvgp_kron_selinv  <- what TF reverse mode / cholesky_solve extract from P^-1 (gpr.py:307, 319-326): the entries of
+//                         P^-1 on the stencil pattern and P^-1 Kuf_y
+//   asvgp_kron_terms   <- the scalar contractions of the bound's derivatives and trace(Kuu^-1 KufKfu) (gpr.py:307)
+//
+// Storage: the band is cut into NB x NB tiles (NB = 64).  Tile (C, d), d = 0..BW, holds block row C+d of
+// block column C as a contiguous column-major 64 x 64 block (32 KB), so one TMA bulk copy (cp.async.bulk, completion
+// on an mbarrier) brings a whole operand into shared memory.  BW = floor((w + NB - 1) / NB) sub-diagonals (10 at
+// 200 x 200, k = 3); entries of a tile beyond the scalar band are structural zeros and stay exact zeros.
+//
+// Factorisation = tiled left-looking Cholesky as ONE persistent cooperative kernel: task (R, C) owns tile (R, C),
+// subtracts sum_J L(R,J) L(C,J)^T as the operand tiles become final (per-tile release/acquire flags in global
+// memory), then either factorises the diagonal tile in registers — right-looking rank-1 sweep that carries L^-1
+// along, one barrier per column — or multiplies by the published inverse L(C,C)^-T.  Tasks are dealt round-robin in
+// column-major order, which is a topological order of the DAG, so the co-resident CTAs cannot deadlock; the chain of
+// diagonal tiles is the critical path, everything else fills the other SMs.  The right-hand side rides along
+// (y = L^-1 b), so do log|P| and ||y||^2.
+//
+// Selected inverse = blocked Takahashi recursion, backwards over block columns, again one persistent kernel:
+// Sigma(R,C) = -sum_K Sigma(R,K) Y(K,C), Y = L(K,C) L(C,C)^-1, Sigma(C,C) = L(C,C)^-T L(C,C)^-1 - sum_K Sigma(K,C)^T Y(K,C),
+// with the diagonal contributions and the back-substitution x = P^-1 b accumulated by fp64 REDs.  Sigma is kept as
+// lower AND upper tiles so that every operand is a plain column-major tile.  No tensor cores: B200's fp64 tensor
+// rate equals its fp64 FMA rate.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "../../include/asvgp_b200.h"
+
+namespace asvgp {
+
+constexpr int NB = 64;
+constexpr int TILE = NB * NB;                   // doubles per tile
+constexpr int TILE_BYTES = TILE * 8;
+constexpr int kTdThreads = 256;                 // 16 x 16 threads, 4 x 4 outputs each
+constexpr long long kSpinLimit = 1LL << 24;     // polls before a wait gives up and raises the abort flag (~ seconds)
+constexpr int kNoBadPivot = 0x7f7f7f7f;         // what cudaMemset(0x7f) leaves in the "first bad pivot" slot
+
+struct TileGeom {
+    int m1, m2, K;
+    int M;          // m1 * m2
+    int nb;         // block rows / columns (M padded to a multiple of NB with unit diagonal)
+    int w;          // scalar bandwidth K * m2 + K
+    int BW;         // block sub-diagonals
+    __host__ __device__ int64_t tile(int C, int d) const { return ((int64_t)C * (BW + 1) + d) * TILE; }
+    __host__ __device__ int n_tiles() const { return nb * (BW + 1); }
+};
+
+static TileGeom make_tile_geom(int m1, int m2, int K) {
+    TileGeom g;
+    g.m1 = m1; g.m2 = m2; g.K = K;
+    g.M = m1 * m2;
+    g.nb = (g.M + NB - 1) / NB;
+    g.w = K * m2 + K;
+    g.BW = std::min((g.w + NB - 1) / NB, g.nb - 1);
+    return g;
+}
+
+// Layout of the factor buffer (`band` of the C ABI), in doubles:
+//   [ tiles n_tiles*TILE | Linv nb*TILE | colstat nb*2 | flags (ints) ]
+struct FactorLayout {
+    int64_t tiles, linv, colstat, flags, total;
+    int64_t n_flag_ints;
+};
+static FactorLayout factor_layout(const TileGeom& g) {
+    FactorLayout L;
+    L.tiles = 0;
+    L.linv = (int64_t)g.n_tiles() * TILE;
+    L.colstat = L.linv + (int64_t)g.nb * TILE;
+    L.flags = L.colstat + (int64_t)g.nb * 2;
+    L.n_flag_ints = (int64_t)g.n_tiles() + 8;                  // ready flags + abort
+    L.total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
+    return L;
+}
+// Layout of the selected-inverse buffers: sig = [ lower tiles | upper tiles ], work = [ xacc nb*NB | flags ]
+struct SelLayout {
+    int64_t sig_lower, sig_upper, sig_total;
+    int64_t xacc, flags, work_total, n_flag_ints;
+};
+static SelLayout sel_layout(const TileGeom& g) {
+    SelLayout L;
+    L.sig_lower = 0;
+    L.sig_upper = (int64_t)g.n_tiles() * TILE;
+    L.sig_total = 2 * L.sig_upper;
+    L.xacc = 0;
+    L.flags = (int64_t)g.nb * NB;
+    L.n_flag_ints = (int64_t)g.n_tiles() + g.nb + 8;           // tile flags + per-column counters + abort
+    L.work_total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared), release/acquire flags
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(double* dst_smem, const double* src_gmem, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"((uint32_t)TILE_BYTES), "r"(smem_u32(bar))
+                 : "memory");
+}
+// generic-proxy writes (ours or, after an acquire, another CTA's) -> async-proxy (TMA) reads
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// Spin until *flag >= want; gives up (and makes everybody give up) after kSpinLimit polls so that a logic error can
+// never hang the device.
+__device__ __forceinline__ void wait_flag(const int* flag, int want, int* abort_flag) {
+    long long spins = 0;
+    while (ld_acquire(flag) < want) {
+        if ((++spins & 1023) == 0) {
+            if (ld_acquire(abort_flag) != 0) return;
+            if (spins > kSpinLimit) { atomicExch(abort_flag, 1); return; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// 64 x 64 x 64 tile product on the fp64 pipe: acc[i][j] (+/-)= sum_k A(tm+i, k) B(tn+j, k),
+// A(m, k) at A[k*LDA + m], B(n, k) at B[k*LDB + n] (shared memory)
+// ------------------------------------------------------------------------------------------------------------------
+template <int LD>
+__device__ __forceinline__ void load4(const double* p, double (&v)[4]) {
+    if (LD % 2 == 0) {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    } else {
+        v[0] = p[0]; v[1] = p[1]; v[2] = p[2]; v[3] = p[3];
+    }
+}
+template <int LDA, int LDB, bool SUB>
+__device__ __forceinline__ void tile_mma(double (&acc)[4][4], const double* __restrict__ A,
+                                         const double* __restrict__ B, int tm, int tn) {
+#pragma unroll 4
+    for (int k = 0; k < NB; ++k) {
+        double a[4], b[4];
+        load4<LDA>(A + k * LDA + tm, a);
+        load4<LDB>(B + k * LDB + tn, b);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double ai = SUB ? -a[i] : a[i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fma(ai, b[j], acc[i][j]);
+        }
+    }
+}
+
+// stage s of a two-stage ring laid out [A0 | B0 | A1 | B1] (pointer arithmetic instead of an indexed pointer array,
+// which would live in local memory)
+struct StageBufs {
+    double* base;
+    __device__ __forceinline__ double* operator[](int s) const { return base + s * 2 * TILE; }
+};
+struct Phases {                // parity bits of the two mbarriers
+    uint32_t bits = 0u;
+    __device__ __forceinline__ uint32_t get(int s) const { return (bits >> s) & 1u; }
+    __device__ __forceinline__ void flip(int s) { bits ^= 1u << s; }
+};
+
+// registers <-> column-major tile (element (r, c) at [c*64 + r]); thread owns rows tm..tm+3, columns tn..tn+3
+__device__ __forceinline__ void regs_from_tile(double (&acc)[4][4], const double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 a = *reinterpret_cast<const double2*>(t + (tn + j) * NB + tm);
+        const double2 b = *reinterpret_cast<const double2*>(t + (tn + j) * NB + tm + 2);
+        acc[0][j] = a.x; acc[1][j] = a.y; acc[2][j] = b.x; acc[3][j] = b.y;
+    }
+}
+__device__ __forceinline__ void regs_to_tile(const double (&acc)[4][4], double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<double2*>(t + (tn + j) * NB + tm) = make_double2(acc[0][j], acc[1][j]);
+        *reinterpret_cast<double2*>(t + (tn + j) * NB + tm + 2) = make_double2(acc[2][j], acc[3][j]);
+    }
+}
+// transposed store: element (r, c) at [r*64 + c]
+__device__ __forceinline__ void regs_to_tile_t(const double (&acc)[4][4], double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<double2*>(t + (tm + i) * NB + tn) = make_double2(acc[i][0], acc[i][1]);
+        *reinterpret_cast<double2*>(t + (tm + i) * NB + tn + 2) = make_double2(acc[i][2], acc[i][3]);
+    }
+}
+
+// out[r] = sum over the 16 column groups of part[q][r]; part is [16][64] in shared memory (deterministic reduction)
+__device__ __forceinline__ double reduce16(const double* part, int r) {
+    double s = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) s += part[q * NB + r];
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// assembly of P into tiles
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) td_assemble_kernel(TileGeom g, const double* __restrict__ K1,
+                                                          const double* __restrict__ K2,
+                                                          const double* __restrict__ Gs, double inv_s2,
+                                                          double* __restrict__ tiles) {
+    const int NS = 2 * g.K + 1;
+    const int n_e = (g.K + 1) * NS;
+    const int64_t Mpad = (int64_t)g.nb * NB;
+    const int64_t total = Mpad * n_e;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = t / n_e;
+        const int e = (int)(t % n_e);
+        const int d1 = e / NS, d2 = e % NS - g.K;
+        const int Cb = (int)(j / NB), c = (int)(j % NB);
+        if (j >= g.M) {                                     // padding columns: unit diagonal
+            if (d1 == 0 && d2 == 0) tiles[g.tile(Cb, 0) + c * NB + c] = 1.0;
+            continue;
+        }
+        if (d1 == 0 && d2 < 0) continue;
+        const int j1 = (int)(j / g.m2), j2 = (int)(j % g.m2);
+        const int i1 = j1 + d1, i2 = j2 + d2;
+        if (i1 >= g.m1 || i2 < 0 || i2 >= g.m2) continue;
+        const int a2 = d2 < 0 ? -d2 : d2, c2 = d2 < 0 ? i2 : j2;
+        const double kv = K1[(int64_t)d1 * g.m1 + j1] * K2[(int64_t)a2 * g.m2 + c2];
+        const double v = fma(inv_s2, Gs[(int64_t)e * g.M + j], kv);
+        const int64_t i = j + (int64_t)d1 * g.m2 + d2;
+        const int Rb = (int)(i / NB), r = (int)(i % NB);
+        tiles[g.tile(Cb, Rb - Cb) + c * NB + r] = v;
+        if (Rb == Cb && r != c) tiles[g.tile(Cb, 0) + r * NB + c] = v;     // diagonal tiles are kept full symmetric
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// factorisation
+// ------------------------------------------------------------------------------------------------------------------
+struct FactorArgs {
+    TileGeom g;
+    double* tiles;      // in: P, out: L
+    double* linv;       // nb tiles: L(C,C)^-1 (lower)
+    double* rhs;        // in: b (zero padded to nb*NB), out: y = L^-1 b
+    double* colstat;    // [nb][2]: 2 sum log L_cc, ||y_C||^2 ; slot [0][..] of the info array below
+    int* ready;         // [n_tiles] + abort at [n_tiles]
+    double* scal;       // [3]: log|P|, ||y||^2, info  (info written here; sums by td_stats_kernel)
+};
+
+// Cholesky of the symmetric 64 x 64 tile held in registers (4 x 4 per thread), right-looking, one barrier per
+// column; carries V = L^-1 along (V starts as the identity, receives the same row operations).  On exit acc holds L
+// (lower incl. diagonal; entries above the diagonal are don't-care) and V holds L^-1 (lower).
+__device__ __forceinline__ void potrf_regs(double (&acc)[4][4], double (&V)[4][4], int tm, int tn, double* scol,
+                                           double* srow, int* first_bad) {
+    // scol/srow: [2][64] doubles each, double buffered across columns
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) V[i][j] = (tm + i == tn + j) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int kb = 0; kb < NB / 4; ++kb) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            const int k = kb * 4 + kk;
+            double* col = scol + (k & 1) * NB;
+            double* row = srow + (k & 1) * NB;
+            if (tn == kb * 4) {                      // owners of column k of A: unscaled column, zero above the pivot
+#pragma unroll
+                for (int i = 0; i < 4; ++i) col[tm + i] = (tm + i >= k) ? acc[i][kk] : 0.0;
+            }
+            if (tm == kb * 4) {                      // owners of row k of V (non-zero for columns <= k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) row[tn + j] = V[kk][j];
+            }
+            __syncthreads();
+            const double p = col[k];
+            if (!(p > 0.0) && *first_bad < 0) *first_bad = k;
+            const double ip = rsqrt(p);
+            double lr[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) lr[i] = col[tm + i] * ip;          // L[tm+i][k]  (0 for rows above k)
+            if (tn + 3 > k) {                        // trailing update of A (columns > k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double lc = col[tn + j] * ip;
+                    if (tn + j > k) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i][j] = fma(-lr[i], lc, acc[i][j]);
+                    }
+                }
+            }
+            if (tn == kb * 4) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[i][kk] = lr[i];            // final column k of L
+            }
+            if (tn <= k) {                           // V: rows > k get -L[r][k] * W_k ; row k becomes W_k = V_k / L_kk
+                double wk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) wk[j] = row[tn + j] * ip;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (tm + i > k) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) V[i][j] = fma(-lr[i], wk[j], V[i][j]);
+                    }
+                }
+                if (tm == kb * 4) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) V[kk][j] = wk[j];
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) {
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ double s_vec[NB];
+    const TileGeom g = a.g;
+    const int tid = threadIdx.x;
+    const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    int* abort_flag = a.ready + g.n_tiles();
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    fence_proxy_async();
+    __syncthreads();
+    Phases ph;
+    const int n_tasks = g.n_tiles();
+
+    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const int C = t / (g.BW + 1), d = t % (g.BW + 1), R = C + d;
+        if (R >= g.nb) continue;
+        double* my_tile = a.tiles + g.tile(C, d);
+        double acc[4][4];
+        regs_from_tile(acc, my_tile, tm, tn);
+        const int J0 = max(0, R - g.BW), nJ = C - J0;
+
+        auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
+            wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (R - J), 1, abort_flag);
+            if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
+            fence_proxy_async();
+            mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
+            tma_load_tile(sA[s], a.tiles + g.tile(J, R - J), &full[s]);
+            if (d != 0) tma_load_tile(sB[s], a.tiles + g.tile(J, C - J), &full[s]);
+        };
+        if (nJ > 0 && tid == 0) issue(J0, 0);
+        for (int q = 0; q < nJ; ++q) {
+            const int s = q & 1;
+            if (q + 1 < nJ && tid == 0) issue(J0 + q + 1, s ^ 1);
+            mbar_wait(&full[s], ph.get(s));
+            ph.flip(s);
+            tile_mma<NB, NB, true>(acc, sA[s], d != 0 ? sB[s] : sA[s], tm, tn);
+            __syncthreads();
+        }
+
+        if (d == 0) {
+            // ---- diagonal tile: POTRF + inverse in registers, forward substitution of the right-hand side ---------
+            double V[4][4];
+            int first_bad = -1;
+            double* scol = sA[0];                    // [2][64]
+            double* srow = sA[0] + 2 * NB;           // [2][64]
+            double* part = sA[0] + 4 * NB;           // [16][64]
+            potrf_regs(acc, V, tm, tn, scol, srow, &first_bad);
+            // y_C = L^-1 b_C (all contributions to b_C have landed: every (C, J) tile is final)
+            {
+                double bv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = __ldcg(a.rhs + (int64_t)C * NB + tn + j);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) s = fma((tm + i >= tn + j) ? V[i][j] : 0.0, bv[j], s);
+                    part[(tn >> 2) * NB + tm + i] = s;
+                }
+            }
+            // publish L and L^-1 (zero above the diagonal)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (tm + i < tn + j) { acc[i][j] = 0.0; V[i][j] = 0.0; }
+                }
+            regs_to_tile(acc, my_tile, tm, tn);
+            regs_to_tile(V, a.linv + (int64_t)C * TILE, tm, tn);
+            __syncthreads();
+            double yv = 0.0, ld = 0.0;
+            if (tid < NB) {
+                yv = reduce16(part, tid);
+                a.rhs[(int64_t)C * NB + tid] = yv;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(a.ready + (int64_t)C * (g.BW + 1), 1);
+            // off the critical path: this block column's share of log|P| and ||y||^2
+            if (tm == tn) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) ld += log(acc[i][i]);
+            }
+            double q = yv * yv;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ld += __shfl_xor_sync(0xffffffffu, ld, o);
+                q += __shfl_xor_sync(0xffffffffu, q, o);
+            }
+            __shared__ double s_ld[kTdThreads / 32], s_q[kTdThreads / 32];
+            if ((tid & 31) == 0) { s_ld[tid >> 5] = ld; s_q[tid >> 5] = q; }
+            __syncthreads();
+            if (tid == 0) {
+                double L = 0.0, Q = 0.0;
+                for (int wv = 0; wv < kTdThreads / 32; ++wv) { L += s_ld[wv]; Q += s_q[wv]; }
+                a.colstat[2 * C] = 2.0 * L;
+                a.colstat[2 * C + 1] = Q;
+                if (first_bad >= 0) atomicMin(a.ready + g.n_tiles() + 1, C * NB + first_bad + 1);
+            }
+            __syncthreads();
+        } else {
+            // ---- off-diagonal tile: L(R,C) = A L(C,C)^-T, then b_R -= L(R,C) y_C ----------------------------------------
+            if (tid == 0) {
+                wait_flag(a.ready + (int64_t)C * (g.BW + 1), 1, abort_flag);
+                fence_proxy_async();
+                mbar_expect_tx(&full[0], TILE_BYTES);
+                tma_load_tile(sB[0], a.linv + (int64_t)C * TILE, &full[0]);
+            }
+            regs_to_tile(acc, sA[0], tm, tn);        // A(m, k) at [k*64 + m]
+            __syncthreads();
+            mbar_wait(&full[0], ph.get(0));
+            ph.flip(0);
+            double L[4][4] = {};
+            tile_mma<NB, NB, false>(L, sA[0], sB[0], tm, tn);      // L[m][n] = sum_k A[m][k] Linv[n][k]
+            regs_to_tile(L, my_tile, tm, tn);
+            if (tid < NB) s_vec[tid] = __ldcg(a.rhs + (int64_t)C * NB + tid);   // y_C (published before the diagonal flag)
+            __syncthreads();
+            double* part = sA[0];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double s = 0.0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s = fma(L[i][j], s_vec[tn + j], s);
+                part[(tn >> 2) * NB + tm + i] = s;
+            }
+            __syncthreads();
+            if (tid < NB) atomicAdd(a.rhs + (int64_t)R * NB + tid, -reduce16(part, tid));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(a.ready + (int64_t)C * (g.BW + 1) + d, 1);
+        }
+    }
+}
+
+// log|P|, ||y||^2 and the info slot from the per-column statistics (deterministic order)
+__global__ void td_stats_kernel(TileGeom g, const double* __restrict__ colstat, const int* __restrict__ ready,
+                                double* __restrict__ scal) {
+    __shared__ double s0[256], s1[256];
+    double a0 = 0.0, a1 = 0.0;
+    for (int c = threadIdx.x; c < g.nb; c += blockDim.x) { a0 += colstat[2 * c]; a1 += colstat[2 * c + 1]; }
+    s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scal[0] = s0[0];
+        scal[1] = s1[0];
+        const int aborted = ready[g.n_tiles()], bad = ready[g.n_tiles() + 1];
+        scal[2] = aborted ? -1.0 : (bad != kNoBadPivot ? (double)bad : 0.0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// selected inverse
+// ------------------------------------------------------------------------------------------------------------------
+// Pre-pass, one CTA per tile, fully parallel: off-diagonal tiles become Y^T (Y = L(R,C) L(C,C)^-1, stored transposed
+// so that it is a plain operand later), diagonal tiles seed Sigma(C,C) = L(C,C)^-T L(C,C)^-1.
+__global__ void __launch_bounds__(kTdThreads) td_ypass_kernel(TileGeom g, double* __restrict__ tiles,
+                                                              const double* __restrict__ linv,
+                                                              double* __restrict__ sig_lower) {
+    constexpr int LDP = NB + 1;
+    extern __shared__ __align__(16) unsigned char yp_smem[];
+    double* sLT = reinterpret_cast<double*>(yp_smem);        // Linv transposed, padded: Linv[k][c] at [k*65 + c]
+    double* sL = sLT + NB * LDP;                             // L tile, column-major
+    const int C = blockIdx.x / (g.BW + 1), d = blockIdx.x % (g.BW + 1), R = C + d;
+    if (R >= g.nb) return;
+    const int tid = threadIdx.x, tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    const double* Li = linv + (int64_t)C * TILE;
+    for (int e = tid; e < TILE; e += kTdThreads) sLT[(e % NB) * LDP + e / NB] = Li[e];     // Li[e] = Linv[r=e%64][c=e/64]
+    double* T = tiles + g.tile(C, d);
+    if (d != 0)
+        for (int e = tid; e < TILE; e += kTdThreads) sL[e] = T[e];
+    __syncthreads();
+    double acc[4][4] = {};
+    if (d == 0) {
+        // S0[m][n] = sum_k Linv[k][m] Linv[k][n]
+        tile_mma<LDP, LDP, false>(acc, sLT, sLT, tm, tn);
+        regs_to_tile(acc, sig_lower + g.tile(C, 0), tm, tn);
+    } else {
+        // Y[m][n] = sum_k L[m][k] Linv[k][n]
+        tile_mma<NB, LDP, false>(acc, sL, sLT, tm, tn);
+        regs_to_tile_t(acc, T, tm, tn);              // in place: every read of T happened before the barrier above
+    }
+}
+
+struct SelArgs {
+    TileGeom g;
+    const double* tiles;    // Y^T tiles (off-diagonal) from the pre-pass
+    const double* linv;
+    double* sig_lower;      // Sigma(C+d, C) tiles
+    double* sig_upper;      // Sigma(C, C+d) tiles (transposes), d >= 1
+    double* x;              // in: y = L^-1 b, out: x = P^-1 b
+    double* xacc;           // [nb*NB] zeroed: -sum_K Y(K,C)^T x_K
+    int* sready;            // [n_tiles] tile flags, [nb] column counters, abort
+};
+
+__global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ double s_vec[NB];
+    const TileGeom g = a.g;
+    const int tid = threadIdx.x;
+    const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    int* cnt = a.sready + g.n_tiles();
+    int* abort_flag = cnt + g.nb;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    fence_proxy_async();
+    __syncthreads();
+    Phases ph;
+    const int n_tasks = g.n_tiles();
+
+    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        // order: block columns descending; inside a column the off-diagonal tiles first (far to near), the diagonal last
+        const int C = g.nb - 1 - t / (g.BW + 1);
+        const int d = g.BW - t % (g.BW + 1);
+        const int R = C + d;
+        if (R >= g.nb) continue;
+        const int Kmax = min(g.nb - 1, C + g.BW);
+
+        if (d != 0) {
+            const int nK = Kmax - C;
+            auto issue = [&](int K, int s) {         // A = Sigma(R, K), B = Y(K, C)^T
+                const double* src;
+                const int* flag;
+                if (K <= R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
+                else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
+                wait_flag(flag, 1, abort_flag);
+                fence_proxy_async();
+                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+                tma_load_tile(sA[s], src, &full[s]);
+                tma_load_tile(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
+            };
+            double acc[4][4] = {};
+            if (tid == 0) issue(Kmax, 0);
+            for (int q = 0; q < nK; ++q) {
+                const int s = q & 1;
+                if (q + 1 < nK && tid == 0) issue(Kmax - q - 1, s ^ 1);
+                mbar_wait(&full[s], ph.get(s));
+                ph.flip(s);
+                tile_mma<NB, NB, true>(acc, sA[s], sB[s], tm, tn);         // acc = -sum_K Sigma(R,K) Y(K,C)
+                __syncthreads();
+            }
+            // Sigma(R, C) = acc: publish both orientations
+            regs_to_tile(acc, a.sig_lower + g.tile(C, d), tm, tn);
+            regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
+            __threadfence();
+            // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
+            if (tid == 0) {
+                mbar_expect_tx(&full[0], TILE_BYTES);
+                tma_load_tile(sB[0], a.tiles + g.tile(C, d), &full[0]);
+            }
+            regs_to_tile_t(acc, sA[0], tm, tn);      // T[m][a] at [m*64 + a]  ==  A'(a, k=m) at [k*64 + a]
+            if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);      // x_R: final (diagonal task R has completed)
+            __syncthreads();
+            if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1);
+            mbar_wait(&full[0], ph.get(0));
+            ph.flip(0);
+            double D[4][4] = {};
+            tile_mma<NB, NB, false>(D, sA[0], sB[0], tm, tn);       // D[a][b] = sum_m T[m][a] Y[m][b]
+            double* Sd = a.sig_lower + g.tile(C, 0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) atomicAdd(Sd + (tn + j) * NB + tm + i, -D[i][j]);
+            // xacc_C[b] -= sum_m Y[m][b] x_R[m];  Y[m][b] at sB[0][m*64 + b]
+            if (tid < NB) {
+                double s = 0.0;
+#pragma unroll 8
+                for (int m = 0; m < NB; ++m) s = fma(sB[0][m * NB + tid], s_vec[m], s);
+                atomicAdd(a.xacc + (int64_t)C * NB + tid, -s);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(cnt + C, 1);
+        } else {
+            // diagonal task: Sigma(C,C) is complete once every off-diagonal tile of the column has contributed
+            if (tid == 0) wait_flag(cnt + C, Kmax - C, abort_flag);
+            __syncthreads();
+            // x_C = L(C,C)^-T y_C + xacc_C
+            double V[4][4];
+            regs_from_tile(V, a.linv + (int64_t)C * TILE, tm, tn);
+            double* part = sA[0];
+            if (tid < NB) s_vec[tid] = a.x[(int64_t)C * NB + tid];
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) s = fma(V[i][j], s_vec[tm + i], s);
+                part[(tm >> 2) * NB + tn + j] = s;
+            }
+            __syncthreads();
+            if (tid < NB) {
+                const double xa = __ldcg(a.xacc + (int64_t)C * NB + tid);
+                a.x[(int64_t)C * NB + tid] = reduce16(part, tid) + xa;
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1), 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// stencil extraction and the scalar contractions needed by the gradients
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) td_extract_stencil_kernel(TileGeom g, const double* __restrict__ sig_lower,
+                                                                 const int* __restrict__ abort_flag,
+                                                                 double* __restrict__ out) {
+    const int NS = 2 * g.K + 1, n_e = (g.K + 1) * NS;
+    const int64_t total = (int64_t)g.M * n_e;
+    const bool aborted = *abort_flag != 0;       // the persistent kernel gave up waiting: poison the result
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t / g.M);
+        const int64_t j = t % g.M;
+        const int d1 = e / NS, d2 = e % NS - g.K;
+        const int j1 = (int)(j / g.m2), j2 = (int)(j % g.m2);
+        const int i1 = j1 + d1, i2 = j2 + d2;
+        double v = 0.0;
+        if (!(d1 == 0 && d2 < 0) && i1 < g.m1 && i2 >= 0 && i2 < g.m2) {
+            const int64_t i = j + (int64_t)d1 * g.m2 + d2;
+            const int Cb = (int)(j / NB), c = (int)(j % NB), Rb = (int)(i / NB), r = (int)(i % NB);
+            v = __ldcg(sig_lower + g.tile(Cb, Rb - Cb) + c * NB + r);
+        }
+        out[t] = aborted ? nan("") : v;
+    }
+}
+
+// For the stencil operators  Op in { G,  dK1 (x) K2,  K1 (x) dK2,  K1 (x) K2 }  and a symmetric stencil field S:
+//   out[o]     = sum_{i,j} S[i,j] Op[i,j]   (full symmetric sum = diagonal once + off-diagonals twice)
+//   out[4 + o] = x^T Op x
+// plus the Kronecker trace terms  out[8..10] = sum G[(i),(j)] T1[i1,j1] T2[i2,j2] for (T1,T2) in
+//   (S1,S2), (dS1,S2), (S1,dS2)   (reference gpr.py:307 trace(cholesky_solve(L_Kuu, KufKfu)) and its derivatives).
+struct StencilTerms {
+    const double *SigP, *Gs, *x;
+    const double *K1, *dK1, *K2, *dK2;        // lower bands (K+1) x m
+    const double *S1, *dS1, *S2, *dS2;        // lower bands of K1^-1, d(K1^-1), K2^-1, d(K2^-1)
+};
+
+__device__ __forceinline__ double band_sym(const double* B, int m, int i, int j) {
+    const int d = i - j;
+    return d >= 0 ? B[(int64_t)d * m + j] : B[(int64_t)(-d) * m + i];
+}
+
+__global__ void __launch_bounds__(256) td_terms_kernel(int m1, int m2, int K, StencilTerms a, double* __restrict__ out) {
+    const int NS = 2 * K + 1, n_e = (K + 1) * NS;
+    const int64_t M = (int64_t)m1 * m2;
+    const int64_t total = M * n_e;
+    double acc[11];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) acc[i] = 0.0;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int e = (int)(t / M);
+        const int64_t j = t % M;
+        const int d1 = e / NS, d2 = e % NS - K;
+        if (d1 == 0 && d2 < 0) continue;
+        const int j1 = (int)(j / m2), j2 = (int)(j % m2);
+        const int i1 = j1 + d1, i2 = j2 + d2;
+        if (i1 >= m1 || i2 < 0 || i2 >= m2) continue;
+        const int64_t i = (int64_t)i1 * m2 + i2;
+        const double wgt = (d1 == 0 && d2 == 0) ? 1.0 : 2.0;
+        const double s = a.SigP[t], gv = a.Gs[t];
+        const double k1 = a.K1[(int64_t)d1 * m1 + j1], dk1 = a.dK1[(int64_t)d1 * m1 + j1];
+        const double k2 = band_sym(a.K2, m2, i2, j2), dk2 = band_sym(a.dK2, m2, i2, j2);
+        const double xx = wgt * a.x[i] * a.x[j], ws = wgt * s;
+        const double op[4] = {gv, dk1 * k2, k1 * dk2, k1 * k2};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) { acc[o] = fma(ws, op[o], acc[o]); acc[4 + o] = fma(xx, op[o], acc[4 + o]); }
+        const double s1 = a.S1[(int64_t)d1 * m1 + j1], ds1 = a.dS1[(int64_t)d1 * m1 + j1];
+        const double s2 = band_sym(a.S2, m2, i2, j2), ds2 = band_sym(a.dS2, m2, i2, j2);
+        const double wg = wgt * gv;
+        acc[8] = fma(wg, s1 * s2, acc[8]);
+        acc[9] = fma(wg, ds1 * s2, acc[9]);
+        acc[10] = fma(wg, s1 * ds2, acc[10]);
+    }
+    __shared__ double s_red[11][8];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) {
+        double v = acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) s_red[i][threadIdx.x >> 5] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 11) {
+        double v = 0.0;
+        for (int wv = 0; wv < 8; ++wv) v += s_red[threadIdx.x][wv];
+        atomicAdd(out + threadIdx.x, v);
+    }
+}
+
+// persistent grid: one CTA per SM (as many as can be co-resident), never more than there are tasks
+template <class Kernel>
+static int persistent_grid(Kernel kernel, size_t smem, int n_tasks, int* grid) {
+    int dev = 0, sms = 0, per_sm = 0;
+    ASVGP_CUDA_OK(cudaGetDevice(&dev));
+    ASVGP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTdThreads, smem));
+    if (per_sm < 1) {
+        set_last_error("tile-DAG kernel does not fit on an SM (%zu bytes of shared memory)", smem);
+        return kCudaError;
+    }
+    *grid = std::max(1, std::min(sms, n_tasks));
+    return kOk;
+}
+
+constexpr size_t kTdSmem = 4 * (size_t)TILE_BYTES;           // two stages of (A, B) tiles
+
+}  // namespace asvgp
+
+using namespace asvgp;
+
+extern "C" int64_t asvgp_kron_band_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return factor_layout(make_tile_geom(m1, m2, order)).total;
+}
+extern "C" int64_t asvgp_kron_sig_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return sel_layout(make_tile_geom(m1, m2, order)).sig_total;
+}
+extern "C" int64_t asvgp_kron_work_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return sel_layout(make_tile_geom(m1, m2, order)).work_total;
+}
+extern "C" int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return (int64_t)make_tile_geom(m1, m2, order).nb * NB;
+}
+
+// Assembles P into `band` (asvgp_kron_band_doubles doubles) and factorises it in place.
+// rhs_io[asvgp_kron_rhs_doubles]: in = Kuf_y (zero padded), out = y = L^-1 Kuf_y.  scal[3] = log|P|, ||y||^2, info.
+extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
+                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream) {
+    ASVGP_REQUIRE(m1 > 0 && m2 > 0 && order >= 1 && order <= kMaxOrder, "kron_factor: m=%d,%d order=%d", m1, m2, order);
+    ASVGP_REQUIRE(sigma2 > 0.0, "kron_factor: sigma2=%g", sigma2);
+    const TileGeom g = make_tile_geom(m1, m2, order);
+    const FactorLayout lay = factor_layout(g);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* flags = reinterpret_cast<int*>(band + lay.flags);
+    ASVGP_CUDA_OK(cudaMemsetAsync(band, 0, (size_t)lay.linv * sizeof(double), st));                       // tiles
+    ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_flag_ints * sizeof(int), st));
+    ASVGP_CUDA_OK(cudaMemsetAsync(flags + g.n_tiles() + 1, 0x7f, sizeof(int), st));                       // first bad pivot = "none"
+    const int64_t total = (int64_t)g.nb * NB * (order + 1) * (2 * order + 1);
+    td_assemble_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(g, K1, K2, Gs, 1.0 / sigma2, band);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    FactorArgs a{g, band, band + lay.linv, rhs_io, band + lay.colstat, flags, scal};
+    int grid = 0;
+    if (int rc = persistent_grid(td_factor_kernel, kTdSmem, g.n_tiles(), &grid)) return rc;
+    void* params[] = {&a};
+    ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(td_factor_kernel), dim3(grid), dim3(kTdThreads),
+                                              params, kTdSmem, st));
+    td_stats_kernel<<<1, 256, 0, st>>>(g, band + lay.colstat, flags, scal);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+// From the factor (overwritten: its off-diagonal tiles become Y^T): sigma_stencil[(order+1)(2 order+1) x M] = entries of
+// P^-1 on the stencil, x_io: in y = L^-1 b, out x = P^-1 b.  sig_band: asvgp_kron_sig_doubles doubles of scratch;
+// work: asvgp_kron_work_doubles doubles.  info[1] (may be NULL): 0 ok, -1 if the kernel gave up waiting.
+extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+                                 double* sigma_stencil, double* work, void* stream) {
+    ASVGP_REQUIRE(m1 > 0 && m2 > 0 && order >= 1 && order <= kMaxOrder, "kron_selinv: m=%d,%d order=%d", m1, m2, order);
+    const TileGeom g = make_tile_geom(m1, m2, order);
+    const FactorLayout fl = factor_layout(g);
+    const SelLayout sl = sel_layout(g);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* flags = reinterpret_cast<int*>(work + sl.flags);
+    ASVGP_CUDA_OK(cudaMemsetAsync(work, 0, (size_t)sl.work_total * sizeof(double), st));                  // xacc + flags
+    const size_t yp_smem = (size_t)(NB * (NB + 1) + TILE) * sizeof(double);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(td_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
+    td_ypass_kernel<<<g.n_tiles(), kTdThreads, yp_smem, st>>>(g, band, band + fl.linv, sig_band + sl.sig_lower);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    SelArgs a{g, band, band + fl.linv, sig_band + sl.sig_lower, sig_band + sl.sig_upper, x_io, work + sl.xacc, flags};
+    int grid = 0;
+    if (int rc = persistent_grid(td_selinv_kernel, kTdSmem, g.n_tiles(), &grid)) return rc;
+    void* params[] = {&a};
+    ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(td_selinv_kernel), dim3(grid), dim3(kTdThreads),
+                                              params, kTdSmem, st));
+    const int64_t total = (int64_t)g.M * (order + 1) * (2 * order + 1);
+    td_extract_stencil_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+        g, sig_band + sl.sig_lower, flags + g.n_tiles() + g.nb, sigma_stencil);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+// out[11] (device, zeroed here): see td_terms_kernel.
+extern "C" int asvgp_kron_terms(const double* SigP, const double* Gs, const double* x, const double* K1,
+                                const double* dK1, const double* K2, const double* dK2, const double* S1,
+                                const double* dS1, const double* S2, const double* dS2, int m1, int m2, int order,
+                                double* out, void* stream) {
+    ASVGP_REQUIRE(m1 > 0 && m2 > 0 && order >= 1 && order <= kMaxOrder, "kron_terms: m=%d,%d order=%d", m1, m2, order);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, 11 * sizeof(double), st));
+    StencilTerms a{SigP, Gs, x, K1, dK1, K2, dK2, S1, dS1, S2, dS2};
+    const int64_t total = (int64_t)m1 * m2 * (order + 1) * (2 * order + 1);
+    td_terms_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 4), 256, 0, st>>>(m1, m2, order, a, out);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}

@@ -387,15 +387,15 @@ class KronWorkspace:
         self.M = m1 * m2
         nb = lib.asvgp_kron_band_doubles(m1, m2, order)
         nw = lib.asvgp_kron_work_doubles(m1, m2, order)
-        if nb < 0 or nw < 0:
+        ns = lib.asvgp_kron_sig_doubles(m1, m2, order)
+        nr = lib.asvgp_kron_rhs_doubles(m1, m2, order)
+        if min(nb, nw, ns, nr) < 0:
             raise _lib.AsvgpNativeError("kron workspace query rejected m=%d,%d order=%d" % (m1, m2, order))
         self.band = torch.empty(nb, dtype=F64, device=dev)
         self.sig_band = None                     # allocated on first selected inverse
-        self.nb = nb
+        self.n_sig = ns
         self.work = torch.empty(nw, dtype=F64, device=dev)
-        self.w = order * m2 + order
-        self.Mpad = -(-self.M // 64) * 64
-        self.rhs = torch.zeros(self.Mpad + self.w + 64, dtype=F64, device=dev)
+        self.rhs = torch.zeros(nr, dtype=F64, device=dev)
         self.scal = torch.zeros(3, dtype=F64, device=dev)
         self.sigma_stencil = torch.zeros((stencil_rows(order), self.M), dtype=F64, device=dev)
         self.terms = torch.zeros(11, dtype=F64, device=dev)
@@ -427,7 +427,7 @@ def kron_selinv(bases, ws):
     """Selected inverse of P on the stencil pattern (ws.sigma_stencil) and x = P^-1 Kuf_y (ws.rhs[:M])."""
     k, m1, m2 = _check_bases_2d(bases)
     if ws.sig_band is None:
-        ws.sig_band = torch.empty(ws.nb, dtype=F64, device=ws.band.device)
+        ws.sig_band = torch.empty(ws.n_sig, dtype=F64, device=ws.band.device)
     _lib.call("asvgp_kron_selinv", _p(ws.band), m1, m2, k, _p(ws.sig_band), _p(ws.rhs), _p(ws.sigma_stencil),
               _p(ws.work), _stream())
     return ws.sigma_stencil, ws.rhs[: ws.M]

@@ -126,18 +126,23 @@ ASVGP_API int asvgp_expand_moments_2d(const double* cellmom, const double* Cprod
 
 /* ---- a13 + a14: block-band factorisation of P = K1 (x) K2 + G / sigma2 -------------------------------------------------------
  * Replaces utils.bands_to_kron_cholesky (utils.py:45-51), tf.linalg.cholesky(P), its log-det and
- * triangular_solve(L_P, Kuf_y) (gpr.py:287-295) with a banded factorisation of scalar bandwidth order*(m2+1).
- * band: asvgp_kron_band_doubles doubles (receives the factor); rhs_io[Mpad + ld]: in Kuf_y zero padded, out L^-1 Kuf_y;
- * scal[3] = { log|P|, ||L^-1 Kuf_y||^2, info }. */
+ * triangular_solve(L_P, Kuf_y) (gpr.py:287-295) with a tiled band factorisation of scalar bandwidth order*(m2+1)
+ * (one persistent kernel).  Buffer sizes (doubles) come from the four queries below.
+ * band: receives the factor (opaque tile layout); rhs_io: in Kuf_y zero padded, out L^-1 Kuf_y;
+ * scal[3] = { log|P|, ||L^-1 Kuf_y||^2, info } with info = 0 ok, j+1 first non-positive pivot, -1 internal time-out. */
 ASVGP_API int64_t asvgp_kron_band_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kron_sig_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_work_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order);
 ASVGP_API int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream);
 
-/* Selected inverse on the stencil pattern (blocked Takahashi recursion) and back-substitution: sigma_stencil = entries
- * of P^-1 in stencil layout, x_io: in L^-1 b, out P^-1 b.  This is what the reference's dense cholesky_solve /
- * TF reverse mode extract from P^-1 (gpr.py:293-307, 319-326). */
-ASVGP_API int asvgp_kron_selinv(const double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+/* Selected inverse on the stencil pattern (blocked Takahashi recursion, one persistent kernel) and back-substitution:
+ * sigma_stencil = entries of P^-1 in stencil layout, x_io: in L^-1 b, out P^-1 b.  This is what the reference's dense
+ * cholesky_solve / TF reverse mode extract from P^-1 (gpr.py:293-307, 319-326).  `band` is CONSUMED (its off-diagonal
+ * tiles are overwritten); sig_band: asvgp_kron_sig_doubles of scratch; work: asvgp_kron_work_doubles.  An internal
+ * time-out poisons sigma_stencil with NaN. */
+ASVGP_API int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
                                 double* sigma_stencil, double* work, void* stream);
 
 /* Scalar contractions for the ELBO gradient and the Kronecker trace term; out[11] (device):
