@@ -38,6 +38,7 @@ VALUE_FUNCTIONS = {
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kron_colstat_offset": (_c_i64, [_c_int, _c_int, _c_int]),
 }
 
 _lib = None

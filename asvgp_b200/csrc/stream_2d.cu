@@ -74,7 +74,8 @@ template <int K, int P0, int P1, bool WITH_Y>
 __global__ void __launch_bounds__(256, 1)
 accum_2d_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
                 const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
-                double* __restrict__ cellmom, double* __restrict__ scal) {
+                double* __restrict__ cellmom, double* __restrict__ scal, const int* __restrict__ select, int want) {
+    if (select != nullptr && *select != want) return;
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY;
     constexpr int NP = P1 - P0;
@@ -183,6 +184,372 @@ accum_2d_kernel(const double* __restrict__ X, const double* __restrict__ y, int6
             atomicAdd(scal, tot);
             if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// "run" path for gridded input (raster order: consecutive points share x1 bit-for-bit, as a flattened lon/lat mesh
+// does).  For a run of points with the same x1 inside one cell the dim-1 factors are constant, so
+//     mom[p][q] += beta_p(t1) * sum_n beta_q(t2_n),      ymom[p][q] += gamma_p(t1) * sum_n y_n gamma_q(t2_n):
+// per point only the (2k+1) + (k+1) dim-2 sums are updated (~35 fp64 instructions for k = 3 instead of ~120), and
+// the outer product with the dim-1 factors happens once per run, straight into the L2-resident moment table.
+// A thread keeps ~4k+4 sums instead of (2k+1)^2 + (k+1)^2, which triples the occupancy.  Any input is still
+// handled correctly (a run may have length 1); asvgp_accum_2d picks this kernel when a probe finds the input
+// gridded.
+// ------------------------------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256, 2)
+accum_2d_run_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
+                    const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
+                    double* __restrict__ cellmom, double* __restrict__ scal, const int* __restrict__ select,
+                    int want) {
+    if (select != nullptr && *select != want) return;
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY;
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int nc2 = nk2 - 1;
+
+    const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (n + n_threads - 1) / n_threads;
+    per = (per + 3) & ~(int64_t)3;                                  // groups of four points, y read as two double2
+    const int64_t begin = tid * per < n ? tid * per : n;
+    const int64_t end = begin + per < n ? begin + per : n;
+
+    double s[NB], sy[NY], b1[NB], g1[NY];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) { s[i] = 0.0; b1[i] = 0.0; }
+#pragma unroll
+    for (int i = 0; i < NY; ++i) { sy[i] = 0.0; g1[i] = 0.0; }
+    double yy = 0.0;
+    long long cur_x1 = 0;              // bit pattern of the run's x1
+    bool have_x1 = false, dirty = false;
+    Interval i1, i2;
+    i1.reset(); i2.reset();
+
+    auto flush = [&]() {
+        if (dirty) {
+            double* dst = cellmom + ((int64_t)i1.idx * nc2 + i2.idx) * Mo::kAll;
+#pragma unroll
+            for (int p = 0; p < NB; ++p)
+#pragma unroll
+                for (int q = 0; q < NB; ++q) atomicAdd(dst + p * NB + q, b1[p] * s[q]);
+#pragma unroll
+            for (int p = 0; p < NY; ++p)
+#pragma unroll
+                for (int q = 0; q < NY; ++q) atomicAdd(dst + Mo::kGram + p * NY + q, g1[p] * sy[q]);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) s[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NY; ++q) sy[q] = 0.0;
+            dirty = false;
+        }
+    };
+    auto add = [&](double x1, double x2, double yv) {
+        const long long bits = __double_as_longlong(x1);
+        const bool same_x1 = have_x1 && bits == cur_x1;
+        if (!(same_x1 && i2.inside(x2))) {
+            flush();
+            if (!same_x1) {
+                if (!i1.inside(x1)) i1.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+                const double t1 = (x1 - i1.u) * mesh1.inv_delta;
+                double tp[2 * K + 1], up[2 * K + 1];
+                powers<2 * K>(t1, tp, up);
+#pragma unroll
+                for (int p = 0; p < NB; ++p) b1[p] = tp[p] * up[2 * K - p];
+#pragma unroll
+                for (int p = 0; p < NY; ++p) g1[p] = tp[p] * up[K - p];
+                cur_x1 = bits;
+                have_x1 = true;
+            }
+            if (!i2.inside(x2)) i2.set(mesh2, locate_interval(mesh2, x2, LdgLoader2()));
+        }
+        const double t2 = (x2 - i2.u) * mesh2.inv_delta;
+        double tp[2 * K + 1], up[2 * K + 1];
+        powers<2 * K>(t2, tp, up);
+#pragma unroll
+        for (int q = 0; q < NB; ++q) s[q] += tp[q] * up[2 * K - q];
+#pragma unroll
+        for (int q = 0; q < NY; ++q) sy[q] = fma(yv, tp[q] * up[K - q], sy[q]);
+        yy = fma(yv, yv, yy);
+        dirty = true;
+    };
+
+    // X is row-major [n, 2]: one 16-byte load per point; begin is a multiple of 4 so y pairs are 16-byte aligned.
+    // The next group's loads are issued before the current group is processed.
+    const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
+    const double2* __restrict__ Y2 = reinterpret_cast<const double2*>(y);
+    const int64_t n_full = begin + ((end - begin) & ~(int64_t)3);
+    double2 pa, pb, pc, pd, ya, yb;
+    int64_t i = begin;
+    if (i < n_full) {
+        pa = __ldg(X2 + i); pb = __ldg(X2 + i + 1); pc = __ldg(X2 + i + 2); pd = __ldg(X2 + i + 3);
+        ya = __ldg(Y2 + (i >> 1)); yb = __ldg(Y2 + (i >> 1) + 1);
+    }
+    for (; i < n_full; i += 4) {
+        const double2 ca = pa, cb = pb, cc = pc, cd = pd, cya = ya, cyb = yb;
+        if (i + 4 < n_full) {
+            pa = __ldg(X2 + i + 4); pb = __ldg(X2 + i + 5); pc = __ldg(X2 + i + 6); pd = __ldg(X2 + i + 7);
+            ya = __ldg(Y2 + (i >> 1) + 2); yb = __ldg(Y2 + (i >> 1) + 3);
+        }
+        add(ca.x, ca.y, cya.x);
+        add(cb.x, cb.y, cya.y);
+        add(cc.x, cc.y, cyb.x);
+        add(cd.x, cd.y, cyb.y);
+    }
+    for (; i < end; ++i) {
+        const double2 p = __ldg(X2 + i);
+        add(p.x, p.y, __ldg(y + i));
+    }
+    flush();
+
+    __shared__ double s_yy[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    if ((threadIdx.x & 31) == 0) s_yy[threadIdx.x >> 5] = yy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_yy[w];
+        atomicAdd(scal, tot);
+        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// "raster" path: the input is a flattened n1 x n2 mesh (x1 slow; every n2 consecutive points share x1 bit for bit).
+// The index space is tiled as (32 rows) x (column segment); the lanes of a warp walk 32 different rows in lock-step,
+// so on a separable mesh all lanes cross a knot of dimension 2 at the same step and the flush is convergent and
+// cooperative: the 32 per-lane dim-2 sums go through shared memory, are contracted with the per-lane dim-1 factors and
+// leave as THREE fp64 REDs per lane per (cell, 32 rows) — 32x fewer atomics than one flush per lane.  Each lane streams
+// its own row with 256-bit loads (LDG.E.256), the next group of four points in flight while the current one is
+// processed.  Correctness never depends on the mesh being regular: every lane handles exactly the index range of its
+// row tile, flushing whenever ITS x1 or ITS cell changes (a warp vote makes the others flush early with it).
+// ------------------------------------------------------------------------------------------------------------------
+struct ProbeResult {      // lives in the trailing slot of the moment table (two ints)
+    int select;           // 0 general, 1 x1-run, 2 raster (per-point loads), 3 raster (256-bit loads)
+    int n2;               // row length of the raster
+};
+
+__device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
+}
+
+template <int K, bool VEC256>
+__global__ void __launch_bounds__(256, 2)
+accum_2d_raster_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
+                       const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
+                       double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe) {
+    if (probe->select != (VEC256 ? 3 : 2)) return;
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;      // sums per lane
+    constexpr int kWarps = 8;
+    extern __shared__ __align__(16) unsigned char raster_smem[];
+    // per warp: [32][NS] dim-2 sums of the run being flushed, then [32][NS] dim-1 factors beta_p(t1), gamma_p(t1)
+    double (*s_S)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem);
+    double (*s_B)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem + sizeof(double) * kWarps * 32 * NS);
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int nc2 = nk2 - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n2 = probe->n2, n1 = n / n2;
+    double (*S)[NS] = s_S[warp];
+    double (*Bf)[NS] = s_B[warp];
+
+    // tasks: 32-row groups x column segments (multiples of 4 columns), dealt round-robin to the warps of the grid
+    const int64_t n_groups = (n1 + 31) / 32;
+    const int64_t total_warps = (int64_t)gridDim.x * kWarps;
+    int64_t n_seg = (4 * total_warps + n_groups - 1) / n_groups;           // ~4 tasks per warp
+    int64_t seg_len = ((n2 + n_seg - 1) / n_seg + 3) & ~(int64_t)3;
+    if (seg_len < 64) seg_len = 64;
+    n_seg = (n2 + seg_len - 1) / seg_len;
+    const int64_t n_tasks = n_groups * n_seg;
+
+    double s[NB], sy[NY];
+    double yy = 0.0;
+
+    for (int64_t task = (int64_t)blockIdx.x * kWarps + warp; task < n_tasks; task += total_warps) {
+        const int64_t g = task / n_seg, sg = task % n_seg;
+        const int64_t row = g * 32 + lane;
+        const bool active = row < n1;
+        const int64_t c_begin = sg * seg_len, c_end = c_begin + seg_len < n2 ? c_begin + seg_len : n2;
+        const double* xr = X + 2 * (row * n2);
+        const double* yr = y + row * n2;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) s[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) sy[i] = 0.0;
+        long long cur_x1 = 0;
+        bool have_x1 = false, dirty = false;
+        Interval i1, i2;
+        i1.reset(); i2.reset();
+
+        // warp-cooperative flush of every lane's current sums
+        auto flush_all = [&]() {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) S[lane][q] = s[q];
+#pragma unroll
+            for (int q = 0; q < NY; ++q) S[lane][NB + q] = sy[q];
+            const int cell = dirty ? i1.idx * nc2 + i2.idx : -1;
+            __syncwarp();
+            unsigned remaining = __ballot_sync(0xffffffffu, cell >= 0);
+            while (remaining) {
+                const int leader = __ffs(remaining) - 1;
+                const int cl = __shfl_sync(0xffffffffu, cell, leader);
+                const unsigned grp = __ballot_sync(0xffffffffu, cell == cl) & remaining;
+                double* dst = cellmom + (int64_t)cl * Mo::kAll;
+                for (int o = lane; o < Mo::kAll; o += 32) {
+                    const int pi = o < Mo::kGram ? o / NB : NB + (o - Mo::kGram) / NY;
+                    const int qi = o < Mo::kGram ? o % NB : NB + (o - Mo::kGram) % NY;
+                    double acc = 0.0;
+                    unsigned m = grp;
+                    while (m) {
+                        const int e = __ffs(m) - 1;
+                        m &= m - 1;
+                        acc = fma(Bf[e][pi], S[e][qi], acc);
+                    }
+                    atomicAdd(dst + o, acc);
+                }
+                remaining &= ~grp;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < NB; ++q) s[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NY; ++q) sy[q] = 0.0;
+            dirty = false;
+        };
+        auto add = [&](double x1, double x2, double yv, bool valid) {
+            const long long bits = __double_as_longlong(x1);
+            const bool same_x1 = have_x1 && bits == cur_x1;
+            const bool need = valid && !(same_x1 && i2.inside(x2));
+            if (__any_sync(0xffffffffu, need)) {
+                flush_all();
+                if (need) {
+                    if (!same_x1) {
+                        if (!i1.inside(x1)) i1.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+                        const double t1 = (x1 - i1.u) * mesh1.inv_delta;
+                        double tp[2 * K + 1], up[2 * K + 1];
+                        powers<2 * K>(t1, tp, up);
+#pragma unroll
+                        for (int p = 0; p < NB; ++p) Bf[lane][p] = tp[p] * up[2 * K - p];
+#pragma unroll
+                        for (int p = 0; p < NY; ++p) Bf[lane][NB + p] = tp[p] * up[K - p];
+                        cur_x1 = bits;
+                        have_x1 = true;
+                    }
+                    if (!i2.inside(x2)) i2.set(mesh2, locate_interval(mesh2, x2, LdgLoader2()));
+                }
+            }
+            if (valid) {
+                const double t2 = (x2 - i2.u) * mesh2.inv_delta;
+                double tp[2 * K + 1], up[2 * K + 1];
+                powers<2 * K>(t2, tp, up);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) s[q] += tp[q] * up[2 * K - q];
+#pragma unroll
+                for (int q = 0; q < NY; ++q) sy[q] = fma(yv, tp[q] * up[K - q], sy[q]);
+                yy = fma(yv, yv, yy);
+                dirty = true;
+            }
+        };
+
+        if (VEC256) {
+            // n2 % 4 == 0 and 32-byte aligned bases: four points = two 256-bit loads of X and one of y
+            double xa[4], xb[4], ya[4];
+            int64_t c = c_begin;
+            if (active && c < c_end) { ldg256(xr + 2 * c, xa); ldg256(xr + 2 * c + 4, xb); ldg256(yr + c, ya); }
+            for (; c < c_end; c += 4) {
+                double ca[4], cb[4], cy[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { ca[i] = xa[i]; cb[i] = xb[i]; cy[i] = ya[i]; }
+                if (active && c + 4 < c_end) { ldg256(xr + 2 * (c + 4), xa); ldg256(xr + 2 * (c + 4) + 4, xb); ldg256(yr + c + 4, ya); }
+                add(ca[0], ca[1], cy[0], active);
+                add(ca[2], ca[3], cy[1], active);
+                add(cb[0], cb[1], cy[2], active);
+                add(cb[2], cb[3], cy[3], active);
+            }
+        } else {
+            const double2* __restrict__ X2 = reinterpret_cast<const double2*>(xr);
+            double2 pn = make_double2(0.0, 0.0);
+            double yn = 0.0;
+            if (active && c_begin < c_end) { pn = __ldg(X2 + c_begin); yn = __ldg(yr + c_begin); }
+            for (int64_t c = c_begin; c < c_end; ++c) {
+                const double2 pc = pn;
+                const double yc = yn;
+                if (active && c + 1 < c_end) { pn = __ldg(X2 + c + 1); yn = __ldg(yr + c + 1); }
+                add(pc.x, pc.y, yc, active);
+            }
+        }
+        flush_all();
+    }
+
+    __shared__ double s_yy[kWarps];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    if (lane == 0) s_yy[warp] = yy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kWarps; ++w) tot += s_yy[w];
+        atomicAdd(scal, tot);
+        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+    }
+}
+
+// Probe (one CTA): classifies the input without a host round trip.
+//   raster  : n2 = position of the first change of x1 (searched in the first 2^20 points) divides n, and at 1024 sampled
+//             rows the first and last point share x1 while the previous row's last point does not
+//   x1-run  : at least three quarters of 4096 sampled points share x1 with their successor
+//   general : everything else
+__global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                             int64_t n, ProbeResult* __restrict__ out) {
+    __shared__ int s_cnt[8];
+    __shared__ long long s_first;
+    const int tid = threadIdx.x;
+    auto x1bits = [&](int64_t i) { return __double_as_longlong(__ldg(X + 2 * i)); };
+    // fraction of points equal to their successor
+    const int n_probe = (int)(n - 1 < 4096 ? n - 1 : 4096);
+    int hits = 0;
+    for (int j = tid; j < n_probe; j += blockDim.x) {
+        const int64_t i = (int64_t)((double)j * (double)(n - 1) / (double)n_probe);
+        hits += x1bits(i) == x1bits(i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    if ((tid & 31) == 0) s_cnt[tid >> 5] = hits;
+    if (tid == 0) s_first = -1;
+    __syncthreads();
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += s_cnt[w];
+    const bool runs = n_probe > 0 && 4 * tot >= 3 * n_probe;
+    // first change of x1
+    const long long b0 = x1bits(0);
+    const int64_t limit = n < (1 << 20) ? n : (1 << 20);
+    for (int64_t base = 1; base < limit; base += blockDim.x) {
+        const int64_t i = base + tid;
+        const bool changed = i < limit && x1bits(i) != b0;
+        if (changed) atomicMin(reinterpret_cast<unsigned long long*>(&s_first), (unsigned long long)i);
+        if (__syncthreads_or(changed)) break;
+    }
+    __syncthreads();
+    const long long n2 = s_first;             // -1 (as unsigned: huge) when no change was found
+    bool raster = runs && n2 > 1 && n % n2 == 0;
+    __syncthreads();
+    if (raster) {
+        const int64_t n1 = n / n2;
+        int bad = 0;
+        for (int j = tid; j < 1024; j += blockDim.x) {
+            const int64_t r = (int64_t)((double)j * (double)(n1 - 1) / 1023.0 + 0.5);
+            const long long a = x1bits(r * n2);
+            bad |= a != x1bits(r * n2 + n2 - 1);
+            if (r > 0) bad |= a == x1bits(r * n2 - 1);
+        }
+        raster = !__syncthreads_or(bad);
+    }
+    if (tid == 0) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(y)) & 31u) == 0;
+        out->select = raster ? ((n2 % 4 == 0 && aligned) ? 3 : 2) : (runs ? 1 : 0);
+        out->n2 = raster ? (int)n2 : 0;
     }
 }
 
@@ -316,28 +683,28 @@ static int sm_count2() {
 
 template <int K, int P0, int P1, bool WITH_Y>
 static int launch_accum_part(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2,
-                             int nk2, double* cellmom, double* scal, cudaStream_t st) {
+                             int nk2, double* cellmom, double* scal, const int* select, cudaStream_t st) {
     const int64_t want = (n + 511) / 512;          // at least ~2 points per thread; at most one CTA per SM
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, sm_count2()));
-    accum_2d_kernel<K, P0, P1, WITH_Y><<<blocks, 256, 0, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal);
+    accum_2d_kernel<K, P0, P1, WITH_Y><<<blocks, 256, 0, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, select, 0);
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
 
 template <int K>
 static int launch_accum_2d(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2,
-                           int nk2, double* cellmom, double* scal, cudaStream_t st);
+                           int nk2, double* cellmom, double* scal, const int* select, cudaStream_t st);
 
 #define ASVGP_ACC2D(K_, ...)                                                                                          \
     template <>                                                                                                       \
     int launch_accum_2d<K_>(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2, \
-                            int nk2, double* cellmom, double* scal, cudaStream_t st) {                                \
+                            int nk2, double* cellmom, double* scal, const int* select, cudaStream_t st) {             \
         int rc = kOk;                                                                                                 \
         __VA_ARGS__                                                                                                   \
         return rc;                                                                                                    \
     }
 #define PART(K_, P0_, P1_, Y_) \
-    if (rc == kOk) rc = launch_accum_part<K_, P0_, P1_, Y_>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, st);
+    if (rc == kOk) rc = launch_accum_part<K_, P0_, P1_, Y_>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, select, st);
 // moment index ranges per launch: <= ~70 register-resident sums per thread
 ASVGP_ACC2D(1, PART(1, 0, 3, true))
 ASVGP_ACC2D(2, PART(2, 0, 5, true))
@@ -345,6 +712,17 @@ ASVGP_ACC2D(3, PART(3, 0, 7, true))
 ASVGP_ACC2D(4, PART(4, 0, 5, true) PART(4, 5, 9, false))
 ASVGP_ACC2D(5, PART(5, 0, 3, true) PART(5, 3, 8, false) PART(5, 8, 11, false))
 ASVGP_ACC2D(6, PART(6, 0, 2, true) PART(6, 2, 6, false) PART(6, 6, 10, false) PART(6, 10, 13, false))
+
+template <int K>
+static int launch_raster(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2, int nk2,
+                         double* cellmom, double* scal, const ProbeResult* probe, int blocks, size_t smem,
+                         cudaStream_t st) {
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    accum_2d_raster_kernel<K, true><<<blocks, 256, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_raster_kernel<K, false><<<blocks, 256, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    return kOk;
+}
 
 }  // namespace asvgp
 
@@ -366,7 +744,7 @@ using namespace asvgp;
 extern "C" int64_t asvgp_accum_2d_moment_doubles(int n_knots1, int n_knots2, int order) {
     if (order < 1 || order > kMaxOrder || n_knots1 < 2 || n_knots2 < 2) return -1;
     const int64_t per = (int64_t)(2 * order + 1) * (2 * order + 1) + (int64_t)(order + 1) * (order + 1);
-    return per * (n_knots1 - 1) * (n_knots2 - 1);
+    return per * (n_knots1 - 1) * (n_knots2 - 1) + 1;          // + 1: path-selection slot of asvgp_accum_2d
 }
 
 extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const double* mesh1, int n_knots1,
@@ -377,7 +755,24 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
                   "accum_2d: X and y must be 16-byte aligned");
     if (n == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, st)) return rc; });
+    // Path selection without a host round trip: a one-CTA probe classifies the input (raster / x1-runs / general) into
+    // the trailing slot of the moment table (asvgp_accum_2d_moment_doubles reserves it); every candidate kernel is
+    // launched and those that are not selected return at once.
+    ProbeResult* probe = reinterpret_cast<ProbeResult*>(cellmom + asvgp_accum_2d_moment_doubles(n_knots1, n_knots2, order) - 1);
+    const int* select = &probe->select;
+    accum_2d_probe_kernel<<<1, 256, 0, st>>>(X, y, n, probe);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    const int blocks2 = 2 * sm_count2();
+    const size_t raster_smem = sizeof(double) * 2 * 8 * 32 * (3 * (size_t)order + 2);       // NS = (2k+1) + (k+1)
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_raster<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, probe, blocks2, raster_smem, st)) return rc; });
+    ASVGP_CUDA_OK(cudaGetLastError());
+    {
+        const int64_t want = (n + 1023) / 1024;
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)blocks2));
+        ASVGP_DISPATCH_ORDER(order, (accum_2d_run_kernel<K><<<blocks, 256, 0, st>>>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, 1)));
+        ASVGP_CUDA_OK(cudaGetLastError());
+    }
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, st)) return rc; });
     return kOk;
 }
 

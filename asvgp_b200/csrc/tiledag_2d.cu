@@ -42,6 +42,7 @@ constexpr int TILE = NB * NB;                   // doubles per tile
 constexpr int TILE_BYTES = TILE * 8;
 constexpr int kTdThreads = 256;                 // 16 x 16 threads, 4 x 4 outputs each
 constexpr long long kSpinLimit = 1LL << 24;     // polls before a wait gives up and raises the abort flag (~ seconds)
+constexpr int kColStat = 8;
 constexpr int kNoBadPivot = 0x7f7f7f7f;         // what cudaMemset(0x7f) leaves in the "first bad pivot" slot
 
 struct TileGeom {
@@ -65,7 +66,9 @@ static TileGeom make_tile_geom(int m1, int m2, int K) {
 }
 
 // Layout of the factor buffer (`band` of the C ABI), in doubles:
-//   [ tiles n_tiles*TILE | Linv nb*TILE | colstat nb*2 | flags (ints) ]
+//   [ tiles n_tiles*TILE | Linv nb*TILE | colstat nb*kColStat | flags (ints) ]
+// colstat[C] = { 2 sum log L_cc, ||y_C||^2, then %globaltimer stamps (ns) of the diagonal task: begin, operands
+// landed, POTRF done, published; and of the first sub-diagonal task: inverse seen, tile published }
 struct FactorLayout {
     int64_t tiles, linv, colstat, flags, total;
     int64_t n_flag_ints;
@@ -75,7 +78,7 @@ static FactorLayout factor_layout(const TileGeom& g) {
     L.tiles = 0;
     L.linv = (int64_t)g.n_tiles() * TILE;
     L.colstat = L.linv + (int64_t)g.nb * TILE;
-    L.flags = L.colstat + (int64_t)g.nb * 2;
+    L.flags = L.colstat + (int64_t)g.nb * kColStat;
     L.n_flag_ints = (int64_t)g.n_tiles() + 8;                  // ready flags + abort
     L.total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
     return L;
@@ -128,6 +131,11 @@ __device__ __forceinline__ void tma_load_tile(double* dst_smem, const double* sr
 // generic-proxy writes (ours or, after an acquire, another CTA's) -> async-proxy (TMA) reads
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
+__device__ __forceinline__ double global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return (double)t;
+}
 __device__ __forceinline__ int ld_acquire(const int* p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -359,6 +367,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
         if (R >= g.nb) continue;
         double* my_tile = a.tiles + g.tile(C, d);
         double acc[4][4];
+        double* stat = a.colstat + (int64_t)C * kColStat;
+        if (tid == 0 && d == 0) stat[2] = global_ns();
         regs_from_tile(acc, my_tile, tm, tn);
         const int J0 = max(0, R - g.BW), nJ = C - J0;
 
@@ -387,7 +397,9 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             double* scol = sA[0];                    // [2][64]
             double* srow = sA[0] + 2 * NB;           // [2][64]
             double* part = sA[0] + 4 * NB;           // [16][64]
+            if (tid == 0) stat[3] = global_ns();
             potrf_regs(acc, V, tm, tn, scol, srow, &first_bad);
+            if (tid == 0) stat[4] = global_ns();
             // y_C = L^-1 b_C (all contributions to b_C have landed: every (C, J) tile is final)
             {
                 double bv[4];
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) st_release(a.ready + (int64_t)C * (g.BW + 1), 1);
+            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1), 1); stat[5] = global_ns(); }
             // off the critical path: this block column's share of log|P| and ||y||^2
             if (tm == tn) {
 #pragma unroll
@@ -436,8 +448,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             if (tid == 0) {
                 double L = 0.0, Q = 0.0;
                 for (int wv = 0; wv < kTdThreads / 32; ++wv) { L += s_ld[wv]; Q += s_q[wv]; }
-                a.colstat[2 * C] = 2.0 * L;
-                a.colstat[2 * C + 1] = Q;
+                stat[0] = 2.0 * L;
+                stat[1] = Q;
                 if (first_bad >= 0) atomicMin(a.ready + g.n_tiles() + 1, C * NB + first_bad + 1);
             }
             __syncthreads();
@@ -445,6 +457,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             // ---- off-diagonal tile: L(R,C) = A L(C,C)^-T, then b_R -= L(R,C) y_C ----------------------------------------
             if (tid == 0) {
                 wait_flag(a.ready + (int64_t)C * (g.BW + 1), 1, abort_flag);
+                if (d == 1) stat[6] = global_ns();
                 fence_proxy_async();
                 mbar_expect_tx(&full[0], TILE_BYTES);
                 tma_load_tile(sB[0], a.linv + (int64_t)C * TILE, &full[0]);
@@ -470,7 +483,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             if (tid < NB) atomicAdd(a.rhs + (int64_t)R * NB + tid, -reduce16(part, tid));
             __threadfence();
             __syncthreads();
-            if (tid == 0) st_release(a.ready + (int64_t)C * (g.BW + 1) + d, 1);
+            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) stat[7] = global_ns(); }
         }
     }
 }
@@ -480,7 +493,7 @@ __global__ void td_stats_kernel(TileGeom g, const double* __restrict__ colstat, 
                                 double* __restrict__ scal) {
     __shared__ double s0[256], s1[256];
     double a0 = 0.0, a1 = 0.0;
-    for (int c = threadIdx.x; c < g.nb; c += blockDim.x) { a0 += colstat[2 * c]; a1 += colstat[2 * c + 1]; }
+    for (int c = threadIdx.x; c < g.nb; c += blockDim.x) { a0 += colstat[kColStat * c]; a1 += colstat[kColStat * c + 1]; }
     s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -760,6 +773,12 @@ using namespace asvgp;
 extern "C" int64_t asvgp_kron_band_doubles(int m1, int m2, int order) {
     if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
     return factor_layout(make_tile_geom(m1, m2, order)).total;
+}
+// Diagnostics: offset (doubles) of the per-block-column statistics inside `band`; 8 doubles per block column, see
+// factor_layout.  n_block_columns = ceil(m1*m2 / 64).
+extern "C" int64_t asvgp_kron_colstat_offset(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return factor_layout(make_tile_geom(m1, m2, order)).colstat;
 }
 extern "C" int64_t asvgp_kron_sig_doubles(int m1, int m2, int order) {
     if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;

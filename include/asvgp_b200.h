@@ -108,7 +108,8 @@ ASVGP_API int asvgp_band_inverse_1d(const double* A, const double* dA, int M, in
  * S[e*M + j], e = d1*(2*order+1) + (d2+order), holding A[(j1+d1, j2+d2), (j1, j2)] for d1 in [0,order],
  * d2 in [-order,order], stored for d1 > 0 or (d1 == 0 and d2 >= 0); everything else is zero. */
 
-/* Doubles of the per-cell moment table used by asvgp_accum_2d ((2o+1)^2 + (o+1)^2 per cell). */
+/* Doubles of the per-cell moment table used by asvgp_accum_2d ((2o+1)^2 + (o+1)^2 per cell, plus one trailing slot the
+ * library uses to select between its gridded-input and general kernels without a host round trip). */
 ASVGP_API int64_t asvgp_accum_2d_moment_doubles(int n_knots1, int n_knots2, int order);
 
 /* ---- a11 + a12: O(N) accumulation for the Kronecker model -----------------------------------------------------------------
@@ -134,6 +135,9 @@ ASVGP_API int64_t asvgp_kron_band_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_sig_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_work_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order);
+/* Diagnostics: offset (doubles) inside `band` of the per-block-column record { 2 sum log L_cc, ||y_C||^2, six
+ * %globaltimer stamps of the critical path }, 8 doubles per block column, ceil(m1*m2/64) block columns. */
+ASVGP_API int64_t asvgp_kron_colstat_offset(int m1, int m2, int order);
 ASVGP_API int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream);
 

@@ -1,0 +1,36 @@
+"""Critical-path breakdown of the tile-DAG factorisation from the %globaltimer stamps it leaves in the band buffer."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from asvgp_b200 import basis as B, kernels as Kn, ops, _lib
+from asvgp_b200.inducing_features import SplineFeatures1D
+
+m = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+k = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+cls = getattr(B, "B%dSpline" % k)
+bases = [cls(-80, -25, m), cls(15, 55, m)]
+n1 = 2000
+x1 = torch.linspace(-75, -30, n1, dtype=torch.float64, device="cuda")
+x2 = torch.linspace(20, 50, n1, dtype=torch.float64, device="cuda")
+X = torch.stack([x1[:, None].expand(n1, n1), x2[None, :].expand(n1, n1)], -1).reshape(-1, 2).contiguous()
+y = torch.sin(X[:, 0] / 4) * torch.cos(X[:, 1] / 3)
+acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+cm = ops.moment_table_2d(bases)
+ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2]); ops.expand_moments_2d(cm, bases, acc)
+kerns = [Kn.Matern32(variance=1.0, lengthscales=5.0), Kn.Matern32(variance=1.0, lengthscales=4.0)]
+Ks = [SplineFeatures1D(kerns[i], bases[i]).make_Kuu_device(kerns[i])[0] for i in range(2)]
+ws = ops.kron_workspace(m, m, k)
+for _ in range(3):
+    ops.kron_factor(Ks[0], Ks[1], acc, bases, 0.01, ws)
+torch.cuda.synchronize()
+off = _lib.load().asvgp_kron_colstat_offset(m, m, k)
+nb = -(-m * m // 64)
+st = ws.band[off: off + 8 * nb].view(nb, 8).cpu().numpy()
+t = st[:, 2:]
+mid = slice(nb // 4, 3 * nb // 4)
+def us(a): return float(np.median(a[mid])) / 1e3
+print("block columns", nb, " total chain %.2f ms" % ((t[-1, 3] - t[0, 0]) / 1e6))
+print("per block column (median, us): period %.2f" % us(np.diff(t[:, 3])))
+print("  diag: begin->operands landed %.2f | potrf+inverse %.2f | publish %.2f" % (us(t[:, 1] - t[:, 0]), us(t[:, 2] - t[:, 1]), us(t[:, 3] - t[:, 2])))
+print("  d=1 : diag published -> inverse seen %.2f | trsm tile done %.2f" % (us(t[:, 4] - t[:, 3]), us(t[:, 5] - t[:, 4])))
+print("  next diag potrf start - d=1 tile published: %.2f" % us(t[1:, 1] - t[:-1, 5]))
