@@ -335,15 +335,18 @@ __device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
 }
 
+constexpr int kRasterWarps = 8;          // 256 threads, two CTAs per SM (<= 128 registers per thread): occupancy beats
+                                         // a deeper register-staged prefetch here (measured: 6 warps x 8-point groups was slower)
+
 template <int K, bool VEC256>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(kRasterWarps * 32, 2)
 accum_2d_raster_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
                        const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
                        double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe) {
     if (probe->select != (VEC256 ? 3 : 2)) return;
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;      // sums per lane
-    constexpr int kWarps = 8;
+    constexpr int kWarps = kRasterWarps;
     extern __shared__ __align__(16) unsigned char raster_smem[];
     // per warp: [32][NS] dim-2 sums of the run being flushed, then [32][NS] dim-1 factors beta_p(t1), gamma_p(t1)
     double (*s_S)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem);
@@ -454,7 +457,8 @@ accum_2d_raster_kernel(const double* __restrict__ X, const double* __restrict__ 
         };
 
         if (VEC256) {
-            // n2 % 4 == 0 and 32-byte aligned bases: four points = two 256-bit loads of X and one of y
+            // n2 % 4 == 0 and 32-byte aligned bases: four points = two 256-bit loads of X and one of y, the next group's
+            // loads in flight while the current one is processed
             double xa[4], xb[4], ya[4];
             int64_t c = c_begin;
             if (active && c < c_end) { ldg256(xr + 2 * c, xa); ldg256(xr + 2 * c + 4, xb); ldg256(yr + c, ya); }
@@ -525,11 +529,15 @@ __global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __res
     // first change of x1
     const long long b0 = x1bits(0);
     const int64_t limit = n < (1 << 20) ? n : (1 << 20);
-    for (int64_t base = 1; base < limit; base += blockDim.x) {
-        const int64_t i = base + tid;
-        const bool changed = i < limit && x1bits(i) != b0;
-        if (changed) atomicMin(reinterpret_cast<unsigned long long*>(&s_first), (unsigned long long)i);
-        if (__syncthreads_or(changed)) break;
+    for (int64_t base = 1; base < limit; base += 16 * blockDim.x) {
+        long long first = -1;
+#pragma unroll
+        for (int u = 15; u >= 0; --u) {                          // 16 independent loads in flight per thread
+            const int64_t i = base + tid + (int64_t)u * blockDim.x;
+            if (i < limit && x1bits(i) != b0) first = i;
+        }
+        if (first >= 0) atomicMin(reinterpret_cast<unsigned long long*>(&s_first), (unsigned long long)first);
+        if (__syncthreads_or(first >= 0)) break;
     }
     __syncthreads();
     const long long n2 = s_first;             // -1 (as unsigned: huge) when no change was found
@@ -719,8 +727,8 @@ static int launch_raster(const double* X, const double* y, int64_t n, const doub
                          cudaStream_t st) {
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    accum_2d_raster_kernel<K, true><<<blocks, 256, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
-    accum_2d_raster_kernel<K, false><<<blocks, 256, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
     return kOk;
 }
 
@@ -763,7 +771,7 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
     accum_2d_probe_kernel<<<1, 256, 0, st>>>(X, y, n, probe);
     ASVGP_CUDA_OK(cudaGetLastError());
     const int blocks2 = 2 * sm_count2();
-    const size_t raster_smem = sizeof(double) * 2 * 8 * 32 * (3 * (size_t)order + 2);       // NS = (2k+1) + (k+1)
+    const size_t raster_smem = sizeof(double) * 2 * kRasterWarps * 32 * (3 * (size_t)order + 2);   // NS = (2k+1) + (k+1)
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_raster<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, probe, blocks2, raster_smem, st)) return rc; });
     ASVGP_CUDA_OK(cudaGetLastError());
     {
