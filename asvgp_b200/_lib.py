@@ -28,7 +28,7 @@ SIGNATURES = {
     "asvgp_kron_factor": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp, _vp, _vp],
     "asvgp_kron_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "asvgp_kron_terms": [_vp] * 11 + [_c_int, _c_int, _c_int, _vp, _vp],
-    "asvgp_predict_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp],
+    "asvgp_predict_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp],
 }
 # functions whose return value is not a status code
 VALUE_FUNCTIONS = {
@@ -39,6 +39,7 @@ VALUE_FUNCTIONS = {
     "asvgp_kron_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_colstat_offset": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_predict_2d_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
 }
 
 _lib = None

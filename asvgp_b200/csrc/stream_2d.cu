@@ -327,9 +327,22 @@ accum_2d_run_kernel(const double* __restrict__ X, const double* __restrict__ y, 
 // row tile, flushing whenever ITS x1 or ITS cell changes (a warp vote makes the others flush early with it).
 // ------------------------------------------------------------------------------------------------------------------
 struct ProbeResult {      // lives in the trailing slot of the moment table (two ints)
-    int select;           // 0 general, 1 x1-run, 2 raster (per-point loads), 3 raster (256-bit loads)
+    int select;           // 0 general, 1 x1-run, 2 raster (per-point loads), 3 raster (256-bit loads), 4 separable raster
     int n2;               // row length of the raster
 };
+
+// Bulk L2 prefetch (UBLKPF.L2): pulls `bytes` (multiple of 16, 16-byte aligned start) from DRAM into L2 without occupying
+// registers or shared memory.  The streaming kernels run at (bytes in flight) / (loaded DRAM latency ~2 us); prefetching a
+// block ahead turns their register-staged loads into L2 hits.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2_span(const double* first, int64_t n_doubles) {
+    // widen [first, first + n) to 16-byte boundaries
+    const uintptr_t a = reinterpret_cast<uintptr_t>(first) & ~(uintptr_t)15;
+    const uintptr_t e = (reinterpret_cast<uintptr_t>(first + n_doubles) + 15) & ~(uintptr_t)15;
+    prefetch_l2_bulk(reinterpret_cast<const void*>(a), (uint32_t)(e - a));
+}
 
 __device__ __forceinline__ void ldg256(const double* p, double (&v)[4]) {
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v[0]), "=d"(v[1]), "=d"(v[2]), "=d"(v[3]) : "l"(p));
@@ -500,9 +513,261 @@ accum_2d_raster_kernel(const double* __restrict__ X, const double* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// "column sweep" path: the raster is separable as well (every row carries the same x2 values, as np.meshgrid /
+// lon-lat grids do).  The lanes of a warp take 32 CONSECUTIVE COLUMNS and sweep down the rows, so every load is a
+// fully coalesced 512-byte (X) / 256-byte (y) request like in the 1-D kernel, each lane's x2 — hence its dim-2
+// factors — never changes, the dim-1 sums are accumulated per lane, and all lanes cross a knot of dimension 1 at the
+// same step (x1 is shared by the whole row), so the flush is again convergent and cooperative.  Roles of the two
+// dimensions are swapped with respect to the row-streaming kernel above; the same per-lane checks keep any input
+// correct.
+// ------------------------------------------------------------------------------------------------------------------
+// Warp-cooperative flush of the column-sweep kernel, out of line (it runs once per ~n1/(m1-k) rows): every lane has put
+// its dim-1 sums in S[lane][*]; lanes are grouped by cell, the sums of a group are contracted with the lanes' dim-2
+// factors Bf and leave as (kAll / 32) fp64 REDs per lane.
+template <int K>
+__device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const double* __restrict__ Bf, int cell,
+                                           double* __restrict__ cellmom) {
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    unsigned remaining = __ballot_sync(0xffffffffu, cell >= 0);
+    while (remaining) {
+        const int leader = __ffs(remaining) - 1;
+        const int cl = __shfl_sync(0xffffffffu, cell, leader);
+        const unsigned grp = __ballot_sync(0xffffffffu, cell == cl) & remaining;
+        double* dst = cellmom + (int64_t)cl * Mo::kAll;
+        for (int o = lane; o < Mo::kAll; o += 32) {
+            const int pi = o < Mo::kGram ? o / NB : NB + (o - Mo::kGram) / NY;
+            const int qi = o < Mo::kGram ? o % NB : NB + (o - Mo::kGram) % NY;
+            double acc = 0.0;
+            if (grp == 0xffffffffu) {                         // the usual case: the whole strip is in one cell
+#pragma unroll 8
+                for (int e = 0; e < 32; ++e) acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
+            } else {
+                unsigned m = grp;
+                while (m) {
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
+                }
+            }
+            atomicAdd(dst + o, acc);
+        }
+        remaining &= ~grp;
+    }
+    __syncwarp();
+}
+
+// A point whose x1 is not its row's x1 (the input is not the raster the probe took it for): added on its own, straight
+// to the moment table.  Kept out of line so that it costs the sweep no registers.
+template <int K>
+__device__ __noinline__ void scatter_point_2d(const Mesh mesh1, const Mesh mesh2, double x1, double x2, double yv,
+                                              double* __restrict__ cellmom) {
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY;
+    const int c1 = locate_interval(mesh1, x1, LdgLoader2()), c2 = locate_interval(mesh2, x2, LdgLoader2());
+    double tp1[2 * K + 1], up1[2 * K + 1], tp2[2 * K + 1], up2[2 * K + 1];
+    powers<2 * K>((x1 - __ldg(mesh1.knots + c1)) * mesh1.inv_delta, tp1, up1);
+    powers<2 * K>((x2 - __ldg(mesh2.knots + c2)) * mesh2.inv_delta, tp2, up2);
+    double* dst = cellmom + ((int64_t)c1 * (mesh2.n_knots - 1) + c2) * Mo::kAll;
+#pragma unroll 1
+    for (int p = 0; p < NB; ++p)
+#pragma unroll 1
+        for (int q = 0; q < NB; ++q) atomicAdd(dst + p * NB + q, tp1[p] * up1[2 * K - p] * tp2[q] * up2[2 * K - q]);
+#pragma unroll 1
+    for (int p = 0; p < NY; ++p)
+#pragma unroll 1
+        for (int q = 0; q < NY; ++q) atomicAdd(dst + Mo::kGram + p * NY + q, yv * tp1[p] * up1[K - p] * tp2[q] * up2[K - q]);
+}
+
+// Measured: the sweep runs at (bytes in flight) / (loaded DRAM latency, ~2 us).  8 warps x 2 CTAs per SM with one
+// group of four rows (3 KB per warp) in flight give 3.3 TB/s; a 16-row register ring in 12 fatter warps was slower
+// (register allocation around the out-of-line calls), so was a bulk L2 prefetch one block ahead.
+constexpr int kColsWarps = kRasterWarps;
+
+template <int K>
+__global__ void __launch_bounds__(kColsWarps * 32, 2)
+accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
+                     const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
+                     double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe) {
+    if (probe->select != 4) return;
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;
+    constexpr int kWarps = kColsWarps;
+    extern __shared__ __align__(16) unsigned char raster_smem[];
+    // per warp: [32][NS] per-lane dim-1 sums being flushed | [32][NS] per-lane dim-2 factors | [32][NS] dim-1 factors of
+    // the next 32 rows (x1 is shared by a whole row, so they are computed once per row, not once per point)
+    double (*s_S)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem);
+    double (*s_B)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem + sizeof(double) * kWarps * 32 * NS);
+    double (*s_T)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem + 2 * sizeof(double) * kWarps * 32 * NS);
+    __shared__ long long s_bits[kWarps][32];     // x1 bit pattern of each table row
+    __shared__ int s_cell[kWarps][32];           // its knot interval
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int nc2 = nk2 - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n2 = probe->n2, n1 = n / n2;
+    double (*S)[NS] = s_S[warp];
+    double (*Bf)[NS] = s_B[warp];
+    double (*T)[NS] = s_T[warp];
+    long long* Tbits = s_bits[warp];
+    int* Tcell = s_cell[warp];
+
+    // tasks: 32-column strips x row segments, dealt round-robin to the warps of the grid
+    const int64_t n_strips = (n2 + 31) / 32;
+    const int64_t total_warps = (int64_t)gridDim.x * kWarps;
+    int64_t n_seg = (4 * total_warps + n_strips - 1) / n_strips;
+    int64_t seg_len = ((n1 + n_seg - 1) / n_seg + 31) & ~(int64_t)31;
+    if (seg_len < 64) seg_len = 64;
+    n_seg = (n1 + seg_len - 1) / seg_len;
+    const int64_t n_tasks = n_strips * n_seg;
+    const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
+
+    double s[NB], sy[NY];
+    double yy = 0.0;
+
+    constexpr long long kNoX2 = 0x7ff8dead0000beefLL;      // a NaN payload no input coordinate carries
+
+    for (int64_t task = (int64_t)blockIdx.x * kWarps + warp; task < n_tasks; task += total_warps) {
+        const int64_t strip = task / n_seg, sg = task % n_seg;
+        const int64_t col = strip * 32 + lane;
+        const bool active = col < n2;
+        const int64_t colc = active ? col : n2 - 1;        // lanes past the last column shadow it; they never flush
+        const int64_t r_begin = sg * seg_len, r_end = r_begin + seg_len < n1 ? r_begin + seg_len : n1;
+#pragma unroll
+        for (int i = 0; i < NB; ++i) s[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) sy[i] = 0.0;
+        long long cur_x2 = kNoX2;
+        bool dirty = false;
+        int cur_c1 = -1;                 // warp-uniform: dim-1 interval the lane sums belong to
+        double yy_task = 0.0;
+        Interval it, i2;                 // it: interval cache of the table builder
+        it.reset(); i2.reset();
+
+        auto flush_all = [&]() {
+#pragma unroll
+            for (int q = 0; q < NB; ++q) S[lane][q] = s[q];
+#pragma unroll
+            for (int q = 0; q < NY; ++q) S[lane][NB + q] = sy[q];
+            flush_cols_2d<K>(&S[0][0], &Bf[0][0], (dirty && active) ? cur_c1 * nc2 + i2.idx : -1, cellmom);
+#pragma unroll
+            for (int q = 0; q < NB; ++q) s[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NY; ++q) sy[q] = 0.0;
+            dirty = false;
+        };
+        // one point of table row `row`; everything here is warp-uniform except inside the `odd` branch
+        auto process = [&](int row, const double2 pt, const double yv) {
+            const int c1 = Tcell[row];
+            if (c1 != cur_c1) {                                   // the row entered another dim-1 interval
+                flush_all();
+                cur_c1 = c1;
+            }
+            const long long bx = __double_as_longlong(pt.x), by = __double_as_longlong(pt.y);
+            bool skip = false;
+            if (__any_sync(0xffffffffu, ((bx ^ Tbits[row]) | (by ^ cur_x2)) != 0)) {
+                flush_all();
+                if (by != cur_x2) {                               // first point of the task, or x2 is not constant
+                    if (!i2.inside(pt.y)) i2.set(mesh2, locate_interval(mesh2, pt.y, LdgLoader2()));
+                    double tp[2 * K + 1], up[2 * K + 1];
+                    powers<2 * K>((pt.y - i2.u) * mesh2.inv_delta, tp, up);
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) Bf[lane][q] = tp[q] * up[2 * K - q];
+#pragma unroll
+                    for (int q = 0; q < NY; ++q) Bf[lane][NB + q] = tp[q] * up[K - q];
+                    cur_x2 = by;
+                }
+                if (bx != Tbits[row]) {                           // not the raster the probe took it for
+                    if (active) scatter_point_2d<K>(mesh1, mesh2, pt.x, pt.y, yv, cellmom);
+                    skip = true;
+                }
+            }
+            yy_task = fma(yv, yv, yy_task);
+            if (!skip) {
+                const double* Tr = T[row];
+#pragma unroll
+                for (int p = 0; p < NB; ++p) s[p] += Tr[p];
+#pragma unroll
+                for (int p = 0; p < NY; ++p) sy[p] = fma(yv, Tr[NB + p], sy[p]);
+                dirty = true;
+            }
+        };
+
+        const double2* xp = X2 + r_begin * n2 + colc;             // walks down the column: += n2 per row
+        const double* yp = y + r_begin * n2 + colc;
+        for (int64_t r0 = r_begin; r0 < r_end; r0 += 32) {
+            // ---- dim-1 factors of rows r0 .. r0+31: lane l does row r0 + l ---------------------------------------------
+            __syncwarp();
+            {
+                const int64_t r = r0 + lane;
+                if (r < r_end) {
+                    const double x1 = __ldg(X + 2 * (r * n2 + strip * 32));
+                    if (!it.inside(x1)) it.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+                    double tp[2 * K + 1], up[2 * K + 1];
+                    powers<2 * K>((x1 - it.u) * mesh1.inv_delta, tp, up);
+#pragma unroll
+                    for (int p = 0; p < NB; ++p) T[lane][p] = tp[p] * up[2 * K - p];
+#pragma unroll
+                    for (int p = 0; p < NY; ++p) T[lane][NB + p] = tp[p] * up[K - p];
+                    Tbits[lane] = __double_as_longlong(x1);
+                    Tcell[lane] = it.idx;
+                }
+            }
+            __syncwarp();
+            const int n_rows = (int)(r_end - r0 < 32 ? r_end - r0 : 32);
+            const int n_full = n_rows & ~3;
+            // ---- sweep: four rows per group, the next group's eight loads in flight ---------------------------------
+            double2 px[4];
+            double py[4];
+            if (n_full > 0) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { px[u] = __ldg(xp + u * n2); py[u] = __ldg(yp + u * n2); }
+            }
+            for (int u0 = 0; u0 < n_full; u0 += 4) {
+                double2 cx[4];
+                double cy[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { cx[u] = px[u]; cy[u] = py[u]; }
+                xp += 4 * n2;
+                yp += 4 * n2;
+                if (u0 + 4 < n_full) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) { px[u] = __ldg(xp + u * n2); py[u] = __ldg(yp + u * n2); }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) process(u0 + u, cx[u], cy[u]);
+            }
+            for (int u = n_full; u < n_rows; ++u) {                 // ragged end of the segment
+                const double2 pt = __ldg(xp);
+                const double yv = __ldg(yp);
+                xp += n2;
+                yp += n2;
+                process(u, pt, yv);
+            }
+        }
+        flush_all();
+        if (active) yy += yy_task;
+    }
+
+    __shared__ double s_yy[kWarps];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    if (lane == 0) s_yy[warp] = yy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kWarps; ++w) tot += s_yy[w];
+        atomicAdd(scal, tot);
+        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+    }
+}
+
 // Probe (one CTA): classifies the input without a host round trip.
 //   raster  : n2 = position of the first change of x1 (searched in the first 2^20 points) divides n, and at 1024 sampled
 //             rows the first and last point share x1 while the previous row's last point does not
+//   separable raster : additionally x2 of 1024 sampled points equals x2 of the same column in the first row
 //   x1-run  : at least three quarters of 4096 sampled points share x1 with their successor
 //   general : everything else
 __global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __restrict__ X, const double* __restrict__ y,
@@ -554,9 +819,20 @@ __global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __res
         }
         raster = !__syncthreads_or(bad);
     }
+    bool separable = raster;
+    if (raster) {
+        const int64_t n1 = n / n2;
+        int bad = 0;
+        for (int j = tid; j < 1024; j += blockDim.x) {
+            const int64_t r = 1 + (int64_t)((double)j * (double)(n1 - 2) / 1023.0 + 0.5);
+            const int64_t c = (int64_t)(((unsigned long long)j * 2654435761ull) % (unsigned long long)n2);
+            if (r < n1) bad |= __double_as_longlong(__ldg(X + 2 * (r * n2 + c) + 1)) != __double_as_longlong(__ldg(X + 2 * c + 1));
+        }
+        separable = !__syncthreads_or(bad);
+    }
     if (tid == 0) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(y)) & 31u) == 0;
-        out->select = raster ? ((n2 % 4 == 0 && aligned) ? 3 : 2) : (runs ? 1 : 0);
+        out->select = raster ? (separable ? 4 : ((n2 % 4 == 0 && aligned) ? 3 : 2)) : (runs ? 1 : 0);
         out->n2 = raster ? (int)n2 : 0;
     }
 }
@@ -617,65 +893,218 @@ __global__ void __launch_bounds__(256) expand_moments_2d_kernel(const double* __
 // ------------------------------------------------------------------------------------------------------------------
 // predictor: mean = w^T alpha, var = v1 v2 + w^T Sigma_P w - (a^T S1 a)(b^T S2 b),  w = a (x) b
 // (reference gpr.py:321-332).  Only the stencil entries of P^-1 and the bands of K1^-1, K2^-1 are needed.
+//
+// Inside one cell (c1, c2) both are bivariate polynomials in the local coordinates (t1, t2): the mean of degree k, the
+// variance of degree 2k per dimension.  A first kernel (one CTA per cell) turns the posterior into that
+// piecewise-polynomial form — (k+1)^2 + (2k+1)^2 monomial coefficients per cell plus the two univariate factors —
+// and the streaming kernel then needs no gathers from the stencil at all.  Every thread walks a contiguous slice of the
+// test points and keeps, for the (x1, cell) it is in, the mean/variance reduced to polynomials in t2 alone; on a
+// gridded test set (x1 constant along a row, ~n2/(m2-k) consecutive points per cell) a point costs one Horner of
+// degree k and one of degree 2k (~12 fp64 instructions), scattered points cost one (k+1)^2 + (2k+1)^2 contraction
+// each.  32 B of traffic per point (X in, mean and var out).
 // ------------------------------------------------------------------------------------------------------------------
+template <int K> struct PredTable {
+    static constexpr int NM = (K + 1) * (K + 1);          // mean coefficients  [p][q], p, q = 0..k
+    static constexpr int NV = (2 * K + 1) * (2 * K + 1);  // variance coefficients [P][Q], P, Q = 0..2k
+    static constexpr int kCell = NM + NV;
+    static constexpr int NQ = 2 * K + 1;                  // univariate a^T S1 a / b^T S2 b per 1-D cell
+};
+
 template <int K>
-__global__ void __launch_bounds__(256) predict_2d_kernel(const double* __restrict__ X, int64_t n,
-                                                         const double* __restrict__ knots1, int nk1,
-                                                         const double* __restrict__ knots2, int nk2, int m1, int m2,
-                                                         const double* __restrict__ alpha,
-                                                         const double* __restrict__ SigP,      // stencil layout
-                                                         const double* __restrict__ S1,        // (K+1) x m1 lower band
-                                                         const double* __restrict__ S2,        // (K+1) x m2 lower band
-                                                         double prior_var, double* __restrict__ mean,
-                                                         double* __restrict__ var) {
+__global__ void __launch_bounds__(256) predict_2d_table_kernel(int nc1, int nc2, int m1, int m2,
+                                                              const double* __restrict__ alpha,
+                                                              const double* __restrict__ SigP,
+                                                              const double* __restrict__ S1,
+                                                              const double* __restrict__ S2,
+                                                              double* __restrict__ table) {
+    using PT = PredTable<K>;
+    constexpr int K1 = K + 1, NS = 2 * K + 1, W = K1 * K1;
+    __shared__ double s_A[K1][K1];               // A[r][p]
+    __shared__ double s_AA[K1][K1][NS];          // AA[r][s][P]
+    extern __shared__ __align__(16) double s_win[];   // [W][W] window of Sigma_P, then alpha window [W]
+    double* s_alpha = s_win + W * W;
+    const int64_t M = (int64_t)m1 * m2;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < K1 * K1; i += blockDim.x) s_A[i / K1][i % K1] = 0.0;
+    __syncthreads();
+    if (tid < K1 * K1) {
+        constexpr PieceTable<K> tab = make_piece_table<K>();
+        const int r = tid / K1, p = tid % K1;
+        s_A[r][p] = (double)tab.c[r][p] / (double)tab.fact;
+    }
+    for (int i = tid; i < K1 * K1 * NS; i += blockDim.x) {
+        constexpr PieceTable<K> tab = make_piece_table<K>();
+        const int P = i % NS, sidx = (i / NS) % K1, r = i / (NS * K1);
+        long long acc = 0;
+        for (int p = 0; p <= K; ++p) {
+            const int pp = P - p;
+            if (pp >= 0 && pp <= K) acc += tab.c[r][p] * tab.c[sidx][pp];
+        }
+        s_AA[r][sidx][P] = (double)acc / ((double)tab.fact * (double)tab.fact);
+    }
+    const int n_cells = nc1 * nc2;
+    if ((int)blockIdx.x < n_cells) {
+        const int c1 = blockIdx.x / nc2, c2 = blockIdx.x % nc2;
+        // window of the symmetric Sigma_P: rows/cols (r1, r2) -> basis index (c1 + r1, c2 + r2)
+        for (int i = tid; i < W * W; i += blockDim.x) {
+            const int a = i / W, b = i % W;
+            const int r1 = a / K1, r2 = a % K1, s1 = b / K1, s2 = b % K1;
+            int d1 = r1 - s1, d2 = r2 - s2;
+            int j1 = c1 + s1, j2 = c2 + s2;
+            if (d1 < 0 || (d1 == 0 && d2 < 0)) { d1 = -d1; d2 = -d2; j1 = c1 + r1; j2 = c2 + r2; }
+            s_win[i] = __ldg(SigP + (int64_t)(d1 * NS + d2 + K) * M + (int64_t)j1 * m2 + j2);
+        }
+        for (int i = tid; i < W; i += blockDim.x) s_alpha[i] = __ldg(alpha + (int64_t)(c1 + i / K1) * m2 + (c2 + i % K1));
+        __syncthreads();
+        double* out = table + (int64_t)blockIdx.x * PT::kCell;
+        for (int o = tid; o < PT::NM; o += blockDim.x) {
+            const int p = o / K1, q = o % K1;
+            double v = 0.0;
+            for (int r1 = 0; r1 < K1; ++r1) {
+                double inner = 0.0;
+                for (int r2 = 0; r2 < K1; ++r2) inner = fma(s_A[r2][q], s_alpha[r1 * K1 + r2], inner);
+                v = fma(s_A[r1][p], inner, v);
+            }
+            out[o] = v;
+        }
+        for (int o = tid; o < PT::NV; o += blockDim.x) {
+            const int P = o / NS, Q = o % NS;
+            double v = 0.0;
+            for (int r1 = 0; r1 < K1; ++r1)
+                for (int s1 = 0; s1 < K1; ++s1) {
+                    const double c1f = s_AA[r1][s1][P];
+                    double inner = 0.0;
+                    for (int r2 = 0; r2 < K1; ++r2)
+                        for (int s2 = 0; s2 < K1; ++s2)
+                            inner = fma(s_AA[r2][s2][Q], s_win[(r1 * K1 + r2) * W + s1 * K1 + s2], inner);
+                    v = fma(c1f, inner, v);
+                }
+            out[PT::NM + o] = v;
+        }
+    } else {
+        // the two univariate factors: Q1[c][P] = sum_rs S1[c+r, c+s] AA[r][s][P] (and the same for dimension 2)
+        __syncthreads();
+        const int which = blockIdx.x - n_cells;          // 0: dimension 1, 1: dimension 2
+        const int nc = which == 0 ? nc1 : nc2, m = which == 0 ? m1 : m2;
+        const double* Sb = which == 0 ? S1 : S2;
+        double* out = table + (int64_t)n_cells * PT::kCell + (which == 0 ? 0 : (int64_t)nc1 * PT::NQ);
+        for (int o = tid; o < nc * PT::NQ; o += blockDim.x) {
+            const int c = o / PT::NQ, P = o % PT::NQ;
+            double v = 0.0;
+            for (int r = 0; r < K1; ++r)
+                for (int sidx = 0; sidx < K1; ++sidx) {
+                    const int d = r - sidx;
+                    const double sv = d >= 0 ? __ldg(Sb + (int64_t)d * m + c + sidx) : __ldg(Sb + (int64_t)(-d) * m + c + r);
+                    v = fma(s_AA[r][sidx][P], sv, v);
+                }
+            out[o] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ void stg256(double* p, const double (&v)[4]) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(v[0]), "d"(v[1]), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <int K, bool VEC256>
+__global__ void __launch_bounds__(256, 2) predict_2d_kernel(const double* __restrict__ X, int64_t n,
+                                                            const double* __restrict__ knots1, int nk1,
+                                                            const double* __restrict__ knots2, int nk2,
+                                                            const double* __restrict__ table, double prior_var,
+                                                            double* __restrict__ mean, double* __restrict__ var) {
+    using PT = PredTable<K>;
     constexpr int K1 = K + 1, NS = 2 * K + 1;
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
-    const int64_t M = (int64_t)m1 * m2;
+    const int nc1 = nk1 - 1, nc2 = nk2 - 1;
+    const double* Q1 = table + (int64_t)nc1 * nc2 * PT::kCell;
+    const double* Q2 = Q1 + (int64_t)nc1 * PT::NQ;
+
+    const int64_t n_threads = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t per = (n + n_threads - 1) / n_threads;
+    per = (per + 3) & ~(int64_t)3;
+    const int64_t begin = tid * per < n ? tid * per : n;
+    const int64_t end = begin + per < n ? begin + per : n;
+
+    double mc[K1], vc[NS];               // mean / variance as polynomials in t2 for the current (x1, cell)
+    double tp1[NS];                      // powers of t1 of the current x1
+    double q1 = 0.0;
+    long long cur_x1 = 0;
+    bool have_x1 = false;
+    Interval i1, i2;
+    i1.reset(); i2.reset();
+
+    auto eval = [&](double x1, double x2, double& mu, double& vv) {
+        const long long bits = __double_as_longlong(x1);
+        const bool same_x1 = have_x1 && bits == cur_x1;
+        if (!(same_x1 && i2.inside(x2))) {
+            if (!same_x1) {
+                if (!i1.inside(x1)) i1.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+                const double t1 = (x1 - i1.u) * mesh1.inv_delta;
+                tp1[0] = 1.0;
+#pragma unroll
+                for (int i = 1; i < NS; ++i) tp1[i] = tp1[i - 1] * t1;
+                q1 = 0.0;
+#pragma unroll
+                for (int P = NS - 1; P >= 0; --P) q1 = fma(q1, t1, __ldg(Q1 + (int64_t)i1.idx * PT::NQ + P));
+                cur_x1 = bits;
+                have_x1 = true;
+            }
+            if (!i2.inside(x2)) i2.set(mesh2, locate_interval(mesh2, x2, LdgLoader2()));
+            const double* cell = table + ((int64_t)i1.idx * nc2 + i2.idx) * PT::kCell;
+#pragma unroll
+            for (int q = 0; q < K1; ++q) {
+                double v = 0.0;
+#pragma unroll
+                for (int p = 0; p < K1; ++p) v = fma(__ldg(cell + p * K1 + q), tp1[p], v);
+                mc[q] = v;
+            }
+#pragma unroll
+            for (int Q = 0; Q < NS; ++Q) {
+                double v = 0.0;
+#pragma unroll
+                for (int P = 0; P < NS; ++P) v = fma(__ldg(cell + PT::NM + P * NS + Q), tp1[P], v);
+                vc[Q] = fma(-q1, __ldg(Q2 + (int64_t)i2.idx * PT::NQ + Q), v);
+            }
+            vc[0] += prior_var;
+        }
+        const double t2 = (x2 - i2.u) * mesh2.inv_delta;
+        double m = mc[K];
+#pragma unroll
+        for (int q = K - 1; q >= 0; --q) m = fma(m, t2, mc[q]);
+        double v = vc[2 * K];
+#pragma unroll
+        for (int Q = 2 * K - 1; Q >= 0; --Q) v = fma(v, t2, vc[Q]);
+        mu = m;
+        vv = v;
+    };
+
+    int64_t i = begin;
+    if (VEC256) {
+        const int64_t n_full = begin + ((end - begin) & ~(int64_t)3);
+        double xa[4], xb[4];
+        if (i < n_full) { ldg256(X + 2 * i, xa); ldg256(X + 2 * i + 4, xb); }
+        for (; i < n_full; i += 4) {
+            double ca[4], cb[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ca[j] = xa[j]; cb[j] = xb[j]; }
+            if (i + 4 < n_full) { ldg256(X + 2 * (i + 4), xa); ldg256(X + 2 * (i + 4) + 4, xb); }
+            double mu[4], vv[4];
+            eval(ca[0], ca[1], mu[0], vv[0]);
+            eval(ca[2], ca[3], mu[1], vv[1]);
+            eval(cb[0], cb[1], mu[2], vv[2]);
+            eval(cb[2], cb[3], mu[3], vv[3]);
+            stg256(mean + i, mu);
+            stg256(var + i, vv);
+        }
+    }
     const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (; i < end; ++i) {
         const double2 pt = __ldg(X2 + i);
-        const int c1 = locate_interval(mesh1, pt.x, LdgLoader2());
-        const int c2 = locate_interval(mesh2, pt.y, LdgLoader2());
-        double a[K1], bb[K1];
-        bspline_pieces<K>((pt.x - __ldg(knots1 + c1)) * mesh1.inv_delta, a);
-        bspline_pieces<K>((pt.y - __ldg(knots2 + c2)) * mesh2.inv_delta, bb);
-        double mu = 0.0, q = 0.0;
-#pragma unroll
-        for (int r1 = 0; r1 < K1; ++r1) {
-#pragma unroll
-            for (int r2 = 0; r2 < K1; ++r2) {
-                const double wr = a[r1] * bb[r2];
-                const int64_t irow = (int64_t)(c1 + r1) * m2 + (c2 + r2);
-                mu = fma(wr, __ldg(alpha + irow), mu);
-                // row (r1, r2) against all columns (s1, s2) <= (r1, r2) in the stencil's lower part
-                double rowsum = 0.5 * wr * __ldg(SigP + (int64_t)(0 * NS + K) * M + irow);
-#pragma unroll
-                for (int s1 = 0; s1 <= r1; ++s1) {
-#pragma unroll
-                    for (int s2 = 0; s2 < K1; ++s2) {
-                        const int d1 = r1 - s1, d2 = r2 - s2;
-                        if (d1 == 0 && d2 <= 0) continue;
-                        const int64_t j = (int64_t)(c1 + s1) * m2 + (c2 + s2);
-                        rowsum = fma(a[s1] * bb[s2], __ldg(SigP + (int64_t)(d1 * NS + d2 + K) * M + j), rowsum);
-                    }
-                }
-                q = fma(wr, rowsum, q);
-            }
-        }
-        double q1 = 0.0, q2 = 0.0;
-#pragma unroll
-        for (int r = 0; r < K1; ++r) {
-            double row1 = 0.5 * a[r] * __ldg(S1 + c1 + r), row2 = 0.5 * bb[r] * __ldg(S2 + c2 + r);
-#pragma unroll
-            for (int s = 0; s < r; ++s) {
-                row1 = fma(a[s], __ldg(S1 + (int64_t)(r - s) * m1 + c1 + s), row1);
-                row2 = fma(bb[s], __ldg(S2 + (int64_t)(r - s) * m2 + c2 + s), row2);
-            }
-            q1 = fma(a[r], row1, q1);
-            q2 = fma(bb[r], row2, q2);
-        }
+        double mu, vv;
+        eval(pt.x, pt.y, mu, vv);
         mean[i] = mu;
-        var[i] = prior_var + 2.0 * q - (2.0 * q1) * (2.0 * q2);
+        var[i] = vv;
     }
 }
 
@@ -729,6 +1158,9 @@ static int launch_raster(const double* X, const double* y, int64_t n, const doub
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
     accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2);   // sums, factors, per-row table
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    accum_2d_cols_kernel<K><<<blocks, kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
     return kOk;
 }
 
@@ -796,16 +1228,40 @@ extern "C" int asvgp_expand_moments_2d(const double* cellmom, const double* Cpro
     return kOk;
 }
 
+extern "C" int64_t asvgp_predict_2d_work_doubles(int n_knots1, int n_knots2, int order) {
+    if (order < 1 || order > kMaxOrder || n_knots1 < 2 || n_knots2 < 2) return -1;
+    const int64_t nc1 = n_knots1 - 1, nc2 = n_knots2 - 1;
+    const int64_t cell = (int64_t)(order + 1) * (order + 1) + (int64_t)(2 * order + 1) * (2 * order + 1);
+    return nc1 * nc2 * cell + (nc1 + nc2) * (2 * order + 1);
+}
+
+template <int K>
+static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int nk1, const double* mesh2, int nk2,
+                             const double* alpha, const double* SigP, const double* S1, const double* S2,
+                             double prior_var, double* mean, double* var, double* work, cudaStream_t st) {
+    const int nc1 = nk1 - 1, nc2 = nk2 - 1, m1 = nk1 + K - 1, m2 = nk2 + K - 1;
+    constexpr int W = (K + 1) * (K + 1);
+    const size_t smem = sizeof(double) * (size_t)(W * W + W);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(predict_2d_table_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    const bool vec = ((reinterpret_cast<uintptr_t>(Xnew) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 31u) == 0;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, 2 * (int64_t)sm_count2()));
+    if (vec) predict_2d_kernel<K, true><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var);
+    else predict_2d_kernel<K, false><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 extern "C" int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
                                 int n_knots2, int order, const double* alpha, const double* SigP, const double* S1,
-                                const double* S2, double prior_var, double* mean, double* var, void* stream) {
+                                const double* S2, double prior_var, double* mean, double* var, double* work,
+                                void* stream) {
     ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "predict_2d: n=%lld", (long long)n);
     ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(Xnew) & 15u) == 0, "predict_2d: Xnew must be 16-byte aligned");
+    ASVGP_REQUIRE(work != nullptr, "predict_2d: work buffer (asvgp_predict_2d_work_doubles) is required");
     if (n == 0) return kOk;
-    const int m1 = n_knots1 + order - 1, m2 = n_knots2 + order - 1;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count2() * 8);
-    ASVGP_DISPATCH_ORDER(order, (predict_2d_kernel<K><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, n_knots1, mesh2, n_knots2, m1, m2, alpha, SigP, S1, S2, prior_var, mean, var)));
-    ASVGP_CUDA_OK(cudaGetLastError());
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_predict_2d<K>(Xnew, n, mesh1, n_knots1, mesh2, n_knots2, alpha, SigP, S1, S2, prior_var, mean, var, work, st)) return rc; });
     return kOk;
 }

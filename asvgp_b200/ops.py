@@ -451,6 +451,14 @@ def predict_2d(Xnew, bases, alpha, SigP, S1, S2, prior_var):
     mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
     mean = torch.empty(n, dtype=F64, device=X.device)
     var = torch.empty(n, dtype=F64, device=X.device)
+    key = (X.device, mesh1.numel(), mesh2.numel(), k)
+    work = _PREDICT_WORK.get(key)
+    if work is None:
+        nw = _lib.load().asvgp_predict_2d_work_doubles(mesh1.numel(), mesh2.numel(), k)
+        work = _PREDICT_WORK[key] = torch.empty(nw, dtype=F64, device=X.device)
     _lib.call("asvgp_predict_2d", _p(X), n, _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k, _p(alpha),
-              _p(SigP), _p(S1), _p(S2), float(prior_var), _p(mean), _p(var), _stream())
+              _p(SigP), _p(S1), _p(S2), float(prior_var), _p(mean), _p(var), _p(work), _stream())
     return mean, var
+
+
+_PREDICT_WORK = {}

@@ -159,10 +159,14 @@ ASVGP_API int asvgp_kron_terms(const double* SigP, const double* Gs, const doubl
 
 /* ---- a15: 2-D posterior mean / variance ----------------------------------------------------------------------------------------
  * Replaces GPR_kron.predict_f / predict_f_sparse (gpr.py:310-359): mean = w^T alpha, var = prior_var + w^T P^-1 w -
- * (a^T K1^-1 a)(b^T K2^-1 b), w = a (x) b.  SigP in stencil layout, S1/S2 lower bands of K1^-1/K2^-1. */
+ * (a^T K1^-1 a)(b^T K2^-1 b), w = a (x) b.  SigP in stencil layout, S1/S2 lower bands of K1^-1/K2^-1.  The posterior is
+ * first converted to per-cell polynomial form in `work` (asvgp_predict_2d_work_doubles doubles), then streamed over
+ * the test points (32 B of traffic per point). */
+ASVGP_API int64_t asvgp_predict_2d_work_doubles(int n_knots1, int n_knots2, int order);
 ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
                                int n_knots2, int order, const double* alpha, const double* SigP, const double* S1,
-                               const double* S2, double prior_var, double* mean, double* var, void* stream);
+                               const double* S2, double prior_var, double* mean, double* var, double* work,
+                               void* stream);
 
 #ifdef __cplusplus
 }

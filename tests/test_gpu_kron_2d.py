@@ -141,6 +141,13 @@ def test_midsize_rectangular_vs_banded_oracle(cuda):
     mean0, var0 = O.predict_kron_banded(meshes, deltas, k, list(ms), Ks, G0, b0, [h[0] for h in hyp], s2, Xs)
     np.testing.assert_allclose(mean, mean0, atol=1e-9, rtol=0)
     np.testing.assert_allclose(var, var0, atol=1e-9, rtol=0)
+    # gridded test points (x1 constant along a row: the predictor's run path), ragged row length
+    g1, g2 = np.linspace(-74.5, -30.5, 37), np.linspace(20.5, 49.5, 53)
+    Xg = np.stack(np.meshgrid(g1, g2, indexing="ij"), -1).reshape(-1, 2)
+    mean, var = model.predict_f(Xg)
+    mean0, var0 = O.predict_kron_banded(meshes, deltas, k, list(ms), Ks, G0, b0, [h[0] for h in hyp], s2, Xg)
+    np.testing.assert_allclose(mean, mean0, atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, var0, atol=1e-9, rtol=0)
 
 
 def test_accumulate_order_invariance_and_shard_additivity(cuda):
@@ -175,6 +182,52 @@ def test_accumulate_order_invariance_and_shard_additivity(cuda):
     diag = Gs[3].sum()
     assert abs(2 * Gs.sum() - diag - X.shape[0]) <= 1e-9 * X.shape[0]
     assert abs(b.sum() - y.sum()) <= 1e-9 * np.abs(y).sum()
+
+
+@pytest.mark.parametrize("variant,n1,n2", [("separable", 130, 300), ("separable", 67, 301), ("curvilinear", 130, 300),
+                                            ("curvilinear", 67, 301), ("x1-runs", 97, 211), ("separable-dirty", 130, 300), ("separable-dirty-x1", 130, 300)])
+def test_accumulate_raster_variants(cuda, variant, n1, n2):
+    """Every input class of asvgp_accum_2d's probe (separable raster -> column sweep, raster with row-dependent x2 ->
+    row streaming with 256-bit or per-point loads, ragged x1 runs) against the SciPy oracle."""
+    import torch
+
+    from asvgp_b200 import basis as B, ops, utils
+
+    rng = np.random.default_rng(n1 * 1000 + n2)
+    x1 = np.sort(rng.uniform(-74.9, -30.1, n1))
+    x2 = np.sort(rng.uniform(20.1, 49.9, n2))
+    X = np.stack(np.meshgrid(x1, x2, indexing="ij"), -1)
+    if variant == "curvilinear":
+        X[:, :, 1] += 0.01 * np.sin(np.arange(n1))[:, None]            # x2 depends on the row
+    if variant == "separable-dirty-x1":
+        for r, c in ((3, 17), (50, 150), (51, 151), (129, 298)):        # interior points only: the probe cannot see them
+            X[r, c, 0] += 0.013
+    if variant == "separable-dirty":
+        # a few interior points off their row's x1 / their column's x2: the probe still sees a separable raster, the
+        # kernel has to notice point by point
+        for r, c in ((3, 17), (50, 150), (51, 151), (129, 298)):
+            X[r, c, 0] += 0.013
+        for r, c in ((7, 5), (64, 200), (100, 31)):
+            X[r, c, 1] -= 0.021
+    X = X.reshape(-1, 2)
+    if variant == "x1-runs":
+        keep = rng.uniform(size=X.shape[0]) > 0.1                      # rows of different lengths
+        X = X[keep]
+    y = np.sin(X[:, 0] / 4.0) * np.cos(X[:, 1] / 3.0) + 0.05 * rng.standard_normal(X.shape[0])
+    bases = [B.B3Spline(-80, -25, 19), B.B3Spline(15, 55, 23)]
+    acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+    cm = ops.moment_table_2d(bases)
+    ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2])
+    select = int(cm[-1:].view(torch.int32)[0].item())
+    want = {"separable": (4,), "separable-dirty-x1": (4,), "separable-dirty": (3, 4), "curvilinear": (3,) if n2 % 4 == 0 else (2,), "x1-runs": (1,)}[variant]
+    assert select in want, "probe chose path %d for a %s input" % (select, variant)
+    ops.expand_moments_2d(cm, bases, acc)
+    Gs, b, scal = [t.cpu().numpy() for t in ops.split_accum_2d(acc, bases)]
+    G0, b0, yy0 = O.precompute_kron([bb.mesh for bb in bases], [bb.delta for bb in bases], 3, [19, 23], X, y)
+    scale = abs(G0).max()
+    assert abs(utils.stencil_to_sparse(Gs, 19, 23, 3) - G0).max() <= 1e-11 * scale
+    np.testing.assert_allclose(b, b0.ravel(), rtol=0, atol=1e-11 * np.abs(b0).max())
+    assert abs(scal[0] - yy0) <= 1e-12 * yy0 and scal[1] == X.shape[0]
 
 
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 255, 1025])
