@@ -17,6 +17,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libasvgp_sm100a.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]
+NVCC_FLAGS += os.environ.get("ASVGP_NVCC_EXTRA", "").split()          # e.g. -DASVGP_DIAG_L2 for diagnostic builds
 
 
 def _nvcc():

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "../../include/asvgp_b200.h"
 
@@ -522,12 +523,15 @@ accum_2d_raster_kernel(const double* __restrict__ X, const double* __restrict__ 
 // dimensions are swapped with respect to the row-streaming kernel above; the same per-lane checks keep any input
 // correct.
 // ------------------------------------------------------------------------------------------------------------------
-// Warp-cooperative flush of the column-sweep kernel, out of line (it runs once per ~n1/(m1-k) rows): every lane has put
-// its dim-1 sums in S[lane][*]; lanes are grouped by cell, the sums of a group are contracted with the lanes' dim-2
-// factors Bf and leave as (kAll / 32) fp64 REDs per lane.
+// Warp-cooperative flush of the column-sweep kernel, out of line (it runs once per ~n1/(m1-k) rows).  Every lane has
+// put its own dim-1 sums in S[lane][*] (Gram part: only what the row-by-row path added; projection part: everything)
+// and the warp-uniform Gram sums in SU[*]; Bf[lane][*] are the lanes' dim-2 factors.  Lanes are grouped by cell; for a
+// group g the Gram moments are  SU[p] * sum_{e in g} Bf[e][q]  (+ sum_e S[e][p] Bf[e][q] if `per_lane_gram`), the
+// projection moments  sum_e S[e][NB+p] Bf[e][NB+q]; they leave as a few fp64 REDs per lane.
 template <int K>
-__device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const double* __restrict__ Bf, int cell,
-                                           double* __restrict__ cellmom) {
+__device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const double* __restrict__ SU,
+                                           const double* __restrict__ Bf, double* __restrict__ GB, int cell,
+                                           bool per_lane_gram, double* __restrict__ cellmom) {
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;
     const int lane = threadIdx.x & 31;
@@ -537,24 +541,33 @@ __device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const d
         const int leader = __ffs(remaining) - 1;
         const int cl = __shfl_sync(0xffffffffu, cell, leader);
         const unsigned grp = __ballot_sync(0xffffffffu, cell == cl) & remaining;
+        const int e_lo = __ffs(grp) - 1, e_hi = 31 - __clz(grp);
         double* dst = cellmom + (int64_t)cl * Mo::kAll;
-        for (int o = lane; o < Mo::kAll; o += 32) {
-            const int pi = o < Mo::kGram ? o / NB : NB + (o - Mo::kGram) / NY;
-            const int qi = o < Mo::kGram ? o % NB : NB + (o - Mo::kGram) % NY;
+        // GB[q] = sum over the group of the dim-2 Gram factors (lanes 0..NB-1, one q each)
+        if (lane < NB) {
             double acc = 0.0;
-            if (grp == 0xffffffffu) {                         // the usual case: the whole strip is in one cell
-#pragma unroll 8
-                for (int e = 0; e < 32; ++e) acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
-            } else {
-                unsigned m = grp;
-                while (m) {
-                    const int e = __ffs(m) - 1;
-                    m &= m - 1;
-                    acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
-                }
+            for (int e = e_lo; e <= e_hi; ++e)
+                if ((grp >> e) & 1u) acc += Bf[e * NS + lane];
+            GB[lane] = acc;
+        }
+        __syncwarp();
+        for (int o = lane; o < Mo::kGram; o += 32) {
+            const int pi = o / NB, qi = o % NB;
+            double acc = SU[pi] * GB[qi];
+            if (per_lane_gram) {
+                for (int e = e_lo; e <= e_hi; ++e)
+                    if ((grp >> e) & 1u) acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
             }
             atomicAdd(dst + o, acc);
         }
+        for (int o = lane; o < Mo::kProj; o += 32) {
+            const int pi = NB + o / NY, qi = NB + o % NY;
+            double acc = 0.0;
+            for (int e = e_lo; e <= e_hi; ++e)
+                if ((grp >> e) & 1u) acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
+            atomicAdd(dst + Mo::kGram + o, acc);
+        }
+        __syncwarp();
         remaining &= ~grp;
     }
     __syncwarp();
@@ -582,13 +595,27 @@ __device__ __noinline__ void scatter_point_2d(const Mesh mesh1, const Mesh mesh2
         for (int q = 0; q < NY; ++q) atomicAdd(dst + Mo::kGram + p * NY + q, yv * tp1[p] * up1[K - p] * tp2[q] * up2[K - q]);
 }
 
-// Measured: the sweep runs at (bytes in flight) / (loaded DRAM latency, ~2 us).  8 warps x 2 CTAs per SM with one
-// group of four rows (3 KB per warp) in flight give 3.3 TB/s; a 16-row register ring in 12 fatter warps was slower
-// (register allocation around the out-of-line calls), so was a bulk L2 prefetch one block ahead.
-constexpr int kColsWarps = kRasterWarps;
+// Measured: the sweep runs at (bytes in flight) / (loaded DRAM latency, ~2 us) — with one group of four rows staged in
+// registers (3 KB per warp, 48 KB per SM) it sits at 3.3 TB/s whatever the instruction count.  So the column walk is
+// staged through shared memory instead: every lane cp.async's its own 16 B of X and 8 B of y, kColsRing rows deep
+// (18 KB per warp, ~140 KB per SM in flight, no registers, no cross-lane synchronisation because a lane only ever reads
+// what it copied itself).
+constexpr int kColsWarps = 8;
+template <int K> struct ColsRing {       // rows in the ring: what fits beside the (K-dependent) tables in 227 KB
+    static constexpr int kRows = K <= 3 ? 24 : (K == 4 ? 20 : 16);
+};
+
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int K>
-__global__ void __launch_bounds__(kColsWarps * 32, 2)
+__global__ void __launch_bounds__(kColsWarps * 32, 1)
 accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
                      const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
                      double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe) {
@@ -596,14 +623,25 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;
     constexpr int kWarps = kColsWarps;
+    constexpr int kColsRing = ColsRing<K>::kRows;
     extern __shared__ __align__(16) unsigned char raster_smem[];
     // per warp: [32][NS] per-lane dim-1 sums being flushed | [32][NS] per-lane dim-2 factors | [32][NS] dim-1 factors of
     // the next 32 rows (x1 is shared by a whole row, so they are computed once per row, not once per point)
     double (*s_S)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem);
     double (*s_B)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem + sizeof(double) * kWarps * 32 * NS);
     double (*s_T)[32][NS] = reinterpret_cast<double (*)[32][NS]>(raster_smem + 2 * sizeof(double) * kWarps * 32 * NS);
-    __shared__ long long s_bits[kWarps][32];     // x1 bit pattern of each table row
-    __shared__ int s_cell[kWarps][32];           // its knot interval
+    // per warp: ring of kColsRing rows, [row][lane] double2 of X then [row][lane] double of y
+    unsigned char* ring_base = raster_smem + 3 * sizeof(double) * kWarps * 32 * NS;
+    double2* ringX = reinterpret_cast<double2*>(ring_base) + (size_t)(threadIdx.x >> 5) * kColsRing * 32;
+    double* ringY = reinterpret_cast<double*>(ring_base + sizeof(double2) * kWarps * kColsRing * 32) + (size_t)(threadIdx.x >> 5) * kColsRing * 32;
+    __shared__ __align__(16) long long s_bits[kWarps][32];     // x1 bit pattern of each table row
+    __shared__ __align__(16) int s_cell[kWarps][32];           // its knot interval
+    // per group of four table rows: sum over the rows of the Gram factors beta_p(t1) (the same for every column, so on a
+    // separable raster the Gram moments need no per-point work at all), and the group's interval (-1: rows of the group
+    // lie in different intervals or do not all exist -> row-by-row path)
+    __shared__ __align__(16) double s_gsum[kWarps][8][NB + 1];
+    __shared__ int s_gcell[kWarps][8];
+    __shared__ double s_su[kWarps][NB], s_gb[kWarps][NB];      // flush: warp-uniform Gram sums, per-group factor sums
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
     const int nc2 = nk2 - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -613,6 +651,8 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     double (*T)[NS] = s_T[warp];
     long long* Tbits = s_bits[warp];
     int* Tcell = s_cell[warp];
+    double (*Gsum)[NB + 1] = s_gsum[warp];
+    int* Gcell = s_gcell[warp];
 
     // tasks: 32-column strips x row segments, dealt round-robin to the warps of the grid
     const int64_t n_strips = (n2 + 31) / 32;
@@ -625,22 +665,26 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
 
     double s[NB], sy[NY];
+    double su[NB];                       // warp-uniform part of the dim-1 Gram sums (fast path); a lane's sum is s + su
     double yy = 0.0;
 
     constexpr long long kNoX2 = 0x7ff8dead0000beefLL;      // a NaN payload no input coordinate carries
 
     for (int64_t task = (int64_t)blockIdx.x * kWarps + warp; task < n_tasks; task += total_warps) {
-        const int64_t strip = task / n_seg, sg = task % n_seg;
+        // consecutive warps take ADJACENT strips of the same row segment: a CTA then reads 8 x 512 B contiguous bytes of every
+        // row, which keeps DRAM pages open
+        const int64_t sg = task / n_strips, strip = task % n_strips;
         const int64_t col = strip * 32 + lane;
         const bool active = col < n2;
         const int64_t colc = active ? col : n2 - 1;        // lanes past the last column shadow it; they never flush
         const int64_t r_begin = sg * seg_len, r_end = r_begin + seg_len < n1 ? r_begin + seg_len : n1;
 #pragma unroll
-        for (int i = 0; i < NB; ++i) s[i] = 0.0;
+        for (int i = 0; i < NB; ++i) { s[i] = 0.0; su[i] = 0.0; }
 #pragma unroll
         for (int i = 0; i < NY; ++i) sy[i] = 0.0;
         long long cur_x2 = kNoX2;
         bool dirty = false;
+        bool any_slow = false;           // warp-uniform: some lane's own Gram sums s[] are non-zero
         int cur_c1 = -1;                 // warp-uniform: dim-1 interval the lane sums belong to
         double yy_task = 0.0;
         Interval it, i2;                 // it: interval cache of the table builder
@@ -651,9 +695,15 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
             for (int q = 0; q < NB; ++q) S[lane][q] = s[q];
 #pragma unroll
             for (int q = 0; q < NY; ++q) S[lane][NB + q] = sy[q];
-            flush_cols_2d<K>(&S[0][0], &Bf[0][0], (dirty && active) ? cur_c1 * nc2 + i2.idx : -1, cellmom);
+            if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < NB; ++q) s[q] = 0.0;
+                for (int q = 0; q < NB; ++q) s_su[warp][q] = su[q];
+            }
+            flush_cols_2d<K>(&S[0][0], s_su[warp], &Bf[0][0], s_gb[warp], (dirty && active) ? cur_c1 * nc2 + i2.idx : -1,
+                             any_slow, cellmom);
+            any_slow = false;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) { s[q] = 0.0; su[q] = 0.0; }
 #pragma unroll
             for (int q = 0; q < NY; ++q) sy[q] = 0.0;
             dirty = false;
@@ -685,6 +735,7 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
                 }
             }
             yy_task = fma(yv, yv, yy_task);
+            any_slow = true;
             if (!skip) {
                 const double* Tr = T[row];
 #pragma unroll
@@ -695,15 +746,42 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
             }
         };
 
-        const double2* xp = X2 + r_begin * n2 + colc;             // walks down the column: += n2 per row
-        const double* yp = y + r_begin * n2 + colc;
+        // ---- the column walk, pipelined kColsRing rows deep through the shared-memory ring -------------------------
+        const int64_t rows_total = r_end - r_begin;
+        const int64_t n_groups = (rows_total + 3) >> 2;               // groups of four rows (the last may be ragged)
+        const double2* xq = X2 + r_begin * n2 + colc;                 // next row to request: += n2 per row
+        const double* yq = y + r_begin * n2 + colc;
+        int to_request = (int)rows_total;                             // rows not requested yet (a segment is < 2^31 rows)
+        int wslot = 0;                                                // ring slot of the next request (32-bit, no modulo)
+        auto request_group = [&]() {                                  // one commit group = up to four rows
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (to_request > 0) {
+                    cp_async_16(ringX + wslot * 32 + lane, xq);
+                    cp_async_8(ringY + wslot * 32 + lane, yq);
+                    xq += n2;
+                    yq += n2;
+                    --to_request;
+                }
+                wslot = wslot + 1 == kColsRing ? 0 : wslot + 1;       // slots advance in whole groups, rows or not
+            }
+            cp_async_commit();
+        };
+        constexpr int kGroupsInFlight = kColsRing / 4 - 1;            // one group's slots are being read
+#pragma unroll
+        for (int g = 0; g < kGroupsInFlight; ++g) request_group();
+        int rslot = 0;                                                // ring slot of the next row to consume
+        // x1 of table row `lane` of the next 32-row block, requested one block ahead so that its DRAM latency is hidden
+        double x1_next = (r_begin + lane < r_end) ? __ldg(X + 2 * ((r_begin + lane) * n2 + strip * 32)) : 0.0;
+
         for (int64_t r0 = r_begin; r0 < r_end; r0 += 32) {
             // ---- dim-1 factors of rows r0 .. r0+31: lane l does row r0 + l ---------------------------------------------
             __syncwarp();
             {
                 const int64_t r = r0 + lane;
+                const double x1 = x1_next;
+                if (r + 32 < r_end) x1_next = __ldg(X + 2 * ((r + 32) * n2 + strip * 32));
                 if (r < r_end) {
-                    const double x1 = __ldg(X + 2 * (r * n2 + strip * 32));
                     if (!it.inside(x1)) it.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
                     double tp[2 * K + 1], up[2 * K + 1];
                     powers<2 * K>((x1 - it.u) * mesh1.inv_delta, tp, up);
@@ -717,36 +795,65 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
             }
             __syncwarp();
             const int n_rows = (int)(r_end - r0 < 32 ? r_end - r0 : 32);
-            const int n_full = n_rows & ~3;
-            // ---- sweep: four rows per group, the next group's eight loads in flight ---------------------------------
-            double2 px[4];
-            double py[4];
-            if (n_full > 0) {
+            if (lane < 8) {                                      // lane g sums the factors of rows 4g .. 4g+3
+                const int g4 = 4 * lane;
+                int gc = -1;
+                if (g4 + 3 < n_rows) {
+                    gc = Tcell[g4];
+                    if (Tcell[g4 + 1] != gc || Tcell[g4 + 2] != gc || Tcell[g4 + 3] != gc) gc = -1;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { px[u] = __ldg(xp + u * n2); py[u] = __ldg(yp + u * n2); }
+                    for (int p = 0; p < NB; ++p) Gsum[lane][p] = (T[g4][p] + T[g4 + 1][p]) + (T[g4 + 2][p] + T[g4 + 3][p]);
+                }
+                Gcell[lane] = gc;
             }
-            for (int u0 = 0; u0 < n_full; u0 += 4) {
+            __syncwarp();
+            for (int u0 = 0; u0 < n_rows; u0 += 4) {
+                // the oldest group has landed; read it, then hand its slots to a new request
+                cp_async_wait<kGroupsInFlight - 1>();
                 double2 cx[4];
                 double cy[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) { cx[u] = px[u]; cy[u] = py[u]; }
-                xp += 4 * n2;
-                yp += 4 * n2;
-                if (u0 + 4 < n_full) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) { px[u] = __ldg(xp + u * n2); py[u] = __ldg(yp + u * n2); }
+                for (int u = 0; u < 4; ++u) {
+                    cx[u] = ringX[(rslot + u) * 32 + lane];           // groups never straddle the end of the ring
+                    cy[u] = ringY[(rslot + u) * 32 + lane];
                 }
+                rslot = rslot + 4 == kColsRing ? 0 : rslot + 4;
+                request_group();
+                if (u0 + 3 < n_rows) {
+                    // fast path: the four rows lie in one interval and every lane sees its row's x1 and its own x2
+                    const int gc = Gcell[u0 >> 2];
+                    long long odd = 0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) process(u0 + u, cx[u], cy[u]);
-            }
-            for (int u = n_full; u < n_rows; ++u) {                 // ragged end of the segment
-                const double2 pt = __ldg(xp);
-                const double yv = __ldg(yp);
-                xp += n2;
-                yp += n2;
-                process(u, pt, yv);
+                    for (int u = 0; u < 4; ++u)
+                        odd |= (__double_as_longlong(cx[u].x) ^ Tbits[u0 + u]) | (__double_as_longlong(cx[u].y) ^ cur_x2);
+                    if (gc >= 0 && !__any_sync(0xffffffffu, odd != 0)) {
+                        if (gc != cur_c1) {
+                            flush_all();
+                            cur_c1 = gc;
+                        }
+                        const double* gs = Gsum[u0 >> 2];
+#pragma unroll
+                        for (int p = 0; p < NB; ++p) su[p] += gs[p];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const double* Tr = T[u0 + u] + NB;
+#pragma unroll
+                            for (int p = 0; p < NY; ++p) sy[p] = fma(cy[u], Tr[p], sy[p]);
+                            yy_task = fma(cy[u], cy[u], yy_task);
+                        }
+                        dirty = true;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) process(u0 + u, cx[u], cy[u]);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (u0 + u < n_rows) process(u0 + u, cx[u], cy[u]);
+                }
             }
         }
+        cp_async_wait<0>();
         flush_all();
         if (active) yy += yy_task;
     }
@@ -770,18 +877,27 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
 //   separable raster : additionally x2 of 1024 sampled points equals x2 of the same column in the first row
 //   x1-run  : at least three quarters of 4096 sampled points share x1 with their successor
 //   general : everything else
-__global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __restrict__ X, const double* __restrict__ y,
-                                                             int64_t n, ProbeResult* __restrict__ out) {
-    __shared__ int s_cnt[8];
+__global__ void __launch_bounds__(1024) accum_2d_probe_kernel(const double* __restrict__ X, const double* __restrict__ y,
+                                                              int64_t n, ProbeResult* __restrict__ out) {
+    // 1024 threads, every thread's samples issued back to back: the probe costs a handful of DRAM round trips
+    __shared__ int s_cnt[32];
     __shared__ long long s_first;
     const int tid = threadIdx.x;
     auto x1bits = [&](int64_t i) { return __double_as_longlong(__ldg(X + 2 * i)); };
-    // fraction of points equal to their successor
+    // fraction of points equal to their successor (4 samples per thread)
     const int n_probe = (int)(n - 1 < 4096 ? n - 1 : 4096);
     int hits = 0;
-    for (int j = tid; j < n_probe; j += blockDim.x) {
-        const int64_t i = (int64_t)((double)j * (double)(n - 1) / (double)n_probe);
-        hits += x1bits(i) == x1bits(i + 1);
+    {
+        long long a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = tid + u * 1024;
+            const int64_t i = j < n_probe ? (int64_t)((double)j * (double)(n - 1) / (double)n_probe) : 0;
+            a[u] = x1bits(i);
+            b[u] = x1bits(i + (n > 1 ? 1 : 0));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) hits += (tid + u * 1024 < n_probe) && a[u] == b[u];
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
@@ -789,46 +905,41 @@ __global__ void __launch_bounds__(256) accum_2d_probe_kernel(const double* __res
     if (tid == 0) s_first = -1;
     __syncthreads();
     int tot = 0;
-    for (int w = 0; w < 8; ++w) tot += s_cnt[w];
+    for (int w = 0; w < 32; ++w) tot += s_cnt[w];
     const bool runs = n_probe > 0 && 4 * tot >= 3 * n_probe;
-    // first change of x1
+    // first change of x1 (searched in the first 2^20 points, 8192 positions per round)
     const long long b0 = x1bits(0);
     const int64_t limit = n < (1 << 20) ? n : (1 << 20);
-    for (int64_t base = 1; base < limit; base += 16 * blockDim.x) {
+    for (int64_t base = 1; base < limit; base += 8 * 1024) {
+        long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int64_t i = base + tid + (int64_t)u * 1024;
+            v[u] = i < limit ? x1bits(i) : b0;
+        }
         long long first = -1;
 #pragma unroll
-        for (int u = 15; u >= 0; --u) {                          // 16 independent loads in flight per thread
-            const int64_t i = base + tid + (int64_t)u * blockDim.x;
-            if (i < limit && x1bits(i) != b0) first = i;
-        }
+        for (int u = 7; u >= 0; --u)
+            if (v[u] != b0) first = base + tid + (int64_t)u * 1024;
         if (first >= 0) atomicMin(reinterpret_cast<unsigned long long*>(&s_first), (unsigned long long)first);
         if (__syncthreads_or(first >= 0)) break;
     }
     __syncthreads();
-    const long long n2 = s_first;             // -1 (as unsigned: huge) when no change was found
+    const long long n2 = s_first;             // -1 when no change was found
     bool raster = runs && n2 > 1 && n % n2 == 0;
-    __syncthreads();
-    if (raster) {
+    bool separable = false;
+    if (raster) {                             // block-uniform
         const int64_t n1 = n / n2;
-        int bad = 0;
-        for (int j = tid; j < 1024; j += blockDim.x) {
-            const int64_t r = (int64_t)((double)j * (double)(n1 - 1) / 1023.0 + 0.5);
-            const long long a = x1bits(r * n2);
-            bad |= a != x1bits(r * n2 + n2 - 1);
-            if (r > 0) bad |= a == x1bits(r * n2 - 1);
-        }
-        raster = !__syncthreads_or(bad);
-    }
-    bool separable = raster;
-    if (raster) {
-        const int64_t n1 = n / n2;
-        int bad = 0;
-        for (int j = tid; j < 1024; j += blockDim.x) {
-            const int64_t r = 1 + (int64_t)((double)j * (double)(n1 - 2) / 1023.0 + 0.5);
-            const int64_t c = (int64_t)(((unsigned long long)j * 2654435761ull) % (unsigned long long)n2);
-            if (r < n1) bad |= __double_as_longlong(__ldg(X + 2 * (r * n2 + c) + 1)) != __double_as_longlong(__ldg(X + 2 * c + 1));
-        }
-        separable = !__syncthreads_or(bad);
+        // one sampled row per thread: first and last point share x1, the previous row's last point does not; and one
+        // sampled point per thread carries the x2 of its column in the first row
+        const int64_t r = (int64_t)((double)tid * (double)(n1 - 1) / 1023.0 + 0.5);
+        const long long a = x1bits(r * n2), e = x1bits(r * n2 + n2 - 1), pz = r > 0 ? x1bits(r * n2 - 1) : ~a;
+        const int64_t rs = n1 > 1 ? 1 + (int64_t)((double)tid * (double)(n1 - 2) / 1023.0 + 0.5) : 0;
+        const int64_t c = (int64_t)(((unsigned long long)tid * 2654435761ull) % (unsigned long long)n2);
+        const long long s0 = __double_as_longlong(__ldg(X + 2 * c + 1));
+        const long long s1 = rs < n1 ? __double_as_longlong(__ldg(X + 2 * (rs * n2 + c) + 1)) : s0;
+        raster = !__syncthreads_or(a != e || a == pz);
+        separable = !__syncthreads_or(s0 != s1) && raster;
     }
     if (tid == 0) {
         const bool aligned = ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(y)) & 31u) == 0;
@@ -1011,7 +1122,9 @@ __global__ void __launch_bounds__(256, 2) predict_2d_kernel(const double* __rest
                                                             const double* __restrict__ knots1, int nk1,
                                                             const double* __restrict__ knots2, int nk2,
                                                             const double* __restrict__ table, double prior_var,
-                                                            double* __restrict__ mean, double* __restrict__ var) {
+                                                            double* __restrict__ mean, double* __restrict__ var,
+                                                            const ProbeResult* __restrict__ probe) {
+    if (probe->select == 4) return;                  // the column sweep handles separable rasters
     using PT = PredTable<K>;
     constexpr int K1 = K + 1, NS = 2 * K + 1;
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
@@ -1108,6 +1221,128 @@ __global__ void __launch_bounds__(256, 2) predict_2d_kernel(const double* __rest
     }
 }
 
+// Column-sweep predictor for separable raster test sets (same classification probe as the accumulate): the lanes of a
+// warp take 32 consecutive columns and walk down the rows, so loads (512 B) and stores (2 x 256 B) are coalesced; a
+// lane's x2 never changes, so mean and variance are cached as polynomials in t1 for the (x2, dim-1 interval) the lane
+// is in and a point costs two Horner evaluations.
+template <int K>
+__global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* __restrict__ X, int64_t n,
+                                                                 const double* __restrict__ knots1, int nk1,
+                                                                 const double* __restrict__ knots2, int nk2,
+                                                                 const double* __restrict__ table, double prior_var,
+                                                                 double* __restrict__ mean, double* __restrict__ var,
+                                                                 const ProbeResult* __restrict__ probe) {
+    if (probe->select != 4) return;
+    using PT = PredTable<K>;
+    constexpr int K1 = K + 1, NS = 2 * K + 1;
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int nc1 = nk1 - 1, nc2 = nk2 - 1;
+    const double* Q1 = table + (int64_t)nc1 * nc2 * PT::kCell;
+    const double* Q2 = Q1 + (int64_t)nc1 * PT::NQ;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n2 = probe->n2, n1 = n / n2;
+    const int64_t n_strips = (n2 + 31) / 32;
+    const int64_t total_warps = (int64_t)gridDim.x * 8;
+    int64_t n_seg = (4 * total_warps + n_strips - 1) / n_strips;
+    int64_t seg_len = ((n1 + n_seg - 1) / n_seg + 3) & ~(int64_t)3;
+    if (seg_len < 64) seg_len = 64;
+    n_seg = (n1 + seg_len - 1) / seg_len;
+    const int64_t n_tasks = n_strips * n_seg;
+    const double2* __restrict__ X2 = reinterpret_cast<const double2*>(X);
+    constexpr long long kNoX2 = 0x7ff8dead0000beefLL;
+
+    for (int64_t task = (int64_t)blockIdx.x * 8 + warp; task < n_tasks; task += total_warps) {
+        const int64_t sg = task / n_strips, strip = task % n_strips;
+        const int64_t col = strip * 32 + lane;
+        if (col >= n2) continue;                       // no warp-level cooperation in this kernel
+        const int64_t r_begin = sg * seg_len, r_end = r_begin + seg_len < n1 ? r_begin + seg_len : n1;
+        double mc[K1], vc[NS], tp2[NS];
+        double q2 = 0.0;
+        long long cur_x2 = kNoX2;
+        Interval i1, i2;
+        i1.reset(); i2.reset();
+
+        auto eval = [&](const double2 pt, double& mu, double& vv) {
+            const long long by = __double_as_longlong(pt.y);
+            if (by != cur_x2 || !i1.inside(pt.x)) {
+                if (by != cur_x2) {
+                    if (!i2.inside(pt.y)) i2.set(mesh2, locate_interval(mesh2, pt.y, LdgLoader2()));
+                    const double t2 = (pt.y - i2.u) * mesh2.inv_delta;
+                    tp2[0] = 1.0;
+#pragma unroll
+                    for (int i = 1; i < NS; ++i) tp2[i] = tp2[i - 1] * t2;
+                    q2 = 0.0;
+#pragma unroll
+                    for (int Q = NS - 1; Q >= 0; --Q) q2 = fma(q2, t2, __ldg(Q2 + (int64_t)i2.idx * PT::NQ + Q));
+                    cur_x2 = by;
+                }
+                if (!i1.inside(pt.x)) i1.set(mesh1, locate_interval(mesh1, pt.x, LdgLoader2()));
+                const double* cell = table + ((int64_t)i1.idx * nc2 + i2.idx) * PT::kCell;
+#pragma unroll
+                for (int p = 0; p < K1; ++p) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int q = 0; q < K1; ++q) v = fma(__ldg(cell + p * K1 + q), tp2[q], v);
+                    mc[p] = v;
+                }
+#pragma unroll
+                for (int P = 0; P < NS; ++P) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int Q = 0; Q < NS; ++Q) v = fma(__ldg(cell + PT::NM + P * NS + Q), tp2[Q], v);
+                    vc[P] = fma(-q2, __ldg(Q1 + (int64_t)i1.idx * PT::NQ + P), v);
+                }
+                vc[0] += prior_var;
+            }
+            const double t1 = (pt.x - i1.u) * mesh1.inv_delta;
+            double m = mc[K];
+#pragma unroll
+            for (int p = K - 1; p >= 0; --p) m = fma(m, t1, mc[p]);
+            double v = vc[2 * K];
+#pragma unroll
+            for (int P = 2 * K - 1; P >= 0; --P) v = fma(v, t1, vc[P]);
+            mu = m;
+            vv = v;
+        };
+
+        const double2* xp = X2 + r_begin * n2 + col;
+        double* mp = mean + r_begin * n2 + col;
+        double* vp = var + r_begin * n2 + col;
+        const int64_t rows = r_end - r_begin, rows8 = rows & ~(int64_t)7;
+        double2 px[8];
+        if (rows8 > 0) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) px[u] = __ldg(xp + u * n2);
+        }
+        for (int64_t r = 0; r < rows8; r += 8) {
+            double2 cx[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cx[u] = px[u];
+            xp += 8 * n2;
+            if (r + 8 < rows8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) px[u] = __ldg(xp + u * n2);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                double mu, vv;
+                eval(cx[u], mu, vv);
+                mp[u * n2] = mu;
+                vp[u * n2] = vv;
+            }
+            mp += 8 * n2;
+            vp += 8 * n2;
+        }
+        for (int64_t r = rows8; r < rows; ++r) {
+            double mu, vv;
+            eval(__ldg(xp), mu, vv);
+            *mp = mu;
+            *vp = vv;
+            xp += n2; mp += n2; vp += n2;
+        }
+    }
+}
+
 static int sm_count2() {
     static int cached = 0;
     if (cached == 0) {
@@ -1158,9 +1393,10 @@ static int launch_raster(const double* X, const double* y, int64_t n, const doub
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
     accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
-    const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2);   // sums, factors, per-row table
+    const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2)     // sums, factors, per-row table
+                             + (size_t)kColsWarps * ColsRing<K>::kRows * 32 * 24;            // the ring
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    accum_2d_cols_kernel<K><<<blocks, kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
     return kOk;
 }
 
@@ -1200,7 +1436,7 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
     // launched and those that are not selected return at once.
     ProbeResult* probe = reinterpret_cast<ProbeResult*>(cellmom + asvgp_accum_2d_moment_doubles(n_knots1, n_knots2, order) - 1);
     const int* select = &probe->select;
-    accum_2d_probe_kernel<<<1, 256, 0, st>>>(X, y, n, probe);
+    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(X, y, n, probe);
     ASVGP_CUDA_OK(cudaGetLastError());
     const int blocks2 = 2 * sm_count2();
     const size_t raster_smem = sizeof(double) * 2 * kRasterWarps * 32 * (3 * (size_t)order + 2);   // NS = (2k+1) + (k+1)
@@ -1232,7 +1468,7 @@ extern "C" int64_t asvgp_predict_2d_work_doubles(int n_knots1, int n_knots2, int
     if (order < 1 || order > kMaxOrder || n_knots1 < 2 || n_knots2 < 2) return -1;
     const int64_t nc1 = n_knots1 - 1, nc2 = n_knots2 - 1;
     const int64_t cell = (int64_t)(order + 1) * (order + 1) + (int64_t)(2 * order + 1) * (2 * order + 1);
-    return nc1 * nc2 * cell + (nc1 + nc2) * (2 * order + 1);
+    return nc1 * nc2 * cell + (nc1 + nc2) * (2 * order + 1) + 1;        // + 1: slot of the input classification probe
 }
 
 template <int K>
@@ -1245,10 +1481,17 @@ static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1,
     ASVGP_CUDA_OK(cudaFuncSetAttribute(predict_2d_table_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work);
     ASVGP_CUDA_OK(cudaGetLastError());
+    // classification probe (as in asvgp_accum_2d): separable raster test sets take the coalesced column sweep, anything else
+    // the thread-contiguous kernel; the one that is not selected returns at once
+    ProbeResult* probe = reinterpret_cast<ProbeResult*>(work + asvgp_predict_2d_work_doubles(nk1, nk2, K) - 1);
+    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(Xnew, Xnew, n, probe);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
+    ASVGP_CUDA_OK(cudaGetLastError());
     const bool vec = ((reinterpret_cast<uintptr_t>(Xnew) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 31u) == 0;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, 2 * (int64_t)sm_count2()));
-    if (vec) predict_2d_kernel<K, true><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var);
-    else predict_2d_kernel<K, false><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var);
+    if (vec) predict_2d_kernel<K, true><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
+    else predict_2d_kernel<K, false><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

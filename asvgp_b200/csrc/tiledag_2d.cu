@@ -32,6 +32,7 @@
 
 #include <algorithm>
 
+#include "async_copy.cuh"
 #include "common.cuh"
 #include "../../include/asvgp_b200.h"
 
@@ -100,53 +101,10 @@ static SelLayout sel_layout(const TileGeom& g) {
     return L;
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (global -> shared), release/acquire flags
-// ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_load_tile_(double* dst_smem, const double* src_gmem, uint64_t* bar) {
+    tma_load_bulk(dst_smem, src_gmem, (uint32_t)TILE_BYTES, bar);
+}
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_tile(double* dst_smem, const double* src_gmem, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"((uint32_t)TILE_BYTES), "r"(smem_u32(bar))
-                 : "memory");
-}
-// generic-proxy writes (ours or, after an acquire, another CTA's) -> async-proxy (TMA) reads
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ double global_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return (double)t;
-}
-__device__ __forceinline__ int ld_acquire(const int* p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ void red_release_add(int* p, int v) {
-    asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // Spin until *flag >= want; gives up (and makes everybody give up) after kSpinLimit polls so that a logic error can
 // never hang the device.
 __device__ __forceinline__ void wait_flag(const int* flag, int want, int* abort_flag) {
@@ -377,8 +335,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
             fence_proxy_async();
             mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
-            tma_load_tile(sA[s], a.tiles + g.tile(J, R - J), &full[s]);
-            if (d != 0) tma_load_tile(sB[s], a.tiles + g.tile(J, C - J), &full[s]);
+            tma_load_tile_(sA[s], a.tiles + g.tile(J, R - J), &full[s]);
+            if (d != 0) tma_load_tile_(sB[s], a.tiles + g.tile(J, C - J), &full[s]);
         };
         if (nJ > 0 && tid == 0) issue(J0, 0);
         for (int q = 0; q < nJ; ++q) {
@@ -460,7 +418,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
                 if (d == 1) stat[6] = global_ns();
                 fence_proxy_async();
                 mbar_expect_tx(&full[0], TILE_BYTES);
-                tma_load_tile(sB[0], a.linv + (int64_t)C * TILE, &full[0]);
+                tma_load_tile_(sB[0], a.linv + (int64_t)C * TILE, &full[0]);
             }
             regs_to_tile(acc, sA[0], tm, tn);        // A(m, k) at [k*64 + m]
             __syncthreads();
@@ -586,8 +544,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 wait_flag(flag, 1, abort_flag);
                 fence_proxy_async();
                 mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                tma_load_tile(sA[s], src, &full[s]);
-                tma_load_tile(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
+                tma_load_tile_(sA[s], src, &full[s]);
+                tma_load_tile_(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
             };
             double acc[4][4] = {};
             if (tid == 0) issue(Kmax, 0);
@@ -606,7 +564,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
             if (tid == 0) {
                 mbar_expect_tx(&full[0], TILE_BYTES);
-                tma_load_tile(sB[0], a.tiles + g.tile(C, d), &full[0]);
+                tma_load_tile_(sB[0], a.tiles + g.tile(C, d), &full[0]);
             }
             regs_to_tile_t(acc, sA[0], tm, tn);      // T[m][a] at [m*64 + a]  ==  A'(a, k=m) at [k*64 + a]
             if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);      // x_R: final (diagonal task R has completed)

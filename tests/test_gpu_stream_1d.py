@@ -110,6 +110,21 @@ def test_accum_ragged_sizes_and_misaligned_views(cuda, n):
     torch.cuda.synchronize()
 
 
+@pytest.mark.parametrize("n", [65536, 65537, 65538, 2 * 148 * 1024 + 1, 2 * 148 * 1024 * 3, 1_000_001])
+def test_accum_tma_path_sizes(cuda, n):
+    """Sizes that exercise the TMA-fed kernel's chunking: whole chunks, an odd last point, CTAs with a lone tail chunk."""
+    rng = np.random.default_rng(n % 1000)
+    m, k = 500, 3
+    basis = _basis(k, -1, m + 1, m)
+    x = np.sort(rng.uniform(0.0, m, n))
+    y = np.cos(x / 5.0) + 0.2 * rng.standard_normal(n)
+    G0, b0, yy0 = O.precompute_1d_chunked(basis.mesh, basis.delta, k, m, x, y)
+    G, b, scal = _accum(x, y, basis)
+    _close(G, G0)
+    _close(b, b0.ravel())
+    assert abs(scal[0] - yy0) <= RTOL * yy0 and scal[1] == n
+
+
 def test_accum_points_on_knots_and_edges(cuda):
     """Points exactly on knots go to the LEFT interval (searchsorted side='left'); x=a+eps, x=b-eps."""
     m, k = 30, 3
