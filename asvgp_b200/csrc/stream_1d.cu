@@ -16,7 +16,6 @@
 
 #include <algorithm>
 
-#include "async_copy.cuh"
 #include "common.cuh"
 #include "../../include/asvgp_b200.h"
 
@@ -274,153 +273,6 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// TMA-fed variant (the one asvgp_accum_1d launches for 16-byte aligned inputs).  The LDG kernel above is bound by
-// (bytes in flight) / (loaded DRAM latency ~2 us) and its loads are staged in registers (64 KB per SM in flight, 68-70 %
-// of the measured HBM peak).  Here a producer warp streams the CTA's contiguous slice of x and y through a ring of
-// shared-memory stages with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier), kTmaStages - 1 stages
-// = 128 KB per SM in flight without a single register; eight consumer warps take 128 consecutive points of each stage,
-// run the same per-warp interval accumulation (WarpAccum) out of shared memory and hand the stage back through an
-// "empty" mbarrier.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int kTmaChunk = 1024;                 // points per stage (8 KB of x + 8 KB of y)
-constexpr int kTmaStages = 5;
-constexpr int kTmaConsumerWarps = 8;
-constexpr int kTmaThreads = (kTmaConsumerWarps + 1) * 32;
-constexpr size_t kTmaSmemBytes = (size_t)kTmaStages * kTmaChunk * 2 * sizeof(double);
-
-template <int K>
-__global__ void __launch_bounds__(kTmaThreads, 2)
-accum_1d_tma_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
-                    const double* __restrict__ knots, int n_knots, int M,
-                    double* __restrict__ G, double* __restrict__ b, double* __restrict__ scal) {
-    extern __shared__ __align__(128) unsigned char tma_smem[];
-    double* ring = reinterpret_cast<double*>(tma_smem);          // stage s: x at [s*2*CH, +CH), y right behind it
-    __shared__ __align__(8) uint64_t full[kTmaStages], empty[kTmaStages];
-    __shared__ double s_yy[kTmaConsumerWarps];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < kTmaStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kTmaConsumerWarps); }
-    }
-    fence_proxy_async();
-    __syncthreads();
-
-    // CTA c owns the contiguous point range [p0, p1), boundaries on even points (16-byte aligned bulk copies)
-    int64_t per_cta = (n + gridDim.x - 1) / gridDim.x;
-    per_cta = (per_cta + 1) & ~(int64_t)1;
-    const int64_t p0 = imin64((int64_t)blockIdx.x * per_cta, n), p1 = imin64(p0 + per_cta, n);
-    const int64_t n_chunks = (p1 - p0 + kTmaChunk - 1) / kTmaChunk;
-
-    if (warp == kTmaConsumerWarps) {
-        // ---- producer: one lane feeds the ring ---------------------------------------------------------------------------
-        if (lane == 0) {
-            for (int64_t c = 0; c < n_chunks; ++c) {
-                const int s = (int)(c % kTmaStages);
-                const uint32_t use = (uint32_t)(c / kTmaStages);
-                mbar_wait(&empty[s], (use & 1u) ^ 1u);                // the consumers have drained the previous use
-                const int64_t q0 = p0 + c * kTmaChunk;
-                const int64_t cnt = imin64(kTmaChunk, p1 - q0) & ~(int64_t)1;     // whole pairs only
-                if (cnt > 0) {
-                    mbar_expect_tx(&full[s], (uint32_t)(2 * cnt * sizeof(double)));
-                    tma_load_bulk(ring + (size_t)s * 2 * kTmaChunk, x + q0, (uint32_t)(cnt * sizeof(double)), &full[s]);
-                    tma_load_bulk(ring + (size_t)s * 2 * kTmaChunk + kTmaChunk, y + q0, (uint32_t)(cnt * sizeof(double)), &full[s]);
-                } else {
-                    mbar_arrive(&full[s]);                             // a chunk that holds only the odd last point
-                }
-            }
-        }
-        return;
-    }
-
-    // ---- consumers ------------------------------------------------------------------------------------------------------
-    const Mesh mesh = load_mesh(knots, n_knots);
-    WarpAccum<K> wa;
-    wa.clear();
-    wa.cur = -1;
-    wa.u = 0.0;
-    wa.lo = INFINITY;
-    wa.hi = -INFINITY;
-    double yy = 0.0;
-
-    // one pair of points (p, p+1) per call; `valid` counts how many of the two exist
-    auto consume_pair = [&](double xa, double xb, double ya, double yb, int valid) {
-        const bool va = valid > 0, vb = valid > 1;
-        const bool ina = wa.inside(xa), inb = wa.inside(xb);
-        if (va) yy = fma(ya, ya, yy);
-        if (vb) yy = fma(yb, yb, yy);
-        if (__all_sync(0xffffffffu, (ina || !va) && (inb || !vb))) {
-            if (va) wa.add(mesh, xa, ya);
-            if (vb) wa.add(mesh, xb, yb);
-            wa.dirty = true;
-        } else {
-            // interval crossing (or unsorted input): same protocol as the LDG kernel
-            int wha = -1, whb = -1, cand = -1;
-            bool pending = false, added_old = false;
-            if (va) {
-                if (ina) { wa.add(mesh, xa, ya); added_old = true; }
-                else { wha = locate_interval(mesh, xa, LdgLoader()); pending = true; cand = wha; }
-            }
-            if (vb) {
-                if (inb) { wa.add(mesh, xb, yb); added_old = true; }
-                else { whb = locate_interval(mesh, xb, LdgLoader()); pending = true; cand = whb; }
-            }
-            wa.dirty = wa.dirty || __any_sync(0xffffffffu, added_old);
-            wa.flush(G, b, M, lane);
-            const unsigned pend = __ballot_sync(0xffffffffu, pending);   // non-zero here
-            wa.set_interval(mesh, __shfl_sync(0xffffffffu, cand, 31 - __clz(pend)));
-            bool added = false;
-            if (wha >= 0) {
-                if (wha == wa.cur) { wa.add(mesh, xa, ya); added = true; }
-                else scatter_point<K>(mesh, wha, xa, ya, G, b, M);
-            }
-            if (whb >= 0) {
-                if (whb == wa.cur) { wa.add(mesh, xb, yb); added = true; }
-                else scatter_point<K>(mesh, whb, xb, yb, G, b, M);
-            }
-            wa.dirty = __any_sync(0xffffffffu, added);
-        }
-    };
-
-    constexpr int kPerWarp = kTmaChunk / kTmaConsumerWarps;       // 128 points: two pairs per lane
-    for (int64_t c = 0; c < n_chunks; ++c) {
-        const int s = (int)(c % kTmaStages);
-        const uint32_t use = (uint32_t)(c / kTmaStages);
-        mbar_wait(&full[s], use & 1u);
-        const double* xs = ring + (size_t)s * 2 * kTmaChunk + warp * kPerWarp;
-        const double* ys = xs + kTmaChunk;
-        const double2 xa = *reinterpret_cast<const double2*>(xs + 2 * lane);
-        const double2 xb = *reinterpret_cast<const double2*>(xs + 64 + 2 * lane);
-        const double2 ya = *reinterpret_cast<const double2*>(ys + 2 * lane);
-        const double2 yb = *reinterpret_cast<const double2*>(ys + 64 + 2 * lane);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);                       // the stage can be refilled
-        const int64_t q0 = p0 + c * kTmaChunk;
-        const int64_t cnt = imin64(kTmaChunk, p1 - q0) & ~(int64_t)1;  // points of this chunk that came through the ring
-        const int64_t base = (int64_t)warp * kPerWarp;
-        const int64_t ia = base + 2 * lane, ib = base + 64 + 2 * lane;
-        consume_pair(xa.x, xa.y, ya.x, ya.y, ia < cnt ? 2 : 0);
-        consume_pair(xb.x, xb.y, yb.x, yb.y, ib < cnt ? 2 : 0);
-    }
-    // the odd last point of the whole array (n odd) never goes through the ring
-    if (warp == 0 && ((p1 - p0) & 1) && p1 == n) {
-        const double xl = __ldg(x + n - 1), yl = __ldg(y + n - 1);
-        consume_pair(xl, 0.0, yl, 0.0, lane == 0 ? 1 : 0);
-    }
-    wa.flush(G, b, M, lane);
-
-    yy = warp_sum(yy);
-    if (lane == 0) s_yy[warp] = yy;
-    // consumer-only barrier (the producer warp has left)
-    asm volatile("bar.sync 1, %0;" ::"n"(kTmaConsumerWarps * 32));
-    if (threadIdx.x == 0) {
-        double tot = 0.0;
-#pragma unroll
-        for (int w = 0; w < kTmaConsumerWarps; ++w) tot += s_yy[w];
-        atomicAdd(scal, tot);
-        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // predictor
 // ------------------------------------------------------------------------------------------------------------------
 template <int K>
@@ -460,14 +312,6 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
             var[i] = variance + 2.0 * q;
         }
     }
-}
-
-template <int K>
-static int launch_accum_1d_tma(const double* x, const double* y, int64_t n, const double* mesh, int n_knots, int M,
-                               double* G, double* b, double* scal, int blocks, cudaStream_t st) {
-    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_1d_tma_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmemBytes));
-    accum_1d_tma_kernel<K><<<blocks, kTmaThreads, kTmaSmemBytes, st>>>(x, y, n, mesh, n_knots, M, G, b, scal);
-    return kOk;
 }
 
 static int sm_count() {
@@ -524,10 +368,7 @@ extern "C" int asvgp_accum_1d(const double* x, const double* y, int64_t n, const
     const int64_t per_tile = 32 * kAccumUnroll * (vec ? 2 : 1);
     const int64_t n_tiles = (n + per_tile - 1) / per_tile;
     const int blocks = (int)std::min<int64_t>((n_tiles + 7) / 8, (int64_t)sm_count() * 2);
-    if (vec && n >= 64 * 1024) {
-        const int tma_blocks = 2 * sm_count();
-        ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_1d_tma<K>(x, y, n, mesh, n_knots, M, G, b, scal, tma_blocks, st)) return rc; });
-    } else if (vec) {
+    if (vec) {
         ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 2><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal)));
     } else {
         ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 1><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal)));

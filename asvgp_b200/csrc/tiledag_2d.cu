@@ -43,7 +43,7 @@ constexpr int TILE = NB * NB;                   // doubles per tile
 constexpr int TILE_BYTES = TILE * 8;
 constexpr int kTdThreads = 256;                 // 16 x 16 threads, 4 x 4 outputs each
 constexpr long long kSpinLimit = 1LL << 24;     // polls before a wait gives up and raises the abort flag (~ seconds)
-constexpr int kColStat = 8;
+constexpr int kColStat = 12;
 constexpr int kNoBadPivot = 0x7f7f7f7f;         // what cudaMemset(0x7f) leaves in the "first bad pivot" slot
 
 struct TileGeom {
@@ -80,7 +80,7 @@ static FactorLayout factor_layout(const TileGeom& g) {
     L.linv = (int64_t)g.n_tiles() * TILE;
     L.colstat = L.linv + (int64_t)g.nb * TILE;
     L.flags = L.colstat + (int64_t)g.nb * kColStat;
-    L.n_flag_ints = (int64_t)g.n_tiles() + 8;                  // ready flags + abort
+    L.n_flag_ints = (int64_t)g.n_tiles() + 8 + 2 * (int64_t)g.nb;   // tile flags, abort, first bad pivot, y flags, rhs counters
     L.total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
     return L;
 }
@@ -239,69 +239,168 @@ struct FactorArgs {
     double* scal;       // [3]: log|P|, ||y||^2, info  (info written here; sums by td_stats_kernel)
 };
 
-// Cholesky of the symmetric 64 x 64 tile held in registers (4 x 4 per thread), right-looking, one barrier per
-// column; carries V = L^-1 along (V starts as the identity, receives the same row operations).  On exit acc holds L
-// (lower incl. diagonal; entries above the diagonal are don't-care) and V holds L^-1 (lower).
-__device__ __forceinline__ void potrf_regs(double (&acc)[4][4], double (&V)[4][4], int tm, int tn, double* scol,
-                                           double* srow, int* first_bad) {
-    // scol/srow: [2][64] doubles each, double buffered across columns
+__device__ __forceinline__ long long clock_mem() {          // clock64 that the compiler cannot move across memory ops / barriers
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+    return t;
+}
+
+// Cholesky of the symmetric 64 x 64 tile held in registers (4 x 4 per thread), right-looking in 16 block steps of four
+// columns, carrying V = L^-1 along (V starts as the identity and receives the same row operations).  Per block step:
+//   the thread that owns the 4 x 4 diagonal block factorises it and inverts its factor in registers   -> s11 (barrier)
+//   the 16 threads that own the block column form their rows of the panel  L = A L11^-T               -> spanel
+//   the 16 threads that own the block row of V form the final rows           W = L11^-1 V             -> swrow (barrier)
+//   every thread applies the rank-4 update to its 4 x 4 block of A (columns to the right) or of V (rows below).
+// Two barriers per FOUR columns instead of one per column, and the scalar sqrt chain runs in one thread's registers.
+// On exit acc holds L (lower incl. diagonal; entries above the diagonal are zero) and V holds L^-1 (lower).
+__device__ __forceinline__ void potrf_regs(double (&acc)[4][4], double (&V)[4][4], int tm, int tn, double* s11,
+                                           double* spanel, double* swrow, int* s_bad, double* prof) {
+    long long t_diag = 0, t_b1 = 0, t_b2 = 0, t_upd = 0;        // thread 0's clock64 per phase (diagnostics)
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) V[i][j] = (tm + i == tn + j) ? 1.0 : 0.0;
 #pragma unroll 1
-    for (int kb = 0; kb < NB / 4; ++kb) {
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+        const long long c0 = clock_mem();
+        if (tm == k0 && tn == k0) {
+            // ---- 4 x 4 diagonal block: Cholesky in registers; s11 <- { l (row-major 4 x 4, lower), 1 / l_cc } -----------------
+            double l[4][4], r[4];
+            bool bad = false;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-            const int k = kb * 4 + kk;
-            double* col = scol + (k & 1) * NB;
-            double* row = srow + (k & 1) * NB;
-            if (tn == kb * 4) {                      // owners of column k of A: unscaled column, zero above the pivot
+            for (int c = 0; c < 4; ++c) {
+                double d = acc[c][c];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) col[tm + i] = (tm + i >= k) ? acc[i][kk] : 0.0;
+                for (int q = 0; q < c; ++q) d = fma(-l[c][q], l[c][q], d);
+                bad = bad || !(d > 0.0);
+                if (bad && *s_bad < 0) *s_bad = k0 + c;
+                r[c] = rsqrt(d);
+                l[c][c] = d * r[c];
+#pragma unroll
+                for (int i = c + 1; i < 4; ++i) {
+                    double v = acc[i][c];
+#pragma unroll
+                    for (int q = 0; q < c; ++q) v = fma(-l[i][q], l[c][q], v);
+                    l[i][c] = v * r[c];
+                }
             }
-            if (tm == kb * 4) {                      // owners of row k of V (non-zero for columns <= k)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) row[tn + j] = V[kk][j];
-            }
-            __syncthreads();
-            const double p = col[k];
-            if (!(p > 0.0) && *first_bad < 0) *first_bad = k;
-            const double ip = rsqrt(p);
-            double lr[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) lr[i] = col[tm + i] * ip;          // L[tm+i][k]  (0 for rows above k)
-            if (tn + 3 > k) {                        // trailing update of A (columns > k)
+            for (int i = 0; i < 4; ++i) {
+                s11[16 + i] = r[i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const double lc = col[tn + j] * ip;
-                    if (tn + j > k) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[i][j] = fma(-lr[i], lc, acc[i][j]);
-                    }
-                }
-            }
-            if (tn == kb * 4) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) acc[i][kk] = lr[i];            // final column k of L
-            }
-            if (tn <= k) {                           // V: rows > k get -L[r][k] * W_k ; row k becomes W_k = V_k / L_kk
-                double wk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) wk[j] = row[tn + j] * ip;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    if (tm + i > k) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) V[i][j] = fma(-lr[i], wk[j], V[i][j]);
-                    }
-                }
-                if (tm == kb * 4) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) V[kk][j] = wk[j];
+                    s11[i * 4 + j] = (j <= i) ? l[i][j] : 0.0;
+                    acc[i][j] = (j <= i) ? l[i][j] : 0.0;
                 }
             }
         }
+        const long long c1 = clock_mem();
+        __syncthreads();
+        const long long c2 = clock_mem();
+        if (tn == k0 || tm == k0) {
+            double l[4][4], r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                r[i] = s11[16 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) l[i][j] = s11[i * 4 + j];
+            }
+            if (tn == k0) {
+                // ---- panel rows below the block: X L11^T = A by forward substitution, x_c = (a_c - sum_{q<c} x_q l[c][q]) / l[c][c]
+                if (tm > k0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            double v = acc[i][c];
+#pragma unroll
+                            for (int q = 0; q < c; ++q) v = fma(-acc[i][q], l[c][q], v);
+                            acc[i][c] = v * r[c];
+                        }
+                    }
+                } else if (tm < k0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[i][c] = 0.0;
+                }
+                // spanel is stored TRANSPOSED, [c][row]: the 16 owners write (and everybody later reads) consecutive 32-byte
+                // chunks, free of bank conflicts
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    *reinterpret_cast<double2*>(spanel + c * NB + tm) = make_double2(acc[0][c], acc[1][c]);
+                    *reinterpret_cast<double2*>(spanel + c * NB + tm + 2) = make_double2(acc[2][c], acc[3][c]);
+                }
+            }
+            if (tm == k0) {
+                // ---- final rows k0..k0+3 of L^-1: L11 W = V_block by forward substitution -----------------------------------------
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        double v = V[i][j];
+#pragma unroll
+                        for (int q = 0; q < i; ++q) v = fma(-l[i][q], V[q][j], v);
+                        V[i][j] = v * r[i];
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    *reinterpret_cast<double2*>(swrow + i * NB + tn) = make_double2(V[i][0], V[i][1]);
+                    *reinterpret_cast<double2*>(swrow + i * NB + tn + 2) = make_double2(V[i][2], V[i][3]);
+                }
+            }
+        }
+        __syncthreads();
+        const long long c3 = clock_mem();
+        if (tn > k0) {
+            // ---- rank-4 update of A: acc[i][j] -= sum_c L[tm+i][k0+c] L[tn+j][k0+c]   (rows above the block carry zeros) -------
+            if (tm + 3 >= tn) {                      // blocks strictly above the diagonal are never read
+                double pr[4][4], pc[4][4];           // [c][i]
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const double2 a0 = *reinterpret_cast<const double2*>(spanel + c * NB + tm);
+                    const double2 a1 = *reinterpret_cast<const double2*>(spanel + c * NB + tm + 2);
+                    pr[c][0] = a0.x; pr[c][1] = a0.y; pr[c][2] = a1.x; pr[c][3] = a1.y;
+                    const double2 b0 = *reinterpret_cast<const double2*>(spanel + c * NB + tn);
+                    const double2 b1 = *reinterpret_cast<const double2*>(spanel + c * NB + tn + 2);
+                    pc[c][0] = b0.x; pc[c][1] = b0.y; pc[c][2] = b1.x; pc[c][3] = b1.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(-pr[c][i], pc[c][j], acc[i][j]);
+            }
+        } else if (tm > k0) {
+            // ---- rank-4 update of V (columns <= k0+3, rows below the block): V[i][j] -= sum_c L[tm+i][k0+c] W[c][tn+j] --------
+            double pr[4][4], w[4][4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const double2 a0 = *reinterpret_cast<const double2*>(spanel + c * NB + tm);
+                const double2 a1 = *reinterpret_cast<const double2*>(spanel + c * NB + tm + 2);
+                pr[c][0] = a0.x; pr[c][1] = a0.y; pr[c][2] = a1.x; pr[c][3] = a1.y;
+                const double2 w0 = *reinterpret_cast<const double2*>(swrow + c * NB + tn);
+                const double2 w1 = *reinterpret_cast<const double2*>(swrow + c * NB + tn + 2);
+                w[c][0] = w0.x; w[c][1] = w0.y; w[c][2] = w1.x; w[c][3] = w1.y;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) V[i][j] = fma(-pr[c][i], w[c][j], V[i][j]);
+        }
+#ifdef ASVGP_DIAG_POTRF
+        __syncthreads();                 // diagnostic build: barrier-to-barrier phase times
+#endif
+        const long long c4 = clock_mem();
+        if (k0 == 0) t_diag = c1 - c0;
+        t_b1 += c2 - c1; t_b2 += c3 - c2; t_upd += c4 - c3;
+    }
+    if (threadIdx.x == 0 && prof != nullptr) {
+        prof[0] = (double)t_diag; prof[1] = (double)t_b1; prof[2] = (double)t_b2; prof[3] = (double)t_upd;
     }
 }
 
@@ -314,6 +413,10 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
     const int tid = threadIdx.x;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     int* abort_flag = a.ready + g.n_tiles();
+    // the right-hand side y = L^-1 b rides along as a chain of its own, off the critical path of the tiles:
+    // yflag[C] = y_C is final;  rhs_cnt[R] = how many tiles of block row R have subtracted L(R,J) y_J from b_R
+    int* yflag = a.ready + g.n_tiles() + 8;
+    int* rhs_cnt = yflag + g.nb;
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
     fence_proxy_async();
     __syncthreads();
@@ -351,14 +454,32 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
         if (d == 0) {
             // ---- diagonal tile: POTRF + inverse in registers, forward substitution of the right-hand side ---------
             double V[4][4];
-            int first_bad = -1;
-            double* scol = sA[0];                    // [2][64]
-            double* srow = sA[0] + 2 * NB;           // [2][64]
-            double* part = sA[0] + 4 * NB;           // [16][64]
-            if (tid == 0) stat[3] = global_ns();
-            potrf_regs(acc, V, tm, tn, scol, srow, &first_bad);
+            double* s11 = sA[0];                     // [16] l + [4] 1/l_cc (+ padding)
+            double* spanel = sA[0] + 32;             // [4][64] panel, transposed
+            double* swrow = sA[0] + 32 + 4 * NB;     // [4][64]
+            double* part = sA[0] + 32 + 8 * NB;      // [16][64]
+            __shared__ int s_bad;
+            if (tid == 0) { s_bad = -1; stat[3] = global_ns(); }
+            __syncthreads();
+            potrf_regs(acc, V, tm, tn, s11, spanel, swrow, &s_bad, stat + 8);
+            __syncthreads();
+            const int first_bad = s_bad;
             if (tid == 0) stat[4] = global_ns();
-            // y_C = L^-1 b_C (all contributions to b_C have landed: every (C, J) tile is final)
+            // publish L^-1 first (it is what the tiles below wait for), then L (zero above the diagonal)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (tm + i < tn + j) { acc[i][j] = 0.0; V[i][j] = 0.0; }
+                }
+            regs_to_tile(V, a.linv + (int64_t)C * TILE, tm, tn);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1), 1); stat[5] = global_ns(); }
+            regs_to_tile(acc, my_tile, tm, tn);
+            // y_C = L^-1 b_C once every tile of block row C has subtracted its share from b_C
+            if (tid == 0) wait_flag(rhs_cnt + C, min(g.BW, C), abort_flag);
+            __syncthreads();
             {
                 double bv[4];
 #pragma unroll
@@ -367,19 +488,10 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
                 for (int i = 0; i < 4; ++i) {
                     double s = 0.0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) s = fma((tm + i >= tn + j) ? V[i][j] : 0.0, bv[j], s);
+                    for (int j = 0; j < 4; ++j) s = fma(V[i][j], bv[j], s);
                     part[(tn >> 2) * NB + tm + i] = s;
                 }
             }
-            // publish L and L^-1 (zero above the diagonal)
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (tm + i < tn + j) { acc[i][j] = 0.0; V[i][j] = 0.0; }
-                }
-            regs_to_tile(acc, my_tile, tm, tn);
-            regs_to_tile(V, a.linv + (int64_t)C * TILE, tm, tn);
             __syncthreads();
             double yv = 0.0, ld = 0.0;
             if (tid < NB) {
@@ -388,7 +500,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1), 1); stat[5] = global_ns(); }
+            if (tid == 0) st_release(yflag + C, 1);
             // off the critical path: this block column's share of log|P| and ||y||^2
             if (tm == tn) {
 #pragma unroll
@@ -427,7 +539,13 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             double L[4][4] = {};
             tile_mma<NB, NB, false>(L, sA[0], sB[0], tm, tn);      // L[m][n] = sum_k A[m][k] Linv[n][k]
             regs_to_tile(L, my_tile, tm, tn);
-            if (tid < NB) s_vec[tid] = __ldcg(a.rhs + (int64_t)C * NB + tid);   // y_C (published before the diagonal flag)
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) stat[7] = global_ns(); }
+            // off the critical path: b_R -= L(R,C) y_C as soon as y_C exists
+            if (tid == 0) wait_flag(yflag + C, 1, abort_flag);
+            __syncthreads();
+            if (tid < NB) s_vec[tid] = __ldcg(a.rhs + (int64_t)C * NB + tid);
             __syncthreads();
             double* part = sA[0];
 #pragma unroll
@@ -441,7 +559,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             if (tid < NB) atomicAdd(a.rhs + (int64_t)R * NB + tid, -reduce16(part, tid));
             __threadfence();
             __syncthreads();
-            if (tid == 0) { st_release(a.ready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) stat[7] = global_ns(); }
+            if (tid == 0) red_release_add(rhs_cnt + R, 1);
         }
     }
 }

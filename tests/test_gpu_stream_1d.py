@@ -111,8 +111,8 @@ def test_accum_ragged_sizes_and_misaligned_views(cuda, n):
 
 
 @pytest.mark.parametrize("n", [65536, 65537, 65538, 2 * 148 * 1024 + 1, 2 * 148 * 1024 * 3, 1_000_001])
-def test_accum_tma_path_sizes(cuda, n):
-    """Sizes that exercise the TMA-fed kernel's chunking: whole chunks, an odd last point, CTAs with a lone tail chunk."""
+def test_accum_chunk_boundary_sizes(cuda, n):
+    """Sizes around the per-CTA / per-warp tile boundaries of the accumulate kernel, odd and even."""
     rng = np.random.default_rng(n % 1000)
     m, k = 500, 3
     basis = _basis(k, -1, m + 1, m)

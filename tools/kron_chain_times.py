@@ -25,8 +25,9 @@ for _ in range(3):
 torch.cuda.synchronize()
 off = _lib.load().asvgp_kron_colstat_offset(m, m, k)
 nb = -(-m * m // 64)
-st = ws.band[off: off + 8 * nb].view(nb, 8).cpu().numpy()
-t = st[:, 2:]
+st = ws.band[off: off + 12 * nb].view(nb, 12).cpu().numpy()
+t = st[:, 2:8]
+prof = st[:, 8:12]
 mid = slice(nb // 4, 3 * nb // 4)
 def us(a): return float(np.median(a[mid])) / 1e3
 print("block columns", nb, " total chain %.2f ms" % ((t[-1, 3] - t[0, 0]) / 1e6))
@@ -34,3 +35,4 @@ print("per block column (median, us): period %.2f" % us(np.diff(t[:, 3])))
 print("  diag: begin->operands landed %.2f | potrf+inverse %.2f | publish %.2f" % (us(t[:, 1] - t[:, 0]), us(t[:, 2] - t[:, 1]), us(t[:, 3] - t[:, 2])))
 print("  d=1 : diag published -> inverse seen %.2f | trsm tile done %.2f" % (us(t[:, 4] - t[:, 3]), us(t[:, 5] - t[:, 4])))
 print("  next diag potrf start - d=1 tile published: %.2f" % us(t[1:, 1] - t[:-1, 5]))
+print("  potrf (thread 0, SM cycles, median): 4x4 diag block %d | wait barrier 1 (sum of 16) %d | panel+barrier 2 %d | rank-4 updates %d" % tuple(np.median(prof[mid], axis=0)))
