@@ -83,15 +83,21 @@ template <int K>
 struct WarpAccum {
     static constexpr int kPairs = Counts<K>::kPairs;
     static constexpr int kAcc = Counts<K>::kAcc;
-    double acc[kAcc];
+    static constexpr int NG = 2 * K;          // Gram moments sum tau^j, j = 1..2K (j = 0 is the point count)
+    static constexpr int NY = K + 1;          // projection moments sum y tau^j, j = 0..K
+    double mg[NG], my[NY];
+    int cnt;          // points added by this lane
     int cur;          // interval the register sums belong to (warp-uniform), -1 = none
     double u;         // mesh[cur]
     double lo, hi;    // x in (lo, hi]  <=>  locate_interval(x) == cur
-    bool dirty;       // warp-uniform: acc holds something
+    bool dirty;       // warp-uniform: the sums hold something
 
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+        for (int i = 0; i < NG; ++i) mg[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NY; ++i) my[i] = 0.0;
+        cnt = 0;
         dirty = false;
     }
     __device__ __forceinline__ void set_interval(const Mesh& mesh, int idx) {
@@ -102,29 +108,47 @@ struct WarpAccum {
     }
     __device__ __forceinline__ bool inside(double x) const { return x > lo && x <= hi; }
 
+    // centred monomial moments of the point (see MomentCoef in common.cuh): 5K+2 fp64 instructions
     __device__ __forceinline__ void add(const Mesh& mesh, double x, double y) {
-        const double t = (x - u) * mesh.inv_delta;
-        double w[K + 1];
-        bspline_pieces<K>(t, w);
+        const double tau = fma(x - u, mesh.inv_delta, -0.5);
+        double p = tau;
+        mg[0] += p;
+        my[0] += y;
 #pragma unroll
-        for (int r = 0; r <= K; ++r) {
-#pragma unroll
-            for (int s = 0; s <= r; ++s) acc[tri_index(r, s)] = fma(w[r], w[s], acc[tri_index(r, s)]);
-            acc[kPairs + r] = fma(w[r], y, acc[kPairs + r]);
+        for (int j = 2; j <= NG; ++j) {
+            if (j - 1 <= K) my[j - 1] = fma(y, p, my[j - 1]);        // y tau^(j-1)
+            p *= tau;
+            mg[j - 1] += p;
         }
+        ++cnt;
     }
-    // shuffle-reduce the register sums over the warp and add them to the band: one RED per entry per warp
+    // shuffle-reduce the moments over the warp, convert them to band entries and add those to the band: one RED per
+    // entry per warp, issued by lane `entry`
     __device__ __forceinline__ void flush(double* __restrict__ G, double* __restrict__ b, int M, int lane) {
         if (dirty) {
+            double Mg[NG + 1], My[NY];
+            Mg[0] = (double)__reduce_add_sync(0xffffffffu, cnt);
 #pragma unroll
-            for (int r = 0; r <= K; ++r) {
+            for (int j = 0; j < NG; ++j) Mg[j + 1] = warp_sum(mg[j]);
 #pragma unroll
-                for (int s = 0; s <= r; ++s) {
-                    const double v = warp_sum(acc[tri_index(r, s)]);
-                    if (lane == (tri_index(r, s) & 31)) atomicAdd(G + (int64_t)(r - s) * M + cur + s, v);
+            for (int j = 0; j < NY; ++j) My[j] = warp_sum(my[j]);
+            const MomentCoef<K>& mc = g_moment_coef<K>;
+#pragma unroll
+            for (int e0 = 0; e0 < kAcc; e0 += 32) {               // kAcc = 35 for K = 6: a second round for three entries
+                const int e = e0 + lane;
+                if (e < kPairs) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j <= NG; ++j) v = fma(mc.cg[e][j], Mg[j], v);
+                    const int r = mc.rr[e], s = mc.ss[e];
+                    atomicAdd(G + (int64_t)(r - s) * M + cur + s, v);
+                } else if (e < kAcc) {
+                    const int r = e - kPairs;
+                    double v = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NY; ++j) v = fma(mc.cb[r][j], My[j], v);
+                    atomicAdd(b + cur + r, v);
                 }
-                const double v = warp_sum(acc[kPairs + r]);
-                if (lane == ((kPairs + r) & 31)) atomicAdd(b + cur + r, v);
             }
         }
         clear();
