@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) basis_eval_1d_kernel(const double* __rest
 // fused accumulation
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kAccumThreads = 256;
-constexpr int kAccumUnroll = 4;
+constexpr int kAccumUnroll = 8;
 
 template <int K>
 struct WarpAccum {
