@@ -22,6 +22,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = os.environ.get("ASVGP_NCCL_DEBUG", "WARN")   # NCCL's version banner would share stdout with the JSON line
 
 WORKLOADS = {
     # name: (N per rank, M, spline order, kernel, sorted?)
@@ -45,7 +46,7 @@ BYTES_PER_POINT_ACCUM = 16         # x and y read once
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="1d", choices=sorted(WORKLOADS) + sorted(WORKLOADS_2D))
@@ -68,15 +69,40 @@ def measured_peaks():
 # clocks sampler (nvidia-smi, in the background, during the timed region)
 # ---------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clocks and throttle reasons of GPU `index` DURING the timed region: NVML (pynvml) every 2 ms when it
+    is importable, else `nvidia-smi` as fast as it answers."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def _run(self):
+        nv = self.nvml
         while not self.stop_flag.is_set():
             try:
+                if nv is not None:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle) if hasattr(
+                        nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                            nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+                    self.samples.append([sm, self.max_sm] + ["Active" if r & b else "Not Active" for b in bits])
+                    self.stop_flag.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
@@ -84,7 +110,7 @@ class ClockSampler:
                     self.samples.append(parts)
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.02)
 
     def __enter__(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -97,12 +123,12 @@ class ClockSampler:
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples (NVML and nvidia-smi unavailable)"]}
         sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        reasons = [n for i, n in enumerate(self.NAMES)
+                   if any(str(s[2 + i]).lower().startswith("active") for s in self.samples)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1,12 +1,16 @@
+#!/bin/bash
+# r01 profiling recipe (B200_PROFILING.md): launch lists (device time of every launch) and one --set full capture per hot
+# kernel.  Every ncu run follows a plain run of the same command that exited 0.
 set -x
 B1="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline --no-2d"
 B2="python bench.py --workload 2d --steps 1 --warmup 3 --no-e2e --no-cpu-baseline"
-$B1 > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_1d.csv $B1 > gpurun_out/ncu_l1.log 2>&1
-$B2 > gpurun_out/plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file gpurun_out/launches_2d.csv $B2 > gpurun_out/ncu_l2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:accum_1d_kernel -s 3 -c 1 -o gpurun_out/prof_accum_1d -f $B1 > gpurun_out/ncu_f1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:elbo_chains_kernel -s 3 -c 1 -o gpurun_out/prof_chains_1d -f $B1 > gpurun_out/ncu_f2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:accum_2d_kernel -s 3 -c 1 -o gpurun_out/prof_accum_2d -f $B2 > gpurun_out/ncu_f3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bb_syrk_kernel -s 300 -c 1 -o gpurun_out/prof_bb_syrk -f $B2 > gpurun_out/ncu_f4.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bb_potrf_kernel -s 300 -c 1 -o gpurun_out/prof_bb_potrf -f $B2 > gpurun_out/ncu_f5.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bb_sel_symm_kernel -s 300 -c 1 -o gpurun_out/prof_bb_sel_symm -f $B2 > gpurun_out/ncu_f6.log 2>&1
+$B1 > gpurun_out/plain1.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_1d.csv $B1 > gpurun_out/ncu_l1.log 2>&1
+$B2 > gpurun_out/plain2.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_2d.csv $B2 > gpurun_out/ncu_l2.log 2>&1
+full() { ncu --set full --clock-control none --import-source on -k regex:$1 -s $2 -c 1 -o gpurun_out/prof_$3 -f ${@:4} > gpurun_out/ncu_$3.log 2>&1; }
+full accum_1d_kernel 3 accum_1d $B1
+full elbo_chains_kernel 3 chains_1d $B1
+full accum_2d_cols_kernel 3 accum_2d_cols $B2
+full td_factor_kernel 3 td_factor $B2
+full td_selinv_kernel 3 td_selinv $B2
+full predict_2d_cols_kernel 1 predict_2d_cols $B2
 ls -la gpurun_out/*.ncu-rep
