@@ -1078,18 +1078,23 @@ __global__ void __launch_bounds__(256) predict_2d_table_kernel(int nc1, int nc2,
             }
             out[o] = v;
         }
+        // variance coefficients in two stages: contract dimension 2 first,
+        //   U[(r1,s1)][Q] = sum_{r2,s2} AA[r2][s2][Q] Sigma[(r1,r2),(s1,s2)],   then   Cv[P][Q] = sum_{r1,s1} AA[r1][s1][P] U[(r1,s1)][Q]
+        double* s_U = s_alpha + W;                       // [K1*K1][NS]
+        for (int o = tid; o < K1 * K1 * NS; o += blockDim.x) {
+            const int Q = o % NS, s1 = (o / NS) % K1, r1 = o / (NS * K1);
+            double v = 0.0;
+            for (int r2 = 0; r2 < K1; ++r2)
+                for (int s2 = 0; s2 < K1; ++s2)
+                    v = fma(s_AA[r2][s2][Q], s_win[(r1 * K1 + r2) * W + s1 * K1 + s2], v);
+            s_U[o] = v;
+        }
+        __syncthreads();
         for (int o = tid; o < PT::NV; o += blockDim.x) {
             const int P = o / NS, Q = o % NS;
             double v = 0.0;
             for (int r1 = 0; r1 < K1; ++r1)
-                for (int s1 = 0; s1 < K1; ++s1) {
-                    const double c1f = s_AA[r1][s1][P];
-                    double inner = 0.0;
-                    for (int r2 = 0; r2 < K1; ++r2)
-                        for (int s2 = 0; s2 < K1; ++s2)
-                            inner = fma(s_AA[r2][s2][Q], s_win[(r1 * K1 + r2) * W + s1 * K1 + s2], inner);
-                    v = fma(c1f, inner, v);
-                }
+                for (int s1 = 0; s1 < K1; ++s1) v = fma(s_AA[r1][s1][P], s_U[(r1 * K1 + s1) * NS + Q], v);
             out[PT::NM + o] = v;
         }
     } else {
@@ -1477,7 +1482,7 @@ static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1,
                              double prior_var, double* mean, double* var, double* work, cudaStream_t st) {
     const int nc1 = nk1 - 1, nc2 = nk2 - 1, m1 = nk1 + K - 1, m2 = nk2 + K - 1;
     constexpr int W = (K + 1) * (K + 1);
-    const size_t smem = sizeof(double) * (size_t)(W * W + W);
+    const size_t smem = sizeof(double) * (size_t)(W * W + W + W * (2 * K + 1));      // window, alpha, stage-1 result
     ASVGP_CUDA_OK(cudaFuncSetAttribute(predict_2d_table_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work);
     ASVGP_CUDA_OK(cudaGetLastError());
