@@ -50,11 +50,11 @@ inline ChunkLayout make_layout(int M, int K, int P) {
     return L;
 }
 
-// Heuristic chunk count: balance the chunk sweep (M/P columns) against the reduced sweep ((P-1)K columns of a
-// matrix 2K-1 wide, ~1.5x the work per column).
+// Chunk count: with the separator system solved by block cyclic reduction (log2 P levels) the chunk sweeps (M/P
+// columns) dominate, so as many lanes as the CTA has; the callers cap it by what fits in shared memory.
 inline int default_chunks(int M, int K) {
     if (M < 64 * (K + 1)) return 1;
-    int P = (int)(sqrt((double)M / (1.5 * K)) + 0.5);
+    int P = M / (4 * (K + 1));          // keep chunks at least a few bandwidths long
     if (P > 128) P = 128;
     if (P < 1) P = 1;
     return P;
@@ -401,37 +401,54 @@ ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const C
 // =====================================================================================================================
 namespace asvgp {
 
+// ---- the separator system: block cyclic reduction -----------------------------------------------------------------------
+// The (P-1) separators form an SPD block-tridiagonal system with K x K blocks.  A serial sweep over its (P-1) K columns
+// was the longest phase of a chain; block cyclic reduction needs ceil(log2(P-1)) levels instead, every level handled by
+// one lane per separator: level l (stride s = 2^l) eliminates the nodes i = s (2j+1), whose neighbours a = i - s and
+// b = i + s stay; it is a Cholesky factorisation in nested-dissection order, so log-det, forward substitution, back
+// substitution and the Takahashi recursion (Sigma_ai = -Sigma_aa Y_a - Sigma_ab Y_b, ..., run over the levels in reverse)
+// all carry over block by block, and the tangents ride along because everything is templated on the scalar.
+template <class T, int B>
+struct CrNode {
+    T D[B][B];    // diagonal block (lower used) -> its Cholesky factor L_i (lower) -> Sigma_ii (full symmetric)
+    T E[B][B];    // coupling with the previous node still present: rows = this node, columns = that node
+    T Wa[B][B];   // factor block of this node's column in the rows of neighbour a:  W_a = R_{a,i} L_i^-T
+    T Wb[B][B];   // ... in the rows of neighbour b
+    T Sa[B][B];   // Sigma_{a,i}
+    T Sb[B][B];   // Sigma_{b,i}
+    T r[B];       // right-hand side -> y_i = L_i^-1 (...) -> x_i
+    T ip[B];      // 1 / L_i[j][j]
+    T logdet, quad;
+    int info;
+};
+
 template <class T, int K>
 struct ChainWork {
     ColumnStore<T, K, true> cols;              // chunk columns (global memory): kFields x n_steps x P
     // everything below is small and lives in shared memory inside the kernels (host memory in the test harness)
     ChunkSchur<T, K>* schur;                   // [P]
-    T* red_band;                               // (2K) x n_red   reduced lower band (bandwidth 2K-1)
-    T* red_rhs;                                // n_red
-    ColumnStore<T, 2 * K - 1, false> red_cols; // reduced columns: (2K+1) x n_red x 1
-    T* x_red;                                  // n_red
-    T* sig_red;                                // (2K) x n_red
+    CrNode<T, K>* nodes;                       // [P-1] separator system
+    T* x_red;                                  // n_red            } written by cr_export when the Schur pieces are dead:
+    T* sig_red;                                // (2K) x n_red     } they alias the schur array
 };
 
 // bytes of the small (shared-memory) part of a ChainWork and its carving; the same code sizes the host harness
 template <class T, int K>
 struct ChainSmall {
-    static constexpr int KR = 2 * K - 1;
     ASVGP_HD static size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
-    ASVGP_HD static size_t bytes(int P) {
+    ASVGP_HD static size_t head_bytes(int P) {
         const size_t nred = (size_t)(P - 1) * K + 1;
-        return align16((size_t)P * sizeof(ChunkSchur<T, K>)) + 2 * align16((size_t)(KR + 1) * nred * sizeof(T))
-               + 2 * align16(nred * sizeof(T)) + align16(ColumnStore<T, KR, false>::count((int)nred, 1) * sizeof(T));
+        const size_t a = align16((size_t)P * sizeof(ChunkSchur<T, K>));
+        const size_t b = align16((size_t)(2 * K) * nred * sizeof(T)) + align16(nred * sizeof(T));
+        return a > b ? a : b;
     }
+    ASVGP_HD static size_t bytes(int P) { return head_bytes(P) + align16((size_t)(P > 1 ? P - 1 : 1) * sizeof(CrNode<T, K>)); }
     ASVGP_HD static void carve(int P, char* base, ChainWork<T, K>& w) {
         const size_t nred = (size_t)(P - 1) * K + 1;
-        char* p = base;
-        w.schur = reinterpret_cast<ChunkSchur<T, K>*>(p); p += align16((size_t)P * sizeof(ChunkSchur<T, K>));
-        w.red_band = reinterpret_cast<T*>(p); p += align16((size_t)(KR + 1) * nred * sizeof(T));
-        w.sig_red = reinterpret_cast<T*>(p); p += align16((size_t)(KR + 1) * nred * sizeof(T));
-        w.red_rhs = reinterpret_cast<T*>(p); p += align16(nred * sizeof(T));
-        w.x_red = reinterpret_cast<T*>(p); p += align16(nred * sizeof(T));
-        w.red_cols = ColumnStore<T, KR, false>{reinterpret_cast<T*>(p), (int)(nred - 1), 1};
+        w.schur = reinterpret_cast<ChunkSchur<T, K>*>(base);
+        w.sig_red = reinterpret_cast<T*>(base);
+        w.x_red = reinterpret_cast<T*>(base + align16((size_t)(2 * K) * nred * sizeof(T)));
+        w.nodes = reinterpret_cast<CrNode<T, K>*>(base + head_bytes(P));
     }
 };
 
@@ -445,59 +462,298 @@ ASVGP_HD void chain_phase1(const ChunkLayout& lay, int p, MatFn A, RhsFn rhs, co
     else eliminate_columns<T, K, true, STORE>(lay.start(p), lay.size(p), n_steps, A, rhs, w.cols, p, w.schur[p]);
 }
 
-template <class T, int KR>
-struct RedMat {
-    const T* band; int n;
-    ASVGP_HD T operator()(int d, int j) const {
-        const bool ok = (j >= 0) & (j + d < n);
-        const T v = band[ok ? (size_t)d * n + j : 0];      // branch-free: the load always issues
-        return ok ? v : zero_of<T>();
-    }
-};
-template <class T>
-struct RedRhs {
-    const T* v; int n;
-    ASVGP_HD T operator()(int j) const {
-        const bool ok = (j >= 0) & (j < n);
-        const T x = v[ok ? j : 0];
-        return ok ? x : zero_of<T>();
-    }
-};
-
-// Phase 2a, executed by thread t of n_threads: zero the reduced band (strided).  Barrier afterwards.
+// Executed by lane q < P-1: node q of the separator system from the Schur pieces of the chunks on either side of S_q.
 template <class T, int K>
-ASVGP_HD void chain_phase2_zero(const ChunkLayout& lay, int t, int n_threads, const ChainWork<T, K>& w) {
-    const int total = 2 * K * lay.n_reduced();
-    for (int i = t; i < total; i += n_threads) w.red_band[i] = zero_of<T>();
-}
-
-// Phase 2b, executed by thread q < P-1: block row q of the reduced (separator) system from the Schur pieces of the
-// chunks on either side of S_q.  Barrier afterwards.
-template <class T, int K>
-ASVGP_HD void chain_phase2_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
-    const int nred = lay.n_reduced();
+ASVGP_HD void cr_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
     const ChunkSchur<T, K>& left = w.schur[q];        // chunk q ends at S_q
     const ChunkSchur<T, K>& right = w.schur[q + 1];   // chunk q+1 starts after S_q
+    CrNode<T, K>& nd = w.nodes[q];
 #pragma unroll
     for (int a = 0; a < K; ++a) {
-        w.red_rhs[q * K + a] = left.rend[a] - right.rhsL[a];
+        nd.r[a] = left.rend[a] - right.rhsL[a];
 #pragma unroll
-        for (int b = 0; b <= a; ++b)
-            w.red_band[(size_t)(a - b) * nred + q * K + b] = left.Dend[a][b] - right.SLL[a][b];
-        if (q >= 1) {
-            // rows of S_q, columns of S_{q-1}: produced by chunk q (its E)
+        for (int b = 0; b < K; ++b) {
+            nd.D[a][b] = (b <= a) ? left.Dend[a][b] - right.SLL[a][b] : zero_of<T>();
+            nd.E[a][b] = left.E[a][b];                // rows of S_q, columns of S_{q-1} (zero for q = 0)
+        }
+    }
+    nd.logdet = zero_of<T>();
+    nd.quad = zero_of<T>();
+    nd.info = 0;
+}
+
+// Executed by the lane of node i when it is eliminated at stride s (neighbours a = i - s, b = i + s when they exist):
+// Cholesky of D_i, y_i, its share of log-det and quadratic form, and the factor blocks W_a, W_b.
+template <class T, int K>
+ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T, K>& w) {
+    CrNode<T, K>& nd = w.nodes[i];
+    LogAccum<T> logdet;
+    logdet.init();
+    T quad = zero_of<T>();
 #pragma unroll
-            for (int rho = 0; rho < K; ++rho)
-                w.red_band[(size_t)(K + a - rho) * nred + (q - 1) * K + rho] = left.E[a][rho];
+    for (int j = 0; j < K; ++j) {
+        T d = nd.D[j][j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) d -= nd.D[j][q] * nd.D[j][q];
+        if (!(value_of(d) > 0.0) && nd.info == 0) nd.info = g_offset + i * K + j + 1;
+        const T ip = rsqrt_of(d);
+        logdet.add(d, ip);
+        nd.ip[j] = ip;
+        nd.D[j][j] = d * ip;
+#pragma unroll
+        for (int r = j + 1; r < K; ++r) {
+            T v = nd.D[r][j];
+#pragma unroll
+            for (int q = 0; q < j; ++q) v -= nd.D[r][q] * nd.D[j][q];
+            nd.D[r][j] = v * ip;
+        }
+        T y = nd.r[j];
+#pragma unroll
+        for (int q = 0; q < j; ++q) y -= nd.D[j][q] * nd.r[q];
+        y = y * ip;
+        nd.r[j] = y;
+        quad += y * y;
+    }
+    nd.logdet = logdet.result();
+    nd.quad = quad;
+    const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
+    if (has_a) {                                      // W_a = E_i^T L^-T : row x solves L z = E_i[:, x]
+#pragma unroll
+        for (int x = 0; x < K; ++x)
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                T v = nd.E[j][x];
+#pragma unroll
+                for (int q = 0; q < j; ++q) v -= nd.D[j][q] * nd.Wa[x][q];
+                nd.Wa[x][j] = v * nd.ip[j];
+            }
+    }
+    if (has_b) {                                      // W_b = E_b L^-T : row x solves L z = E_b[x, :]^T
+        const CrNode<T, K>& nb = w.nodes[i + s];
+#pragma unroll
+        for (int x = 0; x < K; ++x)
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                T v = nb.E[x][j];
+#pragma unroll
+                for (int q = 0; q < j; ++q) v -= nd.D[j][q] * nd.Wb[x][q];
+                nd.Wb[x][j] = v * nd.ip[j];
+            }
+    }
+}
+
+// Executed by the lane of node c that STAYS at stride s (c is a multiple of 2s): Schur updates from the eliminated
+// neighbours c + s (c is their `a`) and c - s (c is their `b`), and the new coupling with c - 2s.
+template <class T, int K>
+ASVGP_HD void cr_update(int n, int s, int c, const ChainWork<T, K>& w) {
+    CrNode<T, K>& nd = w.nodes[c];
+    if (c + s < n) {
+        const CrNode<T, K>& e = w.nodes[c + s];
+#pragma unroll
+        for (int x = 0; x < K; ++x) {
+            T rr = nd.r[x];
+#pragma unroll
+            for (int j = 0; j < K; ++j) rr -= e.Wa[x][j] * e.r[j];
+            nd.r[x] = rr;
+#pragma unroll
+            for (int y = 0; y <= x; ++y) {
+                T v = nd.D[x][y];
+#pragma unroll
+                for (int j = 0; j < K; ++j) v -= e.Wa[x][j] * e.Wa[y][j];
+                nd.D[x][y] = v;
+            }
+        }
+    }
+    if (c - s >= 0) {
+        const CrNode<T, K>& e = w.nodes[c - s];
+        const bool has_a = c - 2 * s >= 0;
+#pragma unroll
+        for (int x = 0; x < K; ++x) {
+            T rr = nd.r[x];
+#pragma unroll
+            for (int j = 0; j < K; ++j) rr -= e.Wb[x][j] * e.r[j];
+            nd.r[x] = rr;
+#pragma unroll
+            for (int y = 0; y <= x; ++y) {
+                T v = nd.D[x][y];
+#pragma unroll
+                for (int j = 0; j < K; ++j) v -= e.Wb[x][j] * e.Wb[y][j];
+                nd.D[x][y] = v;
+            }
+#pragma unroll
+            for (int y = 0; y < K; ++y) {             // new coupling R'_{c, c-2s} = -W_b W_a^T
+                T v = zero_of<T>();
+                if (has_a) {
+#pragma unroll
+                    for (int j = 0; j < K; ++j) v -= e.Wb[x][j] * e.Wa[y][j];
+                }
+                nd.E[x][y] = v;
+            }
         }
     }
 }
 
-// Phase 2c, executed by ONE thread: eliminate the reduced system and (optionally) back-substitute / run the
-// Takahashi recursion on it; also sums the per-chunk log-determinants and quadratic forms.
+// Back substitution and Takahashi recursion for node i eliminated at stride s (s = 0: the root, no neighbours).
 template <class T, int K, bool SOLVE, bool SELINV>
-ASVGP_HD ChainTotals<T, K> chain_phase2_solve(const ChunkLayout& lay, const ChainWork<T, K>& w) {
-    constexpr int KR = 2 * K - 1;
+ASVGP_HD void cr_back(int n, int s, int i, const ChainWork<T, K>& w) {
+    CrNode<T, K>& nd = w.nodes[i];
+    const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
+    const CrNode<T, K>* na = has_a ? &w.nodes[i - s] : nullptr;
+    const CrNode<T, K>* nb = has_b ? &w.nodes[i + s] : nullptr;
+    if (SOLVE) {
+        T t[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            T v = nd.r[j];
+            if (has_a) {
+#pragma unroll
+                for (int x = 0; x < K; ++x) v -= nd.Wa[x][j] * na->r[x];
+            }
+            if (has_b) {
+#pragma unroll
+                for (int x = 0; x < K; ++x) v -= nd.Wb[x][j] * nb->r[x];
+            }
+            t[j] = v;
+        }
+#pragma unroll
+        for (int j = K - 1; j >= 0; --j) {
+            T v = t[j];
+#pragma unroll
+            for (int q = j + 1; q < K; ++q) v -= nd.D[q][j] * t[q];
+            t[j] = v * nd.ip[j];
+        }
+#pragma unroll
+        for (int j = 0; j < K; ++j) nd.r[j] = t[j];
+    }
+    if (SELINV) {
+        // L^-1 (lower), column by column
+        T Li[K][K];
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                if (r < c) { Li[r][c] = zero_of<T>(); continue; }
+                T v = (r == c) ? make_scalar<T>(1.0, 0.0) : zero_of<T>();
+#pragma unroll
+                for (int q = c; q < r; ++q) v -= nd.D[r][q] * Li[q][c];
+                Li[r][c] = v * nd.ip[r];
+            }
+        T S[K][K];                                    // Sigma_ii, starts as L^-T L^-1
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int c2 = 0; c2 < K; ++c2) {
+                T v = zero_of<T>();
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    if (r >= c && r >= c2) v += Li[r][c] * Li[r][c2];
+                }
+                S[c][c2] = v;
+            }
+        T Ya[K][K], Yb[K][K];                         // Y_k = W_k L^-1
+        if (has_a) {
+#pragma unroll
+            for (int x = 0; x < K; ++x)
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                    T v = zero_of<T>();
+#pragma unroll
+                    for (int j = c; j < K; ++j) v += nd.Wa[x][j] * Li[j][c];
+                    Ya[x][c] = v;
+                }
+        }
+        if (has_b) {
+#pragma unroll
+            for (int x = 0; x < K; ++x)
+#pragma unroll
+                for (int c = 0; c < K; ++c) {
+                    T v = zero_of<T>();
+#pragma unroll
+                    for (int j = c; j < K; ++j) v += nd.Wb[x][j] * Li[j][c];
+                    Yb[x][c] = v;
+                }
+        }
+        // Sigma_ba: a and b are neighbours one level up, where exactly one of them was eliminated
+        const bool a_is_odd = has_a && has_b && (((i - s) / (2 * s)) & 1);
+#pragma unroll
+        for (int x = 0; x < K; ++x)
+#pragma unroll
+            for (int c = 0; c < K; ++c) {
+                T va = zero_of<T>(), vb = zero_of<T>();
+                if (has_a) {
+#pragma unroll
+                    for (int y = 0; y < K; ++y) va -= na->D[x][y] * Ya[y][c];              // Sigma_aa Y_a
+                }
+                if (has_b) {
+#pragma unroll
+                    for (int y = 0; y < K; ++y) vb -= nb->D[x][y] * Yb[y][c];              // Sigma_bb Y_b
+                }
+                if (has_a && has_b) {
+#pragma unroll
+                    for (int y = 0; y < K; ++y) {
+                        // Sigma_ba[u][v]: rows of b, columns of a
+                        const T sba_xy = a_is_odd ? na->Sb[x][y] : nb->Sa[y][x];           // Sigma_ba[x][y]
+                        const T sba_yx = a_is_odd ? na->Sb[y][x] : nb->Sa[x][y];           // Sigma_ba[y][x] = Sigma_ab[x][y]
+                        va -= sba_yx * Yb[y][c];                                            // Sigma_ab Y_b
+                        vb -= sba_xy * Ya[y][c];                                            // Sigma_ba Y_a
+                    }
+                }
+                nd.Sa[x][c] = va;
+                nd.Sb[x][c] = vb;
+            }
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int c2 = 0; c2 < K; ++c2) {
+                T v = S[c][c2];
+                if (has_a) {
+#pragma unroll
+                    for (int x = 0; x < K; ++x) v -= Ya[x][c] * nd.Sa[x][c2];
+                }
+                if (has_b) {
+#pragma unroll
+                    for (int x = 0; x < K; ++x) v -= Yb[x][c] * nd.Sb[x][c2];
+                }
+                S[c][c2] = v;
+            }
+#pragma unroll
+        for (int c = 0; c < K; ++c)
+#pragma unroll
+            for (int c2 = 0; c2 < K; ++c2) nd.D[c][c2] = S[c][c2];
+    }
+}
+
+// Executed by lane q < P-1 once the recursion is complete: separator solution and the block-tridiagonal part of the
+// inverse in the band layout phase 3 reads (x_red, sig_red alias the Schur pieces, which are dead by now).
+template <class T, int K, bool SOLVE, bool SELINV>
+ASVGP_HD void cr_export(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
+    const int nred = lay.n_reduced();
+    const CrNode<T, K>& nd = w.nodes[q];
+    if (SOLVE) {
+#pragma unroll
+        for (int a = 0; a < K; ++a) w.x_red[q * K + a] = nd.r[a];
+    }
+    if (SELINV) {
+#pragma unroll
+        for (int a = 0; a < K; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) w.sig_red[(size_t)(a - b) * nred + q * K + b] = nd.D[a][b];
+        if (q >= 1) {
+            // Sigma_{q,q-1}: the odd one of (q-1, q) was eliminated at stride 1 with the other as its neighbour
+            const bool q_odd = q & 1;
+            const CrNode<T, K>& prev = w.nodes[q - 1];
+#pragma unroll
+            for (int a = 0; a < K; ++a)
+#pragma unroll
+                for (int rho = 0; rho < K; ++rho)
+                    w.sig_red[(size_t)(K + a - rho) * nred + (q - 1) * K + rho] = q_odd ? nd.Sa[rho][a] : prev.Sb[a][rho];
+        }
+    }
+}
+
+// Sums of the per-chunk and per-separator log-determinants and quadratic forms (one lane).
+template <class T, int K>
+ASVGP_HD ChainTotals<T, K> chain_totals(const ChunkLayout& lay, const ChainWork<T, K>& w) {
     ChainTotals<T, K> tot;
     tot.logdet = zero_of<T>();
     tot.quad = zero_of<T>();
@@ -507,18 +763,23 @@ ASVGP_HD ChainTotals<T, K> chain_phase2_solve(const ChunkLayout& lay, const Chai
         tot.quad += w.schur[p].quad;
         if (w.schur[p].info != 0 && (tot.info == 0 || w.schur[p].info < tot.info)) tot.info = w.schur[p].info;
     }
-    const int nred = lay.n_reduced();
-    if (nred == 0) return tot;
-    ChunkSchur<T, KR> red_out;
-    RedMat<T, KR> RA{w.red_band, nred};
-    RedRhs<T> Rb{w.red_rhs, nred};
-    eliminate_columns<T, KR, false, (SOLVE || SELINV)>(0, nred, nred, RA, Rb, w.red_cols, 0, red_out);
-    tot.logdet += red_out.logdet;
-    tot.quad += red_out.quad;
-    if (red_out.info != 0 && tot.info == 0) tot.info = lay.M + red_out.info;   // failure inside the separator system
-    if (SOLVE) backsolve_serial<T, KR>(nred, w.red_cols, w.x_red);
-    if (SELINV) selinv_serial<T, KR>(nred, w.red_cols, w.sig_red);
+    for (int q = 0; q + 1 < lay.P; ++q) {
+        tot.logdet += w.nodes[q].logdet;
+        tot.quad += w.nodes[q].quad;
+        if (w.nodes[q].info != 0 && tot.info == 0) tot.info = w.nodes[q].info;   // failure inside the separator system
+    }
     return tot;
+}
+
+// The level schedule of the separator recursion, shared by the kernels and the host harness:
+//   forward : for (s = 1; s < n; s *= 2) { nodes i % 2s == s: cr_eliminate(i, s);  barrier;  nodes c % 2s == 0: cr_update(c, s);  barrier }
+//             node 0: cr_eliminate(0, s = 0);  chain_totals (needs the Schur pieces: before cr_export)
+//   backward: node 0: cr_back(0, s = 0);  barrier;  for (s = top; s >= 1; s /= 2) { nodes i % 2s == s: cr_back(i, s);  barrier }
+//             nodes q: cr_export(q)
+ASVGP_HD int cr_top_stride(int n) {
+    int s = 1;
+    while (2 * s < n) s *= 2;
+    return n > 1 ? s : 0;
 }
 
 template <class T, int K, bool SOLVE, bool SELINV>

@@ -117,14 +117,33 @@ __device__ __forceinline__ void run_chain(const ChunkLayout& lay, const ColumnSt
     w.cols = cols;
     ChainSmall<T, K>::carve(lay.P, smem, w);
     if (p == 0 && clk) clk[0] = clock64();
-    if (lay.P > 1) chain_phase2_zero<T, K>(lay, p, blockDim.x, w);
     if (p < lay.P) chain_phase1<T, K, STORE>(lay, p, A, rhs, w);
     __syncthreads();
     if (p == 0 && clk) clk[1] = clock64();
-    if (p < lay.P - 1) chain_phase2_assemble<T, K>(lay, p, w);
+    // separator system: block cyclic reduction, one lane per separator, two barriers per level (band_engine.cuh)
+    const int n = lay.P - 1;
+    if (p < n) cr_assemble<T, K>(lay, p, w);
     __syncthreads();
-    if (p == 0) *tot = chain_phase2_solve<T, K, SOLVE, SELINV>(lay, w);
+    for (int s = 1; s < n; s *= 2) {
+        if (p < n && (p & (2 * s - 1)) == s) cr_eliminate<T, K>(n, s, p, lay.M, w);
+        __syncthreads();
+        if (p < n && (p & (2 * s - 1)) == 0) cr_update<T, K>(n, s, p, w);
+        __syncthreads();
+    }
+    if (p == 0) {
+        if (n > 0) cr_eliminate<T, K>(n, 0, 0, lay.M, w);
+        *tot = chain_totals<T, K>(lay, w);
+        if ((SOLVE || SELINV) && n > 0) cr_back<T, K, SOLVE, SELINV>(n, 0, 0, w);
+    }
     __syncthreads();
+    if ((SOLVE || SELINV) && n > 0) {
+        for (int s = cr_top_stride(n); s >= 1; s /= 2) {
+            if (p < n && (p & (2 * s - 1)) == s) cr_back<T, K, SOLVE, SELINV>(n, s, p, w);
+            __syncthreads();
+        }
+        if (p < n) cr_export<T, K, SOLVE, SELINV>(lay, p, w);
+        __syncthreads();
+    }
     if (p == 0 && clk) clk[2] = clock64();
     if ((SOLVE || SELINV) && p < lay.P) chain_phase3<T, K, SOLVE, SELINV>(lay, p, w, x_out, sig_out);
     __syncthreads();

@@ -40,9 +40,21 @@ static int run_chain(int M, int P, const double* band, const double* dband, cons
     HostMat<T> A{band, dband, M};
     HostRhs<T> b{rhs, M};
     for (int p = 0; p < lay.P; ++p) chain_phase1<T, K, true>(lay, p, A, b, w);
-    for (int t = 0; t < 7; ++t) chain_phase2_zero<T, K>(lay, t, 7, w);
-    for (int q = 0; q + 1 < lay.P; ++q) chain_phase2_assemble<T, K>(lay, q, w);
-    ChainTotals<T, K> tot = chain_phase2_solve<T, K, true, true>(lay, w);
+    // the separator system by block cyclic reduction; every inner loop over nodes is one barrier-separated phase of the kernel
+    const int n = lay.P - 1;
+    for (int q = 0; q < n; ++q) cr_assemble<T, K>(lay, q, w);
+    for (int s = 1; s < n; s *= 2) {
+        for (int i = s; i < n; i += 2 * s) cr_eliminate<T, K>(n, s, i, lay.M, w);
+        for (int c = 0; c < n; c += 2 * s) cr_update<T, K>(n, s, c, w);
+    }
+    if (n > 0) cr_eliminate<T, K>(n, 0, 0, lay.M, w);
+    ChainTotals<T, K> tot = chain_totals<T, K>(lay, w);
+    if (n > 0) {
+        cr_back<T, K, true, true>(n, 0, 0, w);
+        for (int s = cr_top_stride(n); s >= 1; s /= 2)
+            for (int i = s; i < n; i += 2 * s) cr_back<T, K, true, true>(n, s, i, w);
+        for (int q = 0; q < n; ++q) cr_export<T, K, true, true>(lay, q, w);
+    }
     std::vector<T> xo(M), so((size_t)(K + 1) * M, zero_of<T>());
     for (int p = 0; p < lay.P; ++p) chain_phase3<T, K, true, true>(lay, p, w, xo.data(), so.data());
     const int nt = sizeof(T) / sizeof(double);
