@@ -15,6 +15,8 @@
 // because Kuu is proportional to 1/variance (see elbo_finalize_kernel).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "band_engine.cuh"
 #include "../../include/asvgp_b200.h"
 
@@ -90,6 +92,67 @@ template <class T> struct VecRhs {      // use == 0: zero right-hand side (b mus
 };
 
 // ------------------------------------------------------------------------------------------------------------------
+// lane-interleaved row tables
+// ------------------------------------------------------------------------------------------------------------------
+// The P lanes of a chain sweep P different chunks in lock-step, so reading the band directly costs 32 separate sectors
+// per load instruction (the sweeps were LSU-bound: per-column time GREW with P).  A fully parallel pre-pass therefore
+// tabulates, for every chain, what lane p needs at row rho of its chunk —
+//     rows[(rho * (K+1) + bidx) * P + p] = A[g0(p) + rho, g0(p) + rho - K + bidx],     rhs[rho * P + p] = b[g0(p) + rho]
+// — and the sweeps read those tables with fully coalesced loads.  Every access A(d, col) of the engine maps to
+// rho = col + d - g0, bidx = K - d.
+template <class T, int K>
+struct RowsMat {
+    const T* rows; int g0, P, p, n_rho;
+    __device__ __forceinline__ T operator()(int d, int col) const {
+        const int rho = col + d - g0;
+        const bool ok = (rho >= 0) & (rho < n_rho);
+        const T v = rows[ok ? ((size_t)rho * (K + 1) + (K - d)) * P + p : (size_t)p];      // branch-free
+        return ok ? v : zero_of<T>();
+    }
+};
+template <class T>
+struct RowsRhs {
+    const T* r; int g0, P, p, n_rho;
+    __device__ __forceinline__ T operator()(int j) const {
+        const int rho = j - g0;
+        const bool ok = (rho >= 0) & (rho < n_rho);
+        const T v = r[ok ? (size_t)rho * P + p : (size_t)p];
+        return ok ? v : zero_of<T>();
+    }
+};
+__host__ __device__ inline int chain_n_rho(const ChunkLayout& lay, int K) { return lay.max_size() + K + 4; }
+template <class T, int K>
+__host__ __device__ inline size_t chain_rows_count(const ChunkLayout& lay) {
+    return (size_t)chain_n_rho(lay, K) * (K + 2) * lay.P;            // (K+1) window entries + the right-hand side
+}
+
+template <class T> struct ChainSpec { BandMat<T> A; VecRhs<T> rhs; };
+
+template <class T, int K, int NCHAINS>
+__global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainSpec<T> s0, ChainSpec<T> s1, ChainSpec<T> s2,
+                                                         T* __restrict__ out) {
+    const int n_rho = chain_n_rho(lay, K), P = lay.P;
+    const size_t per_chain = chain_rows_count<T, K>(lay);
+    const size_t total = per_chain * NCHAINS;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int chain = (int)(t / per_chain);
+        const size_t e = t % per_chain;
+        const ChainSpec<T>& sp = chain == 0 ? s0 : (chain == 1 ? s1 : s2);
+        const int p = (int)(e % P);
+        const size_t q = e / P;
+        const int g0 = P > 1 ? lay.start(p) : 0;
+        if (q < (size_t)n_rho * (K + 1)) {
+            const int bidx = (int)(q % (K + 1)), rho = (int)(q / (K + 1));
+            const int row = g0 + rho, col = row - K + bidx;
+            out[t] = sp.A(K - bidx, col);
+        } else {
+            const int rho = (int)(q - (size_t)n_rho * (K + 1));
+            out[t] = sp.rhs(g0 + rho);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // workspace carving (host) — one ChainWork per chain out of a caller-provided buffer
 // ------------------------------------------------------------------------------------------------------------------
 template <class T, int K>
@@ -161,6 +224,7 @@ struct ElboArgs {
     double sigma2;
     Dual<1>* sigK;          // (K+1) x M   band(Kuu^-1) with d/dl tangent
     double* partial;        // [3 chains][16]: logdet, dlogdet, quad, dquad, trace, dtrace, info, -, clocks[4]
+    const Dual<1>* rows;    // lane-interleaved row tables of the three chains (chain_rows_kernel)
 };
 
 template <int K>
@@ -175,9 +239,11 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
     __shared__ long long clk[4];
     double* out = a.partial + chain * 16;
 
+    const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
+    const T* tab = a.rows + (size_t)chain * chain_rows_count<T, K>(lay);
+    const RowsMat<T, K> A{tab, g0, lay.P, pp, n_rho};
+    const RowsRhs<T> rhs{tab + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
     if (chain == 0) {
-        BandMat<T> A{a.Kuu, a.dKuu, nullptr, 0.0, 0.0, 1, M};
-        VecRhs<T> rhs{a.Kuu, M, 0};
         run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, clk);
         // trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G), off-diagonals twice (reference gpr.py:60-70)
         double tr = 0.0, dtr = 0.0;
@@ -201,10 +267,7 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
             out[4] = tr; out[5] = dtr;
         }
     } else {
-        const double inv_s2 = 1.0 / a.sigma2;
-        // chain 1: tangent d/dl (dKuu);  chain 2: tangent d/dsigma2 (-G/sigma2^2)
-        BandMat<T> A{a.Kuu, a.dKuu, a.G, inv_s2, chain == 1 ? 0.0 : -inv_s2 * inv_s2, chain == 1 ? 1 : 0, M};
-        VecRhs<T> rhs{a.b, M, 1};
+        // chain 1: P with tangent d/dl;  chain 2: P with tangent d/dsigma2 (tables built by launch_elbo)
         run_chain<T, K, false, false, false>(lay, a.cols[chain], smem, A, rhs, static_cast<T*>(nullptr),
                                              static_cast<T*>(nullptr), &tot, clk);
     }
@@ -267,6 +330,7 @@ struct PosteriorArgs {
     double sigma2;
     double* sigK; double* sigP; double* x;       // (K+1) x M, (K+1) x M, M
     double* info;                                // [2]
+    const double* rows;                          // lane-interleaved row tables of the two chains
 };
 
 template <int K>
@@ -277,15 +341,13 @@ __global__ void __launch_bounds__(kChainThreads) posterior_chains_kernel(Posteri
     const ChunkLayout lay = a.lay;
     const int M = lay.M;
     __shared__ ChainTotals<T, K> tot;
-    if (chain == 0) {
-        BandMat<T> A{a.Kuu, nullptr, nullptr, 0.0, 0.0, 0, M};
-        VecRhs<T> rhs{a.Kuu, M, 0};
-        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, nullptr);
-    } else {
-        BandMat<T> A{a.Kuu, nullptr, a.G, 1.0 / a.sigma2, 0.0, 0, M};
-        VecRhs<T> rhs{a.b, M, 1};
-        run_chain<T, K, true, true, true>(lay, a.cols[1], smem, A, rhs, a.x, a.sigP, &tot, nullptr);
-    }
+    (void)M;
+    const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
+    const T* tab = a.rows + (size_t)chain * chain_rows_count<T, K>(lay);
+    const RowsMat<T, K> A{tab, g0, lay.P, pp, n_rho};
+    const RowsRhs<T> rhs{tab + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
+    if (chain == 0) run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, nullptr);
+    else run_chain<T, K, true, true, true>(lay, a.cols[1], smem, A, rhs, a.x, a.sigP, &tot, nullptr);
     if (p == 0) a.info[chain] = (double)tot.info;
 }
 
@@ -314,6 +376,7 @@ struct BandInvArgs {
     Dual<1>* sig;             // scratch (K+1) x M duals
     double* sig_val; double* sig_tan;
     double* scal;             // [4]: log|A|, d log|A|, info, -
+    const Dual<1>* rows;      // lane-interleaved row table
 };
 
 template <int K>
@@ -324,8 +387,9 @@ __global__ void __launch_bounds__(kChainThreads) band_inverse_kernel(BandInvArgs
     const ChunkLayout lay = a.lay;
     const int M = lay.M;
     __shared__ ChainTotals<T, K> tot;
-    BandMat<T> A{a.A, a.dA, nullptr, 0.0, 0.0, 1, M};
-    VecRhs<T> rhs{a.A, M, 0};
+    const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
+    const RowsMat<T, K> A{a.rows, g0, lay.P, pp, n_rho};
+    const RowsRhs<T> rhs{a.rows + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
     run_chain<T, K, true, false, true>(lay, a.cols, smem, A, rhs, static_cast<T*>(nullptr), a.sig, &tot, nullptr);
     for (int i = p; i < (K + 1) * M; i += kChainThreads) {
         const T s = a.sig[i];
@@ -347,6 +411,16 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
     p += ChainPlan<Dual<1>, K>::bytes(lay);
     a.sig = reinterpret_cast<Dual<1>*>(p);
     a.A = A; a.dA = dA; a.sig_val = sig_val; a.sig_tan = sig_tan; a.scal = scal;
+    p += ((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255;
+    Dual<1>* rows = reinterpret_cast<Dual<1>*>(p);
+    a.rows = rows;
+    {
+        using T = Dual<1>;
+        ChainSpec<T> s0{BandMat<T>{A, dA, nullptr, 0.0, 0.0, 1, lay.M}, VecRhs<T>{A, lay.M, 0}};
+        const size_t total = chain_rows_count<T, K>(lay);
+        chain_rows_kernel<T, K, 1><<<(int)((total + 255) / 256), 256, 0, st>>>(lay, s0, s0, s0, rows);
+        ASVGP_CUDA_OK(cudaGetLastError());
+    }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sig, 0, (size_t)(K + 1) * lay.M * sizeof(Dual<1>), st));
     const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(band_inverse_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -358,12 +432,12 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
 template <int K>
 static size_t elbo_work_bytes(const ChunkLayout& lay) {
     return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
-           + 512;
+           + 512 + 3 * chain_rows_count<Dual<1>, K>(lay) * sizeof(Dual<1>) + 256;
 }
 template <int K>
 static size_t posterior_work_bytes(const ChunkLayout& lay) {
     return 2 * ChainPlan<double, K>::bytes(lay) + 3 * ((((size_t)(K + 1) * lay.M * sizeof(double)) + 255) & ~(size_t)255)
-           + 256;
+           + 256 + (((size_t)lay.M * sizeof(double) + 255) & ~(size_t)255) + 2 * chain_rows_count<double, K>(lay) * sizeof(double) + 256;
 }
 
 template <int K>
@@ -376,9 +450,23 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
     a.sigK = reinterpret_cast<Dual<1>*>(p);
     p += ((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255;
     a.partial = reinterpret_cast<double*>(p);
+    p += 512;
     const int M = lay.M;
     a.Kuu = Kuu; a.dKuu = dKuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
     a.sigma2 = sigma2;
+    {
+        using T = Dual<1>;
+        T* rows = reinterpret_cast<T*>(p);
+        a.rows = rows;
+        const double inv_s2 = 1.0 / sigma2;
+        // chain 0: Kuu with tangent d/dl;  chain 1: P = Kuu + G/s2 with d/dl;  chain 2: P with d/dsigma2 = -G/s2^2
+        ChainSpec<T> s0{BandMat<T>{Kuu, dKuu, nullptr, 0.0, 0.0, 1, M}, VecRhs<T>{Kuu, M, 0}};
+        ChainSpec<T> s1{BandMat<T>{Kuu, dKuu, a.G, inv_s2, 0.0, 1, M}, VecRhs<T>{a.b, M, 1}};
+        ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, a.G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{a.b, M, 1}};
+        const size_t total = 3 * chain_rows_count<T, K>(lay);
+        chain_rows_kernel<T, K, 3><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, rows);
+        ASVGP_CUDA_OK(cudaGetLastError());
+    }
     const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(elbo_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     elbo_chains_kernel<K><<<3, kChainThreads, smem, st>>>(a);
@@ -400,9 +488,20 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
     a.sigK = reinterpret_cast<double*>(p); p += band_bytes;
     a.sigP = reinterpret_cast<double*>(p); p += band_bytes;
     a.x = reinterpret_cast<double*>(p);
+    p += ((size_t)M * sizeof(double) + 255) & ~(size_t)255;
     a.Kuu = Kuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
     a.sigma2 = sigma2;
     a.info = info;
+    {
+        using T = double;
+        T* rows = reinterpret_cast<T*>(p);
+        a.rows = rows;
+        ChainSpec<T> s0{BandMat<T>{Kuu, nullptr, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};
+        ChainSpec<T> s1{BandMat<T>{Kuu, nullptr, a.G, 1.0 / sigma2, 0.0, 0, M}, VecRhs<T>{a.b, M, 1}};
+        const size_t total = 2 * chain_rows_count<T, K>(lay);
+        chain_rows_kernel<T, K, 2><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s1, rows);
+        ASVGP_CUDA_OK(cudaGetLastError());
+    }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sigK, 0, 2 * band_bytes, st));
     const size_t smem = ChainSmall<double, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(posterior_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
