@@ -487,59 +487,72 @@ ASVGP_HD void cr_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& 
 template <class T, int K>
 ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T, K>& w) {
     CrNode<T, K>& nd = w.nodes[i];
+    const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
+    // work on register copies: the node lives in shared memory, where every dependent access costs a round trip
+    T D[K][K], r[K], ipv[K], E[K][K], Eb[K][K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        r[a] = nd.r[a];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            D[a][b] = (b <= a) ? nd.D[a][b] : zero_of<T>();
+            E[a][b] = has_a ? nd.E[a][b] : zero_of<T>();
+            Eb[a][b] = has_b ? w.nodes[i + s].E[a][b] : zero_of<T>();
+        }
+    }
     LogAccum<T> logdet;
     logdet.init();
     T quad = zero_of<T>();
+    int info = 0;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-        T d = nd.D[j][j];
+        T d = D[j][j];
 #pragma unroll
-        for (int q = 0; q < j; ++q) d -= nd.D[j][q] * nd.D[j][q];
-        if (!(value_of(d) > 0.0) && nd.info == 0) nd.info = g_offset + i * K + j + 1;
+        for (int q = 0; q < j; ++q) d -= D[j][q] * D[j][q];
+        if (!(value_of(d) > 0.0) && info == 0) info = g_offset + i * K + j + 1;
         const T ip = rsqrt_of(d);
         logdet.add(d, ip);
-        nd.ip[j] = ip;
-        nd.D[j][j] = d * ip;
+        ipv[j] = ip;
+        D[j][j] = d * ip;
 #pragma unroll
-        for (int r = j + 1; r < K; ++r) {
-            T v = nd.D[r][j];
+        for (int rr = j + 1; rr < K; ++rr) {
+            T v = D[rr][j];
 #pragma unroll
-            for (int q = 0; q < j; ++q) v -= nd.D[r][q] * nd.D[j][q];
-            nd.D[r][j] = v * ip;
+            for (int q = 0; q < j; ++q) v -= D[rr][q] * D[j][q];
+            D[rr][j] = v * ip;
         }
-        T y = nd.r[j];
+        T y = r[j];
 #pragma unroll
-        for (int q = 0; q < j; ++q) y -= nd.D[j][q] * nd.r[q];
+        for (int q = 0; q < j; ++q) y -= D[j][q] * r[q];
         y = y * ip;
-        nd.r[j] = y;
+        r[j] = y;
         quad += y * y;
+    }
+    T Wa[K][K], Wb[K][K];
+#pragma unroll
+    for (int x = 0; x < K; ++x)
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            T va = E[j][x], vb = Eb[x][j];            // W_a = E_i^T L^-T,  W_b = E_b L^-T (row x solves L z = ...)
+#pragma unroll
+            for (int q = 0; q < j; ++q) { va -= D[j][q] * Wa[x][q]; vb -= D[j][q] * Wb[x][q]; }
+            Wa[x][j] = va * ipv[j];
+            Wb[x][j] = vb * ipv[j];
+        }
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        nd.r[a] = r[a];
+        nd.ip[a] = ipv[a];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            if (b <= a) nd.D[a][b] = D[a][b];
+            if (has_a) nd.Wa[a][b] = Wa[a][b];
+            if (has_b) nd.Wb[a][b] = Wb[a][b];
+        }
     }
     nd.logdet = logdet.result();
     nd.quad = quad;
-    const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
-    if (has_a) {                                      // W_a = E_i^T L^-T : row x solves L z = E_i[:, x]
-#pragma unroll
-        for (int x = 0; x < K; ++x)
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                T v = nd.E[j][x];
-#pragma unroll
-                for (int q = 0; q < j; ++q) v -= nd.D[j][q] * nd.Wa[x][q];
-                nd.Wa[x][j] = v * nd.ip[j];
-            }
-    }
-    if (has_b) {                                      // W_b = E_b L^-T : row x solves L z = E_b[x, :]^T
-        const CrNode<T, K>& nb = w.nodes[i + s];
-#pragma unroll
-        for (int x = 0; x < K; ++x)
-#pragma unroll
-            for (int j = 0; j < K; ++j) {
-                T v = nb.E[x][j];
-#pragma unroll
-                for (int q = 0; q < j; ++q) v -= nd.D[j][q] * nd.Wb[x][q];
-                nd.Wb[x][j] = v * nd.ip[j];
-            }
-    }
+    if (info != 0 && nd.info == 0) nd.info = info;
 }
 
 // Executed by the lane of node c that STAYS at stride s (c is a multiple of 2s): Schur updates from the eliminated
@@ -547,46 +560,40 @@ ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T,
 template <class T, int K>
 ASVGP_HD void cr_update(int n, int s, int c, const ChainWork<T, K>& w) {
     CrNode<T, K>& nd = w.nodes[c];
-    if (c + s < n) {
-        const CrNode<T, K>& e = w.nodes[c + s];
+    const bool has_p = c + s < n, has_m = c - s >= 0, has_a = c - 2 * s >= 0;
+    T D[K][K], r[K], Wp[K][K], yp[K], Wm[K][K], Wma[K][K], ym[K];
 #pragma unroll
-        for (int x = 0; x < K; ++x) {
-            T rr = nd.r[x];
+    for (int a = 0; a < K; ++a) {
+        r[a] = nd.r[a];
+        yp[a] = has_p ? w.nodes[c + s].r[a] : zero_of<T>();
+        ym[a] = has_m ? w.nodes[c - s].r[a] : zero_of<T>();
 #pragma unroll
-            for (int j = 0; j < K; ++j) rr -= e.Wa[x][j] * e.r[j];
-            nd.r[x] = rr;
-#pragma unroll
-            for (int y = 0; y <= x; ++y) {
-                T v = nd.D[x][y];
-#pragma unroll
-                for (int j = 0; j < K; ++j) v -= e.Wa[x][j] * e.Wa[y][j];
-                nd.D[x][y] = v;
-            }
+        for (int b = 0; b < K; ++b) {
+            D[a][b] = (b <= a) ? nd.D[a][b] : zero_of<T>();
+            Wp[a][b] = has_p ? w.nodes[c + s].Wa[a][b] : zero_of<T>();       // c is the `a` of node c + s
+            Wm[a][b] = has_m ? w.nodes[c - s].Wb[a][b] : zero_of<T>();       // c is the `b` of node c - s
+            Wma[a][b] = (has_m && has_a) ? w.nodes[c - s].Wa[a][b] : zero_of<T>();
         }
     }
-    if (c - s >= 0) {
-        const CrNode<T, K>& e = w.nodes[c - s];
-        const bool has_a = c - 2 * s >= 0;
 #pragma unroll
-        for (int x = 0; x < K; ++x) {
-            T rr = nd.r[x];
+    for (int x = 0; x < K; ++x) {
+        T rr = r[x];
 #pragma unroll
-            for (int j = 0; j < K; ++j) rr -= e.Wb[x][j] * e.r[j];
-            nd.r[x] = rr;
+        for (int j = 0; j < K; ++j) { rr -= Wp[x][j] * yp[j]; rr -= Wm[x][j] * ym[j]; }
+        nd.r[x] = rr;
 #pragma unroll
-            for (int y = 0; y <= x; ++y) {
-                T v = nd.D[x][y];
+        for (int y = 0; y <= x; ++y) {
+            T v = D[x][y];
 #pragma unroll
-                for (int j = 0; j < K; ++j) v -= e.Wb[x][j] * e.Wb[y][j];
-                nd.D[x][y] = v;
-            }
+            for (int j = 0; j < K; ++j) { v -= Wp[x][j] * Wp[y][j]; v -= Wm[x][j] * Wm[y][j]; }
+            nd.D[x][y] = v;
+        }
+        if (has_m) {
 #pragma unroll
             for (int y = 0; y < K; ++y) {             // new coupling R'_{c, c-2s} = -W_b W_a^T
                 T v = zero_of<T>();
-                if (has_a) {
 #pragma unroll
-                    for (int j = 0; j < K; ++j) v -= e.Wb[x][j] * e.Wa[y][j];
-                }
+                for (int j = 0; j < K; ++j) v -= Wm[x][j] * Wma[y][j];
                 nd.E[x][y] = v;
             }
         }
@@ -598,34 +605,58 @@ template <class T, int K, bool SOLVE, bool SELINV>
 ASVGP_HD void cr_back(int n, int s, int i, const ChainWork<T, K>& w) {
     CrNode<T, K>& nd = w.nodes[i];
     const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
-    const CrNode<T, K>* na = has_a ? &w.nodes[i - s] : nullptr;
-    const CrNode<T, K>* nb = has_b ? &w.nodes[i + s] : nullptr;
+    const CrNode<T, K>& na = w.nodes[has_a ? i - s : i];
+    const CrNode<T, K>& nb = w.nodes[has_b ? i + s : i];
+    // register copies of everything that is read (the node lives in shared memory)
+    T L[K][K], ipv[K], Wa[K][K], Wb[K][K];
+#pragma unroll
+    for (int a = 0; a < K; ++a) {
+        ipv[a] = nd.ip[a];
+#pragma unroll
+        for (int b = 0; b < K; ++b) {
+            L[a][b] = (b <= a) ? nd.D[a][b] : zero_of<T>();
+            Wa[a][b] = has_a ? nd.Wa[a][b] : zero_of<T>();
+            Wb[a][b] = has_b ? nd.Wb[a][b] : zero_of<T>();
+        }
+    }
     if (SOLVE) {
-        T t[K];
+        T t[K], xa[K], xb[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            T v = nd.r[j];
-            if (has_a) {
+            t[j] = nd.r[j];
+            xa[j] = has_a ? na.r[j] : zero_of<T>();
+            xb[j] = has_b ? nb.r[j] : zero_of<T>();
+        }
 #pragma unroll
-                for (int x = 0; x < K; ++x) v -= nd.Wa[x][j] * na->r[x];
-            }
-            if (has_b) {
+        for (int j = 0; j < K; ++j) {
+            T v = t[j];
 #pragma unroll
-                for (int x = 0; x < K; ++x) v -= nd.Wb[x][j] * nb->r[x];
-            }
+            for (int x = 0; x < K; ++x) { v -= Wa[x][j] * xa[x]; v -= Wb[x][j] * xb[x]; }
             t[j] = v;
         }
 #pragma unroll
         for (int j = K - 1; j >= 0; --j) {
             T v = t[j];
 #pragma unroll
-            for (int q = j + 1; q < K; ++q) v -= nd.D[q][j] * t[q];
-            t[j] = v * nd.ip[j];
+            for (int q = j + 1; q < K; ++q) v -= L[q][j] * t[q];
+            t[j] = v * ipv[j];
         }
 #pragma unroll
         for (int j = 0; j < K; ++j) nd.r[j] = t[j];
     }
     if (SELINV) {
+        // Sigma_aa, Sigma_bb and Sigma_ba (a and b are neighbours one level up, where exactly one of them was eliminated)
+        const bool both = has_a && has_b;
+        const bool a_is_odd = both && (((i - s) / (2 * s)) & 1);
+        T Saa[K][K], Sbb[K][K], Sba[K][K];
+#pragma unroll
+        for (int x = 0; x < K; ++x)
+#pragma unroll
+            for (int y = 0; y < K; ++y) {
+                Saa[x][y] = has_a ? na.D[x][y] : zero_of<T>();
+                Sbb[x][y] = has_b ? nb.D[x][y] : zero_of<T>();
+                Sba[x][y] = both ? (a_is_odd ? na.Sb[x][y] : nb.Sa[y][x]) : zero_of<T>();      // rows of b, columns of a
+            }
         // L^-1 (lower), column by column
         T Li[K][K];
 #pragma unroll
@@ -635,91 +666,51 @@ ASVGP_HD void cr_back(int n, int s, int i, const ChainWork<T, K>& w) {
                 if (r < c) { Li[r][c] = zero_of<T>(); continue; }
                 T v = (r == c) ? make_scalar<T>(1.0, 0.0) : zero_of<T>();
 #pragma unroll
-                for (int q = c; q < r; ++q) v -= nd.D[r][q] * Li[q][c];
-                Li[r][c] = v * nd.ip[r];
-            }
-        T S[K][K];                                    // Sigma_ii, starts as L^-T L^-1
-#pragma unroll
-        for (int c = 0; c < K; ++c)
-#pragma unroll
-            for (int c2 = 0; c2 < K; ++c2) {
-                T v = zero_of<T>();
-#pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    if (r >= c && r >= c2) v += Li[r][c] * Li[r][c2];
-                }
-                S[c][c2] = v;
+                for (int q = c; q < r; ++q) v -= L[r][q] * Li[q][c];
+                Li[r][c] = v * ipv[r];
             }
         T Ya[K][K], Yb[K][K];                         // Y_k = W_k L^-1
-        if (has_a) {
-#pragma unroll
-            for (int x = 0; x < K; ++x)
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    T v = zero_of<T>();
-#pragma unroll
-                    for (int j = c; j < K; ++j) v += nd.Wa[x][j] * Li[j][c];
-                    Ya[x][c] = v;
-                }
-        }
-        if (has_b) {
-#pragma unroll
-            for (int x = 0; x < K; ++x)
-#pragma unroll
-                for (int c = 0; c < K; ++c) {
-                    T v = zero_of<T>();
-#pragma unroll
-                    for (int j = c; j < K; ++j) v += nd.Wb[x][j] * Li[j][c];
-                    Yb[x][c] = v;
-                }
-        }
-        // Sigma_ba: a and b are neighbours one level up, where exactly one of them was eliminated
-        const bool a_is_odd = has_a && has_b && (((i - s) / (2 * s)) & 1);
 #pragma unroll
         for (int x = 0; x < K; ++x)
 #pragma unroll
             for (int c = 0; c < K; ++c) {
                 T va = zero_of<T>(), vb = zero_of<T>();
-                if (has_a) {
 #pragma unroll
-                    for (int y = 0; y < K; ++y) va -= na->D[x][y] * Ya[y][c];              // Sigma_aa Y_a
-                }
-                if (has_b) {
+                for (int j = c; j < K; ++j) { va += Wa[x][j] * Li[j][c]; vb += Wb[x][j] * Li[j][c]; }
+                Ya[x][c] = va;
+                Yb[x][c] = vb;
+            }
+        T Sai[K][K], Sbi[K][K];                       // Sigma_ai = -Sigma_aa Y_a - Sigma_ab Y_b,  Sigma_bi = -Sigma_ba Y_a - Sigma_bb Y_b
 #pragma unroll
-                    for (int y = 0; y < K; ++y) vb -= nb->D[x][y] * Yb[y][c];              // Sigma_bb Y_b
-                }
-                if (has_a && has_b) {
+        for (int x = 0; x < K; ++x)
 #pragma unroll
-                    for (int y = 0; y < K; ++y) {
-                        // Sigma_ba[u][v]: rows of b, columns of a
-                        const T sba_xy = a_is_odd ? na->Sb[x][y] : nb->Sa[y][x];           // Sigma_ba[x][y]
-                        const T sba_yx = a_is_odd ? na->Sb[y][x] : nb->Sa[x][y];           // Sigma_ba[y][x] = Sigma_ab[x][y]
-                        va -= sba_yx * Yb[y][c];                                            // Sigma_ab Y_b
-                        vb -= sba_xy * Ya[y][c];                                            // Sigma_ba Y_a
-                    }
+            for (int c = 0; c < K; ++c) {
+                T va = zero_of<T>(), vb = zero_of<T>();
+#pragma unroll
+                for (int y = 0; y < K; ++y) {
+                    va -= Saa[x][y] * Ya[y][c];
+                    va -= Sba[y][x] * Yb[y][c];
+                    vb -= Sba[x][y] * Ya[y][c];
+                    vb -= Sbb[x][y] * Yb[y][c];
                 }
-                nd.Sa[x][c] = va;
-                nd.Sb[x][c] = vb;
+                Sai[x][c] = va;
+                Sbi[x][c] = vb;
             }
 #pragma unroll
         for (int c = 0; c < K; ++c)
 #pragma unroll
             for (int c2 = 0; c2 < K; ++c2) {
-                T v = S[c][c2];
-                if (has_a) {
+                T v = zero_of<T>();                   // (L^-T L^-1)[c][c2] - (Y_a^T Sigma_ai)[c][c2] - (Y_b^T Sigma_bi)[c][c2]
 #pragma unroll
-                    for (int x = 0; x < K; ++x) v -= Ya[x][c] * nd.Sa[x][c2];
+                for (int r = 0; r < K; ++r) {
+                    if (r >= c && r >= c2) v += Li[r][c] * Li[r][c2];
                 }
-                if (has_b) {
 #pragma unroll
-                    for (int x = 0; x < K; ++x) v -= Yb[x][c] * nd.Sb[x][c2];
-                }
-                S[c][c2] = v;
+                for (int x = 0; x < K; ++x) { v -= Ya[x][c] * Sai[x][c2]; v -= Yb[x][c] * Sbi[x][c2]; }
+                nd.D[c][c2] = v;
+                if (has_a) nd.Sa[c][c2] = Sai[c][c2];
+                if (has_b) nd.Sb[c][c2] = Sbi[c][c2];
             }
-#pragma unroll
-        for (int c = 0; c < K; ++c)
-#pragma unroll
-            for (int c2 = 0; c2 < K; ++c2) nd.D[c][c2] = S[c][c2];
     }
 }
 

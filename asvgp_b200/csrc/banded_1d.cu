@@ -247,12 +247,26 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
         run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, clk);
         // trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G), off-diagonals twice (reference gpr.py:60-70)
         double tr = 0.0, dtr = 0.0;
-        for (int i = p; i < (K + 1) * M; i += kChainThreads) {
-            const double wgt = (i < M) ? 1.0 : 2.0;
-            const double g = wgt * __ldg(a.G + i);
-            const T s = a.sigK[i];
-            tr = fma(s.v, g, tr);
-            dtr = fma(s.d[0], g, dtr);
+        {
+            const int total = (K + 1) * M;
+            const T* __restrict__ sg = a.sigK;
+            constexpr int U = 16;            // L2-latency bound (sigK was just written by this CTA): 16 loads in flight per thread
+            for (int base = p; base < total; base += U * kChainThreads) {
+                T sv[U];
+                double gv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + u * kChainThreads;
+                    const bool ok = i < total;
+                    sv[u] = sg[ok ? i : 0];
+                    gv[u] = ok ? ((i < M) ? 1.0 : 2.0) * __ldg(a.G + i) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    tr = fma(sv[u].v, gv[u], tr);
+                    dtr = fma(sv[u].d[0], gv[u], dtr);
+                }
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
