@@ -233,8 +233,15 @@ ASVGP_HD void backsolve_serial(int n, const Store& store, T* x) {
 }
 
 // ---- serial Takahashi recursion on stored columns: lower band of (L L^T)^-1, sig[d * n + j] ---------------------------
-template <class T, int K, class Store>
-ASVGP_HD void selinv_serial(int n, const Store& store, T* sig) {
+// Where the entries of the inverse band go: sink(d, col, v) receives entry (row col + d, column col).
+template <class T>
+struct BandSink {                 // lower band (K+1) x M, row-major
+    T* sig; int M;
+    ASVGP_HD void operator()(int d, int col, const T& v) const { sig[(size_t)d * M + col] = v; }
+};
+
+template <class T, int K, class Store, class Sink>
+ASVGP_HD void selinv_serial(int n, const Store& store, Sink& sink) {
     T Z[K][K];     // Sigma[g+1+a, g+1+b] of the columns already done (symmetric, full storage)
 #pragma unroll
     for (int a = 0; a < K; ++a)
@@ -256,12 +263,12 @@ ASVGP_HD void selinv_serial(int n, const Store& store, T* sig) {
         }
         const T ip2 = ip * ip;
         const T sjj = ip2 + dot * ip2;
-        sig[j] = sjj;
+        sink(0, j, sjj);
         T col[K];
 #pragma unroll
         for (int a = 0; a < K; ++a) {
             col[a] = -(w[a] * ip);
-            if (j + 1 + a < n) sig[(size_t)(a + 1) * n + j] = col[a];
+            if (j + 1 + a < n) sink(a + 1, j, col[a]);
         }
         // shift: new neighbour set is {j, j+1, .., j+K-1}
 #pragma unroll
@@ -277,9 +284,9 @@ ASVGP_HD void selinv_serial(int n, const Store& store, T* sig) {
 // ---- phase 3: backward sweep inside chunk p (solve and/or selected inverse) --------------------------------------------
 // x_red / sig_red: solution and selected-inverse band ((2K) x n_red, row-major) of the reduced system (may be null
 // when the corresponding output is not requested).  x_out[M]; sig_out[(K+1) x M] lower band of A^-1.
-template <class T, int K, bool SOLVE, bool SELINV>
+template <class T, int K, bool SOLVE, bool SELINV, class Sink>
 ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const ColumnStore<T, K, true>& store,
-                             const T* x_red, const T* sig_red, T* x_out, T* sig_out) {
+                             const T* x_red, const T* sig_red, T* x_out, Sink& sink) {
     constexpr int KR = 2 * K - 1;
     const int n = lay.size(p), s = lay.start(p), M = lay.M, nred = lay.n_reduced();
     const bool has_left = p > 0, has_right = p < lay.P - 1;
@@ -354,15 +361,15 @@ ASVGP_HD void chunk_backward(const ChunkLayout& lay, int p, int n_steps, const C
             }
             const T ip2 = ip * ip;
             const T sjj = ip2 + dot * ip2;
-            sig_out[g] = sjj;
+            sink(0, g, sjj);
             T col[2 * K];
 #pragma unroll
             for (int a = 0; a < 2 * K; ++a) col[a] = -(w[a] * ip);
 #pragma unroll
             for (int a = 0; a < K; ++a) {
-                if (g + 1 + a < M) sig_out[(size_t)(a + 1) * M + g] = col[a];            // rows below, same band
+                if (g + 1 + a < M) sink(a + 1, g, col[a]);                              // rows below, same band
                 // (row g, column S_{p-1}[rho]) lies inside the band iff j <= rho
-                if (has_left && j <= a) sig_out[(size_t)(j + K - a) * M + (s - K + a)] = col[K + a];
+                if (has_left && j <= a) sink(j + K - a, s - K + a, col[K + a]);
             }
             // shift the band part of Z; the separator part stays
 #pragma unroll
@@ -773,12 +780,12 @@ ASVGP_HD int cr_top_stride(int n) {
     return n > 1 ? s : 0;
 }
 
-template <class T, int K, bool SOLVE, bool SELINV>
-ASVGP_HD void chain_phase3(const ChunkLayout& lay, int p, const ChainWork<T, K>& w, T* x_out, T* sig_out) {
+template <class T, int K, bool SOLVE, bool SELINV, class Sink>
+ASVGP_HD void chain_phase3(const ChunkLayout& lay, int p, const ChainWork<T, K>& w, T* x_out, Sink& sink) {
     const int n_steps = lay.max_size();
     if (lay.P == 1) {
         if (SOLVE) backsolve_serial<T, K>(lay.M, w.cols, x_out);
-        if (SELINV) selinv_serial<T, K>(lay.M, w.cols, sig_out);
+        if (SELINV) selinv_serial<T, K>(lay.M, w.cols, sink);
         return;
     }
     const int nred = lay.n_reduced();
@@ -788,10 +795,10 @@ ASVGP_HD void chain_phase3(const ChunkLayout& lay, int p, const ChainWork<T, K>&
             if (SOLVE) x_out[g + a] = w.x_red[p * K + a];
             if (SELINV)
                 for (int b = 0; b <= a; ++b)
-                    sig_out[(size_t)(a - b) * lay.M + g + b] = w.sig_red[(size_t)(a - b) * nred + p * K + b];
+                    sink(a - b, g + b, w.sig_red[(size_t)(a - b) * nred + p * K + b]);
         }
     }
-    chunk_backward<T, K, SOLVE, SELINV>(lay, p, n_steps, w.cols, w.x_red, w.sig_red, x_out, sig_out);
+    chunk_backward<T, K, SOLVE, SELINV>(lay, p, n_steps, w.cols, w.x_red, w.sig_red, x_out, sink);
 }
 
 }  // namespace asvgp

@@ -128,8 +128,23 @@ __host__ __device__ inline size_t chain_rows_count(const ChunkLayout& lay) {
 
 template <class T> struct ChainSpec { BandMat<T> A; VecRhs<T> rhs; };
 
+// Sink of the ELBO's Kuu chain: trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G) (off-diagonals twice, reference
+// gpr.py:60-70) is accumulated entry by entry as the Takahashi recursion produces band(Kuu^-1), against a row table of
+// G in the lanes' interleaved layout — the inverse band is never stored and there is no separate trace pass.
+template <class T, int K>
+struct TraceSink {
+    const T* gtab; int g0, P, p, n_rho;
+    T acc;
+    __device__ __forceinline__ void operator()(int d, int col, const T& v) {
+        const int rho = col + d - g0;
+        const double g = (d == 0 ? 1.0 : 2.0) * gtab[((size_t)rho * (K + 1) + (K - d)) * P + p].v;
+        acc.v = fma(v.v, g, acc.v);
+        acc.d[0] = fma(v.d[0], g, acc.d[0]);
+    }
+};
+
 template <class T, int K, int NCHAINS>
-__global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainSpec<T> s0, ChainSpec<T> s1, ChainSpec<T> s2,
+__global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainSpec<T> s0, ChainSpec<T> s1, ChainSpec<T> s2, ChainSpec<T> s3,
                                                          T* __restrict__ out) {
     const int n_rho = chain_n_rho(lay, K), P = lay.P;
     const size_t per_chain = chain_rows_count<T, K>(lay);
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainS
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int chain = (int)(t / per_chain);
         const size_t e = t % per_chain;
-        const ChainSpec<T>& sp = chain == 0 ? s0 : (chain == 1 ? s1 : s2);
+        const ChainSpec<T>& sp = chain == 0 ? s0 : (chain == 1 ? s1 : (chain == 2 ? s2 : s3));
         const int p = (int)(e % P);
         const size_t q = e / P;
         const int g0 = P > 1 ? lay.start(p) : 0;
@@ -171,9 +186,9 @@ struct ChainPlan {
 constexpr size_t kChainSmemLimit = 200 * 1024;
 
 // One CTA = one chain.  `Mat`/`Rhs` feed the matrix; logdet/quad totals go to `tot`.
-template <class T, int K, bool STORE, bool SOLVE, bool SELINV, class Mat, class Rhs>
+template <class T, int K, bool STORE, bool SOLVE, bool SELINV, class Mat, class Rhs, class Sink>
 __device__ __forceinline__ void run_chain(const ChunkLayout& lay, const ColumnStore<T, K, true>& cols, char* smem,
-                                          Mat A, Rhs rhs, T* x_out, T* sig_out, ChainTotals<T, K>* tot,
+                                          Mat A, Rhs rhs, T* x_out, Sink& sink, ChainTotals<T, K>* tot,
                                           long long* clk) {
     const int p = threadIdx.x;
     ChainWork<T, K> w;
@@ -208,7 +223,7 @@ __device__ __forceinline__ void run_chain(const ChunkLayout& lay, const ColumnSt
         __syncthreads();
     }
     if (p == 0 && clk) clk[2] = clock64();
-    if ((SOLVE || SELINV) && p < lay.P) chain_phase3<T, K, SOLVE, SELINV>(lay, p, w, x_out, sig_out);
+    if ((SOLVE || SELINV) && p < lay.P) chain_phase3<T, K, SOLVE, SELINV>(lay, p, w, x_out, sink);
     __syncthreads();
     if (p == 0 && clk) clk[3] = clock64();
 }
@@ -222,7 +237,6 @@ struct ElboArgs {
     ColumnStore<Dual<1>, K, true> cols[3];
     const double* Kuu; const double* dKuu; const double* G; const double* b;
     double sigma2;
-    Dual<1>* sigK;          // (K+1) x M   band(Kuu^-1) with d/dl tangent
     double* partial;        // [3 chains][16]: logdet, dlogdet, quad, dquad, trace, dtrace, info, -, clocks[4]
     const Dual<1>* rows;    // lane-interleaved row tables of the three chains (chain_rows_kernel)
 };
@@ -243,31 +257,11 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
     const T* tab = a.rows + (size_t)chain * chain_rows_count<T, K>(lay);
     const RowsMat<T, K> A{tab, g0, lay.P, pp, n_rho};
     const RowsRhs<T> rhs{tab + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
+    BandSink<T> no_sink{nullptr, M};
     if (chain == 0) {
-        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, clk);
-        // trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G), off-diagonals twice (reference gpr.py:60-70)
-        double tr = 0.0, dtr = 0.0;
-        {
-            const int total = (K + 1) * M;
-            const T* __restrict__ sg = a.sigK;
-            constexpr int U = 16;            // L2-latency bound (sigK was just written by this CTA): 16 loads in flight per thread
-            for (int base = p; base < total; base += U * kChainThreads) {
-                T sv[U];
-                double gv[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = base + u * kChainThreads;
-                    const bool ok = i < total;
-                    sv[u] = sg[ok ? i : 0];
-                    gv[u] = ok ? ((i < M) ? 1.0 : 2.0) * __ldg(a.G + i) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    tr = fma(sv[u].v, gv[u], tr);
-                    dtr = fma(sv[u].d[0], gv[u], dtr);
-                }
-            }
-        }
+        TraceSink<T, K> sink{a.rows + 3 * chain_rows_count<T, K>(lay), g0, lay.P, pp, n_rho, zero_of<T>()};
+        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), sink, &tot, clk);
+        double tr = sink.acc.v, dtr = sink.acc.d[0];           // this lane's share of trace(Kuu^-1 G) and of its d/dl
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             tr += __shfl_xor_sync(0xffffffffu, tr, o);
@@ -282,8 +276,7 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
         }
     } else {
         // chain 1: P with tangent d/dl;  chain 2: P with tangent d/dsigma2 (tables built by launch_elbo)
-        run_chain<T, K, false, false, false>(lay, a.cols[chain], smem, A, rhs, static_cast<T*>(nullptr),
-                                             static_cast<T*>(nullptr), &tot, clk);
+        run_chain<T, K, false, false, false>(lay, a.cols[chain], smem, A, rhs, static_cast<T*>(nullptr), no_sink, &tot, clk);
     }
     if (p == 0) {
         out[0] = tot.logdet.v; out[1] = tot.logdet.d[0];
@@ -360,8 +353,9 @@ __global__ void __launch_bounds__(kChainThreads) posterior_chains_kernel(Posteri
     const T* tab = a.rows + (size_t)chain * chain_rows_count<T, K>(lay);
     const RowsMat<T, K> A{tab, g0, lay.P, pp, n_rho};
     const RowsRhs<T> rhs{tab + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
-    if (chain == 0) run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), a.sigK, &tot, nullptr);
-    else run_chain<T, K, true, true, true>(lay, a.cols[1], smem, A, rhs, a.x, a.sigP, &tot, nullptr);
+    BandSink<T> sinkK{a.sigK, lay.M}, sinkP{a.sigP, lay.M};
+    if (chain == 0) run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), sinkK, &tot, nullptr);
+    else run_chain<T, K, true, true, true>(lay, a.cols[1], smem, A, rhs, a.x, sinkP, &tot, nullptr);
     if (p == 0) a.info[chain] = (double)tot.info;
 }
 
@@ -404,7 +398,8 @@ __global__ void __launch_bounds__(kChainThreads) band_inverse_kernel(BandInvArgs
     const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
     const RowsMat<T, K> A{a.rows, g0, lay.P, pp, n_rho};
     const RowsRhs<T> rhs{a.rows + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
-    run_chain<T, K, true, false, true>(lay, a.cols, smem, A, rhs, static_cast<T*>(nullptr), a.sig, &tot, nullptr);
+    BandSink<T> sink{a.sig, lay.M};
+    run_chain<T, K, true, false, true>(lay, a.cols, smem, A, rhs, static_cast<T*>(nullptr), sink, &tot, nullptr);
     for (int i = p; i < (K + 1) * M; i += kChainThreads) {
         const T s = a.sig[i];
         a.sig_val[i] = s.v;
@@ -432,7 +427,7 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
         using T = Dual<1>;
         ChainSpec<T> s0{BandMat<T>{A, dA, nullptr, 0.0, 0.0, 1, lay.M}, VecRhs<T>{A, lay.M, 0}};
         const size_t total = chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 1><<<(int)((total + 255) / 256), 256, 0, st>>>(lay, s0, s0, s0, rows);
+        chain_rows_kernel<T, K, 1><<<(int)((total + 255) / 256), 256, 0, st>>>(lay, s0, s0, s0, s0, rows);
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sig, 0, (size_t)(K + 1) * lay.M * sizeof(Dual<1>), st));
@@ -446,7 +441,7 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
 template <int K>
 static size_t elbo_work_bytes(const ChunkLayout& lay) {
     return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
-           + 512 + 3 * chain_rows_count<Dual<1>, K>(lay) * sizeof(Dual<1>) + 256;
+           + 512 + 4 * chain_rows_count<Dual<1>, K>(lay) * sizeof(Dual<1>) + 256;
 }
 template <int K>
 static size_t posterior_work_bytes(const ChunkLayout& lay) {
@@ -461,8 +456,6 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
     a.lay = lay;
     char* p = work;
     for (int c = 0; c < 3; ++c) { a.cols[c] = ChainPlan<Dual<1>, K>::carve(lay, p); p += ChainPlan<Dual<1>, K>::bytes(lay); }
-    a.sigK = reinterpret_cast<Dual<1>*>(p);
-    p += ((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255;
     a.partial = reinterpret_cast<double*>(p);
     p += 512;
     const int M = lay.M;
@@ -477,8 +470,9 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
         ChainSpec<T> s0{BandMat<T>{Kuu, dKuu, nullptr, 0.0, 0.0, 1, M}, VecRhs<T>{Kuu, M, 0}};
         ChainSpec<T> s1{BandMat<T>{Kuu, dKuu, a.G, inv_s2, 0.0, 1, M}, VecRhs<T>{a.b, M, 1}};
         ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, a.G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{a.b, M, 1}};
-        const size_t total = 3 * chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 3><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, rows);
+        ChainSpec<T> s3{BandMat<T>{a.G, a.G, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};      // G itself (for the trace)
+        const size_t total = 4 * chain_rows_count<T, K>(lay);
+        chain_rows_kernel<T, K, 4><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, s3, rows);
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
@@ -513,7 +507,7 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
         ChainSpec<T> s0{BandMat<T>{Kuu, nullptr, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};
         ChainSpec<T> s1{BandMat<T>{Kuu, nullptr, a.G, 1.0 / sigma2, 0.0, 0, M}, VecRhs<T>{a.b, M, 1}};
         const size_t total = 2 * chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 2><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s1, rows);
+        chain_rows_kernel<T, K, 2><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s1, s1, rows);
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sigK, 0, 2 * band_bytes, st));

@@ -22,7 +22,14 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-os.environ["NCCL_DEBUG"] = os.environ.get("ASVGP_NCCL_DEBUG", "WARN")   # NCCL's version banner would share stdout with the JSON line
+# stdout carries exactly ONE JSON line: library chatter (NCCL's version banner, torchrun notices) goes to stderr instead
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
 
 WORKLOADS = {
     # name: (N per rank, M, spline order, kernel, sorted?)
@@ -232,7 +239,7 @@ def reference_arm(args):
         sample = ("O(N) precompute timed on the first %d raster points over %d processes (%.2f s) and extrapolated "
                   "linearly to N=%d, plus one LAPACK banded ELBO evaluation at full M (%.2f s); no gradients"
                   % (n_sample, cores, t_acc, n1 * n2, t_fac))
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -246,7 +253,7 @@ def reference_arm(args):
     value, dt = run_cpu(n_sample, m, k, kind, args.steps, max(args.warmup, 1), cores)
     sample = "first %d of the %d points per step, %d processes (SciPy sparsetools/LAPACK are single-threaded)" % (
         n_sample, n, cores)
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "elbo_grad_datapoints_per_s", "value": value, "unit": "datapoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -542,7 +549,7 @@ def main():
                     "value": v, "unit": "datapoints/s", "cores": 1, "kind": "port",
                     "sample": "precompute on the first %d raster points (%.1f s, extrapolated linearly to N) + one "
                               "LAPACK banded ELBO at full M (%.1f s), no gradients, single thread" % (n_sample, t_acc, t_fac)}
-            print(json.dumps(line))
+            emit(line)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -671,7 +678,7 @@ def main():
         line["cpu_baseline"] = {"value": v1, "unit": "datapoints/s", "cores": 1, "kind": "port",
                                 "sample": "one step on the first %d sorted points of the workload (%.1f s), single "
                                           "thread like the reference's SciPy/LAPACK path" % (n_sample, dt1)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -56,7 +56,8 @@ static int run_chain(int M, int P, const double* band, const double* dband, cons
         for (int q = 0; q < n; ++q) cr_export<T, K, true, true>(lay, q, w);
     }
     std::vector<T> xo(M), so((size_t)(K + 1) * M, zero_of<T>());
-    for (int p = 0; p < lay.P; ++p) chain_phase3<T, K, true, true>(lay, p, w, xo.data(), so.data());
+    BandSink<T> sink{so.data(), M};
+    for (int p = 0; p < lay.P; ++p) chain_phase3<T, K, true, true>(lay, p, w, xo.data(), sink);
     const int nt = sizeof(T) / sizeof(double);
     scal[0] = value_of(tot.logdet); scal[1] = value_of(tot.quad);
     scal[2] = tangent_of(tot.logdet, 0); scal[3] = tangent_of(tot.quad, 0);
