@@ -96,7 +96,7 @@ static SelLayout sel_layout(const TileGeom& g) {
     L.sig_total = 2 * L.sig_upper;
     L.xacc = 0;
     L.flags = (int64_t)g.nb * NB;
-    L.n_flag_ints = (int64_t)g.n_tiles() + g.nb + 8;           // tile flags + per-column counters + abort
+    L.n_flag_ints = (int64_t)g.n_tiles() + 3 * (int64_t)g.nb + 8;   // tile flags, per-column counters, abort, x flags, x counters
     L.work_total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
     return L;
 }
@@ -636,8 +636,12 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
     const TileGeom g = a.g;
     const int tid = threadIdx.x;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
-    int* cnt = a.sready + g.n_tiles();
+    int* cnt = a.sready + g.n_tiles();            // cnt[C]: off-diagonal tiles of column C that have added their share to Sigma(C,C)
     int* abort_flag = cnt + g.nb;
+    // the back substitution x = P^-1 b is a chain of its own, off the critical path of the tiles:
+    // xflag[C] = x_C is final;  xcnt[C] = off-diagonal tiles of column C that have added -Y(K,C)^T x_K
+    int* xflag = abort_flag + 8;
+    int* xcnt = xflag + g.nb;
     if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
     fence_proxy_async();
     __syncthreads();
@@ -657,9 +661,11 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             auto issue = [&](int K, int s) {         // A = Sigma(R, K), B = Y(K, C)^T
                 const double* src;
                 const int* flag;
-                if (K <= R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
+                int want = 1;
+                if (K == R) { src = a.sig_lower + g.tile(R, 0); flag = cnt + R; want = min(g.BW, g.nb - 1 - R); }   // Sigma(R,R): all shares in
+                else if (K < R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
                 else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
-                wait_flag(flag, 1, abort_flag);
+                wait_flag(flag, want, abort_flag);
                 fence_proxy_async();
                 mbar_expect_tx(&full[s], 2 * TILE_BYTES);
                 tma_load_tile_(sA[s], src, &full[s]);
@@ -685,7 +691,6 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 tma_load_tile_(sB[0], a.tiles + g.tile(C, d), &full[0]);
             }
             regs_to_tile_t(acc, sA[0], tm, tn);      // T[m][a] at [m*64 + a]  ==  A'(a, k=m) at [k*64 + a]
-            if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);      // x_R: final (diagonal task R has completed)
             __syncthreads();
             if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1);
             mbar_wait(&full[0], ph.get(0));
@@ -697,7 +702,14 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             for (int j = 0; j < 4; ++j)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) atomicAdd(Sd + (tn + j) * NB + tm + i, -D[i][j]);
-            // xacc_C[b] -= sum_m Y[m][b] x_R[m];  Y[m][b] at sB[0][m*64 + b]
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) red_release_add(cnt + C, 1);
+            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[0][m*64 + b]
+            if (tid == 0) wait_flag(xflag + R, 1, abort_flag);
+            __syncthreads();
+            if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);
+            __syncthreads();
             if (tid < NB) {
                 double s = 0.0;
 #pragma unroll 8
@@ -706,10 +718,11 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) red_release_add(cnt + C, 1);
+            if (tid == 0) red_release_add(xcnt + C, 1);
         } else {
-            // diagonal task: Sigma(C,C) is complete once every off-diagonal tile of the column has contributed
-            if (tid == 0) wait_flag(cnt + C, Kmax - C, abort_flag);
+            // diagonal task: only the back substitution is left to do (Sigma(C,C) is complete when cnt[C] is, which is
+            // what its readers wait for)
+            if (tid == 0) wait_flag(xcnt + C, Kmax - C, abort_flag);
             __syncthreads();
             // x_C = L(C,C)^-T y_C + xacc_C
             double V[4][4];
@@ -731,7 +744,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1), 1);
+            if (tid == 0) st_release(xflag + C, 1);
         }
     }
 }

@@ -69,3 +69,20 @@ def stencil_to_sparse(Gs, m1, m2, order):
                 rows.append(j[ok]); cols.append(i[ok]); vals.append(v[ok])
     A = sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols))), shape=(M, M))
     return A.tocsr()
+
+
+def sparse_to_stencil(A, m1, m2, order):
+    """Inverse of stencil_to_sparse: the lower part of a block-banded sparse matrix in stencil layout."""
+    A = sparse.csr_matrix(A)
+    k, M = order, m1 * m2
+    out = np.zeros(((k + 1) * (2 * k + 1), M))
+    j = np.arange(M)
+    j1, j2 = j // m2, j % m2
+    for d1 in range(k + 1):
+        for d2 in range(-k, k + 1):
+            if d1 == 0 and d2 < 0:
+                continue
+            ok = (j1 + d1 < m1) & (j2 + d2 >= 0) & (j2 + d2 < m2)
+            i = (j1 + d1) * m2 + (j2 + d2)
+            out[d1 * (2 * k + 1) + d2 + k, j[ok]] = np.asarray(A[i[ok], j[ok]]).ravel()
+    return out

@@ -138,3 +138,46 @@ def test_two_rank_gloo_allreduce_of_packed_accumulator(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_gloo_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
+
+
+def _gloo_worker_2d(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from asvgp_b200 import utils
+    from asvgp_b200.dist import allreduce_packed, shard_bounds
+    from oracle import asvgp_oracle as O          # stands in for the CUDA accumulate on this CPU-only box
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(12)
+    n, k, ms = 6001, 3, [11, 13]
+    X = np.stack([rng.uniform(.01, .99, n), rng.uniform(.01, 1.99, n)], 1)
+    y = rng.standard_normal(n)
+    meshes, deltas = zip(*[O.make_mesh(0, 1, ms[0], k), O.make_mesh(0, 2, ms[1], k)])
+
+    def packed(Xs, ys):          # [G stencil | Kuf_y | sum y^2 | count]: the layout of ops.accum_size_2d
+        G, b, yy = O.precompute_kron(meshes, deltas, k, ms, Xs, ys)
+        return np.concatenate([utils.sparse_to_stencil(G, ms[0], ms[1], k).ravel(), b.ravel(), [yy, Xs.shape[0]]])
+
+    lo, hi = shard_bounds(n, rank, world)
+    acc = torch.from_numpy(packed(X[lo:hi], y[lo:hi]))
+    allreduce_packed(acc)
+    want = packed(X, y)
+    np.testing.assert_allclose(acc.numpy(), want, rtol=1e-12, atol=1e-12)
+    # and the stencil layout round-trips through the sparse form the reference exposes (KufKfu_sparse)
+    ne = (k + 1) * (2 * k + 1)
+    G = utils.stencil_to_sparse(acc.numpy()[: ne * ms[0] * ms[1]].reshape(ne, -1), ms[0], ms[1], k)
+    G0, _, _ = O.precompute_kron(meshes, deltas, k, ms, X, y)
+    assert abs(G - G0).max() < 1e-11
+    open(os.path.join(tmp, "ok%d" % rank), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduce_of_packed_2d_accumulator(tmp_path):
+    import torch.multiprocessing as mp
+
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker_2d, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
