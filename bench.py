@@ -637,6 +637,27 @@ def main():
                "api": "GPR_1d((X_host, y_host), kernel, basis).training_loss_and_gradients()"}
         del xh, yh
 
+    # 1-D predictor on the same points (sharded over ranks, no collective): posterior weights once, then mean/variance
+    from asvgp_b200.gpr import GPR_1d as _G1
+
+    pm = _G1.__new__(_G1)
+    pm.kernel, pm.basis, pm.inducing_features, pm._acc, pm._chunks = kern, basis, feats, acc, 0
+    pm.likelihood = Kn.Gaussian(HYPERS[2])
+    alpha, S_band, _info = pm.posterior_weights()
+    for _ in range(2):
+        ops.predict_1d(x, basis, alpha, S_band, HYPERS[0])
+    q0, q1 = ev(), ev()
+    barrier()
+    q0.record()
+    for _ in range(5):
+        ops.predict_1d(x, basis, alpha, S_band, HYPERS[0])
+    q1.record()
+    barrier()
+    pred_ms = torch.tensor([q0.elapsed_time(q1) / 5], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(pred_ms, op=dist.ReduceOp.MAX)
+    pred_ms = pred_ms.item()
+
     kron = None
     if args.workload == "1d" and not args.no_2d and not args.n:
         del x, y
@@ -659,7 +680,9 @@ def main():
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.workload, n, m, k, kind, is_sorted),
-        "phases_ms": {"accumulate": accum_ms, "allreduce": allred_ms, "kuu_elbo_grad": elbo_ms},
+        "phases_ms": {"accumulate": accum_ms, "allreduce": allred_ms, "kuu_elbo_grad": elbo_ms,
+                      "predict_same_points": pred_ms},
+        "predict_points_per_s": world * n / (pred_ms * 1e-3),
         "elbo": float(res0[0]), "grad": [float(v) for v in res0[1:4]],
         "roofline": {"kernel": "accum_1d_kernel<%d,2>" % k, "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
