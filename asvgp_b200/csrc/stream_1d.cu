@@ -299,42 +299,127 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
 // ------------------------------------------------------------------------------------------------------------------
 // predictor
 // ------------------------------------------------------------------------------------------------------------------
+// Inside one knot interval the posterior mean is a polynomial of degree K and the variance one of degree 2K in
+// tau = t - 1/2 (the same conversion tables as the accumulate, MomentCoef<K>): every lane caches the K+1 + 2K+1 coefficients
+// of the interval it is in, so that a point of a time-ordered test set costs two Horner evaluations (3K+2 fp64
+// instructions) and no gathers; lanes take consecutive pairs of points, loads and stores are fully coalesced 128-bit
+// accesses.  A lane whose points jump between intervals (unordered test sets) evaluates pieces and window entries
+// directly instead of refreshing its cache every time.  24 B of traffic per point.
 template <int K>
 __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restrict__ xs, int64_t n, const double* __restrict__ knots,
                                                          int n_knots, int M,
                                                          const double* __restrict__ alpha,
                                                          const double* __restrict__ S, double variance,
                                                          double* __restrict__ mean, double* __restrict__ var) {
-    constexpr int U = 4;
+    constexpr int U = 4;                 // pairs of points in flight per thread (8 measured no faster)
     const Mesh mesh = load_mesh(knots, n_knots);
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < n; base += stride * U) {
-        double xv[U];
+    const MomentCoef<K>& mc = g_moment_coef<K>;
+    const bool vec = ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 15u) == 0;
+
+    double cm[K + 1], cv[2 * K + 1];     // mean / variance polynomials (ascending powers of tau) of the cached interval
+    int cur = -1, since_refresh = 1 << 20;
+    double u = 0.0, lo = INFINITY, hi = -INFINITY;
+
+    auto eval = [&](double x, double& mu, double& vv) {
+        if (x > lo && x <= hi) {
+            const double tau = fma(x - u, mesh.inv_delta, -0.5);
+            double m = cm[K];
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int64_t i = base + j * stride;
-            xv[j] = (i < n) ? __ldg(xs + i) : 0.0;
+            for (int j = K - 1; j >= 0; --j) m = fma(m, tau, cm[j]);
+            double v = cv[2 * K];
+#pragma unroll
+            for (int j = 2 * K - 1; j >= 0; --j) v = fma(v, tau, cv[j]);
+            mu = m;
+            vv = v;
+            ++since_refresh;
+            return;
         }
+        const int idx = locate_interval(mesh, x, LdgLoader());
+        const double ui = __ldg(mesh.knots + idx);
+        if (since_refresh >= 8) {
+            // the lane has been sitting in one interval: adopt the new one
+            cur = idx;
+            u = ui;
+            lo = (idx == 0) ? -INFINITY : ui;
+            hi = (idx == mesh.n_knots - 2) ? INFINITY : __ldg(mesh.knots + idx + 1);
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-            const int64_t i = base + j * stride;
-            if (i >= n) break;
-            const int idx = locate_interval(mesh, xv[j], LdgLoader());
-            const double t = (xv[j] - __ldg(mesh.knots + idx)) * mesh.inv_delta;
-            double w[K + 1];
-            bspline_pieces<K>(t, w);
-            double mu = 0.0, q = 0.0;
+            for (int j = 0; j <= K; ++j) cm[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j <= 2 * K; ++j) cv[j] = 0.0;
 #pragma unroll
             for (int r = 0; r <= K; ++r) {
-                mu = fma(w[r], __ldg(alpha + idx + r), mu);
-                double row = 0.5 * w[r] * __ldg(S + idx + r);                       // diagonal counted once
+                const double ar = __ldg(alpha + idx + r);
 #pragma unroll
-                for (int s = 0; s < r; ++s) row = fma(w[s], __ldg(S + (int64_t)(r - s) * M + idx + s), row);
-                q = fma(w[r], row, q);
+                for (int j = 0; j <= K; ++j) cm[j] = fma(mc.cb[r][j], ar, cm[j]);
+#pragma unroll
+                for (int q = 0; q <= r; ++q) {
+                    const double sv = (q == r ? 1.0 : 2.0) * __ldg(S + (int64_t)(r - q) * M + idx + q);
+#pragma unroll
+                    for (int j = 0; j <= 2 * K; ++j) cv[j] = fma(mc.cg[tri_index(r, q)][j], sv, cv[j]);
+                }
             }
-            mean[i] = mu;
-            var[i] = variance + 2.0 * q;
+            cv[0] += variance;
+            since_refresh = 0;
+            const double tau = fma(x - u, mesh.inv_delta, -0.5);
+            double m = cm[K];
+#pragma unroll
+            for (int j = K - 1; j >= 0; --j) m = fma(m, tau, cm[j]);
+            double v = cv[2 * K];
+#pragma unroll
+            for (int j = 2 * K - 1; j >= 0; --j) v = fma(v, tau, cv[j]);
+            mu = m;
+            vv = v;
+            return;
         }
+        // unordered points: direct evaluation from the pieces and the window entries
+        since_refresh = 0;
+        const double t = (x - ui) * mesh.inv_delta;
+        double w[K + 1];
+        bspline_pieces<K>(t, w);
+        double m = 0.0, q = 0.0;
+#pragma unroll
+        for (int r = 0; r <= K; ++r) {
+            m = fma(w[r], __ldg(alpha + idx + r), m);
+            double row = 0.5 * w[r] * __ldg(S + idx + r);                       // diagonal counted once
+#pragma unroll
+            for (int sidx = 0; sidx < r; ++sidx) row = fma(w[sidx], __ldg(S + (int64_t)(r - sidx) * M + idx + sidx), row);
+            q = fma(w[r], row, q);
+        }
+        mu = m;
+        vv = variance + 2.0 * q;
+    };
+
+    if (vec) {
+        // every CTA walks its own contiguous range of pairs in tiles of 256 * U, so that for an ordered test set a lane's
+        // successive points are 2 * 256 * U apart and stay in one knot interval for many tiles
+        const int64_t n_pairs = n >> 1;
+        const int64_t per_cta = (n_pairs + gridDim.x - 1) / gridDim.x;
+        const int64_t c_begin = blockIdx.x * per_cta, c_end = imin64(c_begin + per_cta, n_pairs);
+        const double2* __restrict__ x2 = reinterpret_cast<const double2*>(xs);
+        double2* __restrict__ m2 = reinterpret_cast<double2*>(mean);
+        double2* __restrict__ v2 = reinterpret_cast<double2*>(var);
+        for (int64_t base = c_begin + threadIdx.x; base < c_end; base += (int64_t)blockDim.x * U) {
+            double2 xv[U];
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int64_t i = base + j * (int64_t)blockDim.x;
+                xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int j = 0; j < U; ++j) {
+                const int64_t i = base + j * (int64_t)blockDim.x;
+                if (i >= c_end) break;
+                double2 mo, vo;
+                eval(xv[j].x, mo.x, vo.x);
+                eval(xv[j].y, mo.y, vo.y);
+                m2[i] = mo;
+                v2[i] = vo;
+            }
+        }
+        if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval(__ldg(xs + n - 1), mean[n - 1], var[n - 1]);
+    } else {
+        const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) eval(__ldg(xs + i), mean[i], var[i]);
     }
 }
 
@@ -408,7 +493,7 @@ extern "C" int asvgp_predict_1d(const double* xnew, int64_t n, const double* mes
     if (n == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int M = n_knots + order - 1;
-    const int blocks = (int)std::min<int64_t>((n + 256 * 4 - 1) / (256 * 4), (int64_t)sm_count() * 8);
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), (int64_t)sm_count() * 4));
     ASVGP_DISPATCH_ORDER(order, (predict_1d_kernel<K><<<blocks, 256, 0, st>>>(xnew, n, mesh, n_knots, M, alpha, S_band, variance, mean, var)));
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
