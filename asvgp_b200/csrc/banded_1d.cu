@@ -323,7 +323,7 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ partial, const d
     // diagnostics: SM cycles of the Kuu chain's phases (chunk sweep, separator system, back sweep, trace)
     out[9] = cK[8]; out[10] = cK[9]; out[11] = cK[10]; out[12] = cK[11];
     out[13] = cL[8]; out[14] = cL[9];
-    out[15] = cL[0] - cS[0];      // consistency of the two P chains (must be ~0)
+    out[15] = dtr_dl;             // d trace(Kuu^-1 G) / d lengthscale (multi-output bound: trace terms count once)
 }
 
 // ------------------------------------------------------------------------------------------------------------------

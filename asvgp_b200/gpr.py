@@ -59,9 +59,8 @@ class GPR_1d(_ModelBase):
         assert X.shape[1] == 1
         if y.ndim == 1:
             y = y.reshape(-1, 1)
-        if y.shape[1] != 1:
-            raise NotImplementedError("multi-output y (D > 1) is not implemented yet")
         self.X, self.y = X, y
+        n_out = int(y.shape[1])
         on_device = isinstance(X, torch.Tensor) and X.is_cuda
         if check_inputs and X.shape[0]:
             lo, hi = (torch.aminmax(X) if isinstance(X, torch.Tensor) else (X.min(), X.max()))
@@ -80,21 +79,33 @@ class GPR_1d(_ModelBase):
 
         # Precompute static quantities (reference gpr.py:39-44): one fused pass over this rank's points,
         # then (multi-GPU) one all-reduce of the packed buffer.
-        if on_device:
-            self._acc = ops.accum_1d(X.reshape(-1), y.reshape(-1), basis)
-        else:                       # host data: streamed through pinned staging buffers, never fully resident
-            self._acc = ops.accum_1d_host(X, y, basis)
+        # Multi-output y (D columns, gpr.py:40,78-79) keeps one packed accumulator per column: G and N are
+        # shared, Kuf_y and sum(y^2) are per column.
+        self._accs = []
+        for d in range(n_out):
+            yd = y[:, d] if n_out > 1 else y.reshape(-1)
+            if on_device:
+                self._accs.append(ops.accum_1d(X.reshape(-1), yd.contiguous(), basis))
+            else:                   # host data: streamed through pinned staging buffers, never fully resident
+                self._accs.append(ops.accum_1d_host(X, np.ascontiguousarray(yd), basis))
         self._distributed = _dist.is_distributed(distributed)
         if self._distributed:
-            _dist.allreduce_packed(self._acc)
+            for acc in self._accs:
+                _dist.allreduce_packed(acc)
+        self._acc = self._accs[0]
         self._G, self._b, self._scal = ops.split_accum_1d(self._acc, basis)
         self._host = None
-        self._out = torch.empty(16, dtype=torch.float64, device=self._acc.device)
+        self._outs = [torch.empty(16, dtype=torch.float64, device=self._acc.device) for _ in self._accs]
+        self._out = self._outs[0]
 
     # -- the reference's cached attributes (host copies, fetched lazily) --------------------------------------
     def _host_stats(self):
         if self._host is None:
-            self._host = (self._G.cpu().numpy(), self._b.cpu().numpy().reshape(-1, 1), self._scal.cpu().numpy())
+            parts = [ops.split_accum_1d(acc, self.basis) for acc in self._accs]
+            b = torch.stack([p[1] for p in parts], 1).cpu().numpy()
+            scal = self._scal.cpu().numpy().copy()
+            scal[0] = float(sum(p[2][0] for p in parts).item())
+            self._host = (self._G.cpu().numpy(), b, scal)
         return self._host
 
     @property
@@ -130,12 +141,32 @@ class GPR_1d(_ModelBase):
         var = hyper_value(self.kernel.variance)
         s2 = hyper_value(self.likelihood.variance)
         Kuu, dKuu = self.inducing_features.make_Kuu_device(self.kernel, want_grad=True)
-        ops.elbo_grad_1d(Kuu, dKuu, self._acc, self.basis, var, s2, chunks=self._chunks, out=self._out)
+        for acc, out in zip(self._accs, self._outs):
+            ops.elbo_grad_1d(Kuu, dKuu, acc, self.basis, var, s2, chunks=self._chunks, out=out)
         return self._out
+
+    def _combine_outputs(self):
+        """Bound for D output columns from the D single-column evaluations.  The reference scales the log-dets by
+        D and sums the data-fit terms over columns, but counts -sum(K_diag)/2s2 + trace/2s2 ONCE (gpr.py:81-87);
+        summing the columns counts it D times, so D - 1 copies of T = (-N v + trace)/(2 s2) are taken out again:
+        dT/dv = (-N + trace/v)/(2 s2) (trace is linear in v), dT/dl = (dtrace/dl)/(2 s2), dT/ds2 = -T/s2."""
+        outs = torch.stack(self._outs).cpu().numpy()
+        out = outs[0].copy()
+        extra = len(self._outs) - 1
+        if extra:
+            v, s2 = hyper_value(self.kernel.variance), hyper_value(self.likelihood.variance)
+            n, tr, dtr_dl = float(self._scal[1].item()), out[7], out[15]
+            T = 0.5 * (-n * v + tr) / s2
+            out[0:4] = outs[:, 0:4].sum(0) - extra * np.array([T, 0.5 * (-n + tr / v) / s2, 0.5 * dtr_dl / s2, -T / s2])
+            out[6] = outs[:, 6].sum()
+            bad = outs[:, 8][outs[:, 8] != 0]
+            out[8] = bad[0] if bad.size else 0.0
+        return out
 
     def elbo_and_grad(self):
         """ELBO (reference gpr.py:49-89) and {id(param): dELBO/dparam} for variance, lengthscales, sigma^2."""
-        out = self._launch_elbo().cpu().numpy()
+        self._launch_elbo()
+        out = self._combine_outputs()
         if out[8] != 0:
             raise np.linalg.LinAlgError("banded Cholesky failed: non-positive pivot %d" % int(out[8]))
         grads = {id(self.kernel.variance): out[1], id(self.kernel.lengthscales): out[2],
@@ -153,10 +184,17 @@ class GPR_1d(_ModelBase):
         s2 = hyper_value(self.likelihood.variance)
         Kuu, _ = self.inducing_features.make_Kuu_device(self.kernel, want_grad=False)
         alpha, S, info = ops.posterior_1d(Kuu, self._acc, self.basis, s2, chunks=self._chunks)
+        if len(self._accs) > 1:          # one solve per output column; S does not depend on y
+            cols = [alpha]
+            for acc in self._accs[1:]:
+                a_d, _, info_d = ops.posterior_1d(Kuu, acc, self.basis, s2, chunks=self._chunks)
+                cols.append(a_d)
+                info = torch.maximum(info, info_d)
+            alpha = torch.stack(cols, 0)
         return alpha, S, info
 
     def predict_f(self, Xnew, full_cov=False, full_output_cov=False, batch=False):
-        """Posterior mean and variance at Xnew, each (n*, 1) (reference gpr.py:91-136).  numpy in -> numpy out,
+        """Posterior mean (n*, D) and variance (n*, 1) at Xnew (reference gpr.py:91-136).  numpy in -> numpy out,
         CUDA tensor in -> CUDA tensors out.  `batch` is accepted for compatibility; no chunking is needed (and the
         reference's silent drop of the last n* mod 10000 points, SURVEY Q6, is not reproduced)."""
         assert not full_output_cov
@@ -164,10 +202,16 @@ class GPR_1d(_ModelBase):
             raise NotImplementedError
         alpha, S, info = self.posterior_weights()
         xs = ops.to_device(Xnew).reshape(-1)
-        mean, var = ops.predict_1d(xs, self.basis, alpha, S, hyper_value(self.kernel.variance))
+        v = hyper_value(self.kernel.variance)
+        if alpha.dim() == 1:
+            mean, var = ops.predict_1d(xs, self.basis, alpha, S, v)
+            mean = mean.view(-1, 1)
+        else:
+            cols = [ops.predict_1d(xs, self.basis, a_d, S, v) for a_d in alpha]
+            mean, var = torch.stack([c[0] for c in cols], 1), cols[0][1]
         if info.any().item():
             raise np.linalg.LinAlgError("banded Cholesky failed in predict_f")
-        mean, var = mean.view(-1, 1), var.view(-1, 1)
+        var = var.view(-1, 1)
         if isinstance(Xnew, torch.Tensor) and Xnew.is_cuda:
             return mean, var
         return mean.cpu().numpy(), var.cpu().numpy()

@@ -83,7 +83,7 @@ ASVGP_API int64_t asvgp_workspace_bytes_1d(int M, int order, int chunks);
  * banded sweeps (0 = default).  out[16] (device):
  *   [0] ELBO  [1] dELBO/dvariance  [2] dELBO/dlengthscale  [3] dELBO/dsigma2
  *   [4] log|Kuu|  [5] log|P|  [6] b^T P^-1 b  [7] trace(Kuu^-1 G)  [8] info (0 ok, j+1 first non-positive pivot)
- *   [9..15] diagnostics (individual derivatives). */
+ *   [9..14] diagnostics (SM cycles of the chain phases)  [15] d trace(Kuu^-1 G) / d lengthscale. */
 ASVGP_API int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const double* acc, int M, int order,
                                  double variance, double sigma2, int chunks, double* out, void* work,
                                  int64_t work_bytes, void* stream);

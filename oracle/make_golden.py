@@ -155,10 +155,36 @@ def kron_2d(ns):
     print("kron_2d:", {k: v for k, v in out.items() if k.endswith("elbo")})
 
 
+def multi_output_1d(ns):
+    """y with D = 3 columns (reference gpr.py:39-44,78-85 carry D through Kuf_y, tr_yTy and the bound)."""
+    out = {}
+    rng = np.random.default_rng(2024)
+    n, m, k = 6000, 48, 3
+    x = rng.uniform(0.0, m, n)
+    f = np.stack([np.sin(2 * np.pi * x / 17), np.cos(2 * np.pi * x / 5.3), 0.02 * x], 1)
+    y = f + 0.2 * rng.standard_normal((n, 3))
+    basis = ns.basis.B3Spline(-1, m + 1, m)
+    out.update(x=x, y=y, m=m, order=k)
+    for kind in KINDS:
+        kern = getattr(ns.gpflow.kernels, kind)()
+        model = ns.gpr.GPR_1d((x.reshape(-1, 1), y), kern, basis)
+        for tag, (v, l, s2) in (("a", (1.0, 1.0, 0.1)), ("b", (0.6, 3.5, 0.3))):
+            set_hypers(ns, model, [kern], [(v, l)], s2)
+            out["elbo_%s_%s" % (kind, tag)] = float(model.elbo())
+    out["Kuf_y"] = np.asarray(model.Kuf_y)
+    out["tr_yTy"] = float(model.tr_yTy)
+    xs = rng.uniform(0.5, m - 0.5, 50).reshape(-1, 1)
+    mu, var = model.predict_f(xs)
+    out["xs"], out["mean"], out["var"] = xs, np.asarray(mu), np.asarray(var)
+    out["pred_hypers"] = np.array([0.6, 3.5, 0.3])
+    np.savez_compressed(os.path.join(OUT, "multi_output_1d.npz"), **out)
+    print("multi_output_1d: Kuf_y", out["Kuf_y"].shape, "mean", out["mean"].shape, out["elbo_Matern52_b"])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ns = ref_under_shim.load()
-    snelson(ns)
-    basis_eval(ns)
-    synth_1d(ns)
-    kron_2d(ns)
+    only = sys.argv[1:]
+    for fn in (snelson, basis_eval, synth_1d, kron_2d, multi_output_1d):
+        if not only or fn.__name__ in only:
+            fn(ns)

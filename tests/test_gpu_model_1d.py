@@ -86,6 +86,41 @@ def test_gradients_match_autograd_oracle(cuda, golden, kind, k, chunks):
     np.testing.assert_allclose(got, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
 
 
+def test_multi_output_golden_and_gradients(cuda, golden):
+    """y with D = 3 columns (reference gpr.py:39-44,78-87): bound vs reference-under-shim at rel 1e-10, gradients vs the
+    autograd oracle at 1e-8, mean (n*, D) / var (n*, 1) at 1e-9; numpy and device inputs agree."""
+    import torch
+    from asvgp_b200 import basis as B, kernels as Kn
+    from asvgp_b200.gpr import GPR_1d
+
+    g = golden("multi_output_1d")
+    m, k = int(g["m"]), int(g["order"])
+    X, y = g["x"].reshape(-1, 1), g["y"]
+    for kind in KINDS:
+        for tag, hyp in (("a", (1.0, 1.0, 0.1)), ("b", (0.6, 3.5, 0.3))):
+            kern = getattr(Kn, kind)()
+            model = GPR_1d((X, y), kern, B.B3Spline(-1, m + 1, m))
+            kern.variance.assign(hyp[0]); kern.lengthscales.assign(hyp[1]); model.likelihood.variance.assign(hyp[2])
+            want = float(g["elbo_%s_%s" % (kind, tag)])
+            elbo, grads = model.elbo_and_grad()
+            assert abs(elbo - want) <= 1e-10 * abs(want), (kind, tag)
+            np.testing.assert_allclose(model.Kuf_y, g["Kuf_y"], rtol=1e-11, atol=1e-11)
+            assert abs(model.tr_yTy - float(g["tr_yTy"])) <= 1e-12 * model.tr_yTy
+            tables = O.static_bands(k, m, model.basis.delta)
+            e0, g0 = O.elbo_grad_1d_dense(kind, tables, model.KufKfu, g["Kuf_y"], float(g["tr_yTy"]), X.shape[0], *hyp)
+            assert abs(elbo - e0) <= 1e-10 * abs(e0)
+            got = np.array([grads[id(kern.variance)], grads[id(kern.lengthscales)], grads[id(model.likelihood.variance)]])
+            np.testing.assert_allclose(got, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
+    mean, var = model.predict_f(g["xs"])                      # last model: Matern52 at pred_hypers
+    assert mean.shape == (50, 3) and var.shape == (50, 1)
+    np.testing.assert_allclose(mean, g["mean"], atol=1e-9, rtol=0)
+    np.testing.assert_allclose(var, g["var"], atol=1e-9, rtol=0)
+    kern = Kn.Matern52()
+    dev = GPR_1d((torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()), kern, B.B3Spline(-1, m + 1, m))
+    kern.variance.assign(0.6); kern.lengthscales.assign(3.5); dev.likelihood.variance.assign(0.3)
+    assert abs(dev.elbo() - elbo) <= 1e-12 * abs(elbo)
+
+
 def test_medium_m_partitioned_vs_oracle(cuda):
     """C2 shape (N=1e6, M=1000): default chunking (P>1) against the SciPy banded oracle."""
     rng = np.random.default_rng(1997)

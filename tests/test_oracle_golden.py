@@ -158,3 +158,25 @@ def test_oracle_matches_live_reference_when_present(golden):
     basis = ns.basis.B3Spline(-3.5, 10.5, 100)
     model = ns.gpr.GPR_1d((g["X"], g["y"]), ns.gpflow.kernels.Matern52(), basis)
     assert abs(float(model.elbo()) - float(g["elbo111_Matern52"])) < 1e-9
+
+
+def test_multi_output_1d_golden(golden):
+    """D = 3 output columns: Kuf_y is M x D, the log-dets count D times, the K_diag and trace terms once (gpr.py:78-87)."""
+    g = golden("multi_output_1d")
+    m, k = int(g["m"]), int(g["order"])
+    mesh, delta = O.make_mesh(-1, m + 1, m, k)
+    T = O.static_bands(k, m, delta)
+    x, y = g["x"], g["y"]
+    G, b, yy = O.precompute_1d(mesh, delta, k, m, x, y)
+    assert b.shape == (m, 3)
+    np.testing.assert_allclose(b, g["Kuf_y"], rtol=1e-12, atol=1e-12)
+    assert abs(yy - float(g["tr_yTy"])) <= 1e-12 * yy
+    for kind in KINDS:
+        for tag, (v, l, s2) in (("a", (1.0, 1.0, 0.1)), ("b", (0.6, 3.5, 0.3))):
+            want = float(g["elbo_%s_%s" % (kind, tag)])
+            e = O.elbo_1d(O.make_Kuu(kind, l, v, T), G, b, yy, x.shape[0], v, s2)
+            assert abs(e - want) <= 1e-10 * abs(want), (kind, tag)
+    v, l, s2 = g["pred_hypers"]
+    mean, var = O.predict_1d(mesh, delta, k, m, O.make_Kuu("Matern52", l, v, T), G, b, v, s2, g["xs"])
+    np.testing.assert_allclose(mean, g["mean"], atol=1e-9)
+    np.testing.assert_allclose(var, g["var"], atol=1e-9)
