@@ -18,6 +18,8 @@ _vp = ctypes.c_void_p
 SIGNATURES = {
     "asvgp_basis_eval_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
     "asvgp_accum_1d": [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp],
+    "asvgp_accum_1d_binned": [_vp, _vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_i64, _vp],
+    "asvgp_order_probe_1d": [_vp, _c_i64, _vp, _c_int, _vp, _vp],
     "asvgp_predict_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp],
     "asvgp_kuu_assemble": [_vp, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
     "asvgp_elbo_grad_1d": [_vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp],
@@ -33,6 +35,7 @@ SIGNATURES = {
 # functions whose return value is not a status code
 VALUE_FUNCTIONS = {
     "asvgp_workspace_bytes_1d": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_accum_1d_binned_work_bytes": (_c_i64, [_c_i64]),
     "asvgp_accum_2d_moment_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_band_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),

@@ -17,6 +17,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "partition.cuh"
 #include "../../include/asvgp_b200.h"
 
 namespace asvgp {
@@ -110,7 +111,9 @@ struct WarpAccum {
 
     // centred monomial moments of the point (see MomentCoef in common.cuh): 5K+2 fp64 instructions
     __device__ __forceinline__ void add(const Mesh& mesh, double x, double y) {
-        const double tau = fma(x - u, mesh.inv_delta, -0.5);
+        add_tau(fma(x - u, mesh.inv_delta, -0.5), y);
+    }
+    __device__ __forceinline__ void add_tau(double tau, double y) {
         double p = tau;
         mg[0] += p;
         my[0] += y;
@@ -154,6 +157,53 @@ struct WarpAccum {
         clear();
     }
 };
+
+// Same as WarpAccum::flush for GL-lane groups that each hold their own interval: the moments are reduced inside every
+// group (log2 GL shuffle steps serve all 32/GL groups at once), lane l of a group converts and adds entries l, l + GL, ...
+template <int K, int GL>
+__device__ __forceinline__ void flush_groups(WarpAccum<K>& wa, bool any, double* __restrict__ G, double* __restrict__ b, int M, int lane) {
+    constexpr int NG = WarpAccum<K>::NG, NY = WarpAccum<K>::NY, kPairs = WarpAccum<K>::kPairs, kAcc = WarpAccum<K>::kAcc;
+    double Mg[NG + 1], My[NY];
+    int c = wa.cnt;
+#pragma unroll
+    for (int o = GL / 2; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    Mg[0] = (double)c;
+#pragma unroll
+    for (int j = 0; j < NG; ++j) {
+        double v = wa.mg[j];
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        Mg[j + 1] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NY; ++j) {
+        double v = wa.my[j];
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        My[j] = v;
+    }
+    if (any) {
+        const MomentCoef<K>& mc = g_moment_coef<K>;
+#pragma unroll
+        for (int e0 = 0; e0 < kAcc; e0 += GL) {
+            const int e = e0 + (lane & (GL - 1));
+            if (e < kPairs) {
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j <= NG; ++j) v = fma(mc.cg[e][j], Mg[j], v);
+                const int r = mc.rr[e], q = mc.ss[e];
+                atomicAdd(G + (int64_t)(r - q) * M + wa.cur + q, v);
+            } else if (e < kAcc) {
+                const int r = e - kPairs;
+                double v = 0.0;
+#pragma unroll
+                for (int j = 0; j < NY; ++j) v = fma(mc.cb[r][j], My[j], v);
+                atomicAdd(b + wa.cur + r, v);
+            }
+        }
+    }
+    wa.clear();
+}
 
 // one point straight to global memory (unsorted-input slow path)
 template <int K>
@@ -294,6 +344,180 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
         atomicAdd(scal, tot);
         if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// accumulate for inputs in no particular order: bucket partition (partition.cuh), then per-unit shared-memory sort
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kUnitMargin = 2;      // intervals either side of a bucket the exact interval may fall into (a float32-built
+                                    // mesh is not the uniform grid the bucket guess assumes); beyond: per-point REDs
+
+struct Points1D {
+    const double* x;
+    const double* y;
+    const double* knots;
+    int n_knots;
+    int ipb;            // knot intervals per bucket
+    Mesh mesh;
+    __device__ __forceinline__ void init() { mesh = load_mesh(knots, n_knots); }
+    __device__ __forceinline__ int guess(double xv) const {
+        const double g = floor((xv - mesh.x0) * mesh.inv_delta);
+        const int hi = n_knots - 2;
+        return g < 0.0 ? 0 : (g > (double)hi ? hi : (int)g);
+    }
+    __device__ __forceinline__ int bucket(int64_t i) const { return guess(__ldg(x + i)) / ipb; }
+    __device__ __forceinline__ void load(int64_t i, double (&v)[2]) const { v[0] = __ldg(x + i); v[1] = __ldg(y + i); }
+    __device__ __forceinline__ int bucket_of(const double (&v)[2]) const { return guess(v[0]) / ipb; }
+};
+
+// knots of the unit's window staged in shared memory; anything outside falls back to the global array
+struct WindowKnots {
+    const double* g_knots;
+    const double* s_knots;
+    int first, count;
+    __device__ __forceinline__ double operator()(const double* p) const {
+        const int j = (int)(p - g_knots) - first;
+        return (j >= 0 && j < count) ? s_knots[j] : __ldg(p);
+    }
+};
+
+// One unit = up to kUnitPoints records of one bucket (= ipb consecutive knot intervals).  The CTA counting-sorts the unit
+// by interval in shared memory (tau = t - 1/2 and y are what is staged), then each warp takes whole intervals: lanes
+// stride over the interval's run with the register moment sums of WarpAccum and the warp flushes once per run.
+template <int K>
+__global__ void __launch_bounds__(kPartThreads, 2)
+accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, int n_knots, int ipb, int M,
+                      double* __restrict__ G, double* __restrict__ b, double* __restrict__ scal) {
+    constexpr int PER = kUnitPoints / kPartThreads;
+    constexpr int kGroup = 8;
+    extern __shared__ double s_dyn[];
+    double* s_tau = s_dyn;                                            // [kUnitPoints]
+    double* s_y = s_tau + kUnitPoints;                                // [kUnitPoints]
+    double* s_knots = s_y + kUnitPoints;                              // [n_bins + 1]
+    int* s_off = reinterpret_cast<int*>(s_knots + ipb + 2 * kUnitMargin + 1);   // [n_bins + 2]
+    __shared__ UnitTable tab;
+    __shared__ double s_yy[kPartThreads / 32];
+    __shared__ int s_wsum[kPartThreads / 32];
+    __shared__ int s_carry;
+    const Mesh mesh = load_mesh(knots, n_knots);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_bins = ipb + 2 * kUnitMargin;
+    const double* rx = w.rec;
+    const double* ry = w.rec + n;
+    tab.stage(w);
+    __syncthreads();
+    const int64_t n_units = tab.n_units();
+    double yy = 0.0;
+    WarpAccum<K> wa;
+    wa.clear();
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int bucket, count;
+        int64_t first;
+        tab.find(u, bucket, first, count);
+        const int idx0 = bucket * ipb - kUnitMargin;          // interval of bin 0 (may be negative: those bins stay empty)
+        double xs[PER], ys[PER];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int q = p * kPartThreads + threadIdx.x;
+            if (q < count) { xs[p] = __ldg(rx + first + q); ys[p] = __ldg(ry + first + q); }
+        }
+        for (int j = threadIdx.x; j <= n_bins; j += kPartThreads) {
+            s_off[j] = 0;
+            const int kn = idx0 + j;
+            s_knots[j] = (kn >= 0 && kn < n_knots) ? __ldg(knots + kn) : 0.0;
+        }
+        __syncthreads();
+        WindowKnots wk;
+        wk.g_knots = knots; wk.s_knots = s_knots; wk.first = idx0; wk.count = n_bins + 1;
+        // exact interval (reference basis.py:58) and count per bin (bin j counts into s_off[j + 1])
+        int bin[PER];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int q = p * kPartThreads + threadIdx.x;
+            bin[p] = -1;
+            if (q < count) {
+                yy = fma(ys[p], ys[p], yy);
+                const int idx = locate_interval(mesh, xs[p], wk);
+                const int j = idx - idx0;
+                if (j >= 0 && j < n_bins) {
+                    bin[p] = j;
+                    atomicAdd(&s_off[j + 1], 1);
+                } else {
+                    scatter_point<K>(mesh, idx, xs[p], ys[p], G, b, M);
+                }
+            }
+        }
+        __syncthreads();
+        // inclusive scan of s_off[1..n_bins] in place (s_off[j] becomes the first slot of bin j): chunks of 256 + carry
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 1; base <= n_bins; base += kPartThreads) {
+            const int j = base + threadIdx.x;
+            int v = j <= n_bins ? s_off[j] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (lane == 31) s_wsum[warp] = v;
+            __syncthreads();
+            int add = s_carry;
+            for (int q = 0; q < warp; ++q) add += s_wsum[q];
+            v += add;
+            __syncthreads();
+            if (j <= n_bins) s_off[j] = v;
+            if (threadIdx.x == kPartThreads - 1) s_carry = v;
+            __syncthreads();
+        }
+        // the placement advances s_off[j] from the start to the end of bin j, so afterwards bin j is
+        // [j ? s_off[j - 1] : 0, s_off[j])
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            if (bin[p] >= 0) {
+                const int slot = atomicAdd(&s_off[bin[p]], 1);
+                s_tau[slot] = fma(xs[p] - s_knots[bin[p]], mesh.inv_delta, -0.5);
+                s_y[slot] = ys[p];
+            }
+        }
+        __syncthreads();
+        // kGroup lanes per interval, 32 / kGroup intervals per warp at a time
+        for (int jb = warp * (32 / kGroup); jb < n_bins; jb += (kPartThreads / 32) * (32 / kGroup)) {
+            const int j = jb + lane / kGroup;
+            int begin = 0, end = 0;
+            if (j < n_bins) { begin = j ? s_off[j - 1] : 0; end = s_off[j]; }
+            wa.cur = idx0 + j;
+            for (int q = begin + (lane & (kGroup - 1)); q < end; q += kGroup) wa.add_tau(s_tau[q], s_y[q]);
+            flush_groups<K, kGroup>(wa, end > begin, G, b, M, lane);
+        }
+        __syncthreads();
+    }
+    yy = warp_sum(yy);
+    if (lane == 0) s_yy[warp] = yy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < kPartThreads / 32; ++q) tot += s_yy[q];
+        atomicAdd(scal, tot);
+        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+    }
+}
+
+static size_t accum_1d_units_smem(int n_bins) { return (size_t)2 * kUnitPoints * 8 + (size_t)(n_bins + 1) * 8 + (size_t)(n_bins + 2) * 4; }
+
+// Fraction of sampled neighbours (x[i], x[i+1]) that lie more than one knot interval apart: ~0 for time-series order,
+// ~1 for shuffled input.  out[0] += jumps / samples.
+__global__ void __launch_bounds__(256) order_probe_1d_kernel(const double* __restrict__ x, int64_t n, const double* __restrict__ knots,
+                                                             int n_knots, int samples, double* __restrict__ out) {
+    const Mesh mesh = load_mesh(knots, n_knots);
+    int jumps = 0;
+    for (int s = threadIdx.x; s < samples; s += blockDim.x) {
+        const int64_t i = (int64_t)((double)s * (double)(n - 1) / (double)samples);
+        const int a = locate_interval(mesh, __ldg(x + i), LdgLoader()), c = locate_interval(mesh, __ldg(x + i + 1), LdgLoader());
+        jumps += (a - c > 1 || c - a > 1) ? 1 : 0;
+    }
+    jumps = __reduce_add_sync(0xffffffffu, jumps);
+    if ((threadIdx.x & 31) == 0 && jumps) atomicAdd(out, (double)jumps / (double)samples);
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -482,6 +706,59 @@ extern "C" int asvgp_accum_1d(const double* x, const double* y, int64_t n, const
     } else {
         ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 1><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal)));
     }
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+extern "C" int64_t asvgp_accum_1d_binned_work_bytes(int64_t n) { return PartWork::bytes(n < 0 ? 0 : n, 2); }
+
+extern "C" int asvgp_order_probe_1d(const double* x, int64_t n, const double* mesh, int n_knots, double* out, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots >= 2 && out != nullptr, "order_probe_1d: n=%lld n_knots=%d", (long long)n, n_knots);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (n < 2) return kOk;
+    const int samples = (int)std::min<int64_t>(n - 1, 4096);
+    order_probe_1d_kernel<<<1, 256, 0, st>>>(x, n, mesh, n_knots, samples, out);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <int K>
+static int launch_accum_1d_units(const PartWork& w, int64_t n, const double* mesh, int n_knots, int ipb, int M, double* G,
+                                 double* b, double* scal, cudaStream_t st) {
+    const size_t smem = accum_1d_units_smem(ipb + 2 * kUnitMargin);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_1d_units_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_1d_units_kernel<K>, kPartThreads, smem));
+    const int64_t max_units = n / kUnitPoints + kPartBuckets;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count() * std::max(per_sm, 1)));
+    accum_1d_units_kernel<K><<<blocks, kPartThreads, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
+    return kOk;
+}
+
+extern "C" int asvgp_accum_1d_binned(const double* x, const double* y, int64_t n, const double* mesh, int n_knots, int order,
+                                     double* acc, void* work, int64_t work_bytes, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots >= 2, "accum_1d_binned: n=%lld n_knots=%d", (long long)n, n_knots);
+    ASVGP_REQUIRE(order >= 1 && order <= kMaxOrder, "accum_1d_binned: spline order %d not in 1..6", order);
+    const int n_int = n_knots - 1;
+    const int ipb = (n_int + kPartBuckets - 1) / kPartBuckets;
+    if (ipb + 2 * kUnitMargin > kUnitMaxBins)  // more than ~2^20 knot intervals: the general kernel handles any order
+        return asvgp_accum_1d(x, y, n, mesh, n_knots, order, acc, stream);
+    ASVGP_REQUIRE(work != nullptr && work_bytes >= PartWork::bytes(n, 2), "accum_1d_binned: work_bytes=%lld < %lld",
+                  (long long)work_bytes, (long long)PartWork::bytes(n, 2));
+    if (n == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int M = n_knots + order - 1;
+    double* G = acc;
+    double* b = acc + (int64_t)(order + 1) * M;
+    double* scal = b + M;
+    const PartWork w = PartWork::carve(work);
+    ASVGP_CUDA_OK(cudaMemsetAsync(w.count, 0, kPartBuckets * sizeof(u64), st));
+    Points1D src;
+    src.x = x; src.y = y; src.knots = mesh; src.n_knots = n_knots; src.ipb = ipb;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count() * 2));
+    ASVGP_CUDA_OK((launch_partition<Points1D, 2>(src, n, w, blocks, st)));
+    ASVGP_DISPATCH_ORDER(order, (launch_accum_1d_units<K>(w, n, mesh, n_knots, ipb, M, G, b, scal, st)));
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

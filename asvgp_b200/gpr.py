@@ -85,7 +85,7 @@ class GPR_1d(_ModelBase):
         for d in range(n_out):
             yd = y[:, d] if n_out > 1 else y.reshape(-1)
             if on_device:
-                self._accs.append(ops.accum_1d(X.reshape(-1), yd.contiguous(), basis))
+                self._accs.append(ops.accum_1d(X.reshape(-1), yd.contiguous(), basis, binned="auto"))
             else:                   # host data: streamed through pinned staging buffers, never fully resident
                 self._accs.append(ops.accum_1d_host(X, np.ascontiguousarray(yd), basis))
         self._distributed = _dist.is_distributed(distributed)

@@ -64,9 +64,25 @@ def accum_size_1d(basis):
     return (basis.order + 2) * basis.m + 2
 
 
-def accum_1d(x, y, basis, acc=None):
+BINNED_MIN_POINTS = 1 << 18      # below this the partition passes cost more than the REDs they save
+BINNED_JUMP_FRACTION = 0.05
+
+
+def order_probe_1d(x, basis):
+    """Fraction of sampled neighbour pairs of x that lie more than one knot interval apart (one small D2H read)."""
+    x = to_device(x).reshape(-1)
+    mesh = device_mesh(basis)
+    out = torch.empty(1, dtype=F64, device=x.device)
+    _lib.call("asvgp_order_probe_1d", _p(x), x.numel(), _p(mesh), mesh.numel(), _p(out), _stream())
+    return float(out.item())
+
+
+def accum_1d(x, y, basis, acc=None, binned=False):
     """Adds sum_n w_n w_n^T (lower band), sum_n w_n y_n, sum y^2 and the count of the points (x, y) into the
-    packed accumulator [G_band | b | sum(y^2) | count] (allocated zeroed if None).  Reference gpr.py:39-44."""
+    packed accumulator [G_band | b | sum(y^2) | count] (allocated zeroed if None).  Reference gpr.py:39-44.
+    binned: False = streaming kernel (any order is exact; fast when consecutive points share knot intervals),
+    True = bucket-partition first (inputs in no particular order), "auto" = sample the order on the device and choose
+    (one host synchronisation)."""
     x = to_device(x).reshape(-1)
     y = to_device(y).reshape(-1)
     if x.numel() != y.numel():
@@ -74,6 +90,14 @@ def accum_1d(x, y, basis, acc=None):
     mesh = device_mesh(basis)
     if acc is None:
         acc = torch.zeros(accum_size_1d(basis), dtype=F64, device=x.device)
+    if binned == "auto":
+        binned = x.numel() >= BINNED_MIN_POINTS and order_probe_1d(x, basis) > BINNED_JUMP_FRACTION
+    if binned:
+        nbytes = _lib.load().asvgp_accum_1d_binned_work_bytes(x.numel())
+        work = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        _lib.call("asvgp_accum_1d_binned", _p(x), _p(y), x.numel(), _p(mesh), mesh.numel(), basis.order, _p(acc),
+                  _p(work), nbytes, _stream())
+        return acc
     _lib.call("asvgp_accum_1d", _p(x), _p(y), x.numel(), _p(mesh), mesh.numel(), basis.order, _p(acc), _stream())
     return acc
 

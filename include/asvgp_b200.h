@@ -59,6 +59,18 @@ ASVGP_API int asvgp_basis_eval_1d(const double* x, int64_t n, const double* mesh
 ASVGP_API int asvgp_accum_1d(const double* x, const double* y, int64_t n, const double* mesh, int n_knots, int order,
                    double* acc, void* stream);
 
+/* Same sums for points in NO PARTICULAR ORDER ("random order, any binning pass included").
+ * asvgp_accum_1d is exact for any order but spends one fp64 RED per band entry per point once consecutive points stop
+ * sharing knot intervals; this variant first partitions the points into <= 256 buckets of consecutive intervals
+ * (histogram, scan, shared-memory staged scatter), then sorts each 4096-point unit by interval in shared memory and
+ * accumulates every run in registers.  `work`: asvgp_accum_1d_binned_work_bytes(n) bytes of device scratch
+ * (16 B per point + 8 KB).  asvgp_order_probe_1d writes to out[0] (device) the fraction of 4096 sampled neighbour
+ * pairs that lie more than one knot interval apart (~0 time-series order, ~1 shuffled) so a caller can choose. */
+ASVGP_API int64_t asvgp_accum_1d_binned_work_bytes(int64_t n);
+ASVGP_API int asvgp_accum_1d_binned(const double* x, const double* y, int64_t n, const double* mesh, int n_knots,
+                                    int order, double* acc, void* work, int64_t work_bytes, void* stream);
+ASVGP_API int asvgp_order_probe_1d(const double* x, int64_t n, const double* mesh, int n_knots, double* out, void* stream);
+
 /* ---- a10: 1-D posterior mean / variance over test points ----------------------------------------------------------------
  * Replaces GPR_1d.predict_f (gpr.py:91-136): mean[i] = sum_r w_r alpha[idx+r],
  * var[i] = variance + sum_{r,s} w_r w_s S[idx+r, idx+s] with S = band(P^-1) - band(Kuu^-1) (lower band, (order+1) x M). */

@@ -59,6 +59,67 @@ def test_accum_matches_reference_unsorted(cuda, golden, k):
     assert scal[1] == g[key + "_x"].shape[0]
 
 
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_accum_binned_matches_reference(cuda, golden, k):
+    """The bucket-partition path on the reference's own (random-order) inputs."""
+    from asvgp_b200 import ops
+
+    g = golden("synth_1d")
+    key = "k%d" % k
+    m = int(g[key + "_m"])
+    basis = _basis(k, -1, m + 1, m)
+    acc = ops.accum_1d(g[key + "_x"], g[key + "_y"], basis, binned=True)
+    G, b, scal = [t.cpu().numpy() for t in ops.split_accum_1d(acc, basis)]
+    _close(G, g[key + "_G"])
+    _close(b, g[key + "_Kuf_y"].ravel())
+    assert abs(scal[0] - float(g[key + "_tr_yTy"])) <= RTOL * float(g[key + "_tr_yTy"])
+    assert scal[1] == g[key + "_x"].shape[0]
+
+
+@pytest.mark.parametrize("n,m,k,dist", [(1, 30, 3, "uniform"), (4095, 30, 3, "uniform"), (4097, 700, 2, "uniform"),
+                                        (300_001, 3000, 3, "uniform"), (250_000, 10_000, 4, "clustered"),
+                                        (123_457, 40, 6, "one-interval"), (200_000, 300, 1, "knots")])
+def test_accum_binned_matches_oracle(cuda, n, m, k, dist):
+    """Shuffled inputs through the partition path: several intervals per bucket (m > 256), empty buckets, every point
+    in one interval, points exactly on knots (quirk Q2), unit and tile boundaries."""
+    from asvgp_b200 import ops
+
+    rng = np.random.default_rng(n + m)
+    basis = _basis(k, -1, m + 1, m)
+    lo, hi = 0.0, float(m)
+    if dist == "uniform":
+        x = rng.uniform(lo, hi, n)
+    elif dist == "clustered":
+        x = np.concatenate([rng.normal(0.31 * m, 0.002 * m, n // 2), rng.uniform(0.8 * m, 0.85 * m, n - n // 2)])
+    elif dist == "one-interval":
+        x = rng.uniform(7.01, 7.49, n)
+    else:
+        x = rng.choice(np.asarray(basis.mesh)[1:-1], n)
+    y = np.cos(x / 7.0) + 0.1 * rng.standard_normal(n)
+    acc = ops.accum_1d(x, y, basis, binned=True)
+    G, b, scal = [t.cpu().numpy() for t in ops.split_accum_1d(acc, basis)]
+    G0, b0, yy0 = O.precompute_1d_chunked(basis.mesh, basis.delta, k, m, x, y)
+    _close(G, G0)
+    _close(b, b0.ravel())
+    assert abs(scal[0] - yy0) <= RTOL * yy0 and scal[1] == n
+
+
+def test_accum_order_probe_and_auto(cuda):
+    from asvgp_b200 import ops
+
+    rng = np.random.default_rng(5)
+    m, n = 2000, 1 << 19
+    basis = _basis(3, -1, m + 1, m)
+    xs = np.sort(rng.uniform(0, m, n))
+    xr = rng.permutation(xs)
+    assert ops.order_probe_1d(xs, basis) == 0.0
+    assert ops.order_probe_1d(xr, basis) > 0.9
+    y = np.sin(xr / 11)
+    a_auto = ops.accum_1d(xr, y, basis, binned="auto").cpu().numpy()
+    a_plain = ops.accum_1d(xr, y, basis).cpu().numpy()
+    _close(a_auto, a_plain)
+
+
 def test_accum_snelson_golden(cuda, golden):
     g = golden("snelson")
     basis = _basis(3, -3.5, 10.5, 100)

@@ -14,6 +14,7 @@ def timeit(fn, reps=5):
     return ev[0].elapsed_time(ev[1]) / reps
 
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 100_000_000
+only_1d = len(sys.argv) > 2 and sys.argv[2] == "1d"
 g = torch.Generator(device="cuda"); g.manual_seed(1997)
 m = 10_000
 b = B.B3Spline(-1, m + 1, m)
@@ -21,11 +22,16 @@ x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * m
 y = torch.sin(x / 37)
 acc = torch.zeros(ops.accum_size_1d(b), dtype=torch.float64, device="cuda")
 t_rand = timeit(lambda: ops.accum_1d(x, y, b, acc))
+t_binned = timeit(lambda: ops.accum_1d(x, y, b, acc, binned=True))
+t_auto = timeit(lambda: ops.accum_1d(x, y, b, acc, binned="auto"))
 xs, order = torch.sort(x)
 ys = y[order]
 t_sorted = timeit(lambda: ops.accum_1d(xs, ys, b, acc))
 t_sort = timeit(lambda: torch.sort(x), 2)
-print("1-D n=%d: random order %.3f ms, sorted %.3f ms, torch.sort alone %.3f ms" % (n, t_rand, t_sorted, t_sort))
+print("1-D n=%d: random order %.3f ms streaming, %.3f ms binned (%.3f ms with the order probe); sorted %.3f ms; torch.sort alone %.3f ms"
+      % (n, t_rand, t_binned, t_auto, t_sorted, t_sort))
+if only_1d:
+    sys.exit(0)
 del xs, ys, order, x, y
 
 n1 = int(round(n ** 0.5))
