@@ -26,6 +26,8 @@ SIGNATURES = {
     "asvgp_posterior_1d": [_vp, _vp, _c_int, _c_int, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
     "asvgp_band_inverse_1d": [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
     "asvgp_accum_2d": [_vp, _vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp],
+    "asvgp_accum_2d_binned": [_vp, _vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_i64, _vp],
+    "asvgp_order_probe_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _vp, _vp],
     "asvgp_expand_moments_2d": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp],
     "asvgp_kron_factor": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp, _vp, _vp],
     "asvgp_kron_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
@@ -36,6 +38,7 @@ SIGNATURES = {
 VALUE_FUNCTIONS = {
     "asvgp_workspace_bytes_1d": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_accum_1d_binned_work_bytes": (_c_i64, [_c_i64]),
+    "asvgp_accum_2d_binned_work_bytes": (_c_i64, [_c_i64]),
     "asvgp_accum_2d_moment_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_band_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),

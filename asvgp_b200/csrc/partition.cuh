@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kPartThreads) part_hist_kernel(Src src, int64_
         if (s_cnt[b]) atomicAdd(count + b, (u64)s_cnt[b]);
 }
 
-__global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork w) {
+static __global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork w) {
     __shared__ u64 s_a[kPartBuckets], s_u[kPartBuckets];
     const int b = threadIdx.x;
     const u64 c = w.count[b];

@@ -370,38 +370,30 @@ struct Points1D {
     __device__ __forceinline__ int bucket_of(const double (&v)[2]) const { return guess(v[0]) / ipb; }
 };
 
-// knots of the unit's window staged in shared memory; anything outside falls back to the global array
-struct WindowKnots {
-    const double* g_knots;
-    const double* s_knots;
-    int first, count;
-    __device__ __forceinline__ double operator()(const double* p) const {
-        const int j = (int)(p - g_knots) - first;
-        return (j >= 0 && j < count) ? s_knots[j] : __ldg(p);
-    }
-};
-
 // One unit = up to kUnitPoints records of one bucket (= ipb consecutive knot intervals).  The CTA counting-sorts the unit
-// by interval in shared memory (tau = t - 1/2 and y are what is staged), then each warp takes whole intervals: lanes
-// stride over the interval's run with the register moment sums of WarpAccum and the warp flushes once per run.
-template <int K>
-__global__ void __launch_bounds__(kPartThreads, 2)
+// by interval in shared memory (tau = t - 1/2 and y are what is staged), then groups of 8 lanes take whole intervals:
+// the lanes of a group stride over the interval's run with the register moment sums of WarpAccum and the group flushes
+// once per run (flush_groups).
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2)
 accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, int n_knots, int ipb, int M,
                       double* __restrict__ G, double* __restrict__ b, double* __restrict__ scal) {
-    constexpr int PER = kUnitPoints / kPartThreads;
+    constexpr int PER = kUnitPoints / THREADS;
     constexpr int kGroup = 8;
+    constexpr int kWarps = THREADS / 32;
     extern __shared__ double s_dyn[];
     double* s_tau = s_dyn;                                            // [kUnitPoints]
     double* s_y = s_tau + kUnitPoints;                                // [kUnitPoints]
     double* s_knots = s_y + kUnitPoints;                              // [n_bins + 1]
     int* s_off = reinterpret_cast<int*>(s_knots + ipb + 2 * kUnitMargin + 1);   // [n_bins + 2]
     __shared__ UnitTable tab;
-    __shared__ double s_yy[kPartThreads / 32];
-    __shared__ int s_wsum[kPartThreads / 32];
+    __shared__ double s_yy[kWarps];
+    __shared__ int s_wsum[kWarps];
     __shared__ int s_carry;
     const Mesh mesh = load_mesh(knots, n_knots);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_bins = ipb + 2 * kUnitMargin;
+    const int last = n_knots - 2;                     // last interval
     const double* rx = w.rec;
     const double* ry = w.rec + n;
     tab.stage(w);
@@ -415,43 +407,49 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
         int64_t first;
         tab.find(u, bucket, first, count);
         const int idx0 = bucket * ipb - kUnitMargin;          // interval of bin 0 (may be negative: those bins stay empty)
+        const int jlo = idx0 < 0 ? -idx0 : 0;                 // bins [jlo, jhi] are real intervals
+        const int jhi = (last - idx0 < n_bins - 1) ? last - idx0 : n_bins - 1;
         double xs[PER], ys[PER];
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
-            const int q = p * kPartThreads + threadIdx.x;
+            const int q = p * THREADS + threadIdx.x;
             if (q < count) { xs[p] = __ldg(rx + first + q); ys[p] = __ldg(ry + first + q); }
         }
-        for (int j = threadIdx.x; j <= n_bins; j += kPartThreads) {
+        for (int j = threadIdx.x; j <= n_bins; j += THREADS) {
             s_off[j] = 0;
             const int kn = idx0 + j;
             s_knots[j] = (kn >= 0 && kn < n_knots) ? __ldg(knots + kn) : 0.0;
         }
         __syncthreads();
-        WindowKnots wk;
-        wk.g_knots = knots; wk.s_knots = s_knots; wk.first = idx0; wk.count = n_bins + 1;
-        // exact interval (reference basis.py:58) and count per bin (bin j counts into s_off[j + 1])
+        // exact interval (reference basis.py:58: largest idx with mesh[idx] < x) inside the staged window; count per bin
+        // (bin j counts into s_off[j + 1])
         int bin[PER];
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
-            const int q = p * kPartThreads + threadIdx.x;
+            const int q = p * THREADS + threadIdx.x;
             bin[p] = -1;
             if (q < count) {
+                const double xv = xs[p];
                 yy = fma(ys[p], ys[p], yy);
-                const int idx = locate_interval(mesh, xs[p], wk);
-                const int j = idx - idx0;
-                if (j >= 0 && j < n_bins) {
+                const double g = floor((xv - mesh.x0) * mesh.inv_delta);
+                int j = (g < (double)(idx0 + jlo)) ? jlo : (g > (double)(idx0 + jhi) ? jhi : (int)g - idx0);
+                while (j > jlo && !(s_knots[j] < xv)) --j;
+                while (j < jhi && s_knots[j + 1] < xv) ++j;
+                const bool below = j == jlo && idx0 + jlo > 0 && !(s_knots[jlo] < xv);
+                const bool above = j == jhi && idx0 + jhi < last && s_knots[jhi + 1] < xv;
+                if (below || above) {       // outside the window (mesh far from uniform): per-point REDs
+                    scatter_point<K>(mesh, locate_interval(mesh, xv, LdgLoader()), xv, ys[p], G, b, M);
+                } else {
                     bin[p] = j;
                     atomicAdd(&s_off[j + 1], 1);
-                } else {
-                    scatter_point<K>(mesh, idx, xs[p], ys[p], G, b, M);
                 }
             }
         }
         __syncthreads();
-        // inclusive scan of s_off[1..n_bins] in place (s_off[j] becomes the first slot of bin j): chunks of 256 + carry
+        // inclusive scan of s_off[1..n_bins] in place (s_off[j] becomes the first slot of bin j): chunks of THREADS + carry
         if (threadIdx.x == 0) s_carry = 0;
         __syncthreads();
-        for (int base = 1; base <= n_bins; base += kPartThreads) {
+        for (int base = 1; base <= n_bins; base += THREADS) {
             const int j = base + threadIdx.x;
             int v = j <= n_bins ? s_off[j] : 0;
 #pragma unroll
@@ -466,7 +464,7 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
             v += add;
             __syncthreads();
             if (j <= n_bins) s_off[j] = v;
-            if (threadIdx.x == kPartThreads - 1) s_carry = v;
+            if (threadIdx.x == THREADS - 1) s_carry = v;
             __syncthreads();
         }
         // the placement advances s_off[j] from the start to the end of bin j, so afterwards bin j is
@@ -481,7 +479,7 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
         }
         __syncthreads();
         // kGroup lanes per interval, 32 / kGroup intervals per warp at a time
-        for (int jb = warp * (32 / kGroup); jb < n_bins; jb += (kPartThreads / 32) * (32 / kGroup)) {
+        for (int jb = warp * (32 / kGroup); jb < n_bins; jb += kWarps * (32 / kGroup)) {
             const int j = jb + lane / kGroup;
             int begin = 0, end = 0;
             if (j < n_bins) { begin = j ? s_off[j - 1] : 0; end = s_off[j]; }
@@ -497,7 +495,7 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
     if (threadIdx.x == 0) {
         double tot = 0.0;
 #pragma unroll
-        for (int q = 0; q < kPartThreads / 32; ++q) tot += s_yy[q];
+        for (int q = 0; q < kWarps; ++q) tot += s_yy[q];
         atomicAdd(scal, tot);
         if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
     }
@@ -726,13 +724,14 @@ extern "C" int asvgp_order_probe_1d(const double* x, int64_t n, const double* me
 template <int K>
 static int launch_accum_1d_units(const PartWork& w, int64_t n, const double* mesh, int n_knots, int ipb, int M, double* G,
                                  double* b, double* scal, cudaStream_t st) {
+    constexpr int THREADS = 256;         // (512 threads at 64 registers spill the moment sums and measured no faster)
     const size_t smem = accum_1d_units_smem(ipb + 2 * kUnitMargin);
-    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_1d_units_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_1d_units_kernel<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_1d_units_kernel<K>, kPartThreads, smem));
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_1d_units_kernel<K, THREADS>, THREADS, smem));
     const int64_t max_units = n / kUnitPoints + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count() * std::max(per_sm, 1)));
-    accum_1d_units_kernel<K><<<blocks, kPartThreads, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
+    accum_1d_units_kernel<K, THREADS><<<blocks, THREADS, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
     return kOk;
 }
 

@@ -21,6 +21,7 @@
 
 #include "async_copy.cuh"
 #include "common.cuh"
+#include "partition.cuh"
 #include "../../include/asvgp_b200.h"
 
 namespace asvgp {
@@ -1358,6 +1359,259 @@ static int sm_count2() {
     return cached;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// accumulate for inputs in no particular order: bucket partition on dimension 1 (partition.cuh), then per-unit
+// shared-memory sort by cell.  (The thread-private kernel above degenerates to (2k+1)^2 + (k+1)^2 REDs per point
+// once consecutive points stop sharing a cell: 35 ms per 1e8 shuffled points.)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kUnitMargin2 = 1;       // dim-1 intervals either side of a bucket the exact interval may fall into
+constexpr int kUnitKnots2 = 2048;     // dim-2 knots staged in shared memory (longer meshes are read through L1)
+
+struct Points2D {
+    const double* X;
+    const double* y;
+    const double* knots1;
+    int n_knots1;
+    int ipb;            // dim-1 knot intervals per bucket
+    double x0, inv_delta;
+    __device__ __forceinline__ void init() {
+        x0 = __ldg(knots1);
+        inv_delta = 1.0 / (__ldg(knots1 + 1) - x0);
+    }
+    __device__ __forceinline__ int guess(double xv) const {
+        const double g = floor((xv - x0) * inv_delta);
+        const int hi = n_knots1 - 2;
+        return g < 0.0 ? 0 : (g > (double)hi ? hi : (int)g);
+    }
+    __device__ __forceinline__ int bucket(int64_t i) const { return guess(__ldg(X + 2 * i)) / ipb; }
+    __device__ __forceinline__ void load(int64_t i, double (&v)[3]) const {
+        const double2 p = __ldg(reinterpret_cast<const double2*>(X) + i);
+        v[0] = p.x; v[1] = p.y; v[2] = __ldg(y + i);
+    }
+    __device__ __forceinline__ int bucket_of(const double (&v)[3]) const { return guess(v[0]) / ipb; }
+};
+
+// exact interval inside a window of knots staged in shared memory: s[j] = knot of interval first + j, j = 0..count
+// (count intervals jlo..jhi are real).  Returns -1 when x lies outside the window.
+__device__ __forceinline__ int locate_in_window(const double* s, int jlo, int jhi, bool open_lo, bool open_hi, double g_rel, double xv) {
+    int j = (g_rel < (double)jlo) ? jlo : (g_rel > (double)jhi ? jhi : (int)g_rel);
+    while (j > jlo && !(s[j] < xv)) --j;
+    while (j < jhi && s[j + 1] < xv) ++j;
+    const bool below = j == jlo && !open_lo && !(s[jlo] < xv);
+    const bool above = j == jhi && !open_hi && s[jhi + 1] < xv;
+    return (below || above) ? -1 : j;
+}
+
+// One unit = up to kUnitPoints records (x1, x2, y) of one bucket.  The CTA counting-sorts the unit by cell in shared
+// memory ((t1, t2, y) are what is staged).  Then GL lanes take one cell: lane l OWNS the moments with dim-1 index l
+// (beta_l(t1) beta_q(t2), q = 0..2k, and for l <= k the projection moments gamma_l(t1) gamma_q(t2) y), every lane of
+// the group walks all the points of the cell (shared-memory broadcast reads), so there is nothing to reduce and a
+// thread holds 3k + 2 sums instead of (2k+1)^2 + (k+1)^2; at the end of the run each lane adds its sums to the table.
+template <int K>
+__global__ void __launch_bounds__(kPartThreads, 2)
+accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2,
+                      int nk2, int ipb, double* __restrict__ cellmom, double* __restrict__ scal) {
+    using Mo = Moments<K>;
+    constexpr int NB = Mo::NB, NY = Mo::NY;
+    constexpr int GL = NB <= 8 ? 8 : 16;                    // lanes per cell
+    constexpr int PER = kUnitPoints / kPartThreads;
+    constexpr int kWarps = kPartThreads / 32;
+    const int nc2 = nk2 - 1;
+    const int nb1 = ipb + 2 * kUnitMargin2;
+    const int n_bins = nb1 * nc2;
+    const int nk2s = nk2 < kUnitKnots2 ? nk2 : 0;           // dim-2 knots staged (0: read through L1)
+    extern __shared__ double s_dyn[];
+    double* s_t1 = s_dyn;                                   // [kUnitPoints]
+    double* s_t2 = s_t1 + kUnitPoints;
+    double* s_y = s_t2 + kUnitPoints;
+    double* s_k1 = s_y + kUnitPoints;                       // [nb1 + 1]
+    double* s_k2 = s_k1 + nb1 + 1;                          // [nk2s]
+    int* s_off = reinterpret_cast<int*>(s_k2 + nk2s);       // [n_bins + 2]
+    __shared__ UnitTable tab;
+    __shared__ double s_yy[kWarps];
+    __shared__ int s_wsum[kWarps];
+    __shared__ int s_carry;
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int last1 = nk1 - 2, last2 = nk2 - 2;
+    const double* r1 = w.rec;
+    const double* r2 = w.rec + n;
+    const double* ry = w.rec + 2 * n;
+    tab.stage(w);
+    for (int j = threadIdx.x; j < nk2s; j += kPartThreads) s_k2[j] = __ldg(knots2 + j);
+    __syncthreads();
+    const int64_t n_units = tab.n_units();
+    double yy = 0.0;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        int bucket, count;
+        int64_t first;
+        tab.find(u, bucket, first, count);
+        const int idx0 = bucket * ipb - kUnitMargin2;         // dim-1 interval of row 0 of the unit's bins
+        const int jlo = idx0 < 0 ? -idx0 : 0;
+        const int jhi = (last1 - idx0 < nb1 - 1) ? last1 - idx0 : nb1 - 1;
+        double x1s[PER], x2s[PER], ys[PER];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int q = p * kPartThreads + threadIdx.x;
+            if (q < count) { x1s[p] = __ldg(r1 + first + q); x2s[p] = __ldg(r2 + first + q); ys[p] = __ldg(ry + first + q); }
+        }
+        for (int j = threadIdx.x; j <= n_bins; j += kPartThreads) s_off[j] = 0;
+        for (int j = threadIdx.x; j <= nb1; j += kPartThreads) {
+            const int kn = idx0 + j;
+            s_k1[j] = (kn >= 0 && kn < nk1) ? __ldg(knots1 + kn) : 0.0;
+        }
+        __syncthreads();
+        int bin[PER];
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            const int q = p * kPartThreads + threadIdx.x;
+            bin[p] = -1;
+            if (q < count) {
+                yy = fma(ys[p], ys[p], yy);
+                const double g1 = floor((x1s[p] - mesh1.x0) * mesh1.inv_delta) - (double)idx0;
+                const int j1 = locate_in_window(s_k1, jlo, jhi, idx0 + jlo == 0, idx0 + jhi == last1, g1, x1s[p]);
+                int c2;
+                if (nk2s) {
+                    const double g2 = floor((x2s[p] - mesh2.x0) * mesh2.inv_delta);
+                    c2 = locate_in_window(s_k2, 0, last2, true, true, g2, x2s[p]);
+                } else {
+                    c2 = locate_interval(mesh2, x2s[p], LdgLoader2());
+                }
+                if (j1 < 0) {           // outside the unit's rows (mesh far from uniform): straight to the table
+                    scatter_point_2d<K>(mesh1, mesh2, x1s[p], x2s[p], ys[p], cellmom);
+                } else {
+                    bin[p] = j1 * nc2 + c2;
+                    atomicAdd(&s_off[bin[p] + 1], 1);
+                    x1s[p] = (x1s[p] - s_k1[j1]) * mesh1.inv_delta;                        // t1
+                    x2s[p] = (x2s[p] - (nk2s ? s_k2[c2] : __ldg(knots2 + c2))) * mesh2.inv_delta;   // t2
+                }
+            }
+        }
+        __syncthreads();
+        // inclusive scan of s_off[1..n_bins] in place (s_off[j] becomes the first slot of bin j)
+        if (threadIdx.x == 0) s_carry = 0;
+        __syncthreads();
+        for (int base = 1; base <= n_bins; base += kPartThreads) {
+            const int j = base + threadIdx.x;
+            int v = j <= n_bins ? s_off[j] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            if (lane == 31) s_wsum[warp] = v;
+            __syncthreads();
+            int add = s_carry;
+            for (int q = 0; q < warp; ++q) add += s_wsum[q];
+            v += add;
+            __syncthreads();
+            if (j <= n_bins) s_off[j] = v;
+            if (threadIdx.x == kPartThreads - 1) s_carry = v;
+            __syncthreads();
+        }
+#pragma unroll
+        for (int p = 0; p < PER; ++p) {
+            if (bin[p] >= 0) {
+                const int slot = atomicAdd(&s_off[bin[p]], 1);       // advances s_off[j] to the end of bin j
+                s_t1[slot] = x1s[p];
+                s_t2[slot] = x2s[p];
+                s_y[slot] = ys[p];
+            }
+        }
+        __syncthreads();
+        // bin j is now [j ? s_off[j - 1] : 0, s_off[j]); rows outside [jlo, jhi] are empty
+        const int l = lane & (GL - 1);
+        const int bin_lo = jlo * nc2, bin_hi = (jhi + 1) * nc2;
+        for (int jb = bin_lo + warp * (32 / GL); jb < bin_hi; jb += kWarps * (32 / GL)) {
+            const int j = jb + lane / GL;
+            int begin = 0, end = 0;
+            if (j < bin_hi) { begin = j ? s_off[j - 1] : 0; end = s_off[j]; }
+            double g[NB], gy[NY];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) g[q] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NY; ++q) gy[q] = 0.0;
+            for (int pt = begin; pt < end; ++pt) {
+                const double t1 = s_t1[pt], t2 = s_t2[pt], yv = s_y[pt];
+                const double u1 = 1.0 - t1;
+                double bl = 1.0, gl = 1.0;                       // beta_l(t1) = t1^l u1^(2k-l), gamma_l(t1) = t1^l u1^(k-l)
+#pragma unroll
+                for (int i = 0; i < 2 * K; ++i) bl *= (i < l) ? t1 : u1;
+#pragma unroll
+                for (int i = 0; i < K; ++i) gl *= (i < l) ? t1 : u1;
+                double tp[2 * K + 1], up[2 * K + 1];
+                powers<2 * K>(t2, tp, up);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) g[q] = fma(bl, tp[q] * up[2 * K - q], g[q]);
+                gl *= yv;
+#pragma unroll
+                for (int q = 0; q < NY; ++q) gy[q] = fma(gl, tp[q] * up[K - q], gy[q]);
+            }
+            if (end > begin) {
+                const int j1 = j / nc2, c2 = j - j1 * nc2;
+                double* dst = cellmom + ((int64_t)(idx0 + j1) * nc2 + c2) * Mo::kAll;
+                if (l < NB) {
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) atomicAdd(dst + l * NB + q, g[q]);
+                }
+                if (l < NY) {
+#pragma unroll
+                    for (int q = 0; q < NY; ++q) atomicAdd(dst + Mo::kGram + l * NY + q, gy[q]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) yy += __shfl_xor_sync(0xffffffffu, yy, o);
+    if (lane == 0) s_yy[warp] = yy;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+#pragma unroll
+        for (int q = 0; q < kWarps; ++q) tot += s_yy[q];
+        atomicAdd(scal, tot);
+        if (blockIdx.x == 0) atomicAdd(scal + 1, (double)n);
+    }
+}
+
+static size_t accum_2d_units_smem(int nb1, int nc2, int nk2) {
+    const int nk2s = nk2 < kUnitKnots2 ? nk2 : 0;
+    return (size_t)3 * kUnitPoints * 8 + (size_t)(nb1 + 1 + nk2s) * 8 + (size_t)(nb1 * nc2 + 2) * 4;
+}
+
+// Fraction of sampled neighbours (point i, point i+1) that lie more than one cell apart in either dimension: ~0 for
+// raster / run-ordered input, ~1 for shuffled input.
+__global__ void __launch_bounds__(256) order_probe_2d_kernel(const double* __restrict__ X, int64_t n, const double* __restrict__ knots1,
+                                                             int nk1, const double* __restrict__ knots2, int nk2, int samples,
+                                                             double* __restrict__ out) {
+    const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    int jumps = 0;
+    for (int s = threadIdx.x; s < samples; s += blockDim.x) {
+        const int64_t i = (int64_t)((double)s * (double)(n - 1) / (double)samples);
+        const int a1 = locate_interval(mesh1, __ldg(X + 2 * i), LdgLoader2()), b1 = locate_interval(mesh1, __ldg(X + 2 * i + 2), LdgLoader2());
+        const int a2 = locate_interval(mesh2, __ldg(X + 2 * i + 1), LdgLoader2()), b2 = locate_interval(mesh2, __ldg(X + 2 * i + 3), LdgLoader2());
+        const int d1 = a1 > b1 ? a1 - b1 : b1 - a1, d2 = a2 > b2 ? a2 - b2 : b2 - a2;
+        // (a raster row end — x1 moves on by at most one interval, x2 jumps back — is not a sign of disorder)
+        jumps += (d1 > 1 || (d1 == 0 && d2 > 1)) ? 1 : 0;
+    }
+    jumps = __reduce_add_sync(0xffffffffu, jumps);
+    if ((threadIdx.x & 31) == 0 && jumps) atomicAdd(out, (double)jumps / (double)samples);
+}
+
+template <int K>
+static int launch_accum_2d_units(const PartWork& w, int64_t n, const double* k1, int nk1, const double* k2, int nk2, int ipb,
+                                 double* cellmom, double* scal, cudaStream_t st) {
+    const size_t smem = accum_2d_units_smem(ipb + 2 * kUnitMargin2, nk2 - 1, nk2);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_units_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_2d_units_kernel<K>, kPartThreads, smem));
+    const int64_t max_units = n / kUnitPoints + kPartBuckets;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count2() * std::max(per_sm, 1)));
+    accum_2d_units_kernel<K><<<blocks, kPartThreads, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal);
+    return kOk;
+}
+
 template <int K, int P0, int P1, bool WITH_Y>
 static int launch_accum_part(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2,
                              int nk2, double* cellmom, double* scal, const int* select, cudaStream_t st) {
@@ -1454,6 +1708,46 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, st)) return rc; });
+    return kOk;
+}
+
+extern "C" int64_t asvgp_accum_2d_binned_work_bytes(int64_t n) { return PartWork::bytes(n < 0 ? 0 : n, 3); }
+
+extern "C" int asvgp_order_probe_2d(const double* X, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
+                                    int n_knots2, double* out, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2 && out != nullptr, "order_probe_2d: n=%lld knots=%d,%d",
+                  (long long)n, n_knots1, n_knots2);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), st));
+    if (n < 2) return kOk;
+    const int samples = (int)std::min<int64_t>(n - 1, 4096);
+    order_probe_2d_kernel<<<1, 256, 0, st>>>(X, n, mesh1, n_knots1, mesh2, n_knots2, samples, out);
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+extern "C" int asvgp_accum_2d_binned(const double* X, const double* y, int64_t n, const double* mesh1, int n_knots1,
+                                     const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
+                                     void* work, int64_t work_bytes, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "accum_2d_binned: n=%lld knots=%d,%d", (long long)n, n_knots1, n_knots2);
+    ASVGP_REQUIRE(order >= 1 && order <= kMaxOrder, "accum_2d_binned: spline order %d not in 1..6", order);
+    ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15u) == 0, "accum_2d_binned: X must be 16-byte aligned");
+    const int nc1 = n_knots1 - 1, nc2 = n_knots2 - 1;
+    const int ipb = (nc1 + kPartBuckets - 1) / kPartBuckets;
+    if ((int64_t)(ipb + 2 * kUnitMargin2) * nc2 > kUnitMaxBins)      // too many cells per bucket for the shared-memory sort
+        return asvgp_accum_2d(X, y, n, mesh1, n_knots1, mesh2, n_knots2, order, cellmom, scal, stream);
+    ASVGP_REQUIRE(work != nullptr && work_bytes >= PartWork::bytes(n, 3), "accum_2d_binned: work_bytes=%lld < %lld",
+                  (long long)work_bytes, (long long)PartWork::bytes(n, 3));
+    if (n == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const PartWork w = PartWork::carve(work);
+    ASVGP_CUDA_OK(cudaMemsetAsync(w.count, 0, kPartBuckets * sizeof(u64), st));
+    Points2D src;
+    src.X = X; src.y = y; src.knots1 = mesh1; src.n_knots1 = n_knots1; src.ipb = ipb;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count2() * 2));
+    ASVGP_CUDA_OK((launch_partition<Points2D, 3>(src, n, w, blocks, st)));
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d_units<K>(w, n, mesh1, n_knots1, mesh2, n_knots2, ipb, cellmom, scal, st)) return rc; });
+    ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
 

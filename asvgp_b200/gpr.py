@@ -273,7 +273,7 @@ class GPR_kron(_ModelBase):
         _, _, scal = ops.split_accum_2d(self._acc, self.bases)
         cellmom = ops.moment_table_2d(self.bases)
         if isinstance(X, torch.Tensor) and X.is_cuda:
-            ops.accum_2d(X, y.reshape(-1), self.bases, cellmom, scal)
+            ops.accum_2d(X, y.reshape(-1), self.bases, cellmom, scal, binned="auto")
         else:
             ops.accum_2d_host(X, y, self.bases, cellmom, scal)
         ops.expand_moments_2d(cellmom, self.bases, self._acc)

@@ -293,9 +293,18 @@ def moment_table_2d(bases):
     return torch.zeros(n, dtype=F64, device=device())
 
 
-def accum_2d(X, y, bases, cellmom, scal):
+def order_probe_2d(X, bases):
+    """Fraction of sampled neighbour pairs of X[n,2] that lie more than one cell apart (one small D2H read)."""
+    X = to_device(X)
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    out = torch.empty(1, dtype=F64, device=X.device)
+    _lib.call("asvgp_order_probe_2d", _p(X), X.shape[0], _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), _p(out), _stream())
+    return float(out.item())
+
+
+def accum_2d(X, y, bases, cellmom, scal, binned=False):
     """Adds the per-cell moments of the points (X[n,2], y[n]) into `cellmom` and (sum y^2, n) into `scal`
-    (reference gpr.py:268-274 without materialising the Khatri-Rao Kuf)."""
+    (reference gpr.py:268-274 without materialising the Khatri-Rao Kuf).  binned: as accum_1d."""
     k, _, _ = _check_bases_2d(bases)
     X = to_device(X)
     y = to_device(y).reshape(-1)
@@ -306,6 +315,14 @@ def accum_2d(X, y, bases, cellmom, scal):
     if y.data_ptr() % 16:
         y = y.clone()
     mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    if binned == "auto":
+        binned = X.shape[0] >= BINNED_MIN_POINTS and order_probe_2d(X, bases) > BINNED_JUMP_FRACTION
+    if binned:
+        nbytes = _lib.load().asvgp_accum_2d_binned_work_bytes(X.shape[0])
+        work = torch.empty(nbytes, dtype=torch.uint8, device=X.device)
+        _lib.call("asvgp_accum_2d_binned", _p(X), _p(y), X.shape[0], _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
+                  _p(cellmom), _p(scal), _p(work), nbytes, _stream())
+        return cellmom, scal
     _lib.call("asvgp_accum_2d", _p(X), _p(y), X.shape[0], _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
               _p(cellmom), _p(scal), _stream())
     return cellmom, scal

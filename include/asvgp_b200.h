@@ -132,6 +132,19 @@ ASVGP_API int asvgp_accum_2d(const double* X, const double* y, int64_t n, const 
                              const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
                              void* stream);
 
+/* Same sums for points in NO PARTICULAR ORDER (SURVEY 8(d) C4 "shuffled-order variant").  asvgp_accum_2d is exact for
+ * any order but pays (2o+1)^2 + (o+1)^2 fp64 REDs per point once consecutive points stop sharing a cell; this variant
+ * partitions the points into <= 256 buckets of dimension-1 knot intervals, sorts each 4096-point unit by cell in
+ * shared memory and accumulates every run in registers.  `work`: asvgp_accum_2d_binned_work_bytes(n) bytes of device
+ * scratch (24 B per point + 8 KB).  asvgp_order_probe_2d writes to out[0] (device) the fraction of 4096 sampled
+ * neighbour pairs that lie more than one cell apart (~0 raster / run order, ~1 shuffled). */
+ASVGP_API int64_t asvgp_accum_2d_binned_work_bytes(int64_t n);
+ASVGP_API int asvgp_accum_2d_binned(const double* X, const double* y, int64_t n, const double* mesh1, int n_knots1,
+                                    const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
+                                    void* work, int64_t work_bytes, void* stream);
+ASVGP_API int asvgp_order_probe_2d(const double* X, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
+                                   int n_knots2, double* out, void* stream);
+
 /* Expands the moment table into the Gram stencil Gs[(o+1)(2o+1) x M] and the projection b[M] (both must be zeroed by
  * the caller).  Cprod[(o+1)(o+1)(2o+1)], Dy[(o+1)(o+1)]: exact Bernstein-type expansion tables (host-computed). */
 ASVGP_API int asvgp_expand_moments_2d(const double* cellmom, const double* Cprod, const double* Dy, int n_knots1,

@@ -257,3 +257,57 @@ def test_accumulate_ragged_sizes(cuda, n):
     assert abs(utils.stencil_to_sparse(Gs, 12, 13, 3) - G0).max() <= 1e-12
     np.testing.assert_allclose(b, b0.ravel(), atol=1e-12)
     assert abs(scal[0] - yy0) <= 1e-12 * max(yy0, 1.0)
+
+
+@pytest.mark.parametrize("k,m1,m2,n,dist", [(3, 19, 23, 70_001, "uniform"), (2, 30, 11, 4097, "uniform"), (4, 14, 14, 50_000, "uniform"),
+                                            (3, 400, 12, 150_000, "uniform"), (3, 19, 23, 60_000, "clustered"),
+                                            (1, 25, 40, 30_000, "knots"), (5, 16, 16, 20_000, "uniform"), (6, 15, 15, 9_000, "uniform")])
+def test_accumulate_binned_matches_oracle(cuda, k, m1, m2, n, dist):
+    """Shuffled points through the partition path (asvgp_accum_2d_binned): several dim-1 intervals per bucket (m1 > 256),
+    clustered points, points exactly on knots in both dimensions, unit and tile boundaries, every spline order."""
+    import torch
+
+    from asvgp_b200 import basis as B, ops, utils
+
+    rng = np.random.default_rng(n + 7 * k)
+    cls = getattr(B, "B%dSpline" % k)
+    bases = [cls(-80, -25, m1), cls(15, 55, m2)]
+    if dist == "uniform":
+        X = np.stack([rng.uniform(-79.5, -25.5, n), rng.uniform(15.5, 54.5, n)], 1)
+    elif dist == "clustered":
+        X = np.stack([rng.normal(-50.0, 0.4, n), rng.normal(30.0, 6.0, n)], 1).clip((-79, 16), (-26, 54))
+    else:
+        X = np.stack([rng.choice(np.asarray(bases[0].mesh)[1:-1], n), rng.choice(np.asarray(bases[1].mesh)[1:-1], n)], 1)
+    y = np.sin(X[:, 0] / 4.0) * np.cos(X[:, 1] / 3.0) + 0.05 * rng.standard_normal(n)
+    acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+    cm = ops.moment_table_2d(bases)
+    ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2], binned=True)
+    ops.expand_moments_2d(cm, bases, acc)
+    Gs, b, scal = [t.cpu().numpy() for t in ops.split_accum_2d(acc, bases)]
+    G0, b0, yy0 = O.precompute_kron([bb.mesh for bb in bases], [bb.delta for bb in bases], k, [m1, m2], X, y)
+    scale = abs(G0).max()
+    assert abs(utils.stencil_to_sparse(Gs, m1, m2, k) - G0).max() <= 1e-11 * scale
+    np.testing.assert_allclose(b, b0.ravel(), rtol=0, atol=1e-11 * np.abs(b0).max())
+    assert abs(scal[0] - yy0) <= 1e-12 * yy0 and scal[1] == n
+
+
+def test_accumulate_order_probe_2d(cuda):
+    import torch
+
+    from asvgp_b200 import basis as B, ops
+
+    rng = np.random.default_rng(3)
+    bases = [B.B3Spline(-80, -25, 40), B.B3Spline(15, 55, 40)]
+    X = np.stack(np.meshgrid(np.linspace(-75, -30, 600), np.linspace(20, 50, 700), indexing="ij"), -1).reshape(-1, 2)
+    assert ops.order_probe_2d(X, bases) < 0.01
+    Xs = rng.permutation(X)
+    assert ops.order_probe_2d(Xs, bases) > 0.8
+    y = np.cos(Xs[:, 0]) + Xs[:, 1]
+    res = []
+    for mode in ("auto", False):
+        acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+        cm = ops.moment_table_2d(bases)
+        ops.accum_2d(Xs, y, bases, cm, ops.split_accum_2d(acc, bases)[2], binned=mode)
+        ops.expand_moments_2d(cm, bases, acc)
+        res.append(acc.cpu().numpy())
+    np.testing.assert_allclose(res[0], res[1], rtol=0, atol=1e-11 * np.abs(res[1]).max())

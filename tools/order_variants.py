@@ -48,4 +48,7 @@ perm = torch.randperm(n1 * n1, device="cuda", generator=g)
 Xp = X[perm].contiguous(); yp = yy[perm].contiguous()
 del X, yy, perm
 t_shuf = timeit(lambda: ops.accum_2d(Xp, yp, bases, cm, mom), 2)
-print("2-D n=%d: raster %.3f ms, shuffled %.3f ms" % (n1 * n1, t_raster, t_shuf))
+t_bin = timeit(lambda: ops.accum_2d(Xp, yp, bases, cm, mom, binned=True), 3)
+t_auto = timeit(lambda: ops.accum_2d(Xp, yp, bases, cm, mom, binned="auto"), 3)
+print("2-D n=%d: raster %.3f ms; shuffled %.3f ms streaming, %.3f ms binned (%.3f ms with the order probe)"
+      % (n1 * n1, t_raster, t_shuf, t_bin, t_auto))
