@@ -39,7 +39,7 @@ struct PartWork {
     u64* cursor;
     u64* unit_start;
     double* rec;
-    __host__ __device__ static int64_t head_words() { return 4 * (int64_t)kPartBuckets + 2; }
+    __host__ __device__ static int64_t head_words() { return 4 * (int64_t)kPartBuckets + 4; }   // + max units per bucket, + pad
     __host__ __device__ static int64_t bytes(int64_t n, int rec_doubles) {
         return (head_words() + n * rec_doubles) * 8;
     }
@@ -49,7 +49,7 @@ struct PartWork {
         w.start = w.count + kPartBuckets;
         w.cursor = w.start + kPartBuckets + 1;
         w.unit_start = w.cursor + kPartBuckets;
-        w.rec = reinterpret_cast<double*>(w.unit_start + kPartBuckets + 1);
+        w.rec = reinterpret_cast<double*>(w.count + head_words());
         return w;
     }
 };
@@ -97,6 +97,15 @@ static __global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork
     w.unit_start[b + 1] = s_u[b];
     w.cursor[b] = s_a[b] - c;
     if (b == 0) { w.start[0] = 0; w.unit_start[0] = 0; }
+    // the largest number of units in one bucket (the second half walks units bucket-interleaved)
+    __syncthreads();
+    s_u[b] = (c + kUnitPoints - 1) / kUnitPoints;
+    __syncthreads();
+    for (int o = kPartBuckets / 2; o > 0; o >>= 1) {
+        if (b < o && s_u[b + o] > s_u[b]) s_u[b] = s_u[b + o];
+        __syncthreads();
+    }
+    if (b == 0) w.unit_start[kPartBuckets + 1] = s_u[0];
 }
 
 template <class Src, int REC>
@@ -192,27 +201,24 @@ cudaError_t launch_partition(const Src& src, int64_t n, const PartWork& w, int b
     return cudaGetLastError();
 }
 
-// Which unit is this?  (bucket, first point, number of points) from the tables the scan left in `w`, staged in shared memory.
+// The units of the second half, walked BUCKET-INTERLEAVED: slot i is chunk i / NB of bucket i % NB, so that CTAs running
+// at the same time work on different buckets and their REDs go to different band entries / cells (with units in storage
+// order ~100 CTAs add into the same few hundred addresses at once and the L2 serialises them).
 struct UnitTable {
     u64 start[kPartBuckets + 1];
-    u64 unit_start[kPartBuckets + 1];
+    u64 max_chunks;
     __device__ void stage(const PartWork& w) {
-        for (int b = threadIdx.x; b <= kPartBuckets; b += blockDim.x) {
-            start[b] = w.start[b];
-            unit_start[b] = w.unit_start[b];
-        }
+        for (int b = threadIdx.x; b <= kPartBuckets; b += blockDim.x) start[b] = w.start[b];
+        if (threadIdx.x == 0) max_chunks = w.unit_start[kPartBuckets + 1];
     }
-    __device__ int64_t n_units() const { return (int64_t)unit_start[kPartBuckets]; }
-    __device__ void find(int64_t u, int& bucket, int64_t& first, int& count) const {
-        int lo = 0, hi = kPartBuckets;                 // largest b with unit_start[b] <= u
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if ((int64_t)unit_start[mid] <= u) lo = mid; else hi = mid;
-        }
-        bucket = lo;
-        first = (int64_t)start[lo] + (u - (int64_t)unit_start[lo]) * kUnitPoints;
-        const int64_t left = (int64_t)start[lo + 1] - first;
+    __device__ int64_t n_slots() const { return (int64_t)max_chunks * kPartBuckets; }
+    // false: the slot is past the end of its bucket
+    __device__ bool find(int64_t slot, int& bucket, int64_t& first, int& count) const {
+        bucket = (int)(slot % kPartBuckets);
+        first = (int64_t)start[bucket] + (slot / kPartBuckets) * kUnitPoints;
+        const int64_t left = (int64_t)start[bucket + 1] - first;
         count = (int)(left < kUnitPoints ? left : kUnitPoints);
+        return left > 0;
     }
 };
 

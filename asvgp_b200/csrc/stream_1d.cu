@@ -398,14 +398,14 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
     const double* ry = w.rec + n;
     tab.stage(w);
     __syncthreads();
-    const int64_t n_units = tab.n_units();
+    const int64_t n_slots = tab.n_slots();
     double yy = 0.0;
     WarpAccum<K> wa;
     wa.clear();
-    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int64_t u = blockIdx.x; u < n_slots; u += gridDim.x) {
         int bucket, count;
         int64_t first;
-        tab.find(u, bucket, first, count);
+        if (!tab.find(u, bucket, first, count)) continue;
         const int idx0 = bucket * ipb - kUnitMargin;          // interval of bin 0 (may be negative: those bins stay empty)
         const int jlo = idx0 < 0 ? -idx0 : 0;                 // bins [jlo, jhi] are real intervals
         const int jhi = (last - idx0 < n_bins - 1) ? last - idx0 : n_bins - 1;

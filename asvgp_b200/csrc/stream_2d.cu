@@ -1366,6 +1366,14 @@ static int sm_count2() {
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kUnitMargin2 = 1;       // dim-1 intervals either side of a bucket the exact interval may fall into
 constexpr int kUnitKnots2 = 2048;     // dim-2 knots staged in shared memory (longer meshes are read through L1)
+template <int K> struct Units2 {
+    // one CTA per SM: the unit's points + the exchange areas take 140..208 KB of shared memory
+    static constexpr int THREADS = K <= 4 ? 512 : 256;
+    static constexpr int GL = (2 * K + 1) <= 8 ? 8 : 16;                  // lanes (and points per batch) per cell
+    static constexpr int NV = (2 * K + 1) + (K + 1);                      // factors per dimension per point
+    static constexpr int NVP = (NV + 1) & ~1;                             // ... padded to whole 16-byte pairs
+    static constexpr int EX = NV * GL + 2;                                // doubles of one group's exchange area (+2: groups land on different banks)
+};
 
 struct Points2D {
     const double* X;
@@ -1403,19 +1411,26 @@ __device__ __forceinline__ int locate_in_window(const double* s, int jlo, int jh
 }
 
 // One unit = up to kUnitPoints records (x1, x2, y) of one bucket.  The CTA counting-sorts the unit by cell in shared
-// memory ((t1, t2, y) are what is staged).  Then GL lanes take one cell: lane l OWNS the moments with dim-1 index l
-// (beta_l(t1) beta_q(t2), q = 0..2k, and for l <= k the projection moments gamma_l(t1) gamma_q(t2) y), every lane of
-// the group walks all the points of the cell (shared-memory broadcast reads), so there is nothing to reduce and a
-// thread holds 3k + 2 sums instead of (2k+1)^2 + (k+1)^2; at the end of the run each lane adds its sums to the table.
+// memory ((t1, t2, y) are what is staged).  Then GL lanes take one cell, GL points at a time:
+//   produce  lane i evaluates, for point i of the batch, the dim-1 factors A = (beta_0..2k(t1), gamma_0..k(t1)) and the
+//            dim-2 factors B = (beta_0..2k(t2), y gamma_0..k(t2)) once, and leaves them in the group's exchange area
+//            (A transposed: row v, column i);
+//   consume  lane l OWNS the moment rows with dim-1 index l (beta_l(t1) beta_q(t2), q = 0..2k, and for l <= k the
+//            projection row gamma_l(t1) gamma_q(t2) y): it reads its row of A (GL values) and walks the GL points' B
+//            vectors (broadcast reads) with one FMA per moment.
+// Nothing is reduced across lanes and a thread holds 3k + 2 sums instead of (2k+1)^2 + (k+1)^2; at the end of a
+// cell's run each lane adds its rows to the moment table.  (A first version in which every lane recomputed the factors
+// of every point of its cell was instruction-bound at 5.0 ms per 1e8 points.)
 template <int K>
-__global__ void __launch_bounds__(kPartThreads, 2)
+__global__ void __launch_bounds__(Units2<K>::THREADS, 1)
 accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2,
                       int nk2, int ipb, double* __restrict__ cellmom, double* __restrict__ scal) {
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY;
-    constexpr int GL = NB <= 8 ? 8 : 16;                    // lanes per cell
-    constexpr int PER = kUnitPoints / kPartThreads;
-    constexpr int kWarps = kPartThreads / 32;
+    constexpr int GL = Units2<K>::GL, EX = Units2<K>::EX;
+    constexpr int THREADS = Units2<K>::THREADS;
+    constexpr int PER = kUnitPoints / THREADS;
+    constexpr int kWarps = THREADS / 32;
     const int nc2 = nk2 - 1;
     const int nb1 = ipb + 2 * kUnitMargin2;
     const int n_bins = nb1 * nc2;
@@ -1424,7 +1439,8 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     double* s_t1 = s_dyn;                                   // [kUnitPoints]
     double* s_t2 = s_t1 + kUnitPoints;
     double* s_y = s_t2 + kUnitPoints;
-    double* s_k1 = s_y + kUnitPoints;                       // [nb1 + 1]
+    double* s_ex = s_y + kUnitPoints;                       // [THREADS / GL][EX] exchange areas
+    double* s_k1 = s_ex + (THREADS / GL) * EX;              // [nb1 + 1]
     double* s_k2 = s_k1 + nb1 + 1;                          // [nk2s]
     int* s_off = reinterpret_cast<int*>(s_k2 + nk2s);       // [n_bins + 2]
     __shared__ UnitTable tab;
@@ -1438,25 +1454,26 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     const double* r2 = w.rec + n;
     const double* ry = w.rec + 2 * n;
     tab.stage(w);
-    for (int j = threadIdx.x; j < nk2s; j += kPartThreads) s_k2[j] = __ldg(knots2 + j);
+    for (int j = threadIdx.x; j < nk2s; j += THREADS) s_k2[j] = __ldg(knots2 + j);
+    if (threadIdx.x == 0) { s_t2[0] = 0.0; s_y[0] = 0.0; }      // slot 0 stands in for points past the end of a run (times zero)
     __syncthreads();
-    const int64_t n_units = tab.n_units();
+    const int64_t n_slots = tab.n_slots();
     double yy = 0.0;
-    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+    for (int64_t u = blockIdx.x; u < n_slots; u += gridDim.x) {
         int bucket, count;
         int64_t first;
-        tab.find(u, bucket, first, count);
+        if (!tab.find(u, bucket, first, count)) continue;
         const int idx0 = bucket * ipb - kUnitMargin2;         // dim-1 interval of row 0 of the unit's bins
         const int jlo = idx0 < 0 ? -idx0 : 0;
         const int jhi = (last1 - idx0 < nb1 - 1) ? last1 - idx0 : nb1 - 1;
         double x1s[PER], x2s[PER], ys[PER];
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
-            const int q = p * kPartThreads + threadIdx.x;
+            const int q = p * THREADS + threadIdx.x;
             if (q < count) { x1s[p] = __ldg(r1 + first + q); x2s[p] = __ldg(r2 + first + q); ys[p] = __ldg(ry + first + q); }
         }
-        for (int j = threadIdx.x; j <= n_bins; j += kPartThreads) s_off[j] = 0;
-        for (int j = threadIdx.x; j <= nb1; j += kPartThreads) {
+        for (int j = threadIdx.x; j <= n_bins; j += THREADS) s_off[j] = 0;
+        for (int j = threadIdx.x; j <= nb1; j += THREADS) {
             const int kn = idx0 + j;
             s_k1[j] = (kn >= 0 && kn < nk1) ? __ldg(knots1 + kn) : 0.0;
         }
@@ -1464,7 +1481,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
         int bin[PER];
 #pragma unroll
         for (int p = 0; p < PER; ++p) {
-            const int q = p * kPartThreads + threadIdx.x;
+            const int q = p * THREADS + threadIdx.x;
             bin[p] = -1;
             if (q < count) {
                 yy = fma(ys[p], ys[p], yy);
@@ -1491,7 +1508,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
         // inclusive scan of s_off[1..n_bins] in place (s_off[j] becomes the first slot of bin j)
         if (threadIdx.x == 0) s_carry = 0;
         __syncthreads();
-        for (int base = 1; base <= n_bins; base += kPartThreads) {
+        for (int base = 1; base <= n_bins; base += THREADS) {
             const int j = base + threadIdx.x;
             int v = j <= n_bins ? s_off[j] : 0;
 #pragma unroll
@@ -1506,7 +1523,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
             v += add;
             __syncthreads();
             if (j <= n_bins) s_off[j] = v;
-            if (threadIdx.x == kPartThreads - 1) s_carry = v;
+            if (threadIdx.x == THREADS - 1) s_carry = v;
             __syncthreads();
         }
 #pragma unroll
@@ -1521,31 +1538,57 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
         __syncthreads();
         // bin j is now [j ? s_off[j - 1] : 0, s_off[j]); rows outside [jlo, jhi] are empty
         const int l = lane & (GL - 1);
+        double* sA = s_ex + (size_t)(threadIdx.x / GL) * EX;          // [NV][GL]
+        const int row_g = l < NB ? l : NB - 1, row_y = NB + (l < NY ? l : NY - 1);
         const int bin_lo = jlo * nc2, bin_hi = (jhi + 1) * nc2;
         for (int jb = bin_lo + warp * (32 / GL); jb < bin_hi; jb += kWarps * (32 / GL)) {
             const int j = jb + lane / GL;
             int begin = 0, end = 0;
             if (j < bin_hi) { begin = j ? s_off[j - 1] : 0; end = s_off[j]; }
+            const int n_max = __reduce_max_sync(0xffffffffu, end - begin);
+            if (n_max == 0) continue;
             double g[NB], gy[NY];
 #pragma unroll
             for (int q = 0; q < NB; ++q) g[q] = 0.0;
 #pragma unroll
             for (int q = 0; q < NY; ++q) gy[q] = 0.0;
-            for (int pt = begin; pt < end; ++pt) {
-                const double t1 = s_t1[pt], t2 = s_t2[pt], yv = s_y[pt];
-                const double u1 = 1.0 - t1;
-                double bl = 1.0, gl = 1.0;                       // beta_l(t1) = t1^l u1^(2k-l), gamma_l(t1) = t1^l u1^(k-l)
+            for (int base = 0; base < n_max; base += GL) {
+                {   // produce: the dim-1 factors of point `l` of the batch, transposed (row v, column l); zeros past the run
+                    const int pt = begin + base + l;
+                    const bool have = pt < end;
+                    const double t1 = have ? s_t1[pt] : 0.0;
+                    const double live = have ? 1.0 : 0.0;
+                    double tp[2 * K + 1], up[2 * K + 1];
+                    powers<2 * K>(t1, tp, up);
 #pragma unroll
-                for (int i = 0; i < 2 * K; ++i) bl *= (i < l) ? t1 : u1;
+                    for (int v = 0; v < NB; ++v) sA[v * GL + l] = live * tp[v] * up[2 * K - v];
 #pragma unroll
-                for (int i = 0; i < K; ++i) gl *= (i < l) ? t1 : u1;
-                double tp[2 * K + 1], up[2 * K + 1];
-                powers<2 * K>(t2, tp, up);
+                    for (int v = 0; v < NY; ++v) sA[(NB + v) * GL + l] = live * tp[v] * up[K - v];
+                }
+                __syncwarp();
+                {   // consume
+                    double a[GL], ay[GL];
 #pragma unroll
-                for (int q = 0; q < NB; ++q) g[q] = fma(bl, tp[q] * up[2 * K - q], g[q]);
-                gl *= yv;
+                    for (int i = 0; i < GL; i += 2) {
+                        const double2 va = *reinterpret_cast<const double2*>(sA + row_g * GL + i);
+                        const double2 vy = *reinterpret_cast<const double2*>(sA + row_y * GL + i);
+                        a[i] = va.x; a[i + 1] = va.y; ay[i] = vy.x; ay[i + 1] = vy.y;
+                    }
+                    const int left = end - begin - base;              // points of this batch that exist (may be <= 0)
 #pragma unroll
-                for (int q = 0; q < NY; ++q) gy[q] = fma(gl, tp[q] * up[K - q], gy[q]);
+                    for (int i = 0; i < GL; ++i) {
+                        const int pt = begin + base + (i < left ? i : 0);      // past the run: any valid slot, its row of A is zero
+                        const double t2 = s_t2[pt < kUnitPoints ? pt : 0], yv = s_y[pt < kUnitPoints ? pt : 0];
+                        double tp[2 * K + 1], up[2 * K + 1];
+                        powers<2 * K>(t2, tp, up);
+                        const double ayv = ay[i] * yv;
+#pragma unroll
+                        for (int q = 0; q < NB; ++q) g[q] = fma(a[i], tp[q] * up[2 * K - q], g[q]);
+#pragma unroll
+                        for (int q = 0; q < NY; ++q) gy[q] = fma(ayv, tp[q] * up[K - q], gy[q]);
+                    }
+                }
+                __syncwarp();
             }
             if (end > begin) {
                 const int j1 = j / nc2, c2 = j - j1 * nc2;
@@ -1575,9 +1618,11 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     }
 }
 
+template <int K>
 static size_t accum_2d_units_smem(int nb1, int nc2, int nk2) {
     const int nk2s = nk2 < kUnitKnots2 ? nk2 : 0;
-    return (size_t)3 * kUnitPoints * 8 + (size_t)(nb1 + 1 + nk2s) * 8 + (size_t)(nb1 * nc2 + 2) * 4;
+    return (size_t)3 * kUnitPoints * 8 + (size_t)(Units2<K>::THREADS / Units2<K>::GL) * Units2<K>::EX * 8 +
+           (size_t)(nb1 + 1 + nk2s) * 8 + (size_t)(nb1 * nc2 + 2) * 4;
 }
 
 // Fraction of sampled neighbours (point i, point i+1) that lie more than one cell apart in either dimension: ~0 for
@@ -1602,13 +1647,14 @@ __global__ void __launch_bounds__(256) order_probe_2d_kernel(const double* __res
 template <int K>
 static int launch_accum_2d_units(const PartWork& w, int64_t n, const double* k1, int nk1, const double* k2, int nk2, int ipb,
                                  double* cellmom, double* scal, cudaStream_t st) {
-    const size_t smem = accum_2d_units_smem(ipb + 2 * kUnitMargin2, nk2 - 1, nk2);
+    const size_t smem = accum_2d_units_smem<K>(ipb + 2 * kUnitMargin2, nk2 - 1, nk2);
+    ASVGP_REQUIRE(smem <= 227 * 1024, "accum_2d_binned: %zu bytes of shared memory needed", smem);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_units_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_2d_units_kernel<K>, kPartThreads, smem));
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_2d_units_kernel<K>, Units2<K>::THREADS, smem));
     const int64_t max_units = n / kUnitPoints + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count2() * std::max(per_sm, 1)));
-    accum_2d_units_kernel<K><<<blocks, kPartThreads, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal);
+    accum_2d_units_kernel<K><<<blocks, Units2<K>::THREADS, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal);
     return kOk;
 }
 
@@ -1734,7 +1780,10 @@ extern "C" int asvgp_accum_2d_binned(const double* X, const double* y, int64_t n
     ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15u) == 0, "accum_2d_binned: X must be 16-byte aligned");
     const int nc1 = n_knots1 - 1, nc2 = n_knots2 - 1;
     const int ipb = (nc1 + kPartBuckets - 1) / kPartBuckets;
-    if ((int64_t)(ipb + 2 * kUnitMargin2) * nc2 > kUnitMaxBins)      // too many cells per bucket for the shared-memory sort
+    size_t smem_units = 0;
+    ASVGP_DISPATCH_ORDER(order, (smem_units = accum_2d_units_smem<K>(ipb + 2 * kUnitMargin2, nc2, n_knots2)));
+    // too many cells per bucket for the shared-memory sort: the streaming kernels handle any order
+    if ((int64_t)(ipb + 2 * kUnitMargin2) * nc2 > kUnitMaxBins || smem_units > 227 * 1024)
         return asvgp_accum_2d(X, y, n, mesh1, n_knots1, mesh2, n_knots2, order, cellmom, scal, stream);
     ASVGP_REQUIRE(work != nullptr && work_bytes >= PartWork::bytes(n, 3), "accum_2d_binned: work_bytes=%lld < %lld",
                   (long long)work_bytes, (long long)PartWork::bytes(n, 3));
