@@ -27,7 +27,7 @@ namespace asvgp {
 constexpr int kPartBuckets = 256;     // upper bound on the number of buckets
 constexpr int kPartThreads = 256;
 constexpr int kPartTile = 4096;       // points per tile of the scatter pass (16 per thread)
-constexpr int kUnitPoints = 4096;     // points per unit of the second half
+constexpr int kUnitPoints = 4096;     // largest unit of the second half (each kernel passes the unit size it uses)
 constexpr int kUnitMaxBins = 4096;    // intervals (cells) of one bucket the second half can sort in shared memory
 
 typedef unsigned long long u64;
@@ -79,12 +79,12 @@ __global__ void __launch_bounds__(kPartThreads) part_hist_kernel(Src src, int64_
         if (s_cnt[b]) atomicAdd(count + b, (u64)s_cnt[b]);
 }
 
-static __global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork w) {
+static __global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork w, int unit_points) {
     __shared__ u64 s_a[kPartBuckets], s_u[kPartBuckets];
     const int b = threadIdx.x;
     const u64 c = w.count[b];
     s_a[b] = c;
-    s_u[b] = (c + kUnitPoints - 1) / kUnitPoints;
+    s_u[b] = (c + unit_points - 1) / unit_points;
     __syncthreads();
     for (int o = 1; o < kPartBuckets; o <<= 1) {          // Hillis-Steele inclusive scan of both columns
         const u64 a = b >= o ? s_a[b - o] : 0, u = b >= o ? s_u[b - o] : 0;
@@ -99,7 +99,7 @@ static __global__ void __launch_bounds__(kPartBuckets) part_scan_kernel(PartWork
     if (b == 0) { w.start[0] = 0; w.unit_start[0] = 0; }
     // the largest number of units in one bucket (the second half walks units bucket-interleaved)
     __syncthreads();
-    s_u[b] = (c + kUnitPoints - 1) / kUnitPoints;
+    s_u[b] = (c + unit_points - 1) / unit_points;
     __syncthreads();
     for (int o = kPartBuckets / 2; o > 0; o >>= 1) {
         if (b < o && s_u[b + o] > s_u[b]) s_u[b] = s_u[b + o];
@@ -188,7 +188,7 @@ constexpr size_t part_scatter_smem() {
 
 // histogram -> scan -> scatter on `st`; w.count must have been zeroed on the same stream
 template <class Src, int REC>
-cudaError_t launch_partition(const Src& src, int64_t n, const PartWork& w, int blocks, cudaStream_t st) {
+cudaError_t launch_partition(const Src& src, int64_t n, const PartWork& w, int unit_points, int blocks, cudaStream_t st) {
     const size_t smem = part_scatter_smem<REC>();
     cudaError_t e = cudaFuncSetAttribute(part_scatter_kernel<Src, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -196,7 +196,7 @@ cudaError_t launch_partition(const Src& src, int64_t n, const PartWork& w, int b
     const int hist_blocks = (int)((n + 4 * kPartThreads - 1) / (4 * kPartThreads) < 4 * (int64_t)blocks
                                       ? (n + 4 * kPartThreads - 1) / (4 * kPartThreads) : 4 * (int64_t)blocks);
     part_hist_kernel<Src><<<hist_blocks, kPartThreads, 0, st>>>(src, n, w.count);
-    part_scan_kernel<<<1, kPartBuckets, 0, st>>>(w);
+    part_scan_kernel<<<1, kPartBuckets, 0, st>>>(w, unit_points);
     part_scatter_kernel<Src, REC><<<blocks, kPartThreads, smem, st>>>(src, n, w);
     return cudaGetLastError();
 }
@@ -213,11 +213,11 @@ struct UnitTable {
     }
     __device__ int64_t n_slots() const { return (int64_t)max_chunks * kPartBuckets; }
     // false: the slot is past the end of its bucket
-    __device__ bool find(int64_t slot, int& bucket, int64_t& first, int& count) const {
+    __device__ bool find(int64_t slot, int unit_points, int& bucket, int64_t& first, int& count) const {
         bucket = (int)(slot % kPartBuckets);
-        first = (int64_t)start[bucket] + (slot / kPartBuckets) * kUnitPoints;
+        first = (int64_t)start[bucket] + (slot / kPartBuckets) * unit_points;
         const int64_t left = (int64_t)start[bucket + 1] - first;
-        count = (int)(left < kUnitPoints ? left : kUnitPoints);
+        count = (int)(left < unit_points ? left : unit_points);
         return left > 0;
     }
 };

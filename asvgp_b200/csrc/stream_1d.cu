@@ -349,6 +349,7 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
 // ------------------------------------------------------------------------------------------------------------------
 // accumulate for inputs in no particular order: bucket partition (partition.cuh), then per-unit shared-memory sort
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kUnitPoints1 = 4096;  // points per unit (2048-point units at three CTAs per SM spill and measured slower: 2.31 vs 2.13 ms)
 constexpr int kUnitMargin = 2;      // intervals either side of a bucket the exact interval may fall into (a float32-built
                                     // mesh is not the uniform grid the bucket guess assumes); beyond: per-point REDs
 
@@ -378,13 +379,13 @@ template <int K, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2)
 accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, int n_knots, int ipb, int M,
                       double* __restrict__ G, double* __restrict__ b, double* __restrict__ scal) {
-    constexpr int PER = kUnitPoints / THREADS;
+    constexpr int PER = kUnitPoints1 / THREADS;
     constexpr int kGroup = 8;
     constexpr int kWarps = THREADS / 32;
     extern __shared__ double s_dyn[];
-    double* s_tau = s_dyn;                                            // [kUnitPoints]
-    double* s_y = s_tau + kUnitPoints;                                // [kUnitPoints]
-    double* s_knots = s_y + kUnitPoints;                              // [n_bins + 1]
+    double* s_tau = s_dyn;                                            // [kUnitPoints1]
+    double* s_y = s_tau + kUnitPoints1;                                // [kUnitPoints1]
+    double* s_knots = s_y + kUnitPoints1;                              // [n_bins + 1]
     int* s_off = reinterpret_cast<int*>(s_knots + ipb + 2 * kUnitMargin + 1);   // [n_bins + 2]
     __shared__ UnitTable tab;
     __shared__ double s_yy[kWarps];
@@ -405,7 +406,7 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
     for (int64_t u = blockIdx.x; u < n_slots; u += gridDim.x) {
         int bucket, count;
         int64_t first;
-        if (!tab.find(u, bucket, first, count)) continue;
+        if (!tab.find(u, kUnitPoints1, bucket, first, count)) continue;
         const int idx0 = bucket * ipb - kUnitMargin;          // interval of bin 0 (may be negative: those bins stay empty)
         const int jlo = idx0 < 0 ? -idx0 : 0;                 // bins [jlo, jhi] are real intervals
         const int jhi = (last - idx0 < n_bins - 1) ? last - idx0 : n_bins - 1;
@@ -501,7 +502,7 @@ accum_1d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots, i
     }
 }
 
-static size_t accum_1d_units_smem(int n_bins) { return (size_t)2 * kUnitPoints * 8 + (size_t)(n_bins + 1) * 8 + (size_t)(n_bins + 2) * 4; }
+static size_t accum_1d_units_smem(int n_bins) { return (size_t)2 * kUnitPoints1 * 8 + (size_t)(n_bins + 1) * 8 + (size_t)(n_bins + 2) * 4; }
 
 // Fraction of sampled neighbours (x[i], x[i+1]) that lie more than one knot interval apart: ~0 for time-series order,
 // ~1 for shuffled input.  out[0] += jumps / samples.
@@ -729,7 +730,7 @@ static int launch_accum_1d_units(const PartWork& w, int64_t n, const double* mes
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_1d_units_kernel<K, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_1d_units_kernel<K, THREADS>, THREADS, smem));
-    const int64_t max_units = n / kUnitPoints + kPartBuckets;
+    const int64_t max_units = n / kUnitPoints1 + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count() * std::max(per_sm, 1)));
     accum_1d_units_kernel<K, THREADS><<<blocks, THREADS, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
     return kOk;
@@ -756,7 +757,7 @@ extern "C" int asvgp_accum_1d_binned(const double* x, const double* y, int64_t n
     Points1D src;
     src.x = x; src.y = y; src.knots = mesh; src.n_knots = n_knots; src.ipb = ipb;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count() * 2));
-    ASVGP_CUDA_OK((launch_partition<Points1D, 2>(src, n, w, blocks, st)));
+    ASVGP_CUDA_OK((launch_partition<Points1D, 2>(src, n, w, kUnitPoints1, blocks, st)));
     ASVGP_DISPATCH_ORDER(order, (launch_accum_1d_units<K>(w, n, mesh, n_knots, ipb, M, G, b, scal, st)));
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;

@@ -1462,7 +1462,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     for (int64_t u = blockIdx.x; u < n_slots; u += gridDim.x) {
         int bucket, count;
         int64_t first;
-        if (!tab.find(u, bucket, first, count)) continue;
+        if (!tab.find(u, kUnitPoints, bucket, first, count)) continue;
         const int idx0 = bucket * ipb - kUnitMargin2;         // dim-1 interval of row 0 of the unit's bins
         const int jlo = idx0 < 0 ? -idx0 : 0;
         const int jhi = (last1 - idx0 < nb1 - 1) ? last1 - idx0 : nb1 - 1;
@@ -1794,7 +1794,7 @@ extern "C" int asvgp_accum_2d_binned(const double* X, const double* y, int64_t n
     Points2D src;
     src.X = X; src.y = y; src.knots1 = mesh1; src.n_knots1 = n_knots1; src.ipb = ipb;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count2() * 2));
-    ASVGP_CUDA_OK((launch_partition<Points2D, 3>(src, n, w, blocks, st)));
+    ASVGP_CUDA_OK((launch_partition<Points2D, 3>(src, n, w, kUnitPoints, blocks, st)));
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d_units<K>(w, n, mesh1, n_knots1, mesh2, n_knots2, ipb, cellmom, scal, st)) return rc; });
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;

@@ -521,6 +521,48 @@ def _cpu_chunk_2d(span):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def run_unordered(torch):
+    """Accumulate times for the secondary orderings of SURVEY 8(d): C3-ii (1-D, x in random order) and C4 shuffled,
+    through the bucket-partition entry points (partition passes included), next to the streaming kernels on the same data."""
+    from asvgp_b200 import basis as B, ops
+
+    def timeit(fn, reps):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    out = {}
+    n, m, k = WORKLOADS["1d"][:3]
+    g = torch.Generator(device="cuda"); g.manual_seed(1997)
+    basis = getattr(B, "B%dSpline" % k)(-1, m + 1, m)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * m
+    y = torch.sin(x / 37)
+    acc = torch.zeros(ops.accum_size_1d(basis), dtype=torch.float64, device="cuda")
+    out["accum_1d_random_order_ms"] = {"binned": timeit(lambda: ops.accum_1d(x, y, basis, acc, binned=True), 5),
+                                       "streaming": timeit(lambda: ops.accum_1d(x, y, basis, acc), 2), "points": n}
+    del x, y
+    n1, n2, m2, k2 = WORKLOADS_2D["2d"]
+    cls = getattr(B, "B%dSpline" % k2)
+    bases = [cls(-80, -25, m2), cls(15, 55, m2)]
+    x1 = torch.linspace(-75, -30, n1, dtype=torch.float64, device="cuda")
+    x2 = torch.linspace(20, 50, n2, dtype=torch.float64, device="cuda")
+    X = torch.stack([x1[:, None].expand(n1, n2), x2[None, :].expand(n1, n2)], -1).reshape(-1, 2)
+    X = X[torch.randperm(n1 * n2, device="cuda", generator=g)].contiguous()
+    yy = torch.sin(X[:, 0] / 4) * torch.cos(X[:, 1] / 3)
+    acc2 = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+    cm = ops.moment_table_2d(bases)
+    scal = ops.split_accum_2d(acc2, bases)[2]
+    out["accum_2d_shuffled_ms"] = {"binned": timeit(lambda: ops.accum_2d(X, yy, bases, cm, scal, binned=True), 3),
+                                   "streaming": timeit(lambda: ops.accum_2d(X, yy, bases, cm, scal), 1), "points": n1 * n2}
+    del X, yy
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -567,10 +609,12 @@ def main():
     out = torch.empty(16, dtype=torch.float64, device="cuda")
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
 
+    binned = not is_sorted            # random order: bucket-partition path, the binning passes are inside the timed accumulate
+
     def step(timers=None):
         acc.zero_()
         if timers: timers[0].record()
-        ops.accum_1d(x, y, basis, acc=acc)
+        ops.accum_1d(x, y, basis, acc=acc, binned=binned)
         if timers: timers[1].record()
         if world > 1:
             dist.all_reduce(acc)
@@ -641,7 +685,7 @@ def main():
     from asvgp_b200.gpr import GPR_1d as _G1
 
     pm = _G1.__new__(_G1)
-    pm.kernel, pm.basis, pm.inducing_features, pm._acc, pm._chunks = kern, basis, feats, acc, 0
+    pm.kernel, pm.basis, pm.inducing_features, pm._acc, pm._accs, pm._chunks = kern, basis, feats, acc, [acc], 0
     pm.likelihood = Kn.Gaussian(HYPERS[2])
     alpha, S_band, _info = pm.posterior_weights()
     for _ in range(2):
@@ -667,6 +711,14 @@ def main():
         except Exception as exc:            # the appendix must never take the headline line down with it
             kron = {"error": repr(exc)}
 
+    unordered = None
+    if args.workload == "1d" and world == 1 and not args.no_2d and not args.n:
+        torch.cuda.empty_cache()
+        try:
+            unordered = run_unordered(torch)
+        except Exception as exc:
+            unordered = {"error": repr(exc)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -684,17 +736,22 @@ def main():
                       "predict_same_points": pred_ms},
         "predict_points_per_s": world * n / (pred_ms * 1e-3),
         "elbo": float(res0[0]), "grad": [float(v) for v in res0[1:4]],
-        "roofline": {"kernel": "accum_1d_kernel<%d,2>" % k, "bound": "hbm", "achieved": achieved,
+        "roofline": {"kernel": ("accum_1d_kernel<%d,2>" % k) if not binned else
+                     "asvgp_accum_1d_binned (part_hist + part_scan + part_scatter + accum_1d_units_kernel<%d>)" % k,
+                     "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM * n, "launch_ms": accum_ms, "traffic": traffic},
         "clocks": clocks.summary(),
-        "gpu_launches": args.steps * 4,          # accum_1d + kuu_assemble + elbo_chains + elbo_finalize per step
+        # accum_1d (or the four kernels of the binned path) + kuu_assemble + elbo_chains + elbo_finalize per step
+        "gpu_launches": args.steps * (7 if binned else 4),
     }
     if e2e is not None:
         line["e2e"] = e2e
     if kron is not None:
         line["kron_2d"] = kron
+    if unordered is not None:
+        line["unordered_inputs"] = unordered
     if world == 1 and not args.no_cpu_baseline:
         n_sample = min(n, 20_000_000)
         v1, dt1 = run_cpu(n_sample, m, k, kind, 1, 0, 1)
