@@ -1364,12 +1364,13 @@ static int sm_count2() {
 // shared-memory sort by cell.  (The thread-private kernel above degenerates to (2k+1)^2 + (k+1)^2 REDs per point
 // once consecutive points stop sharing a cell: 35 ms per 1e8 shuffled points.)
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kUnitPoints2 = 4096;     // points per unit (3072-point units at two 256-thread CTAs per SM spill and measured slower: 6.46 vs 6.16 ms)
 constexpr int kUnitMargin2 = 1;       // dim-1 intervals either side of a bucket the exact interval may fall into
 constexpr int kUnitKnots2 = 2048;     // dim-2 knots staged in shared memory (longer meshes are read through L1)
 template <int K> struct Units2 {
-    // one CTA per SM: the unit's points + the exchange areas take 140..208 KB of shared memory
+    // one CTA per SM: the unit's points + the exchange areas take 140..190 KB of shared memory
     static constexpr int THREADS = K <= 4 ? 512 : 256;
-    static constexpr int GL = (2 * K + 1) <= 8 ? 8 : 16;                  // lanes (and points per batch) per cell
+    static constexpr int GL = (2 * K + 1) <= 8 ? 4 : 8;                   // lanes (and points per batch) per cell; a lane owns rows l and l + GL
     static constexpr int NV = (2 * K + 1) + (K + 1);                      // factors per dimension per point
     static constexpr int NVP = (NV + 1) & ~1;                             // ... padded to whole 16-byte pairs
     static constexpr int EX = NV * GL + 2;                                // doubles of one group's exchange area (+2: groups land on different banks)
@@ -1410,17 +1411,17 @@ __device__ __forceinline__ int locate_in_window(const double* s, int jlo, int jh
     return (below || above) ? -1 : j;
 }
 
-// One unit = up to kUnitPoints records (x1, x2, y) of one bucket.  The CTA counting-sorts the unit by cell in shared
-// memory ((t1, t2, y) are what is staged).  Then GL lanes take one cell, GL points at a time:
-//   produce  lane i evaluates, for point i of the batch, the dim-1 factors A = (beta_0..2k(t1), gamma_0..k(t1)) and the
-//            dim-2 factors B = (beta_0..2k(t2), y gamma_0..k(t2)) once, and leaves them in the group's exchange area
-//            (A transposed: row v, column i);
-//   consume  lane l OWNS the moment rows with dim-1 index l (beta_l(t1) beta_q(t2), q = 0..2k, and for l <= k the
-//            projection row gamma_l(t1) gamma_q(t2) y): it reads its row of A (GL values) and walks the GL points' B
-//            vectors (broadcast reads) with one FMA per moment.
-// Nothing is reduced across lanes and a thread holds 3k + 2 sums instead of (2k+1)^2 + (k+1)^2; at the end of a
-// cell's run each lane adds its rows to the moment table.  (A first version in which every lane recomputed the factors
-// of every point of its cell was instruction-bound at 5.0 ms per 1e8 points.)
+// One unit = up to kUnitPoints2 records (x1, x2, y) of one bucket.  The CTA counting-sorts the unit by cell in shared
+// memory ((t1, t2, y) are what is staged).  Then GL = 4 (8 for k >= 4) lanes take one cell, GL points at a time:
+//   produce  lane i evaluates, for point i of the batch, the dim-1 factors A = (beta_0..2k(t1), gamma_0..k(t1)) once and
+//            leaves them in the group's exchange area, transposed (row v, column i);
+//   consume  lane l OWNS the moment rows with dim-1 index l and l + GL (beta_l(t1) beta_q(t2), q = 0..2k) and, for l <= k,
+//            the projection row gamma_l(t1) gamma_q(t2) y: it reads its rows of A (GL values each) and evaluates the dim-2
+//            factors of the GL points itself (exchanging those too made the kernel shared-memory-bandwidth-bound), one FMA
+//            per moment.
+// Nothing is reduced across lanes and a thread holds 5k + 3 sums instead of (2k+1)^2 + (k+1)^2; at the end of a
+// cell's run each lane adds its rows to the moment table.  (Measured per 1e8 shuffled points, k = 3: 8 lanes per cell
+// each recomputing every factor 5.0 ms; A and B exchanged 6.2 ms; A exchanged, 8 lanes 4.65 ms; this version 4.2 ms.)
 template <int K>
 __global__ void __launch_bounds__(Units2<K>::THREADS, 1)
 accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2,
@@ -1429,17 +1430,17 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     constexpr int NB = Mo::NB, NY = Mo::NY;
     constexpr int GL = Units2<K>::GL, EX = Units2<K>::EX;
     constexpr int THREADS = Units2<K>::THREADS;
-    constexpr int PER = kUnitPoints / THREADS;
+    constexpr int PER = kUnitPoints2 / THREADS;
     constexpr int kWarps = THREADS / 32;
     const int nc2 = nk2 - 1;
     const int nb1 = ipb + 2 * kUnitMargin2;
     const int n_bins = nb1 * nc2;
     const int nk2s = nk2 < kUnitKnots2 ? nk2 : 0;           // dim-2 knots staged (0: read through L1)
     extern __shared__ double s_dyn[];
-    double* s_t1 = s_dyn;                                   // [kUnitPoints]
-    double* s_t2 = s_t1 + kUnitPoints;
-    double* s_y = s_t2 + kUnitPoints;
-    double* s_ex = s_y + kUnitPoints;                       // [THREADS / GL][EX] exchange areas
+    double* s_t1 = s_dyn;                                   // [kUnitPoints2]
+    double* s_t2 = s_t1 + kUnitPoints2;
+    double* s_y = s_t2 + kUnitPoints2;
+    double* s_ex = s_y + kUnitPoints2;                       // [THREADS / GL][EX] exchange areas
     double* s_k1 = s_ex + (THREADS / GL) * EX;              // [nb1 + 1]
     double* s_k2 = s_k1 + nb1 + 1;                          // [nk2s]
     int* s_off = reinterpret_cast<int*>(s_k2 + nk2s);       // [n_bins + 2]
@@ -1462,7 +1463,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
     for (int64_t u = blockIdx.x; u < n_slots; u += gridDim.x) {
         int bucket, count;
         int64_t first;
-        if (!tab.find(u, kUnitPoints, bucket, first, count)) continue;
+        if (!tab.find(u, kUnitPoints2, bucket, first, count)) continue;
         const int idx0 = bucket * ipb - kUnitMargin2;         // dim-1 interval of row 0 of the unit's bins
         const int jlo = idx0 < 0 ? -idx0 : 0;
         const int jhi = (last1 - idx0 < nb1 - 1) ? last1 - idx0 : nb1 - 1;
@@ -1539,7 +1540,8 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
         // bin j is now [j ? s_off[j - 1] : 0, s_off[j]); rows outside [jlo, jhi] are empty
         const int l = lane & (GL - 1);
         double* sA = s_ex + (size_t)(threadIdx.x / GL) * EX;          // [NV][GL]
-        const int row_g = l < NB ? l : NB - 1, row_y = NB + (l < NY ? l : NY - 1);
+        const bool has1 = l + GL < NB, hasy = l < NY;                 // second Gram row / projection row of this lane
+        const int row0 = l < NB ? l : NB - 1, row1 = has1 ? l + GL : NB - 1, row_y = NB + (hasy ? l : NY - 1);
         const int bin_lo = jlo * nc2, bin_hi = (jhi + 1) * nc2;
         for (int jb = bin_lo + warp * (32 / GL); jb < bin_hi; jb += kWarps * (32 / GL)) {
             const int j = jb + lane / GL;
@@ -1547,9 +1549,9 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
             if (j < bin_hi) { begin = j ? s_off[j - 1] : 0; end = s_off[j]; }
             const int n_max = __reduce_max_sync(0xffffffffu, end - begin);
             if (n_max == 0) continue;
-            double g[NB], gy[NY];
+            double g0[NB], g1[NB], gy[NY];
 #pragma unroll
-            for (int q = 0; q < NB; ++q) g[q] = 0.0;
+            for (int q = 0; q < NB; ++q) { g0[q] = 0.0; g1[q] = 0.0; }
 #pragma unroll
             for (int q = 0; q < NY; ++q) gy[q] = 0.0;
             for (int base = 0; base < n_max; base += GL) {
@@ -1567,37 +1569,57 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
                 }
                 __syncwarp();
                 {   // consume
-                    double a[GL], ay[GL];
+                    double a0[GL], a1[GL], ay[GL];
 #pragma unroll
                     for (int i = 0; i < GL; i += 2) {
-                        const double2 va = *reinterpret_cast<const double2*>(sA + row_g * GL + i);
+                        const double2 v0 = *reinterpret_cast<const double2*>(sA + row0 * GL + i);
+                        const double2 v1 = *reinterpret_cast<const double2*>(sA + row1 * GL + i);
                         const double2 vy = *reinterpret_cast<const double2*>(sA + row_y * GL + i);
-                        a[i] = va.x; a[i + 1] = va.y; ay[i] = vy.x; ay[i + 1] = vy.y;
+                        a0[i] = v0.x; a0[i + 1] = v0.y;
+                        a1[i] = has1 ? v1.x : 0.0; a1[i + 1] = has1 ? v1.y : 0.0;
+                        ay[i] = vy.x; ay[i + 1] = vy.y;
                     }
                     const int left = end - begin - base;              // points of this batch that exist (may be <= 0)
 #pragma unroll
                     for (int i = 0; i < GL; ++i) {
-                        const int pt = begin + base + (i < left ? i : 0);      // past the run: any valid slot, its row of A is zero
-                        const double t2 = s_t2[pt < kUnitPoints ? pt : 0], yv = s_y[pt < kUnitPoints ? pt : 0];
+                        const int pt = begin + base + (i < left ? i : 0);      // past the run: any valid slot, its column of A is zero
+                        const double t2 = s_t2[pt < kUnitPoints2 ? pt : 0], yv = s_y[pt < kUnitPoints2 ? pt : 0];
                         double tp[2 * K + 1], up[2 * K + 1];
                         powers<2 * K>(t2, tp, up);
                         const double ayv = ay[i] * yv;
 #pragma unroll
-                        for (int q = 0; q < NB; ++q) g[q] = fma(a[i], tp[q] * up[2 * K - q], g[q]);
+                        for (int q = 0; q < NB; ++q) {
+                            const double bq = tp[q] * up[2 * K - q];
+                            g0[q] = fma(a0[i], bq, g0[q]);
+                            g1[q] = fma(a1[i], bq, g1[q]);
+                        }
 #pragma unroll
                         for (int q = 0; q < NY; ++q) gy[q] = fma(ayv, tp[q] * up[K - q], gy[q]);
                     }
                 }
                 __syncwarp();
             }
+#ifdef ASVGP_ABLATE_RED
+            double keep = 0.0;
+#pragma unroll
+            for (int q = 0; q < NB; ++q) keep += g0[q] + g1[q];
+#pragma unroll
+            for (int q = 0; q < NY; ++q) keep += gy[q];
+            if (keep == 1.2345e300) {
+#else
             if (end > begin) {
+#endif
                 const int j1 = j / nc2, c2 = j - j1 * nc2;
                 double* dst = cellmom + ((int64_t)(idx0 + j1) * nc2 + c2) * Mo::kAll;
                 if (l < NB) {
 #pragma unroll
-                    for (int q = 0; q < NB; ++q) atomicAdd(dst + l * NB + q, g[q]);
+                    for (int q = 0; q < NB; ++q) atomicAdd(dst + l * NB + q, g0[q]);
                 }
-                if (l < NY) {
+                if (has1) {
+#pragma unroll
+                    for (int q = 0; q < NB; ++q) atomicAdd(dst + (l + GL) * NB + q, g1[q]);
+                }
+                if (hasy) {
 #pragma unroll
                     for (int q = 0; q < NY; ++q) atomicAdd(dst + Mo::kGram + l * NY + q, gy[q]);
                 }
@@ -1621,7 +1643,7 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
 template <int K>
 static size_t accum_2d_units_smem(int nb1, int nc2, int nk2) {
     const int nk2s = nk2 < kUnitKnots2 ? nk2 : 0;
-    return (size_t)3 * kUnitPoints * 8 + (size_t)(Units2<K>::THREADS / Units2<K>::GL) * Units2<K>::EX * 8 +
+    return (size_t)3 * kUnitPoints2 * 8 + (size_t)(Units2<K>::THREADS / Units2<K>::GL) * Units2<K>::EX * 8 +
            (size_t)(nb1 + 1 + nk2s) * 8 + (size_t)(nb1 * nc2 + 2) * 4;
 }
 
@@ -1652,7 +1674,7 @@ static int launch_accum_2d_units(const PartWork& w, int64_t n, const double* k1,
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_units_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_2d_units_kernel<K>, Units2<K>::THREADS, smem));
-    const int64_t max_units = n / kUnitPoints + kPartBuckets;
+    const int64_t max_units = n / kUnitPoints2 + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count2() * std::max(per_sm, 1)));
     accum_2d_units_kernel<K><<<blocks, Units2<K>::THREADS, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal);
     return kOk;
@@ -1794,7 +1816,7 @@ extern "C" int asvgp_accum_2d_binned(const double* X, const double* y, int64_t n
     Points2D src;
     src.X = X; src.y = y; src.knots1 = mesh1; src.n_knots1 = n_knots1; src.ipb = ipb;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count2() * 2));
-    ASVGP_CUDA_OK((launch_partition<Points2D, 3>(src, n, w, kUnitPoints, blocks, st)));
+    ASVGP_CUDA_OK((launch_partition<Points2D, 3>(src, n, w, kUnitPoints2, blocks, st)));
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d_units<K>(w, n, mesh1, n_knots1, mesh2, n_knots2, ipb, cellmom, scal, st)) return rc; });
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
