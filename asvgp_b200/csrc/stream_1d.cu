@@ -621,12 +621,22 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
         const double2* __restrict__ x2 = reinterpret_cast<const double2*>(xs);
         double2* __restrict__ m2 = reinterpret_cast<double2*>(mean);
         double2* __restrict__ v2 = reinterpret_cast<double2*>(var);
-        for (int64_t base = c_begin + threadIdx.x; base < c_end; base += (int64_t)blockDim.x * U) {
-            double2 xv[U];
+        // the next tile's points are requested before the current tile is evaluated (the kernel was waiting on its loads:
+        // stall_long_sb 43 % of the samples with load -> evaluate -> store per tile)
+        double2 xv[U];
+        const int64_t step = (int64_t)blockDim.x * U;
+        int64_t base = c_begin + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < U; ++j) {
+            const int64_t i = base + j * (int64_t)blockDim.x;
+            xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+        }
+        for (; base < c_end; base += step) {
+            double2 xn[U];
 #pragma unroll
             for (int j = 0; j < U; ++j) {
-                const int64_t i = base + j * (int64_t)blockDim.x;
-                xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                const int64_t i = base + step + j * (int64_t)blockDim.x;
+                xn[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
@@ -635,9 +645,11 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
                 double2 mo, vo;
                 eval(xv[j].x, mo.x, vo.x);
                 eval(xv[j].y, mo.y, vo.y);
-                m2[i] = mo;
-                v2[i] = vo;
+                __stcs(m2 + i, mo);          // written once, never read back here
+                __stcs(v2 + i, vo);
             }
+#pragma unroll
+            for (int j = 0; j < U; ++j) xv[j] = xn[j];
         }
         if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval(__ldg(xs + n - 1), mean[n - 1], var[n - 1]);
     } else {
