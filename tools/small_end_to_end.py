@@ -1,5 +1,6 @@
-"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck): 1-D and 2-D models, all accumulate paths,
-predictors.  Sizes are tiny so that the instrumented run finishes in seconds."""
+"""Small end-to-end run of every kernel family (1-D and 2-D models, every accumulate path, predictors) in a few seconds:
+a quick "does everything still launch and finish" check on a GPU box.  (Written for compute-sanitizer memcheck, which is
+closed on this pool; bounds are covered by the ragged / boundary-size parity tests instead.)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -30,4 +31,4 @@ for name, X in cases.items():
     mu2, var2 = mk.predict_f(Xs.reshape(-1, 2))
     print("2-D", name, e, mu.shape, mu2.shape)
 torch.cuda.synchronize()
-print("sanitize run complete")
+print("small end-to-end run complete")
