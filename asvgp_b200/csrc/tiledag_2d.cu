@@ -105,6 +105,51 @@ __device__ __forceinline__ void tma_load_tile_(double* dst_smem, const double* s
     tma_load_bulk(dst_smem, src_gmem, (uint32_t)TILE_BYTES, bar);
 }
 
+// ---- tile products on the fp64 tensor cores --------------------------------------------------------------------------
+// mma.sync.m8n8k4.f64 sustains the full fp64 rate of the SM (64 FMA/clk, tools/microbench/dmma_bench.cu) where the DFMA
+// outer-product loop of tile_mma reaches 42 %.  A fragment load takes element (row m = lane/4, k = lane%4) of an operand
+// stored k-major; with 64-double columns the four k of a row share a bank, so the operands of the bulk products are staged
+// with a column stride of LDT = 68 doubles (68 mod 16 = 4: the 16 lanes of a half-warp hit 16 different banks): one TMA
+// bulk copy per column (64 x 512 B, spread over the lanes of warp 0) instead of one per tile, same mbarrier, same byte count.
+constexpr int LDT = NB + 4;
+constexpr int PTILE = NB * LDT;                 // doubles of a staged (padded) operand tile
+__device__ __forceinline__ void tma_load_tile_padded(double* dst_smem, const double* src_gmem, uint64_t* bar, int lane) {
+    for (int c = lane; c < NB; c += 32) tma_load_bulk(dst_smem + c * LDT, src_gmem + c * NB, (uint32_t)(NB * 8), bar);
+}
+__device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+// cf += A B^T for operands staged k-major with stride LDT (element (m, k) at [k * LDT + m]); warp w owns rows 8w..8w+7 of
+// the 64 x 64 result as eight 8 x 8 fragments (lane: row lane/4, columns 2 (lane%4) + {0, 1} of each)
+__device__ __forceinline__ void dmma_tile(double (&cf)[8][2], const double* __restrict__ A, const double* __restrict__ B, int warp, int lane) {
+    const double* pa = A + (lane & 3) * LDT + warp * 8 + (lane >> 2);
+    const double* pb = B + (lane & 3) * LDT + (lane >> 2);
+#pragma unroll 4
+    for (int k0 = 0; k0 < NB; k0 += 4) {
+        const double a = pa[k0 * LDT];
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb) dmma_m8n8k4(cf[cb], a, pb[k0 * LDT + cb * 8]);
+    }
+}
+// acc -= (the product held as fragments), through a column-major 64 x 64 scratch tile in shared memory
+__device__ __forceinline__ void frags_subtract(double (&acc)[4][4], const double (&cf)[8][2], double* scratch, int warp, int lane,
+                                               int tm, int tn) {
+    const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
+#pragma unroll
+    for (int cb = 0; cb < 8; ++cb) {
+        scratch[(cb * 8 + col) * NB + row] = cf[cb][0];
+        scratch[(cb * 8 + col + 1) * NB + row] = cf[cb][1];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 a = *reinterpret_cast<const double2*>(scratch + (tn + j) * NB + tm);
+        const double2 b = *reinterpret_cast<const double2*>(scratch + (tn + j) * NB + tm + 2);
+        acc[0][j] -= a.x; acc[1][j] -= a.y; acc[2][j] -= b.x; acc[3][j] -= b.y;
+    }
+    __syncthreads();
+}
+
 // Spin until *flag >= want; gives up (and makes everybody give up) after kSpinLimit polls so that a logic error can
 // never hang the device.
 __device__ __forceinline__ void wait_flag(const int* flag, int want, int* abort_flag) {
@@ -151,7 +196,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[4][4], const double* __re
 // which would live in local memory)
 struct StageBufs {
     double* base;
-    __device__ __forceinline__ double* operator[](int s) const { return base + s * 2 * TILE; }
+    __device__ __forceinline__ double* operator[](int s) const { return base + s * 2 * PTILE; }
 };
 struct Phases {                // parity bits of the two mbarriers
     uint32_t bits = 0u;
@@ -173,6 +218,14 @@ __device__ __forceinline__ void regs_to_tile(const double (&acc)[4][4], double* 
     for (int j = 0; j < 4; ++j) {
         *reinterpret_cast<double2*>(t + (tn + j) * NB + tm) = make_double2(acc[0][j], acc[1][j]);
         *reinterpret_cast<double2*>(t + (tn + j) * NB + tm + 2) = make_double2(acc[2][j], acc[3][j]);
+    }
+}
+template <int LD>
+__device__ __forceinline__ void regs_to_tile_ld(const double (&acc)[4][4], double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        *reinterpret_cast<double2*>(t + (tn + j) * LD + tm) = make_double2(acc[0][j], acc[1][j]);
+        *reinterpret_cast<double2*>(t + (tn + j) * LD + tm + 2) = make_double2(acc[2][j], acc[3][j]);
     }
 }
 // transposed store: element (r, c) at [r*64 + c]
@@ -406,11 +459,11 @@ __device__ __forceinline__ void potrf_regs(double (&acc)[4][4], double (&V)[4][4
 
 __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + PTILE};
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double s_vec[NB];
     const TileGeom g = a.g;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     int* abort_flag = a.ready + g.n_tiles();
     // the right-hand side y = L^-1 b rides along as a chain of its own, off the critical path of the tiles:
@@ -433,22 +486,30 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
         regs_from_tile(acc, my_tile, tm, tn);
         const int J0 = max(0, R - g.BW), nJ = C - J0;
 
-        auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
-            wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (R - J), 1, abort_flag);
-            if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
+        auto issue = [&](int J, int s) {             // warp 0: lane 0 waits for the operand tiles, all lanes fetch their columns by TMA
+            if (lane == 0) {
+                wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (R - J), 1, abort_flag);
+                if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
+            }
+            __syncwarp();
             fence_proxy_async();
-            mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
-            tma_load_tile_(sA[s], a.tiles + g.tile(J, R - J), &full[s]);
-            if (d != 0) tma_load_tile_(sB[s], a.tiles + g.tile(J, C - J), &full[s]);
+            if (lane == 0) mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
+            __syncwarp();
+            tma_load_tile_padded(sA[s], a.tiles + g.tile(J, R - J), &full[s], lane);
+            if (d != 0) tma_load_tile_padded(sB[s], a.tiles + g.tile(J, C - J), &full[s], lane);
         };
-        if (nJ > 0 && tid == 0) issue(J0, 0);
-        for (int q = 0; q < nJ; ++q) {
-            const int s = q & 1;
-            if (q + 1 < nJ && tid == 0) issue(J0 + q + 1, s ^ 1);
-            mbar_wait(&full[s], ph.get(s));
-            ph.flip(s);
-            tile_mma<NB, NB, true>(acc, sA[s], d != 0 ? sB[s] : sA[s], tm, tn);
-            __syncthreads();
+        if (nJ > 0) {
+            double cf[8][2] = {};                    // sum_J L(R,J) L(C,J)^T as tensor-core fragments
+            if (warp == 0) issue(J0, 0);
+            for (int q = 0; q < nJ; ++q) {
+                const int s = q & 1;
+                if (q + 1 < nJ && warp == 0) issue(J0 + q + 1, s ^ 1);
+                mbar_wait(&full[s], ph.get(s));
+                ph.flip(s);
+                dmma_tile(cf, sA[s], d != 0 ? sB[s] : sA[s], warp, lane);
+                __syncthreads();
+            }
+            frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);
         }
 
         if (d == 0) {
@@ -537,6 +598,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
             mbar_wait(&full[0], ph.get(0));
             ph.flip(0);
             double L[4][4] = {};
+            // (stays on the DFMA loop: on the tensor cores the product itself is 2.5 us shorter, but the padded staging and
+            // the fragment -> register conversion give it back on this latency-critical tile: 7.7 vs 7.4 us measured)
             tile_mma<NB, NB, false>(L, sA[0], sB[0], tm, tn);      // L[m][n] = sum_k A[m][k] Linv[n][k]
             regs_to_tile(L, my_tile, tm, tn);
             __threadfence();
@@ -630,11 +693,11 @@ struct SelArgs {
 
 __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + PTILE};
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double s_vec[NB];
     const TileGeom g = a.g;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     int* cnt = a.sready + g.n_tiles();            // cnt[C]: off-diagonal tiles of column C that have added their share to Sigma(C,C)
     int* abort_flag = cnt + g.nb;
@@ -665,22 +728,26 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 if (K == R) { src = a.sig_lower + g.tile(R, 0); flag = cnt + R; want = min(g.BW, g.nb - 1 - R); }   // Sigma(R,R): all shares in
                 else if (K < R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
                 else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
-                wait_flag(flag, want, abort_flag);
+                if (lane == 0) wait_flag(flag, want, abort_flag);
+                __syncwarp();
                 fence_proxy_async();
-                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                tma_load_tile_(sA[s], src, &full[s]);
-                tma_load_tile_(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
+                if (lane == 0) mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+                __syncwarp();
+                tma_load_tile_padded(sA[s], src, &full[s], lane);
+                tma_load_tile_padded(sB[s], a.tiles + g.tile(C, K - C), &full[s], lane);
             };
             double acc[4][4] = {};
-            if (tid == 0) issue(Kmax, 0);
+            double cf[8][2] = {};                    // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
+            if (warp == 0) issue(Kmax, 0);
             for (int q = 0; q < nK; ++q) {
                 const int s = q & 1;
-                if (q + 1 < nK && tid == 0) issue(Kmax - q - 1, s ^ 1);
+                if (q + 1 < nK && warp == 0) issue(Kmax - q - 1, s ^ 1);
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
-                tile_mma<NB, NB, true>(acc, sA[s], sB[s], tm, tn);         // acc = -sum_K Sigma(R,K) Y(K,C)
+                dmma_tile(cf, sA[s], sB[s], warp, lane);
                 __syncthreads();
             }
+            frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);          // acc = -sum_K Sigma(R,K) Y(K,C)
             // Sigma(R, C) = acc: publish both orientations
             regs_to_tile(acc, a.sig_lower + g.tile(C, d), tm, tn);
             regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
@@ -853,7 +920,7 @@ static int persistent_grid(Kernel kernel, size_t smem, int n_tasks, int* grid) {
     return kOk;
 }
 
-constexpr size_t kTdSmem = 4 * (size_t)TILE_BYTES;           // two stages of (A, B) tiles
+constexpr size_t kTdSmem = 4 * (size_t)PTILE * sizeof(double);     // two stages of (A, B) operand tiles, padded columns
 
 }  // namespace asvgp
 
