@@ -1,10 +1,17 @@
 // Standalone timing of potrf_regs (the in-register 64 x 64 Cholesky + inverse of the tile-DAG factorisation).
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -o potrf_bench potrf_bench.cu
+//   (-DFRAG times the tensor-core experiment of potrf_frag_experiment.cuh instead)
 #include "../../asvgp_b200/csrc/runtime.cu"
 #include "../../asvgp_b200/csrc/tiledag_2d.cu"
+#ifdef FRAG
+#include "potrf_frag_experiment.cuh"
+#endif
 
 __global__ void __launch_bounds__(256, 1) bench(const double* A, double* Lout, double* Vout, long long* cyc, int reps) {
     __shared__ __align__(16) double scratch[32 + 8 * 64 + 16 * 64];
+#ifdef FRAG
+    __shared__ __align__(16) double tile_scratch[64 * 64];
+#endif
     __shared__ int s_bad;
     const int tid = threadIdx.x, tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     double acc[4][4], V[4][4];
@@ -14,7 +21,11 @@ __global__ void __launch_bounds__(256, 1) bench(const double* A, double* Lout, d
         if (tid == 0) s_bad = -1;
         __syncthreads();
         const long long t0 = clock64();
+#ifdef FRAG
+        asvgp::potrf_frag(acc, V, tm, tn, scratch, tile_scratch, &s_bad);
+#else
         asvgp::potrf_regs(acc, V, tm, tn, scratch, scratch + 32, scratch + 32 + 256, &s_bad, nullptr);
+#endif
         __syncthreads();
         const long long t1 = clock64();
         if (t1 - t0 < best) best = t1 - t0;
