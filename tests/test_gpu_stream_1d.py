@@ -256,3 +256,26 @@ def test_predict_matches_reference(cuda, golden, k):
     mean, v = ops.predict_1d(g[key + "_xs"], basis, alpha, S, var)
     np.testing.assert_allclose(mean.cpu().numpy(), g[key + "_mean"].ravel(), atol=1e-9, rtol=0)
     np.testing.assert_allclose(v.cpu().numpy(), g[key + "_var"].ravel(), atol=1e-9, rtol=0)
+
+
+def test_accum_binned_large_matches_streaming(cuda):
+    """2e7 shuffled points on the C3 mesh (M = 1e4: 40 intervals per bucket, ~4900 units): the partition path against the
+    streaming kernel on the same device data, and the size-independent checks of the sorted test (count, partition of unity)."""
+    import torch
+    from asvgp_b200 import ops
+
+    m, n = 10_000, 20_000_000
+    basis = _basis(3, -1, m + 1, m)
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    x = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) * m
+    y = torch.sin(x / 37.0) + 0.25
+    a_bin = ops.accum_1d(x, y, basis, binned=True)
+    a_str = ops.accum_1d(x, y, basis)
+    scale = float(a_str[: 4 * m].abs().max())
+    assert float((a_bin - a_str).abs().max()) <= 1e-11 * max(scale, float(a_str.abs().max()))
+    G, b, scal = ops.split_accum_1d(a_bin, basis)
+    assert scal[1].item() == n
+    # partition of unity: sum over the band of G (off-diagonals twice) = number of points; sum of b = sum of y
+    total = float(G[0].sum() + 2 * G[1:].sum())
+    assert abs(total - n) <= 1e-10 * n
+    assert abs(float(b.sum()) - float(y.sum())) <= 1e-10 * float(y.abs().sum())
