@@ -237,6 +237,15 @@ __device__ __forceinline__ void regs_to_tile_t(const double (&acc)[4][4], double
     }
 }
 
+template <int LD>
+__device__ __forceinline__ void regs_to_tile_t_ld(const double (&acc)[4][4], double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<double2*>(t + (tm + i) * LD + tn) = make_double2(acc[i][0], acc[i][1]);
+        *reinterpret_cast<double2*>(t + (tm + i) * LD + tn + 2) = make_double2(acc[i][2], acc[i][3]);
+    }
+}
+
 // out[r] = sum over the 16 column groups of part[q][r]; part is [16][64] in shared memory (deterministic reduction)
 __device__ __forceinline__ double reduce16(const double* part, int r) {
     double s = 0.0;
@@ -753,26 +762,33 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
             __threadfence();
             // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
-            if (tid == 0) {
-                mbar_expect_tx(&full[0], TILE_BYTES);
-                tma_load_tile_(sB[0], a.tiles + g.tile(C, d), &full[0]);
+            if (warp == 0) {
+                if (lane == 0) mbar_expect_tx(&full[0], TILE_BYTES);
+                __syncwarp();
+                tma_load_tile_padded(sB[0], a.tiles + g.tile(C, d), &full[0], lane);
             }
-            regs_to_tile_t(acc, sA[0], tm, tn);      // T[m][a] at [m*64 + a]  ==  A'(a, k=m) at [k*64 + a]
+            regs_to_tile_t_ld<LDT>(acc, sA[0], tm, tn);      // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
             __syncthreads();
             if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1);
             mbar_wait(&full[0], ph.get(0));
             ph.flip(0);
-            double D[4][4] = {};
-            tile_mma<NB, NB, false>(D, sA[0], sB[0], tm, tn);       // D[a][b] = sum_m T[m][a] Y[m][b]
-            double* Sd = a.sig_lower + g.tile(C, 0);
+            {
+                // D[a][b] = sum_m T[m][a] Y[m][b] on the tensor cores (this product is on the chain of diagonal tiles); the
+                // fragments go straight to the diagonal tile as REDs
+                double D[8][2] = {};
+                dmma_tile(D, sA[0], sB[0], warp, lane);
+                double* Sd = a.sig_lower + g.tile(C, 0);
+                const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i) atomicAdd(Sd + (tn + j) * NB + tm + i, -D[i][j]);
+                for (int cb = 0; cb < 8; ++cb) {
+                    atomicAdd(Sd + (cb * 8 + col) * NB + row, -D[cb][0]);
+                    atomicAdd(Sd + (cb * 8 + col + 1) * NB + row, -D[cb][1]);
+                }
+            }
             __threadfence();
             __syncthreads();
             if (tid == 0) red_release_add(cnt + C, 1);
-            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[0][m*64 + b]
+            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[0][m*LDT + b]
             if (tid == 0) wait_flag(xflag + R, 1, abort_flag);
             __syncthreads();
             if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);
@@ -780,7 +796,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             if (tid < NB) {
                 double s = 0.0;
 #pragma unroll 8
-                for (int m = 0; m < NB; ++m) s = fma(sB[0][m * NB + tid], s_vec[m], s);
+                for (int m = 0; m < NB; ++m) s = fma(sB[0][m * LDT + tid], s_vec[m], s);
                 atomicAdd(a.xacc + (int64_t)C * NB + tid, -s);
             }
             __threadfence();
