@@ -750,33 +750,38 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             if (warp == 0) issue(Kmax, 0);
             for (int q = 0; q < nK; ++q) {
                 const int s = q & 1;
-                if (q + 1 < nK && warp == 0) issue(Kmax - q - 1, s ^ 1);
+                if (warp == 0) {
+                    if (q + 1 < nK) {
+                        issue(Kmax - q - 1, s ^ 1);
+                    } else {
+                        // last product: the idle stage already fetches this tile's own Y^T for the diagonal contribution below
+                        if (lane == 0) mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
+                        __syncwarp();
+                        tma_load_tile_padded(sB[s ^ 1], a.tiles + g.tile(C, d), &full[s ^ 1], lane);
+                    }
+                }
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
                 dmma_tile(cf, sA[s], sB[s], warp, lane);
                 __syncthreads();
             }
-            frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);          // acc = -sum_K Sigma(R,K) Y(K,C)
+            const int so = nK & 1;                                          // the stage holding the own tile
+            frags_subtract(acc, cf, sA[so ^ 1], warp, lane, tm, tn);       // acc = -sum_K Sigma(R,K) Y(K,C)
             // Sigma(R, C) = acc: publish both orientations
             regs_to_tile(acc, a.sig_lower + g.tile(C, d), tm, tn);
             regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
             __threadfence();
             // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
-            if (warp == 0) {
-                if (lane == 0) mbar_expect_tx(&full[0], TILE_BYTES);
-                __syncwarp();
-                tma_load_tile_padded(sB[0], a.tiles + g.tile(C, d), &full[0], lane);
-            }
-            regs_to_tile_t_ld<LDT>(acc, sA[0], tm, tn);      // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
+            regs_to_tile_t_ld<LDT>(acc, sA[so], tm, tn);     // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
             __syncthreads();
             if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1);
-            mbar_wait(&full[0], ph.get(0));
-            ph.flip(0);
+            mbar_wait(&full[so], ph.get(so));
+            ph.flip(so);
             {
                 // D[a][b] = sum_m T[m][a] Y[m][b] on the tensor cores (this product is on the chain of diagonal tiles); the
                 // fragments go straight to the diagonal tile as REDs
                 double D[8][2] = {};
-                dmma_tile(D, sA[0], sB[0], warp, lane);
+                dmma_tile(D, sA[so], sB[so], warp, lane);
                 double* Sd = a.sig_lower + g.tile(C, 0);
                 const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
 #pragma unroll
@@ -788,7 +793,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             __threadfence();
             __syncthreads();
             if (tid == 0) red_release_add(cnt + C, 1);
-            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[0][m*LDT + b]
+            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[so][m*LDT + b]
             if (tid == 0) wait_flag(xflag + R, 1, abort_flag);
             __syncthreads();
             if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);
@@ -796,7 +801,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             if (tid < NB) {
                 double s = 0.0;
 #pragma unroll 8
-                for (int m = 0; m < NB; ++m) s = fma(sB[0][m * LDT + tid], s_vec[m], s);
+                for (int m = 0; m < NB; ++m) s = fma(sB[so][m * LDT + tid], s_vec[m], s);
                 atomicAdd(a.xacc + (int64_t)C * NB + tid, -s);
             }
             __threadfence();
