@@ -43,7 +43,7 @@ constexpr int TILE = NB * NB;                   // doubles per tile
 constexpr int TILE_BYTES = TILE * 8;
 constexpr int kTdThreads = 256;                 // 16 x 16 threads, 4 x 4 outputs each
 constexpr long long kSpinLimit = 1LL << 24;     // polls before a wait gives up and raises the abort flag (~ seconds)
-constexpr int kColStat = 12;
+constexpr int kColStat = 20;              // per block column: log-det share, ||y||^2 share, 6 + 4 factorisation stamps, 4 selected-inverse stamps
 constexpr int kNoBadPivot = 0x7f7f7f7f;         // what cudaMemset(0x7f) leaves in the "first bad pivot" slot
 
 struct TileGeom {
@@ -697,6 +697,7 @@ struct SelArgs {
     double* sig_upper;      // Sigma(C, C+d) tiles (transposes), d >= 1
     double* x;              // in: y = L^-1 b, out: x = P^-1 b
     double* xacc;           // [nb*NB] zeroed: -sum_K Y(K,C)^T x_K
+    double* colstat;        // per-block-column record in the factor buffer (slots 12..15: %globaltimer stamps of the d = 1 tile)
     int* sready;            // [n_tiles] tile flags, [nb] column counters, abort
 };
 
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
 
         if (d != 0) {
             const int nK = Kmax - C;
+            double* sstat = a.colstat + (int64_t)C * kColStat;
             auto issue = [&](int K, int s) {         // A = Sigma(R, K), B = Y(K, C)^T
                 const double* src;
                 const int* flag;
@@ -737,13 +739,18 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 if (K == R) { src = a.sig_lower + g.tile(R, 0); flag = cnt + R; want = min(g.BW, g.nb - 1 - R); }   // Sigma(R,R): all shares in
                 else if (K < R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
                 else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
-                if (lane == 0) wait_flag(flag, want, abort_flag);
+                if (lane == 0) {
+                    if (d == 1 && K == R) sstat[16] = global_ns();          // starts waiting for Sigma(R,R)
+                    wait_flag(flag, want, abort_flag);
+                    if (d == 1 && K == R) sstat[17] = global_ns();          // ... complete
+                }
                 __syncwarp();
                 fence_proxy_async();
                 if (lane == 0) mbar_expect_tx(&full[s], 2 * TILE_BYTES);
                 __syncwarp();
                 tma_load_tile_padded(sA[s], src, &full[s], lane);
                 tma_load_tile_padded(sB[s], a.tiles + g.tile(C, K - C), &full[s], lane);
+                if (lane == 0 && d == 1 && K == R) sstat[18] = global_ns();  // copies issued
             };
             double acc[4][4] = {};
             double cf[8][2] = {};                    // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
@@ -762,11 +769,13 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 }
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
+                if (tid == 0 && d == 1 && q + 1 == nK) sstat[12] = global_ns();     // operands of the last product (Sigma(R,R)) landed
                 dmma_tile(cf, sA[s], sB[s], warp, lane);
                 __syncthreads();
             }
             const int so = nK & 1;                                          // the stage holding the own tile
             frags_subtract(acc, cf, sA[so ^ 1], warp, lane, tm, tn);       // acc = -sum_K Sigma(R,K) Y(K,C)
+            if (tid == 0 && d == 1) sstat[13] = global_ns();
             // Sigma(R, C) = acc: publish both orientations
             regs_to_tile(acc, a.sig_lower + g.tile(C, d), tm, tn);
             regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
@@ -774,7 +783,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
             regs_to_tile_t_ld<LDT>(acc, sA[so], tm, tn);     // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
             __syncthreads();
-            if (tid == 0) st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1);
+            if (tid == 0) { st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) sstat[14] = global_ns(); }
             mbar_wait(&full[so], ph.get(so));
             ph.flip(so);
             {
@@ -792,7 +801,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) red_release_add(cnt + C, 1);
+            if (tid == 0) { red_release_add(cnt + C, 1); if (d == 1) sstat[15] = global_ns(); }
             // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[so][m*LDT + b]
             if (tid == 0) wait_flag(xflag + R, 1, abort_flag);
             __syncthreads();
@@ -1013,7 +1022,7 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
     ASVGP_CUDA_OK(cudaFuncSetAttribute(td_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
     td_ypass_kernel<<<g.n_tiles(), kTdThreads, yp_smem, st>>>(g, band, band + fl.linv, sig_band + sl.sig_lower);
     ASVGP_CUDA_OK(cudaGetLastError());
-    SelArgs a{g, band, band + fl.linv, sig_band + sl.sig_lower, sig_band + sl.sig_upper, x_io, work + sl.xacc, flags};
+    SelArgs a{g, band, band + fl.linv, sig_band + sl.sig_lower, sig_band + sl.sig_upper, x_io, work + sl.xacc, band + fl.colstat, flags};
     int grid = 0;
     if (int rc = persistent_grid(td_selinv_kernel, kTdSmem, g.n_tiles(), &grid)) return rc;
     void* params[] = {&a};

@@ -25,7 +25,8 @@ for _ in range(3):
 torch.cuda.synchronize()
 off = _lib.load().asvgp_kron_colstat_offset(m, m, k)
 nb = -(-m * m // 64)
-st = ws.band[off: off + 12 * nb].view(nb, 12).cpu().numpy()
+NS = 20
+st = ws.band[off: off + NS * nb].view(nb, NS).cpu().numpy()
 t = st[:, 2:8]
 prof = st[:, 8:12]
 mid = slice(nb // 4, 3 * nb // 4)
@@ -36,3 +37,16 @@ print("  diag: begin->operands landed %.2f | potrf+inverse %.2f | publish %.2f" 
 print("  d=1 : diag published -> inverse seen %.2f | trsm tile done %.2f" % (us(t[:, 4] - t[:, 3]), us(t[:, 5] - t[:, 4])))
 print("  next diag potrf start - d=1 tile published: %.2f" % us(t[1:, 1] - t[:-1, 5]))
 print("  potrf (thread 0, SM cycles, median): 4x4 diag block %d | wait barrier 1 (sum of 16) %d | panel+barrier 2 %d | rank-4 updates %d" % tuple(np.median(prof[mid], axis=0)))
+
+# selected inverse: stamps of the first sub-diagonal tile (R = C + 1) of every block column (columns run downwards)
+ops.kron_selinv(bases, ws)
+torch.cuda.synchronize()
+st = ws.band[off: off + NS * nb].view(nb, NS).cpu().numpy()
+s = st[:-1, 12:16]                      # the last block column has no sub-diagonal tile
+w = st[:-1, 16:19]
+print("selected inverse, per block column (median, us): period %.2f" % us(-np.diff(s[:, 3])))
+print("  d=1 tile: Sigma(R,R) landed -> product + conversion done %.2f | published %.2f | own Y^T landed, contribution added, counted %.2f"
+      % (us(s[:, 1] - s[:, 0]), us(s[:, 2] - s[:, 1]), us(s[:, 3] - s[:, 2])))
+print("  contribution of tile (C+1, C) counted -> Sigma(C, C) seen landed by tile (C, C-1): %.2f" % us(s[:-1, 0] - s[1:, 3]))
+print("  tile (C, C-1): starts waiting for Sigma(C,C) %.2f before the last contribution is counted | sees it complete %.2f after | copies issued +%.2f | landed +%.2f"
+      % (us(s[1:, 3] - w[:-1, 0]), us(w[:-1, 1] - s[1:, 3]), us(w[:-1, 2] - w[:-1, 1]), us(s[:-1, 0] - w[:-1, 2])))
