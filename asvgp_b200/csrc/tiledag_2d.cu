@@ -116,6 +116,14 @@ constexpr int PTILE = NB * LDT;                 // doubles of a staged (padded) 
 __device__ __forceinline__ void tma_load_tile_padded(double* dst_smem, const double* src_gmem, uint64_t* bar, int lane) {
     for (int c = lane; c < NB; c += 32) tma_load_bulk(dst_smem + c * LDT, src_gmem + c * NB, (uint32_t)(NB * 8), bar);
 }
+// unpadded tile (as the TMA delivered it) -> padded copy, all threads of the CTA
+__device__ __forceinline__ void repack_padded(double* __restrict__ dst, const double* __restrict__ src, int tid) {
+#pragma unroll
+    for (int idx = tid; idx < TILE / 2; idx += kTdThreads) {
+        const int c = idx >> 5, r = (idx & 31) * 2;
+        *reinterpret_cast<double2*>(dst + c * LDT + r) = *reinterpret_cast<const double2*>(src + c * NB + r);
+    }
+}
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
@@ -196,7 +204,7 @@ __device__ __forceinline__ void tile_mma(double (&acc)[4][4], const double* __re
 // which would live in local memory)
 struct StageBufs {
     double* base;
-    __device__ __forceinline__ double* operator[](int s) const { return base + s * 2 * PTILE; }
+    __device__ __forceinline__ double* operator[](int s) const { return base + s * 2 * TILE; }
 };
 struct Phases {                // parity bits of the two mbarriers
     uint32_t bits = 0u;
@@ -468,7 +476,9 @@ __device__ __forceinline__ void potrf_regs(double (&acc)[4][4], double (&V)[4][4
 
 __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + PTILE};
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;      // padded copies of the operands of the current product
+    double* const pB = pA + PTILE;
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double s_vec[NB];
     const TileGeom g = a.g;
@@ -495,27 +505,26 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
         regs_from_tile(acc, my_tile, tm, tn);
         const int J0 = max(0, R - g.BW), nJ = C - J0;
 
-        auto issue = [&](int J, int s) {             // warp 0: lane 0 waits for the operand tiles, all lanes fetch their columns by TMA
-            if (lane == 0) {
-                wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (R - J), 1, abort_flag);
-                if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
-            }
-            __syncwarp();
+        auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
+            wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (R - J), 1, abort_flag);
+            if (d != 0) wait_flag(a.ready + (int64_t)J * (g.BW + 1) + (C - J), 1, abort_flag);
             fence_proxy_async();
-            if (lane == 0) mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
-            __syncwarp();
-            tma_load_tile_padded(sA[s], a.tiles + g.tile(J, R - J), &full[s], lane);
-            if (d != 0) tma_load_tile_padded(sB[s], a.tiles + g.tile(J, C - J), &full[s], lane);
+            mbar_expect_tx(&full[s], d != 0 ? 2 * TILE_BYTES : TILE_BYTES);
+            tma_load_tile_(sA[s], a.tiles + g.tile(J, R - J), &full[s]);
+            if (d != 0) tma_load_tile_(sB[s], a.tiles + g.tile(J, C - J), &full[s]);
         };
         if (nJ > 0) {
             double cf[8][2] = {};                    // sum_J L(R,J) L(C,J)^T as tensor-core fragments
-            if (warp == 0) issue(J0, 0);
+            if (tid == 0) issue(J0, 0);
             for (int q = 0; q < nJ; ++q) {
                 const int s = q & 1;
-                if (q + 1 < nJ && warp == 0) issue(J0 + q + 1, s ^ 1);
+                if (q + 1 < nJ && tid == 0) issue(J0 + q + 1, s ^ 1);
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
-                dmma_tile(cf, sA[s], d != 0 ? sB[s] : sA[s], warp, lane);
+                repack_padded(pA, sA[s], tid);
+                if (d != 0) repack_padded(pB, sB[s], tid);
+                __syncthreads();
+                dmma_tile(cf, pA, d != 0 ? pB : pA, warp, lane);
                 __syncthreads();
             }
             frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);
@@ -703,7 +712,9 @@ struct SelArgs {
 
 __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + PTILE};
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;      // padded copies of the operands of the current product
+    double* const pB = pA + PTILE;
     __shared__ __align__(8) uint64_t full[2];
     __shared__ double s_vec[NB];
     const TileGeom g = a.g;
@@ -739,38 +750,36 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 if (K == R) { src = a.sig_lower + g.tile(R, 0); flag = cnt + R; want = min(g.BW, g.nb - 1 - R); }   // Sigma(R,R): all shares in
                 else if (K < R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
                 else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
-                if (lane == 0) {
-                    if (d == 1 && K == R) sstat[16] = global_ns();          // starts waiting for Sigma(R,R)
-                    wait_flag(flag, want, abort_flag);
-                    if (d == 1 && K == R) sstat[17] = global_ns();          // ... complete
-                }
-                __syncwarp();
+                if (d == 1 && K == R) sstat[16] = global_ns();              // starts waiting for Sigma(R,R)
+                wait_flag(flag, want, abort_flag);
+                if (d == 1 && K == R) sstat[17] = global_ns();              // ... complete
                 fence_proxy_async();
-                if (lane == 0) mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-                __syncwarp();
-                tma_load_tile_padded(sA[s], src, &full[s], lane);
-                tma_load_tile_padded(sB[s], a.tiles + g.tile(C, K - C), &full[s], lane);
-                if (lane == 0 && d == 1 && K == R) sstat[18] = global_ns();  // copies issued
+                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+                tma_load_tile_(sA[s], src, &full[s]);
+                tma_load_tile_(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
+                if (d == 1 && K == R) sstat[18] = global_ns();              // copies issued
             };
             double acc[4][4] = {};
             double cf[8][2] = {};                    // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
-            if (warp == 0) issue(Kmax, 0);
+            if (tid == 0) issue(Kmax, 0);
             for (int q = 0; q < nK; ++q) {
                 const int s = q & 1;
-                if (warp == 0) {
+                if (tid == 0) {
                     if (q + 1 < nK) {
                         issue(Kmax - q - 1, s ^ 1);
                     } else {
                         // last product: the idle stage already fetches this tile's own Y^T for the diagonal contribution below
-                        if (lane == 0) mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
-                        __syncwarp();
-                        tma_load_tile_padded(sB[s ^ 1], a.tiles + g.tile(C, d), &full[s ^ 1], lane);
+                        mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
+                        tma_load_tile_(sB[s ^ 1], a.tiles + g.tile(C, d), &full[s ^ 1]);
                     }
                 }
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
                 if (tid == 0 && d == 1 && q + 1 == nK) sstat[12] = global_ns();     // operands of the last product (Sigma(R,R)) landed
-                dmma_tile(cf, sA[s], sB[s], warp, lane);
+                repack_padded(pA, sA[s], tid);
+                repack_padded(pB, sB[s], tid);
+                __syncthreads();
+                dmma_tile(cf, pA, pB, warp, lane);
                 __syncthreads();
             }
             const int so = nK & 1;                                          // the stage holding the own tile
@@ -781,16 +790,18 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
             __threadfence();
             // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
-            regs_to_tile_t_ld<LDT>(acc, sA[so], tm, tn);     // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
+            regs_to_tile_t_ld<LDT>(acc, pA, tm, tn);         // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
             __syncthreads();
             if (tid == 0) { st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) sstat[14] = global_ns(); }
             mbar_wait(&full[so], ph.get(so));
             ph.flip(so);
+            repack_padded(pB, sB[so], tid);
+            __syncthreads();
             {
                 // D[a][b] = sum_m T[m][a] Y[m][b] on the tensor cores (this product is on the chain of diagonal tiles); the
                 // fragments go straight to the diagonal tile as REDs
                 double D[8][2] = {};
-                dmma_tile(D, sA[so], sB[so], warp, lane);
+                dmma_tile(D, pA, pB, warp, lane);
                 double* Sd = a.sig_lower + g.tile(C, 0);
                 const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
 #pragma unroll
@@ -802,7 +813,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             __threadfence();
             __syncthreads();
             if (tid == 0) { red_release_add(cnt + C, 1); if (d == 1) sstat[15] = global_ns(); }
-            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[so][m*LDT + b]
+            // off the critical path: xacc_C[b] -= sum_m Y[m][b] x_R[m] as soon as x_R exists;  Y[m][b] at sB[so][m*64 + b]
             if (tid == 0) wait_flag(xflag + R, 1, abort_flag);
             __syncthreads();
             if (tid < NB) s_vec[tid] = __ldcg(a.x + (int64_t)R * NB + tid);
@@ -810,7 +821,7 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             if (tid < NB) {
                 double s = 0.0;
 #pragma unroll 8
-                for (int m = 0; m < NB; ++m) s = fma(sB[so][m * LDT + tid], s_vec[m], s);
+                for (int m = 0; m < NB; ++m) s = fma(sB[so][m * NB + tid], s_vec[m], s);
                 atomicAdd(a.xacc + (int64_t)C * NB + tid, -s);
             }
             __threadfence();
@@ -950,7 +961,7 @@ static int persistent_grid(Kernel kernel, size_t smem, int n_tasks, int* grid) {
     return kOk;
 }
 
-constexpr size_t kTdSmem = 4 * (size_t)PTILE * sizeof(double);     // two stages of (A, B) operand tiles, padded columns
+constexpr size_t kTdSmem = (4 * (size_t)TILE + 2 * (size_t)PTILE) * sizeof(double);   // two landing stages of (A, B) + one padded pair
 
 }  // namespace asvgp
 
