@@ -750,14 +750,15 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 if (K == R) { src = a.sig_lower + g.tile(R, 0); flag = cnt + R; want = min(g.BW, g.nb - 1 - R); }   // Sigma(R,R): all shares in
                 else if (K < R) { src = a.sig_lower + g.tile(K, R - K); flag = a.sready + (int64_t)K * (g.BW + 1) + (R - K); }
                 else { src = a.sig_upper + g.tile(R, K - R); flag = a.sready + (int64_t)R * (g.BW + 1) + (K - R); }
+                // the Y^T operand is there since the pre-pass: it is requested before the wait, only Sigma(R,K) after it
+                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+                tma_load_tile_(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
                 if (d == 1 && K == R) sstat[16] = global_ns();              // starts waiting for Sigma(R,R)
                 wait_flag(flag, want, abort_flag);
                 if (d == 1 && K == R) sstat[17] = global_ns();              // ... complete
                 fence_proxy_async();
-                mbar_expect_tx(&full[s], 2 * TILE_BYTES);
                 tma_load_tile_(sA[s], src, &full[s]);
-                tma_load_tile_(sB[s], a.tiles + g.tile(C, K - C), &full[s]);
-                if (d == 1 && K == R) sstat[18] = global_ns();              // copies issued
+                if (d == 1 && K == R) sstat[18] = global_ns();              // copy issued
             };
             double acc[4][4] = {};
             double cf[8][2] = {};                    // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
