@@ -611,14 +611,23 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_factor_kernel(FactorArgs a) 
                 mbar_expect_tx(&full[0], TILE_BYTES);
                 tma_load_tile_(sB[0], a.linv + (int64_t)C * TILE, &full[0]);
             }
-            regs_to_tile(acc, sA[0], tm, tn);        // A(m, k) at [k*64 + m]
+            regs_to_tile_ld<LDT>(acc, pA, tm, tn);   // A(m, k) at [k*LDT + m]
             __syncthreads();
             mbar_wait(&full[0], ph.get(0));
             ph.flip(0);
+            repack_padded(pB, sB[0], tid);
+            __syncthreads();
             double L[4][4] = {};
-            // (stays on the DFMA loop: on the tensor cores the product itself is 2.5 us shorter, but the padded staging and
-            // the fragment -> register conversion give it back on this latency-critical tile: 7.7 vs 7.4 us measured)
-            tile_mma<NB, NB, false>(L, sA[0], sB[0], tm, tn);      // L[m][n] = sum_k A[m][k] Linv[n][k]
+            {
+                // L[m][n] = sum_k A[m][k] Linv[n][k] on the tensor cores (this product is on the chain of diagonal tiles)
+                double cf[8][2] = {};
+                dmma_tile(cf, pA, pB, warp, lane);
+                frags_subtract(L, cf, sA[1], warp, lane, tm, tn);  // (stage 1 is idle here)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) L[i][j] = -L[i][j];
+            }
             regs_to_tile(L, my_tile, tm, tn);
             __threadfence();
             __syncthreads();
