@@ -797,10 +797,19 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
             if (tid == 0 && d == 1) sstat[13] = global_ns();
             // Sigma(R, C) = acc: publish both orientations
             regs_to_tile(acc, a.sig_lower + g.tile(C, d), tm, tn);
-            regs_to_tile_t(acc, a.sig_upper + g.tile(C, d), tm, tn);
-            __threadfence();
-            // own Y^T tile + x_R for the contributions to the diagonal tile and to x_C
+            // the transpose goes through shared memory (it is needed there anyway, as an operand of the diagonal contribution
+            // below) and leaves as whole 512-byte columns; 16-byte stores straight from the registers made the publish 3.8 us
             regs_to_tile_t_ld<LDT>(acc, pA, tm, tn);         // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
+            __syncthreads();
+            {
+                double* up = a.sig_upper + g.tile(C, d);
+#pragma unroll
+                for (int idx = tid; idx < TILE / 2; idx += kTdThreads) {
+                    const int c = idx >> 5, r = (idx & 31) * 2;
+                    *reinterpret_cast<double2*>(up + c * NB + r) = *reinterpret_cast<const double2*>(pA + c * LDT + r);
+                }
+            }
+            __threadfence();
             __syncthreads();
             if (tid == 0) { st_release(a.sready + (int64_t)C * (g.BW + 1) + d, 1); if (d == 1) sstat[14] = global_ns(); }
             mbar_wait(&full[so], ph.get(so));

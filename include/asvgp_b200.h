@@ -160,8 +160,10 @@ ASVGP_API int64_t asvgp_kron_band_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_sig_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_work_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order);
-/* Diagnostics: offset (doubles) inside `band` of the per-block-column record { 2 sum log L_cc, ||y_C||^2, six
- * %globaltimer stamps of the critical path }, 8 doubles per block column, ceil(m1*m2/64) block columns. */
+/* Diagnostics: offset (doubles) inside `band` of the per-block-column record, 20 doubles per block column,
+ * ceil(m1*m2/64) block columns: [0] 2 sum log L_cc, [1] ||y_C||^2, [2..7] %globaltimer stamps of the factorisation's
+ * critical path, [8..11] SM-cycle split of the diagonal tile's POTRF, [12..18] stamps of the first sub-diagonal tile in
+ * asvgp_kron_selinv (tools/kron_chain_times.py prints both chains). */
 ASVGP_API int64_t asvgp_kron_colstat_offset(int m1, int m2, int order);
 ASVGP_API int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream);
