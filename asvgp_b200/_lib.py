@@ -33,6 +33,9 @@ SIGNATURES = {
     "asvgp_kron_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "asvgp_kron_terms": [_vp] * 11 + [_c_int, _c_int, _c_int, _vp, _vp],
     "asvgp_predict_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp],
+    "asvgp_khatri_rao_csc": [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp],
+    "asvgp_kron_dense": [_vp, _c_int, _vp, _c_int, _vp, _vp],
+    "asvgp_cholesky_dense": [_vp, _c_int, _vp, _vp, _vp],
 }
 # functions whose return value is not a status code
 VALUE_FUNCTIONS = {

@@ -745,6 +745,7 @@ static int launch_accum_1d_units(const PartWork& w, int64_t n, const double* mes
     const int64_t max_units = n / kUnitPoints1 + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count() * std::max(per_sm, 1)));
     accum_1d_units_kernel<K, THREADS><<<blocks, THREADS, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
+    ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
 
@@ -770,9 +771,9 @@ extern "C" int asvgp_accum_1d_binned(const double* x, const double* y, int64_t n
     src.x = x; src.y = y; src.knots = mesh; src.n_knots = n_knots; src.ipb = ipb;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + kPartTile - 1) / kPartTile, (int64_t)sm_count() * 2));
     ASVGP_CUDA_OK((launch_partition<Points1D, 2>(src, n, w, kUnitPoints1, blocks, st)));
-    ASVGP_DISPATCH_ORDER(order, (launch_accum_1d_units<K>(w, n, mesh, n_knots, ipb, M, G, b, scal, st)));
-    ASVGP_CUDA_OK(cudaGetLastError());
-    return kOk;
+    int rc = kOk;
+    ASVGP_DISPATCH_ORDER(order, (rc = launch_accum_1d_units<K>(w, n, mesh, n_knots, ipb, M, G, b, scal, st)));
+    return rc;
 }
 
 extern "C" int asvgp_predict_1d(const double* xnew, int64_t n, const double* mesh, int n_knots, int order,

@@ -124,6 +124,20 @@ __device__ __forceinline__ void repack_padded(double* __restrict__ dst, const do
         *reinterpret_cast<double2*>(dst + c * LDT + r) = *reinterpret_cast<const double2*>(src + c * NB + r);
     }
 }
+// Same for a DIAGONAL tile of the selected inverse, which is symmetric only up to rounding (it is a sum of REDs of
+// termwise unsymmetric products): the copy handed to the tensor cores is 0.5 (S + S^T).  The Takahashi recursion
+// amplifies an unsymmetric rounding component by about 2x per block column when Kuu dominates P (l / delta ~ 18 at
+// 200 x 200: 1e-16 -> 1e+60 over 625 block columns), so symmetry is enforced wherever such a tile is consumed.
+// Thread (c = tid % 64, g = tid / 64) walks rows (c + 16 g + j) % 64: both reads and the write are bank-conflict free
+// (banks r % 16, c % 16 and (5 c + j) % 16 over the 16 lanes of a half-warp).
+__device__ __forceinline__ void repack_padded_sym(double* __restrict__ dst, const double* __restrict__ src, int tid) {
+    const int c = tid & (NB - 1), g = tid >> 6;
+#pragma unroll
+    for (int j = 0; j < NB / (kTdThreads / NB); ++j) {
+        const int r = (c + g * (NB / (kTdThreads / NB)) + j) & (NB - 1);
+        dst[c * LDT + r] = 0.5 * (src[c * NB + r] + src[r * NB + c]);
+    }
+}
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
@@ -786,7 +800,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) td_selinv_kernel(SelArgs a) {
                 mbar_wait(&full[s], ph.get(s));
                 ph.flip(s);
                 if (tid == 0 && d == 1 && q + 1 == nK) sstat[12] = global_ns();     // operands of the last product (Sigma(R,R)) landed
-                repack_padded(pA, sA[s], tid);
+                if (Kmax - q == R) repack_padded_sym(pA, sA[s], tid);      // Sigma(R,R): enforce symmetry (see repack_padded_sym)
+                else repack_padded(pA, sA[s], tid);
                 repack_padded(pB, sB[s], tid);
                 __syncthreads();
                 dmma_tile(cf, pA, pB, warp, lane);
@@ -896,6 +911,7 @@ __global__ void __launch_bounds__(256) td_extract_stencil_kernel(TileGeom g, con
             const int64_t i = j + (int64_t)d1 * g.m2 + d2;
             const int Cb = (int)(j / NB), c = (int)(j % NB), Rb = (int)(i / NB), r = (int)(i % NB);
             v = __ldcg(sig_lower + g.tile(Cb, Rb - Cb) + c * NB + r);
+            if (Rb == Cb) v = 0.5 * (v + __ldcg(sig_lower + g.tile(Cb, 0) + r * NB + c));   // diagonal tiles: see repack_padded_sym
         }
         out[t] = aborted ? nan("") : v;
     }
@@ -1038,7 +1054,8 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
 
 // From the factor (overwritten: its off-diagonal tiles become Y^T): sigma_stencil[(order+1)(2 order+1) x M] = entries of
 // P^-1 on the stencil, x_io: in y = L^-1 b, out x = P^-1 b.  sig_band: asvgp_kron_sig_doubles doubles of scratch;
-// work: asvgp_kron_work_doubles doubles.  info[1] (may be NULL): 0 ok, -1 if the kernel gave up waiting.
+// work: asvgp_kron_work_doubles doubles.  If the persistent kernel gives up waiting (abort flag), sigma_stencil is
+// filled with NaN.
 extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
                                  double* sigma_stencil, double* work, void* stream) {
     ASVGP_REQUIRE(m1 > 0 && m2 > 0 && order >= 1 && order <= kMaxOrder, "kron_selinv: m=%d,%d order=%d", m1, m2, order);

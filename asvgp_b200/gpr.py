@@ -45,6 +45,24 @@ class _ModelBase:
         return (-0.5 * np.log(2 * np.pi * s2) - 0.5 * (y - mean) ** 2 / s2).sum(-1)
 
 
+def _grad_dict(pairs):
+    """{id(param): derivative}, summed when the same parameter object appears more than once (e.g. one kernel object
+    shared by both dimensions of a Kronecker model)."""
+    out = {}
+    for p, v in pairs:
+        out[id(p)] = out.get(id(p), 0.0) + v
+    return out
+
+
+def _unique(params):
+    seen, out = set(), []
+    for p in params:
+        if id(p) not in seen:
+            seen.add(id(p))
+            out.append(p)
+    return out
+
+
 def _to_numpy(a):
     return a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else a
 
@@ -169,8 +187,8 @@ class GPR_1d(_ModelBase):
         out = self._combine_outputs()
         if out[8] != 0:
             raise np.linalg.LinAlgError("banded Cholesky failed: non-positive pivot %d" % int(out[8]))
-        grads = {id(self.kernel.variance): out[1], id(self.kernel.lengthscales): out[2],
-                 id(self.likelihood.variance): out[3]}
+        grads = _grad_dict([(self.kernel.variance, out[1]), (self.kernel.lengthscales, out[2]),
+                            (self.likelihood.variance, out[3])])
         self.last_terms = dict(log_det_Kuu=out[4], log_det_P=out[5], quad=out[6], trace=out[7])
         return float(out[0]), grads
 
@@ -320,7 +338,7 @@ class GPR_kron(_ModelBase):
         out = []
         for k in self.kernels:
             out += [k.variance, k.lengthscales]
-        return out + [self.likelihood.variance]
+        return _unique(out + [self.likelihood.variance])
 
     # -- objective ---------------------------------------------------------------------------------------------
     def _factors(self, want_grad):
@@ -370,9 +388,9 @@ class GPR_kron(_ModelBase):
         d_v2 = common / v[1] - 0.5 * N * v[0] / s2
         d_s2 = (-0.5 * N / s2 + 0.5 * trPG / s2**2 + 0.5 * yy / s2**2 + 0.5 * xGx / s2**4 - Q / s2**3
                 + 0.5 * N * v12 / s2**2 - 0.5 * tr / s2**2)
-        grads = {id(self.kernels[0].variance): d_v1, id(self.kernels[0].lengthscales): d_l1,
-                 id(self.kernels[1].variance): d_v2, id(self.kernels[1].lengthscales): d_l2,
-                 id(self.likelihood.variance): d_s2}
+        grads = _grad_dict([(self.kernels[0].variance, d_v1), (self.kernels[0].lengthscales, d_l1),
+                            (self.kernels[1].variance, d_v2), (self.kernels[1].lengthscales, d_l2),
+                            (self.likelihood.variance, d_s2)])
         return float(elbo), grads
 
     def elbo_and_grad(self):

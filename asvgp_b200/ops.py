@@ -236,16 +236,16 @@ def accum_1d_host(x, y, basis, acc=None, chunk=1 << 23):
         lo, hi = c * chunk, min((c + 1) * chunk, n)
         s = c & 1
         dbuf = st["dev"][s]
-        if c >= 2:
-            cs.wait_event(st["drained"][s])            # kernel that read dbuf two chunks ago has finished
+        # the kernel that last read dbuf (two chunks ago, or the previous CALL: the staging buffers are cached and
+        # shared between calls) has finished; waiting on a never-recorded event is a no-op
+        cs.wait_event(st["drained"][s])
         with torch.cuda.stream(cs):
             if pinned:
                 dbuf[0, : hi - lo].copy_(xt[lo:hi], non_blocking=True)
                 dbuf[1, : hi - lo].copy_(yt[lo:hi], non_blocking=True)
             else:
                 hbuf = st["host"][s]
-                if c >= 2:
-                    st["staged"][s].synchronize()      # previous H2D out of this pinned buffer has completed
+                st["staged"][s].synchronize()          # previous H2D out of this pinned buffer (also a previous call's) is done
                 hbuf[0, : hi - lo].copy_(xt[lo:hi])
                 hbuf[1, : hi - lo].copy_(yt[lo:hi])
                 dbuf[:, : hi - lo].copy_(hbuf[:, : hi - lo], non_blocking=True)
@@ -383,16 +383,14 @@ def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22):
         cnt, s = hi - lo, c & 1
         dbuf = st["dev"][s]
         dX, dy = dbuf[: 2 * cnt].view(cnt, 2), dbuf[2 * chunk: 2 * chunk + cnt]
-        if c >= 2:
-            cs.wait_event(st["drained"][s])
+        cs.wait_event(st["drained"][s])                # also covers the previous call (cached, shared staging buffers)
         with torch.cuda.stream(cs):
             if pinned:
                 dX.copy_(Xt[lo:hi], non_blocking=True)
                 dy.copy_(yt[lo:hi], non_blocking=True)
             else:
                 hbuf = st["host"][s]
-                if c >= 2:
-                    st["staged"][s].synchronize()
+                st["staged"][s].synchronize()
                 hbuf[: 2 * cnt].view(cnt, 2).copy_(Xt[lo:hi])
                 hbuf[2 * chunk: 2 * chunk + cnt].copy_(yt[lo:hi])
                 dbuf[: 2 * cnt].copy_(hbuf[: 2 * cnt], non_blocking=True)

@@ -43,6 +43,38 @@ def band_to_dense(K_lower):
     return A
 
 
+def bands_to_kron_cholesky(K_bands, mat_bandwidth=None):
+    """(K1 (x) K2 dense, L1 (x) L2 dense) from two lower bands (reference utils.py:45-51; `mat_bandwidth` is accepted
+    for signature parity — the reference uses it only to unpack the bands).  Dense (m1 m2)^2 outputs: small models only,
+    as in the reference; `GPR_kron` itself never forms them.  GPU: asvgp_cholesky_dense + asvgp_kron_dense."""
+    import torch
+
+    from . import _lib, ops
+
+    dense = [ops.to_device(band_to_dense(np.asarray(_np(k)))) for k in K_bands]
+    if len(dense) != 2:
+        raise NotImplementedError("d = 2 only (as reference utils.py:57)")
+    facs = []
+    for A in dense:
+        L = torch.empty_like(A)
+        info = torch.zeros(1, dtype=torch.float64, device=A.device)
+        _lib.call("asvgp_cholesky_dense", ops._p(A), A.shape[0], ops._p(L), ops._p(info), ops._stream())
+        if info.item() != 0:
+            raise np.linalg.LinAlgError("Cholesky failed: non-positive pivot %d" % int(info.item()))
+        facs.append(L)
+    m1, m2 = dense[0].shape[0], dense[1].shape[0]
+    out = []
+    for a, b in ((dense[0], dense[1]), (facs[0], facs[1])):
+        o = torch.empty((m1 * m2, m1 * m2), dtype=torch.float64, device=a.device)
+        _lib.call("asvgp_kron_dense", ops._p(a), m1, ops._p(b), m2, ops._p(o), ops._stream())
+        out.append(o.cpu().numpy())
+    return out[0], out[1]
+
+
+def _np(a):
+    return a.detach().cpu().numpy() if hasattr(a, "detach") else a
+
+
 def bands_to_sparse(K_bands, mat_bandwidth):
     """Sparse Kronecker product of two banded factors (reference utils.py:53-57, d = 2 only)."""
     Ks = [sparse.csc_matrix(band_to_dense(k)) for k in K_bands]

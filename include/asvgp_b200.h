@@ -195,6 +195,21 @@ ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh
                                const double* S2, double prior_var, double* mean, double* var, double* work,
                                void* stream);
 
+/* ---- name-for-name counterparts of the reference's Kronecker helpers (not used by the models) -------------------------------
+ * asvgp_khatri_rao_csc replaces kronecker.make_kvs_two_sparse (kronecker.py:7-27; make_kvs_sparse folds it over a list,
+ * :29-33): row-wise Khatri-Rao product of two sparse feature matrices in CSC form with int64 indices, column n of the
+ * result holding A[ia, n] * B[ib, n] at row ia * m_b + ib.  out_indptr[n_cols + 1] is the caller's prefix sum of
+ * nnzA(n) * nnzB(n); out_indices / out_data have out_indptr[n_cols] entries.
+ * asvgp_kron_dense / asvgp_cholesky_dense replace the dense Kronecker products and the per-dimension tf.linalg.cholesky
+ * of utils.bands_to_kron_cholesky (utils.py:45-51): row-major dense in, row-major dense out ((m_a m_b)^2 doubles);
+ * info[1] (device) = 0 or the 1-based first non-positive pivot. */
+ASVGP_API int asvgp_khatri_rao_csc(const int64_t* indptr_a, const int64_t* indices_a, const double* data_a,
+                                   const int64_t* indptr_b, const int64_t* indices_b, const double* data_b,
+                                   int64_t n_cols, int64_t m_b, const int64_t* out_indptr, int64_t* out_indices,
+                                   double* out_data, void* stream);
+ASVGP_API int asvgp_kron_dense(const double* A, int m_a, const double* B, int m_b, double* out, void* stream);
+ASVGP_API int asvgp_cholesky_dense(const double* A, int m, double* L, double* info, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
