@@ -476,3 +476,129 @@ def predict_kron_banded(meshes, deltas, k, ms, Kuu_bands, G_sparse, Kuf_y, varia
     q2 = np.sum(K2 * sla.cho_solve_banded((cK[1], True), K2), axis=0)
     var = np.prod(variances) + np.sum(Kus * sla.cho_solve_banded((cP, True), Kus), axis=0) - q1 * q2
     return mean, var.reshape(-1, 1)
+
+
+def predict_kron_banded_cells(meshes, deltas, k, ms, Kuu_bands, G_sparse, Kuf_y, variances, sigma2, Xnew):
+    """predict_kron_banded for MANY test points that share few knot cells, at sizes where a dense M x n* right-hand side
+    is too large (M = 200 x 200): Kus[:, n] has its (k+1)^2 non-zeros at the rows (idx1 + r, idx2 + s) of the point's
+    cell (kronecker.py:24-33), so Kus^T P^-1 Kus (gpr.py:353-356) only reads the entries of P^-1 between those rows —
+    (k+1)^2 LAPACK band solves with unit vectors per distinct cell.  Same numbers as predict_kron_banded (checked in
+    tests/test_oracle_golden.py)."""
+    m1, m2 = ms
+    Xnew = np.asarray(Xnew, dtype=np.float64)
+    Pb = kron_band(Kuu_bands, G_sparse, sigma2, k, ms)
+    cP = sla.cholesky_banded(Pb, lower=True)
+    alpha = sla.cho_solve_banded((cP, True), np.asarray(Kuf_y).reshape(-1, 1)) / sigma2
+    cK = [sla.cholesky_banded(b, lower=True) for b in Kuu_bands]
+    i1, u1 = locate(meshes[0], Xnew[:, 0])
+    i2, u2 = locate(meshes[1], Xnew[:, 1])
+    w1 = pieces(k, Xnew[:, 0] - u1, deltas[0])               # (k+1, n*)
+    w2 = pieces(k, Xnew[:, 1] - u2, deltas[1])
+    mean = np.zeros((Xnew.shape[0], 1))
+    var = np.zeros((Xnew.shape[0], 1))
+    cells = np.unique(np.stack([i1, i2], 1), axis=0)
+    for c1, c2 in cells:
+        rows = ((c1 + np.arange(k + 1))[:, None] * m2 + (c2 + np.arange(k + 1))[None, :]).reshape(-1)
+        E = np.zeros((m1 * m2, rows.size))
+        E[rows, np.arange(rows.size)] = 1.0
+        Pinv = sla.cho_solve_banded((cP, True), E)[rows]     # (k+1)^2 x (k+1)^2 block of P^-1
+        E1 = np.zeros((m1, k + 1)); E1[c1 + np.arange(k + 1), np.arange(k + 1)] = 1.0
+        E2 = np.zeros((m2, k + 1)); E2[c2 + np.arange(k + 1), np.arange(k + 1)] = 1.0
+        K1inv = sla.cho_solve_banded((cK[0], True), E1)[c1:c1 + k + 1]
+        K2inv = sla.cho_solve_banded((cK[1], True), E2)[c2:c2 + k + 1]
+        sel = np.nonzero((i1 == c1) & (i2 == c2))[0]
+        a, b = w1[:, sel], w2[:, sel]
+        w = (a[:, None, :] * b[None, :, :]).reshape(-1, sel.size)
+        mean[sel, 0] = w.T @ alpha[rows, 0]
+        q1 = np.sum(a * (K1inv @ a), axis=0)
+        q2 = np.sum(b * (K2inv @ b), axis=0)
+        var[sel, 0] = np.prod(variances) + np.sum(w * (Pinv @ w), axis=0) - q1 * q2
+    return mean, var
+
+
+def stencil_columns_of_inverse(Kuu_bands, G_sparse, sigma2, k, ms, cols):
+    """Entries of P^-1 = (K1 (x) K2 + G / sigma2)^-1 in the stencil layout of include/asvgp_b200.h for the given columns
+    j (what the reference's dense cholesky_solve would hold at those positions, gpr.py:293-307): out[e, c] with
+    e = d1 (2k+1) + (d2 + k) is P^-1[(j1 + d1, j2 + d2), (j1, j2)], zero outside the matrix or for d1 = 0, d2 < 0.
+    One LAPACK band solve per column."""
+    m1, m2 = ms
+    Pb = kron_band(Kuu_bands, G_sparse, sigma2, k, ms)
+    cP = sla.cholesky_banded(Pb, lower=True)
+    cols = np.asarray(cols, dtype=np.int64)
+    E = np.zeros((m1 * m2, cols.size))
+    E[cols, np.arange(cols.size)] = 1.0
+    Pinv = sla.cho_solve_banded((cP, True), E)
+    out = np.zeros(((k + 1) * (2 * k + 1), cols.size))
+    for c, j in enumerate(cols):
+        j1, j2 = divmod(int(j), m2)
+        for d1 in range(k + 1):
+            for d2 in range(-k, k + 1):
+                if (d1 == 0 and d2 < 0) or j1 + d1 >= m1 or not (0 <= j2 + d2 < m2):
+                    continue
+                out[d1 * (2 * k + 1) + d2 + k, c] = Pinv[(j1 + d1) * m2 + j2 + d2, c]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# a9 at large M: closed-form gradients on LAPACK band routines
+# ---------------------------------------------------------------------------------------------------------------------
+KUU_LENGTHSCALE_POWERS = {          # coefficient of each table is c * ell^p / var (inducing_features.py:17-44)
+    "Matern12": {"A": -1, "B": 1, "BC": 0},
+    "Matern32": {"A": -1, "B": 1, "C": 3, "BC": 0, "BC_grad": 2},
+    "Matern52": {"A": -1, "B": 1, "C": 3, "D": 5, "BC": 0, "BC_grad": 2, "BC_ggrad": 4},
+}
+
+
+def _band_matmul(band, V):
+    """(symmetric matrix given by its lower band) @ V, V dense M x r."""
+    k, m = band.shape[0] - 1, band.shape[1]
+    out = band[0][:, None] * V
+    for d in range(1, k + 1):
+        out[d:] += band[d, : m - d, None] * V[: m - d]
+        out[: m - d] += band[d, : m - d, None] * V[d:]
+    return out
+
+
+def _band_dot(A, B):
+    """trace(A B) of two symmetric matrices given by their lower bands (same bandwidth)."""
+    w = np.full((A.shape[0], 1), 2.0)
+    w[0] = 1.0
+    return float(np.sum(w * A * B))
+
+
+def elbo_grad_1d_banded(kind, tables, G, Kuf_y, tr_yTy, n, var, ell, sigma2, block=1000):
+    """ELBO (elbo_1d) and d/d(var, ell, sigma2) in closed form (what TF reverse mode returns for
+    gpr.py:49-89) on LAPACK band routines — the gradient oracle at M where the dense autograd restatement
+    (elbo_grad_1d_dense) is too slow; validated against it in tests/test_oracle_golden.py.  One output column."""
+    k, m = G.shape[0] - 1, G.shape[1]
+    b = np.asarray(Kuf_y, dtype=np.float64).reshape(m, 1)
+    co = kuu_coefficients(kind, ell, var)
+    Kuu = sum(c * tables[nme] for nme, c in co.items())
+    dK_l = sum(KUU_LENGTHSCALE_POWERS[kind][nme] * c / ell * tables[nme] for nme, c in co.items())
+    dK_v = -Kuu / var
+    cK = sla.cholesky_banded(Kuu, lower=True)
+    P = G / sigma2 + Kuu
+    cP = sla.cholesky_banded(P, lower=True)
+    Kinv, Pinv = takahashi_band(cK), takahashi_band(cP)
+    alpha = sla.cho_solve_banded((cP, True), b) / sigma2
+    # band of W = Kuu^-1 G Kuu^-1, block of columns by block of columns (three band operations per block)
+    W = np.zeros((k + 1, m))
+    for s in range(0, m, block):
+        cols = np.arange(s, min(s + block, m))
+        E = np.zeros((m, cols.size))
+        E[cols, np.arange(cols.size)] = 1.0
+        Wc = sla.cho_solve_banded((cK, True), _band_matmul(G, sla.cho_solve_banded((cK, True), E)))
+        for d in range(k + 1):
+            ok = cols + d < m
+            W[d, cols[ok]] = Wc[cols[ok] + d, np.arange(cols.size)[ok]]
+    elbo = elbo_1d(Kuu, G, b, tr_yTy, n, var, sigma2)
+    bPb = (b.T @ alpha).item() * sigma2
+    grads = []
+    for dK, dvar in ((dK_v, 1.0), (dK_l, 0.0)):
+        g = (-0.5 * _band_dot(Pinv, dK) + 0.5 * _band_dot(Kinv, dK) - 0.5 * (alpha.T @ _band_matmul(dK, alpha)).item()
+             - 0.5 * n * dvar / sigma2 - 0.5 * _band_dot(W, dK) / sigma2)
+        grads.append(g)
+    tr = _band_dot(Kinv, G)
+    g_s2 = (-0.5 * n / sigma2 + 0.5 * _band_dot(Pinv, G) / sigma2**2 + 0.5 * tr_yTy / sigma2**2 - bPb / sigma2**3
+            + 0.5 * (alpha.T @ _band_matmul(G, alpha)).item() / sigma2**2 + 0.5 * n * var / sigma2**2 - 0.5 * tr / sigma2**2)
+    return elbo, np.array(grads + [g_s2])

@@ -180,3 +180,68 @@ def test_multi_output_1d_golden(golden):
     mean, var = O.predict_1d(mesh, delta, k, m, O.make_Kuu("Matern52", l, v, T), G, b, v, s2, g["xs"])
     np.testing.assert_allclose(mean, g["mean"], atol=1e-9)
     np.testing.assert_allclose(var, g["var"], atol=1e-9)
+
+
+@pytest.mark.parametrize("kind,k", [("Matern12", 2), ("Matern32", 3), ("Matern52", 3), ("Matern52", 4)])
+def test_closed_form_banded_gradient_oracle_matches_autograd(kind, k):
+    """elbo_grad_1d_banded (the gradient oracle of the M = 1e4 fixtures) vs torch autograd through the dense algebra."""
+    rng = np.random.default_rng(1)
+    m, n = 60, 5000
+    mesh, delta = O.make_mesh(-1, m + 1, m, k)
+    x = np.sort(rng.uniform(0, m, n))
+    y = np.sin(x / 3) + 0.2 * rng.standard_normal(n)
+    G, b, yy = O.precompute_1d(mesh, delta, k, m, x, y)
+    T = O.static_bands(k, m, delta)
+    e0, g0 = O.elbo_grad_1d_dense(kind, T, G, b, yy, n, 1.1, 2.3, 0.15)
+    e1, g1 = O.elbo_grad_1d_banded(kind, T, G, b, yy, n, 1.1, 2.3, 0.15, block=17)
+    assert abs(e0 - e1) <= 1e-12 * abs(e0)
+    np.testing.assert_allclose(g1, g0, rtol=1e-11, atol=1e-11 * np.abs(g0).max())
+
+
+def test_large_size_kron_oracle_helpers_match_dense(golden):
+    """predict_kron_banded_cells and stencil_columns_of_inverse (used for the 200 x 200 fixtures) vs the dense algebra."""
+    g = golden("kron_2d")
+    k, m = 3, int(g["k3_m"])
+    ms = [m, m]
+    meshes, deltas = zip(*[O.make_mesh(0, 1 + i, m, k) for i in range(2)])
+    G = sp.coo_matrix((g["k3_G_val"], (g["k3_G_row"], g["k3_G_col"])), shape=(m * m, m * m)).tocsr()
+    T = [O.static_bands(k, m, d) for d in deltas]
+    Ks = [O.make_Kuu("Matern32", .3, .7, T[0]), O.make_Kuu("Matern32", .5, 1.3, T[1])]
+    Xs = g["k3_Xs"]
+    mean0, var0 = O.predict_kron_dense(meshes, deltas, k, ms, Ks, G, g["k3_Kuf_y"], [.7, 1.3], .05, Xs)
+    mean1, var1 = O.predict_kron_banded_cells(meshes, deltas, k, ms, Ks, G, g["k3_Kuf_y"], [.7, 1.3], .05, Xs)
+    np.testing.assert_allclose(mean1, mean0.reshape(-1, 1), atol=1e-11, rtol=0)
+    np.testing.assert_allclose(var1, var0, atol=1e-11, rtol=0)
+    np.testing.assert_allclose(mean1, g["k3_mean"], atol=1e-10, rtol=0)           # reference-under-shim
+    P = (sp.kron(sp.csr_matrix(O.band_to_dense_sym(Ks[0])), sp.csr_matrix(O.band_to_dense_sym(Ks[1]))) + G / .05).toarray()
+    Pinv = np.linalg.inv(P)
+    cols = [0, 5, 77, m * m - 1]
+    S = O.stencil_columns_of_inverse(Ks, G, .05, k, ms, cols)
+    for c, j in enumerate(cols):
+        j1, j2 = divmod(j, m)
+        for d1 in range(k + 1):
+            for d2 in range(-k, k + 1):
+                inside = not (d1 == 0 and d2 < 0) and j1 + d1 < m and 0 <= j2 + d2 < m
+                want = Pinv[(j1 + d1) * m + j2 + d2, j] if inside else 0.0
+                assert abs(S[d1 * 7 + d2 + 3, c] - want) <= 1e-11 * np.abs(Pinv).max()
+
+
+def test_scale_fixtures_are_self_consistent(golden):
+    """The committed BASELINE-sized fixtures: closed-form and finite-difference gradients of the oracle agree, inputs
+    regenerate with the recorded sizes."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import scale_cases as SC
+
+    g = golden("scale_1d")
+    assert int(g["n"]) == SC.C3_N and g["G"].shape == (SC.C3_ORDER + 1, SC.C3_M)
+    for name in SC.C3_HYPERS:
+        scale = np.abs(g[name + "_grad"]).max()
+        assert np.abs(g[name + "_grad"] - g[name + "_grad_fd"]).max() <= 1e-6 * scale
+        assert g[name + "_mean"].shape == (500, 1)
+    c4 = golden("scale_kron_c4")
+    assert int(c4["n"]) == SC.C4["raster"][0] * SC.C4["raster"][1]
+    assert np.abs(c4["grad"] - c4["grad_h2"]).max() <= 1e-6 * np.abs(c4["grad"]).max()
+    assert c4["Xs"].shape[0] == c4["mean"].shape[0] == 64 * 157
