@@ -39,6 +39,7 @@ SIGNATURES = {
 }
 # functions whose return value is not a status code
 VALUE_FUNCTIONS = {
+    "asvgp_launch_count": (_c_i64, []),
     "asvgp_workspace_bytes_1d": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_accum_1d_binned_work_bytes": (_c_i64, [_c_i64]),
     "asvgp_accum_2d_binned_work_bytes": (_c_i64, [_c_i64]),

@@ -39,11 +39,15 @@ __global__ void __launch_bounds__(256) kuu_assemble_kernel(const double* __restr
                                                            double* __restrict__ dKuu) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < band_elems;
          i += (int64_t)gridDim.x * blockDim.x) {
+        // The reference's own operation order (inducing_features.py:17-44: every term `coefficient * table` rounded, then
+        // summed left to right) instead of a fused multiply-add chain: at l / delta ~ 18 the bound moves by a few 1e-10
+        // relative per ulp of Kuu (cond(Kuu) ~ 6e4 against 1 / sigma2), so the assembly should round where the
+        // reference's does.
         double v = 0.0, dv = 0.0;
         for (int t = 0; t < terms.n_terms; ++t) {
             const double s = __ldg(tables + (int64_t)t * band_elems + i);
-            v = fma(terms.coef[t], s, v);
-            dv = fma(terms.dcoef[t], s, dv);
+            v = __dadd_rn(v, __dmul_rn(terms.coef[t], s));
+            dv = __dadd_rn(dv, __dmul_rn(terms.dcoef[t], s));
         }
         Kuu[i] = v;
         if (dKuu != nullptr) dKuu[i] = dv;
@@ -427,13 +431,13 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
         using T = Dual<1>;
         ChainSpec<T> s0{BandMat<T>{A, dA, nullptr, 0.0, 0.0, 1, lay.M}, VecRhs<T>{A, lay.M, 0}};
         const size_t total = chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 1><<<(int)((total + 255) / 256), 256, 0, st>>>(lay, s0, s0, s0, s0, rows);
+        chain_rows_kernel<T, K, 1><<<(int)((total + 255) / 256), 256, 0, st>>>(lay, s0, s0, s0, s0, rows); ASVGP_LAUNCHED();
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sig, 0, (size_t)(K + 1) * lay.M * sizeof(Dual<1>), st));
     const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(band_inverse_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    band_inverse_kernel<K><<<1, kChainThreads, smem, st>>>(a);
+    band_inverse_kernel<K><<<1, kChainThreads, smem, st>>>(a); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -472,14 +476,14 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
         ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, a.G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{a.b, M, 1}};
         ChainSpec<T> s3{BandMat<T>{a.G, a.G, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};      // G itself (for the trace)
         const size_t total = 4 * chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 4><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, s3, rows);
+        chain_rows_kernel<T, K, 4><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, s3, rows); ASVGP_LAUNCHED();
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(elbo_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    elbo_chains_kernel<K><<<3, kChainThreads, smem, st>>>(a);
+    elbo_chains_kernel<K><<<3, kChainThreads, smem, st>>>(a); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
-    elbo_finalize_kernel<<<1, 32, 0, st>>>(a.partial, acc + (size_t)(K + 2) * M, M, variance, sigma2, out);
+    elbo_finalize_kernel<<<1, 32, 0, st>>>(a.partial, acc + (size_t)(K + 2) * M, M, variance, sigma2, out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -507,17 +511,17 @@ static int launch_posterior(const ChunkLayout& lay, const double* Kuu, const dou
         ChainSpec<T> s0{BandMat<T>{Kuu, nullptr, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};
         ChainSpec<T> s1{BandMat<T>{Kuu, nullptr, a.G, 1.0 / sigma2, 0.0, 0, M}, VecRhs<T>{a.b, M, 1}};
         const size_t total = 2 * chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 2><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s1, s1, rows);
+        chain_rows_kernel<T, K, 2><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s1, s1, rows); ASVGP_LAUNCHED();
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_CUDA_OK(cudaMemsetAsync(a.sigK, 0, 2 * band_bytes, st));
     const size_t smem = ChainSmall<double, K>::bytes(lay.P);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(posterior_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    posterior_chains_kernel<K><<<2, kChainThreads, smem, st>>>(a);
+    posterior_chains_kernel<K><<<2, kChainThreads, smem, st>>>(a); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     const int band_elems = (K + 1) * M;
     posterior_combine_kernel<<<(band_elems + 255) / 256, 256, 0, st>>>(a.sigK, a.sigP, a.x, 1.0 / sigma2, M, band_elems,
-                                                                      alpha, S);
+                                                                      alpha, S); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -570,7 +574,7 @@ extern "C" int asvgp_kuu_assemble(const double* tables, int n_terms, const doubl
     for (int i = 0; i < n_terms; ++i) { t.coef[i] = h_coef[i]; t.dcoef[i] = h_dcoef ? h_dcoef[i] : 0.0; }
     const int64_t elems = (int64_t)(order + 1) * M;
     const int blocks = (int)((elems + 255) / 256);
-    kuu_assemble_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(tables, t, elems, Kuu, dKuu);
+    kuu_assemble_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(tables, t, elems, Kuu, dKuu); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

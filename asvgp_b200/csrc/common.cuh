@@ -27,6 +27,9 @@ enum Status : int {
 };
 
 void set_last_error(const char* fmt, ...);
+// every kernel launch of the library is counted (asvgp_launch_count(): what bench.py reports as `gpu_launches`)
+void count_launch();
+#define ASVGP_LAUNCHED() ::asvgp::count_launch()
 
 #if defined(__CUDACC__)
 #define ASVGP_CUDA_OK(expr)                                                                         \

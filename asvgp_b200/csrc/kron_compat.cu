@@ -85,7 +85,7 @@ using namespace asvgp;
 
 extern "C" int asvgp_cholesky_dense(const double* A, int m, double* L, double* info, void* stream) {
     ASVGP_REQUIRE(m > 0 && m <= 4096, "cholesky_dense: m=%d (this helper is for the small per-dimension factors)", m);
-    cholesky_dense_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(A, m, L, info);
+    cholesky_dense_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(A, m, L, info); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -99,7 +99,7 @@ extern "C" int asvgp_khatri_rao_csc(const int64_t* indptr_a, const int64_t* indi
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n_cols + 7) / 8, 148 * 8));
     khatri_rao_csc_kernel<<<blocks, 256, 0, st>>>(indptr_a, indices_a, data_a, indptr_b, indices_b, data_b, n_cols, m_b,
-                                                  out_indptr, out_indices, out_data);
+                                                  out_indptr, out_indices, out_data); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -108,7 +108,7 @@ extern "C" int asvgp_kron_dense(const double* A, int m_a, const double* B, int m
     ASVGP_REQUIRE(m_a > 0 && m_b > 0, "kron_dense: m_a=%d m_b=%d", m_a, m_b);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int64_t total = (int64_t)m_a * m_b * m_a * m_b;
-    kron_dense_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(A, m_a, B, m_b, out);
+    kron_dense_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(A, m_a, B, m_b, out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

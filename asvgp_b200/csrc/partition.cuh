@@ -195,9 +195,9 @@ cudaError_t launch_partition(const Src& src, int64_t n, const PartWork& w, int u
     // the histogram pass keeps only four 8-byte loads in flight per thread: 8 CTAs per SM to cover the HBM latency
     const int hist_blocks = (int)((n + 4 * kPartThreads - 1) / (4 * kPartThreads) < 4 * (int64_t)blocks
                                       ? (n + 4 * kPartThreads - 1) / (4 * kPartThreads) : 4 * (int64_t)blocks);
-    part_hist_kernel<Src><<<hist_blocks, kPartThreads, 0, st>>>(src, n, w.count);
-    part_scan_kernel<<<1, kPartBuckets, 0, st>>>(w, unit_points);
-    part_scatter_kernel<Src, REC><<<blocks, kPartThreads, smem, st>>>(src, n, w);
+    part_hist_kernel<Src><<<hist_blocks, kPartThreads, 0, st>>>(src, n, w.count); ASVGP_LAUNCHED();
+    part_scan_kernel<<<1, kPartBuckets, 0, st>>>(w, unit_points); ASVGP_LAUNCHED();
+    part_scatter_kernel<Src, REC><<<blocks, kPartThreads, smem, st>>>(src, n, w); ASVGP_LAUNCHED();
     return cudaGetLastError();
 }
 

@@ -1,4 +1,5 @@
 // Library-wide runtime bits of libasvgp_sm100a: ABI version and the per-thread error message.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -14,7 +15,11 @@ void set_last_error(const char* fmt, ...) {
     vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 }  // namespace asvgp
 
 extern "C" int asvgp_abi_version(void) { return ASVGP_ABI_VERSION; }
 extern "C" const char* asvgp_last_error(void) { return asvgp::g_last_error; }
+extern "C" int64_t asvgp_launch_count(void) { return (int64_t)asvgp::g_launches.load(std::memory_order_relaxed); }

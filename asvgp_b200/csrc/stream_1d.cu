@@ -693,7 +693,7 @@ extern "C" int asvgp_basis_eval_1d(const double* x, int64_t n, const double* mes
     if (n == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
-    ASVGP_DISPATCH_ORDER(order, (basis_eval_1d_kernel<K><<<blocks, 256, 0, st>>>(x, n, mesh, n_knots, dx, coef, idx, vals)));
+    ASVGP_DISPATCH_ORDER(order, (basis_eval_1d_kernel<K><<<blocks, 256, 0, st>>>(x, n, mesh, n_knots, dx, coef, idx, vals))); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -713,9 +713,9 @@ extern "C" int asvgp_accum_1d(const double* x, const double* y, int64_t n, const
     const int64_t n_tiles = (n + per_tile - 1) / per_tile;
     const int blocks = (int)std::min<int64_t>((n_tiles + 7) / 8, (int64_t)sm_count() * 2);
     if (vec) {
-        ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 2><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal)));
+        ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 2><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal))); ASVGP_LAUNCHED();
     } else {
-        ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 1><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal)));
+        ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 1><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal))); ASVGP_LAUNCHED();
     }
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
@@ -729,7 +729,7 @@ extern "C" int asvgp_order_probe_1d(const double* x, int64_t n, const double* me
     ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), st));
     if (n < 2) return kOk;
     const int samples = (int)std::min<int64_t>(n - 1, 4096);
-    order_probe_1d_kernel<<<1, 256, 0, st>>>(x, n, mesh, n_knots, samples, out);
+    order_probe_1d_kernel<<<1, 256, 0, st>>>(x, n, mesh, n_knots, samples, out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -744,7 +744,7 @@ static int launch_accum_1d_units(const PartWork& w, int64_t n, const double* mes
     ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_1d_units_kernel<K, THREADS>, THREADS, smem));
     const int64_t max_units = n / kUnitPoints1 + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count() * std::max(per_sm, 1)));
-    accum_1d_units_kernel<K, THREADS><<<blocks, THREADS, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal);
+    accum_1d_units_kernel<K, THREADS><<<blocks, THREADS, smem, st>>>(w, n, mesh, n_knots, ipb, M, G, b, scal); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -784,7 +784,7 @@ extern "C" int asvgp_predict_1d(const double* xnew, int64_t n, const double* mes
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int M = n_knots + order - 1;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), (int64_t)sm_count() * 4));
-    ASVGP_DISPATCH_ORDER(order, (predict_1d_kernel<K><<<blocks, 256, 0, st>>>(xnew, n, mesh, n_knots, M, alpha, S_band, variance, mean, var)));
+    ASVGP_DISPATCH_ORDER(order, (predict_1d_kernel<K><<<blocks, 256, 0, st>>>(xnew, n, mesh, n_knots, M, alpha, S_band, variance, mean, var))); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

@@ -1676,7 +1676,7 @@ static int launch_accum_2d_units(const PartWork& w, int64_t n, const double* k1,
     ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, accum_2d_units_kernel<K>, Units2<K>::THREADS, smem));
     const int64_t max_units = n / kUnitPoints2 + kPartBuckets;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(max_units, (int64_t)sm_count2() * std::max(per_sm, 1)));
-    accum_2d_units_kernel<K><<<blocks, Units2<K>::THREADS, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal);
+    accum_2d_units_kernel<K><<<blocks, Units2<K>::THREADS, smem, st>>>(w, n, k1, nk1, k2, nk2, ipb, cellmom, scal); ASVGP_LAUNCHED();
     return kOk;
 }
 
@@ -1685,7 +1685,7 @@ static int launch_accum_part(const double* X, const double* y, int64_t n, const 
                              int nk2, double* cellmom, double* scal, const int* select, cudaStream_t st) {
     const int64_t want = (n + 511) / 512;          // at least ~2 points per thread; at most one CTA per SM
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, sm_count2()));
-    accum_2d_kernel<K, P0, P1, WITH_Y><<<blocks, 256, 0, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, select, 0);
+    accum_2d_kernel<K, P0, P1, WITH_Y><<<blocks, 256, 0, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, select, 0); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -1718,12 +1718,12 @@ static int launch_raster(const double* X, const double* y, int64_t n, const doub
                          cudaStream_t st) {
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
-    accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
+    accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
     const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2)     // sums, factors, per-row table
                              + (size_t)kColsWarps * ColsRing<K>::kRows * 32 * 24;            // the ring
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe);
+    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
     return kOk;
 }
 
@@ -1763,7 +1763,7 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
     // launched and those that are not selected return at once.
     ProbeResult* probe = reinterpret_cast<ProbeResult*>(cellmom + asvgp_accum_2d_moment_doubles(n_knots1, n_knots2, order) - 1);
     const int* select = &probe->select;
-    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(X, y, n, probe);
+    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(X, y, n, probe); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     const int blocks2 = 2 * sm_count2();
     const size_t raster_smem = sizeof(double) * 2 * kRasterWarps * 32 * (3 * (size_t)order + 2);   // NS = (2k+1) + (k+1)
@@ -1772,7 +1772,7 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
     {
         const int64_t want = (n + 1023) / 1024;
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)blocks2));
-        ASVGP_DISPATCH_ORDER(order, (accum_2d_run_kernel<K><<<blocks, 256, 0, st>>>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, 1)));
+        ASVGP_DISPATCH_ORDER(order, (accum_2d_run_kernel<K><<<blocks, 256, 0, st>>>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, 1))); ASVGP_LAUNCHED();
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, st)) return rc; });
@@ -1789,7 +1789,7 @@ extern "C" int asvgp_order_probe_2d(const double* X, int64_t n, const double* me
     ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(double), st));
     if (n < 2) return kOk;
     const int samples = (int)std::min<int64_t>(n - 1, 4096);
-    order_probe_2d_kernel<<<1, 256, 0, st>>>(X, n, mesh1, n_knots1, mesh2, n_knots2, samples, out);
+    order_probe_2d_kernel<<<1, 256, 0, st>>>(X, n, mesh1, n_knots1, mesh2, n_knots2, samples, out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -1829,7 +1829,7 @@ extern "C" int asvgp_expand_moments_2d(const double* cellmom, const double* Cpro
     const int m2 = n_knots2 + order - 1;
     const int64_t M = (int64_t)(n_knots1 + order - 1) * m2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ASVGP_DISPATCH_ORDER(order, (expand_moments_2d_kernel<K><<<nc1 * nc2, 256, 0, st>>>(cellmom, Cprod, Dy, nc1, nc2, m2, M, Gs, b)));
+    ASVGP_DISPATCH_ORDER(order, (expand_moments_2d_kernel<K><<<nc1 * nc2, 256, 0, st>>>(cellmom, Cprod, Dy, nc1, nc2, m2, M, Gs, b))); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -1849,19 +1849,20 @@ static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1,
     constexpr int W = (K + 1) * (K + 1);
     const size_t smem = sizeof(double) * (size_t)(W * W + W + W * (2 * K + 1));      // window, alpha, stage-1 result
     ASVGP_CUDA_OK(cudaFuncSetAttribute(predict_2d_table_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work);
+    predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     // classification probe (as in asvgp_accum_2d): separable raster test sets take the coalesced column sweep, anything else
     // the thread-contiguous kernel; the one that is not selected returns at once
     ProbeResult* probe = reinterpret_cast<ProbeResult*>(work + asvgp_predict_2d_work_doubles(nk1, nk2, K) - 1);
-    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(Xnew, Xnew, n, probe);
+    accum_2d_probe_kernel<<<1, 1024, 0, st>>>(Xnew, Xnew, n, probe); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
-    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
+    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     const bool vec = ((reinterpret_cast<uintptr_t>(Xnew) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 31u) == 0;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, 2 * (int64_t)sm_count2()));
     if (vec) predict_2d_kernel<K, true><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
     else predict_2d_kernel<K, false><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
+    ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

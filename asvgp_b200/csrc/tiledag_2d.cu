@@ -1039,7 +1039,7 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_flag_ints * sizeof(int), st));
     ASVGP_CUDA_OK(cudaMemsetAsync(flags + g.n_tiles() + 1, 0x7f, sizeof(int), st));                       // first bad pivot = "none"
     const int64_t total = (int64_t)g.nb * NB * (order + 1) * (2 * order + 1);
-    td_assemble_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(g, K1, K2, Gs, 1.0 / sigma2, band);
+    td_assemble_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(g, K1, K2, Gs, 1.0 / sigma2, band); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     FactorArgs a{g, band, band + lay.linv, rhs_io, band + lay.colstat, flags, scal};
     int grid = 0;
@@ -1047,7 +1047,8 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
     void* params[] = {&a};
     ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(td_factor_kernel), dim3(grid), dim3(kTdThreads),
                                               params, kTdSmem, st));
-    td_stats_kernel<<<1, 256, 0, st>>>(g, band + lay.colstat, flags, scal);
+    ASVGP_LAUNCHED();
+    td_stats_kernel<<<1, 256, 0, st>>>(g, band + lay.colstat, flags, scal); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -1067,7 +1068,7 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
     ASVGP_CUDA_OK(cudaMemsetAsync(work, 0, (size_t)sl.work_total * sizeof(double), st));                  // xacc + flags
     const size_t yp_smem = (size_t)(NB * (NB + 1) + TILE) * sizeof(double);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(td_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
-    td_ypass_kernel<<<g.n_tiles(), kTdThreads, yp_smem, st>>>(g, band, band + fl.linv, sig_band + sl.sig_lower);
+    td_ypass_kernel<<<g.n_tiles(), kTdThreads, yp_smem, st>>>(g, band, band + fl.linv, sig_band + sl.sig_lower); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     SelArgs a{g, band, band + fl.linv, sig_band + sl.sig_lower, sig_band + sl.sig_upper, x_io, work + sl.xacc, band + fl.colstat, flags};
     int grid = 0;
@@ -1075,9 +1076,10 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
     void* params[] = {&a};
     ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(td_selinv_kernel), dim3(grid), dim3(kTdThreads),
                                               params, kTdSmem, st));
+    ASVGP_LAUNCHED();
     const int64_t total = (int64_t)g.M * (order + 1) * (2 * order + 1);
     td_extract_stencil_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
-        g, sig_band + sl.sig_lower, flags + g.n_tiles() + g.nb, sigma_stencil);
+        g, sig_band + sl.sig_lower, flags + g.n_tiles() + g.nb, sigma_stencil); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -1092,7 +1094,7 @@ extern "C" int asvgp_kron_terms(const double* SigP, const double* Gs, const doub
     ASVGP_CUDA_OK(cudaMemsetAsync(out, 0, 11 * sizeof(double), st));
     StencilTerms a{SigP, Gs, x, K1, dK1, K2, dK2, S1, dS1, S2, dS2};
     const int64_t total = (int64_t)m1 * m2 * (order + 1) * (2 * order + 1);
-    td_terms_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 4), 256, 0, st>>>(m1, m2, order, a, out);
+    td_terms_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 4), 256, 0, st>>>(m1, m2, order, a, out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

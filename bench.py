@@ -64,6 +64,13 @@ def parse():
     return ap.parse_args()
 
 
+def launch_count():
+    """Kernels launched by libasvgp_sm100a so far in this process (the library counts every launch it makes)."""
+    from asvgp_b200 import _lib
+
+    return int(_lib.load().asvgp_launch_count())
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -359,15 +366,29 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
     grad0 = [float(result["grads"][id(p)]) for p in model.trainable_variables]
     assert np.isfinite(elbo0) and np.isfinite(grad0).all()
 
+    # gradient sanity, outside the timed region: central difference of the bound itself in one hyper-parameter
+    # (two extra factorisations).  r01's selected inverse returned 1e52-sized noise here and nothing noticed.
+    lpar = kerns[0].lengthscales
+    l0, h = HYPERS_2D[0][1], 1e-4 * HYPERS_2D[0][1]
+    lpar.assign(l0 + h); e_plus = float(model.elbo())
+    lpar.assign(l0 - h); e_minus = float(model.elbo())
+    lpar.assign(l0)
+    fd = (e_plus - e_minus) / (2 * h)
+    grad_check = {"param": "lengthscale of dimension 1", "central_difference": fd, "analytic": grad0[1],
+                  "rel_err": abs(fd - grad0[1]) / max(abs(fd), 1e-300)}
+    assert grad_check["rel_err"] < 1e-5, "2-D gradient fails its finite-difference check: %r" % (grad_check,)
+
     phase_ev = [[ev() for _ in range(4)] for _ in range(steps)]
     t0, t1 = ev(), ev()
     with ClockSampler(int(os.environ.get("LOCAL_RANK", "0"))) as clocks:
         barrier()
+        launches0 = launch_count()
         t0.record()
         for i in range(steps):
             step(phase_ev[i])
         t1.record()
         barrier()
+        launches = launch_count() - launches0
     total_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -375,6 +396,7 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
     accum_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in phase_ev]))
     red_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in phase_ev]))
     fact_ms = float(np.mean([e[2].elapsed_time(e[3]) for e in phase_ev]))
+    assert abs(result["elbo"] - elbo0) <= 1e-12 * abs(elbo0), "2-D ELBO is not reproducible from step to step"
 
     e2e = None
     if with_e2e:
@@ -399,8 +421,29 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
         assert abs(-loss - elbo0) <= 1e-9 * abs(elbo0), "e2e ELBO differs from the device-resident one"
         e2e = {"value": world * n / dt.item(), "unit": "datapoints/s", "h2d_bytes_per_step": 24 * n,
                "d2h_bytes_per_step": 24 * 8, "ms_per_step": dt.item() * 1e3, "steps": k_e2e,
+               "host_buffers": "pinned",
                "api": "GPR_kron((X_host, y_host), kernels, bases).training_loss_and_gradients()"}
-        del Xh, yh
+        if world == 1:
+            # the same call with ordinary (pageable) numpy arrays: the library stages them through its own pinned buffers
+            Xn, yn = Xh.numpy().copy(), yh.numpy().copy()
+            del Xh, yh
+
+            def e2e_np():
+                mdl = GPR_kron((Xn, yn.reshape(-1, 1)), kerns, bases, check_inputs=False)
+                mdl.likelihood.variance.assign(HYPERS_2D[2])
+                return mdl.training_loss_and_gradients()
+
+            e2e_np()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(2):
+                e2e_np()
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - w0) / 2
+            e2e["pageable"] = {"value": n / dtp, "ms_per_step": dtp * 1e3, "host_buffers": "pageable numpy arrays"}
+            del Xn, yn
+        else:
+            del Xh, yh
 
     # predictor on the same raster (BASELINE.json configs[4]): sharded over ranks, no collective
     alpha, SigP, S1, S2, _info = model.posterior_weights()
@@ -431,8 +474,9 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
         "phases_ms": {"accumulate": accum_ms, "expand_allreduce": red_ms, "factor_selinv_grad": fact_ms,
                       "predict_same_raster": pred_ms},
         "predict_points_per_s": world * n / (pred_ms * 1e-3),
-        "elbo": elbo0, "grad": grad0,
-        "roofline": {"kernel": "accum_2d_kernel<%d,...>" % k, "bound": "hbm", "achieved": achieved,
+        "elbo": elbo0, "grad": grad0, "grad_check": grad_check, "parity_checked": True,
+        "roofline": {"kernel": "accum_2d_cols_kernel<%d> (separable raster, chosen by the device-side probe of asvgp_accum_2d)" % k,
+                     "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM_2D * n, "launch_ms": accum_ms,
@@ -443,9 +487,8 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
                                "reported for orientation only" % n_blk,
                        "cholesky_equiv_tflops": 3 * flops / (fact_ms * 1e-3) / 1e12},
         "clocks": clocks.summary(),
-        # per step: accum + expand + 2 kuu_assemble + 2 band_inverse + assemble + 3 per block column (potrf, trsm,
-        # syrk) + trinv + 2 per block column (selected inverse) + stencil extract + contractions
-        "gpu_launches": steps * (10 + 5 * n_blk),
+        # counted by the library itself (asvgp_launch_count) over the timed region
+        "gpu_launches": launches,
         "e2e": e2e,
     }
 
@@ -633,17 +676,31 @@ def main():
     barrier()
     res0 = out.cpu().numpy().copy()
     assert res0[8] == 0 and np.isfinite(res0[:4]).all(), "ELBO evaluation failed: %r" % (res0,)
+    # gradient sanity, outside the timed region: central difference of the bound itself in the lengthscale
+    outp, outm = torch.empty_like(out), torch.empty_like(out)
+    h = 1e-4 * HYPERS[1]
+    for sign, o in ((1.0, outp), (-1.0, outm)):
+        kern.lengthscales.assign(HYPERS[1] + sign * h)
+        Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
+        ops.elbo_grad_1d(Kuu, dKuu, acc, basis, HYPERS[0], HYPERS[2], out=o)
+    kern.lengthscales.assign(HYPERS[1])
+    fd = (outp[0].item() - outm[0].item()) / (2 * h)
+    grad_check = {"param": "lengthscale", "central_difference": fd, "analytic": float(res0[2]),
+                  "rel_err": abs(fd - res0[2]) / max(abs(fd), 1e-300)}
+    assert grad_check["rel_err"] < 1e-5, "1-D gradient fails its finite-difference check: %r" % (grad_check,)
 
     # ---- timed region: exactly K steps, CUDA events, max over ranks ------------------------------------------------
     phase_ev = [[ev() for _ in range(4)] for _ in range(args.steps)]
     t0, t1 = ev(), ev()
     with ClockSampler(local) as clocks:
         barrier()
+        launches0 = launch_count()
         t0.record()
         for i in range(args.steps):
             step(phase_ev[i])
         t1.record()
         barrier()
+        launches = launch_count() - launches0
     total_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device="cuda")
     accum_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in phase_ev]))
     allred_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in phase_ev]))
@@ -652,6 +709,46 @@ def main():
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
     value = world * n / (ms_per_step * 1e-3)
+
+    # ---- strong scaling (SURVEY 8(e) "report both"): the SAME global N split over the ranks ---------------------------------
+    strong = None
+    if world > 1:
+        n_s = n // world
+        xs_, ys_ = x[:n_s], y[:n_s]
+        sev = [[ev() for _ in range(4)] for _ in range(args.steps)]
+
+        def strong_step(t):
+            acc.zero_()
+            t[0].record()
+            ops.accum_1d(xs_, ys_, basis, acc=acc, binned=binned)
+            t[1].record()
+            dist.all_reduce(acc)
+            t[2].record()
+            Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
+            ops.elbo_grad_1d(Kuu, dKuu, acc, basis, HYPERS[0], HYPERS[2], out=out)
+            t[3].record()
+
+        for _ in range(3):
+            strong_step(sev[0])
+        s0, s1 = ev(), ev()
+        barrier()
+        s0.record()
+        for i in range(args.steps):
+            strong_step(sev[i])
+        s1.record()
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sms = sms.item() / args.steps
+        strong = {"scaling": "strong", "n_global": n_s * world, "n_per_gpu": n_s, "ms_per_step": sms,
+                  "value": n_s * world / (sms * 1e-3), "unit": "datapoints/s",
+                  "phases_ms": {"accumulate": float(np.mean([e[0].elapsed_time(e[1]) for e in sev])),
+                                "allreduce": float(np.mean([e[1].elapsed_time(e[2]) for e in sev])),
+                                "kuu_elbo_grad": float(np.mean([e[2].elapsed_time(e[3]) for e in sev]))},
+                  "note": "global N fixed at the 1-GPU workload's N; only the accumulate phase shrinks with the number of "
+                          "ranks, the banded chains are replicated (Amdahl)"}
+        step()          # leave `acc` / `out` as the weak-scaling step left them (the predictor below reuses acc)
+        barrier()
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------------
     e2e = None
@@ -678,8 +775,29 @@ def main():
         assert abs(-loss - res0[0]) <= 1e-9 * abs(res0[0]), "e2e ELBO differs from the device-resident one"
         e2e = {"value": world * n / dt.item(), "unit": "datapoints/s", "h2d_bytes_per_step": 16 * n,
                "d2h_bytes_per_step": 16 * 8, "ms_per_step": dt.item() * 1e3, "steps": k_e2e,
+               "host_buffers": "pinned", "pcie_gb_per_s_per_rank": 16 * n / dt.item() / 1e9,
                "api": "GPR_1d((X_host, y_host), kernel, basis).training_loss_and_gradients()"}
-        del xh, yh
+        if world == 1:
+            # the same call with ordinary (pageable) numpy arrays: staged through the library's pinned buffers
+            xn, yn = xh.numpy().copy(), yh.numpy().copy()
+            del xh, yh
+
+            def e2e_np():
+                mdl = GPR_1d((xn.reshape(-1, 1), yn.reshape(-1, 1)), kern, basis, check_inputs=False)
+                mdl.likelihood.variance.assign(HYPERS[2])
+                return mdl.training_loss_and_gradients()
+
+            e2e_np()
+            torch.cuda.synchronize()
+            w0 = time.perf_counter()
+            for _ in range(3):
+                e2e_np()
+            torch.cuda.synchronize()
+            dtp = (time.perf_counter() - w0) / 3
+            e2e["pageable"] = {"value": n / dtp, "ms_per_step": dtp * 1e3, "host_buffers": "pageable numpy arrays"}
+            del xn, yn
+        else:
+            del xh, yh
 
     # 1-D predictor on the same points (sharded over ranks, no collective): posterior weights once, then mean/variance
     from asvgp_b200.gpr import GPR_1d as _G1
@@ -710,6 +828,14 @@ def main():
             kron = run_2d(args, "2d", torch, dist, world, rank, max(3, min(args.steps, 5)), 3, with_e2e=not args.no_e2e)
         except Exception as exc:            # the appendix must never take the headline line down with it
             kron = {"error": repr(exc)}
+        if world == 1 and isinstance(kron, dict) and "error" not in kron:
+            torch.cuda.empty_cache()
+            try:        # the shape experiments/eNATL60/eNATL60.py:84 itself uses (B4 splines, m = 100 per dimension)
+                k4 = run_2d(args, "2d-k4", torch, dist, world, rank, 3, 3, with_e2e=False)
+                kron["enatl60_k4_m100"] = {key: k4[key] for key in ("ms_per_step", "value", "phases_ms", "elbo", "grad",
+                                                                     "grad_check", "roofline", "config", "gpu_launches")}
+            except Exception as exc:
+                kron["enatl60_k4_m100"] = {"error": repr(exc)}
 
     unordered = None
     if args.workload == "1d" and world == 1 and not args.no_2d and not args.n:
@@ -735,7 +861,7 @@ def main():
         "phases_ms": {"accumulate": accum_ms, "allreduce": allred_ms, "kuu_elbo_grad": elbo_ms,
                       "predict_same_points": pred_ms},
         "predict_points_per_s": world * n / (pred_ms * 1e-3),
-        "elbo": float(res0[0]), "grad": [float(v) for v in res0[1:4]],
+        "elbo": float(res0[0]), "grad": [float(v) for v in res0[1:4]], "grad_check": grad_check, "parity_checked": True,
         "roofline": {"kernel": ("accum_1d_kernel<%d,2>" % k) if not binned else
                      "asvgp_accum_1d_binned (part_hist + part_scan + part_scatter + accum_1d_units_kernel<%d>)" % k,
                      "bound": "hbm", "achieved": achieved,
@@ -743,9 +869,11 @@ def main():
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
                      "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM * n, "launch_ms": accum_ms, "traffic": traffic},
         "clocks": clocks.summary(),
-        # accum_1d (or the four kernels of the binned path) + kuu_assemble + elbo_chains + elbo_finalize per step
-        "gpu_launches": args.steps * (7 if binned else 4),
+        # counted by the library itself (asvgp_launch_count) over the timed region
+        "gpu_launches": launches,
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if e2e is not None:
         line["e2e"] = e2e
     if kron is not None:
@@ -758,6 +886,12 @@ def main():
         line["cpu_baseline"] = {"value": v1, "unit": "datapoints/s", "cores": 1, "kind": "port",
                                 "sample": "one step on the first %d sorted points of the workload (%.1f s), single "
                                           "thread like the reference's SciPy/LAPACK path" % (n_sample, dt1)}
+    if world == 1 and not args.no_cpu_baseline and isinstance(kron, dict) and "error" not in kron:
+        v2, dt2, n_sample2, t_acc2, t_fac2 = run_cpu_2d("2d", 1, 0, 1)
+        kron["cpu_baseline"] = {
+            "value": v2, "unit": "datapoints/s", "cores": 1, "kind": "port",
+            "sample": "precompute on the first %d raster points (%.1f s, extrapolated linearly to N) + one LAPACK banded "
+                      "ELBO at full M (%.1f s), no gradients, single thread" % (n_sample2, t_acc2, t_fac2)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

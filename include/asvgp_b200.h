@@ -42,6 +42,8 @@ extern "C" {
 ASVGP_API int asvgp_abi_version(void);
 /* Message of the last failing call on this thread (empty string if none). */
 ASVGP_API const char* asvgp_last_error(void);
+/* Number of CUDA kernels this library has launched in this process so far (all streams, all entry points). */
+ASVGP_API int64_t asvgp_launch_count(void);
 
 /* ---- a2/a6: basis evaluation = the non-zeros of Kuf -------------------------------------------------------------
  * Replaces SplineBasis.evaluate_basis (basis.py:51-80) / SplineFeatures1D.make_Kuf (inducing_features.py:47-48).

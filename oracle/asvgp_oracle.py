@@ -92,30 +92,91 @@ def make_Kuf(mesh, delta, k, m, X, dx=0):
 # ---------------------------------------------------------------------------------------------------------------------
 # a3/a4: static Gram and boundary bands  (asvgp/basis.py:31-45, 82-114 and the l2_*_inner_product tables)
 # ---------------------------------------------------------------------------------------------------------------------
+def _unit_pieces_exact(k):
+    """Coefficient lists (ascending powers of t, fractions.Fraction) of the k+1 non-zero degree-k B-spline pieces on
+    one knot interval of a UNIT mesh; entry r belongs to basis row idx + r.  Same Cox-de Boor recursion as `pieces`,
+    in exact rational arithmetic."""
+    from fractions import Fraction as F
+
+    def mul(p, q):
+        out = [F(0)] * (len(p) + len(q) - 1)
+        for i, a in enumerate(p):
+            for j, b in enumerate(q):
+                out[i + j] += a * b
+        return out
+
+    def add(p, q):
+        n = max(len(p), len(q))
+        return [(p[i] if i < len(p) else F(0)) + (q[i] if i < len(q) else F(0)) for i in range(n)]
+
+    P = [[F(1)]]
+    for d in range(1, k + 1):
+        new = []
+        for r in range(d + 1):
+            t0 = F(-(d - r))
+            acc = [F(0)]
+            if r - 1 >= 0:
+                acc = add(acc, mul([-t0 / d, F(1, d)], P[r - 1]))
+            if r <= d - 1:
+                acc = add(acc, mul([(t0 + d + 1) / d, F(-1, d)], P[r]))
+            new.append(acc)
+        P = new
+    return P
+
+
+def _poly_deriv(p, times):
+    for _ in range(times):
+        p = [i * c for i, c in enumerate(p)][1:] or [0 * p[0]]
+    return p
+
+
 def gram_band(k, m, delta, q):
     """Lower band (k+1, m) of int_a^b phi_i^(q) phi_j^(q) dx, band[d, j] = S[j+d, j]; truncated edge functions
-    (basis.py:31-45).  Gauss-Legendre with k+2 nodes per interval is exact for these polynomials."""
-    nodes, wts = np.polynomial.legendre.leggauss(k + 2)
-    s = 0.5 * (nodes + 1.0) * delta
-    V = pieces(k, s, delta, q)                                  # (k+1, nq)
-    W = (V * (0.5 * delta * wts)[None, :]) @ V.T               # per-interval Gram, rows/cols = local piece index
+    (basis.py:31-45).  The per-interval Gram of the unit-mesh pieces is an exact rational (the reference tabulates the
+    same rationals in closed form, basis.py:143-798); the contributions of the intervals an entry touches are summed as
+    rationals and scaled by delta^(1-2q) with ONE rounding, so every entry is the correctly rounded value.  (A
+    Gauss-Legendre version of this function was good to 4e-15 only, and at l / delta ~ 18 the bound moves by 1e-10
+    relative per ulp of Kuu.)"""
+    from fractions import Fraction as F
+
+    P = [_poly_deriv(p, q) for p in _unit_pieces_exact(k)]
+    W = [[F(0)] * (k + 1) for _ in range(k + 1)]
+    for r in range(k + 1):
+        for t in range(r + 1):
+            acc = F(0)
+            for i, a in enumerate(P[r]):
+                for j, b in enumerate(P[t]):
+                    acc += a * b / (i + j + 1)                  # int_0^1 t^(i+j) dt
+            W[r][t] = acc
+    scale = F(float(delta)) ** (1 - 2 * q)
+    exact = {}
     band = np.zeros((k + 1, m))
     for c in range(m - k):                                      # interval c touches rows c..c+k
         for r in range(k + 1):
             for t in range(r + 1):
-                band[r - t, c + t] += W[r, t]
+                key = (r - t, c + t)
+                exact[key] = exact.get(key, F(0)) + W[r][t]
+    cache = {}
+    for (d, j), v in exact.items():
+        if v not in cache:
+            cache[v] = float(v * scale)
+        band[d, j] = cache[v]
     return band
 
 
 def boundary_band(k, m, delta, dx):
     """make_boundary_conditions(dx) for dx=0,1,2 (basis.py:82-114): outer product of the first k boundary values
-    at x=a, d-th diagonal written at both ends of row d, last row zero.  dx=3,4 vanish for m>2k."""
+    at x=a, d-th diagonal written at both ends of row d, last row zero.  dx=3,4 vanish for m>2k.
+    Exact rationals scaled by delta^(-2 dx) with one rounding, like gram_band."""
+    from fractions import Fraction as F
+
     band = np.zeros((k + 1, m))
     if dx in (3, 4):
         return band
-    v = pieces(k, np.array(0.0), delta, dx)[:k]
+    v = [_poly_deriv(p, dx)[0] for p in _unit_pieces_exact(k)][:k]      # values of the dx-th derivative at t = 0
+    scale = F(float(delta)) ** (-2 * dx)
     for d in range(k):
-        l = v[d:] * v[: k - d]
+        l = np.array([float(v[d + i] * v[i] * scale) for i in range(k - d)])
         band[d, : k - d] = l
         band[d, m - d - (k - d): m - d] = l
     return band

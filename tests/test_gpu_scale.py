@@ -6,7 +6,16 @@ The oracle's outputs at these sizes were computed once in the build container by
 routines, minutes of CPU) and committed as tests/golden/scale_*.npz; the inputs are regenerated here bit-for-bit from
 tests/scale_cases.py.  Tolerances: rel 1e-10 on the band, the projection and the ELBO, 1e-8 on gradients against the
 closed-form oracle (1e-6 against finite differences, which is what the differences themselves are good for), 1e-9 absolute
-on predictions."""
+on predictions.
+
+ELBO tolerance at long lengthscales.  At l / delta >= 10 Kuu is ill-conditioned (cond ~ 6e4 at the bench's 2-D hypers) and
+the bound carries 1 / sigma2 = 100 and a hundred-fold cancellation between its terms, so re-rounding the entries of Kuu by
+ONE unit roundoff moves the ELBO by about 1e-10 relative (measured with the oracle, stored as `*_elbo_kuu_ulp` in the
+fixtures; an 80-bit evaluation, oracle/extended_check.py, puts the fp64 LAPACK oracle itself 2e-11 off).  The product's Kuu
+and the oracle's agree to an ulp but not bit for bit (correctly rounded rational tables on both sides, 50-75 % of the
+entries bit-equal to the reference's own tables).  So parity is checked twice: (1) the SOLVER, fed the oracle's Kuu bit for
+bit, must match at 1e-10 relative; (2) the public API, assembling its own Kuu, must match within 1e-10 relative plus twice
+the measured one-ulp sensitivity."""
 import os
 import sys
 
@@ -27,6 +36,21 @@ def c3_model_inputs(cuda):
 
     x, y, xs = SC.case_1d()
     return torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), xs
+
+
+def _inject_kuu(features, K_host):
+    """Make a SplineFeatures1D hand the solver `K_host` (the oracle's Kuu, bit for bit) instead of its own assembly;
+    the lengthscale derivative stays the product's."""
+    import torch
+
+    own = features.make_Kuu_device
+    Kdev = torch.from_numpy(np.ascontiguousarray(K_host)).cuda()
+
+    def patched(kernel, want_grad=True):
+        _, dK = own(kernel, want_grad=want_grad)
+        return Kdev, dK
+
+    features.make_Kuu_device = patched
 
 
 def _model_1d(xd, yd, kind, hyp, m=SC.C3_M, k=SC.C3_ORDER):
@@ -59,8 +83,9 @@ def test_c3_elbo_gradients_predictions(c3_model_inputs, golden, name):
     model = _model_1d(xd, yd, kind, (v, l, s2))
     elbo, grads = model.elbo_and_grad()
     want = float(g[name + "_elbo"])
-    assert abs(elbo - want) <= 1e-10 * abs(want), (elbo, want)
-    assert abs(model.elbo() - want) <= 1e-10 * abs(want)
+    tol = 1e-10 * abs(want) + 2 * float(g[name + "_elbo_kuu_ulp"])          # see the module docstring
+    assert abs(elbo - want) <= tol, (elbo, want, tol)
+    assert abs(model.elbo() - want) <= tol
     got = np.array([grads[id(p)] for p in model.trainable_variables])
     g0 = g[name + "_grad"]
     np.testing.assert_allclose(got, g0, rtol=1e-8, atol=1e-8 * np.abs(g0).max())
@@ -68,6 +93,19 @@ def test_c3_elbo_gradients_predictions(c3_model_inputs, golden, name):
     mean, var = model.predict_f(xs.reshape(-1, 1))
     np.testing.assert_allclose(mean, g[name + "_mean"], atol=1e-9, rtol=0)
     np.testing.assert_allclose(var, g[name + "_var"], atol=1e-9, rtol=0)
+
+
+@pytest.mark.parametrize("name", sorted(SC.C3_HYPERS))
+def test_c3_solver_parity_with_the_oracles_kuu(c3_model_inputs, golden, name):
+    """The banded solver alone (chunked Cholesky x2, Takahashi, solve, trace) on the oracle's Kuu, bit for bit: 1e-10."""
+    g = golden("scale_1d")
+    xd, yd, _ = c3_model_inputs
+    kind, v, l, s2 = SC.C3_HYPERS[name]
+    model = _model_1d(xd, yd, kind, (v, l, s2))
+    _inject_kuu(model.inducing_features, g[name + "_Kuu"])
+    want = float(g[name + "_elbo"])
+    elbo = model.elbo()
+    assert abs(elbo - want) <= 1e-10 * abs(want), (elbo, want)
 
 
 @pytest.mark.parametrize("kind,hyp", [("Matern32", (1.0, 1.0, 0.1)), ("Matern52", (1.3, 2.5, 0.7)), ("Matern32", (0.8, 10.0, 0.1))])
@@ -160,8 +198,9 @@ def test_c4_elbo_and_gradients(c4_model, golden):
     g = golden("scale_kron_c4")
     want = float(g["elbo"])
     elbo, grads = c4_model.elbo_and_grad()
-    assert abs(elbo - want) <= 1e-10 * abs(want), (elbo, want)
-    assert abs(c4_model.elbo() - want) <= 1e-10 * abs(want)
+    tol = 1e-10 * abs(want) + 2 * float(g["elbo_kuu_ulp"])                  # see the module docstring
+    assert abs(elbo - want) <= tol, (elbo, want, tol)
+    assert abs(c4_model.elbo() - want) <= tol
     got = np.array([grads[id(p)] for p in c4_model.trainable_variables])
     fd_err = np.abs(g["grad"] - g["grad_h2"]).max() / np.abs(g["grad"]).max()      # what the differences themselves are good for
     assert fd_err < 1e-6
@@ -170,6 +209,18 @@ def test_c4_elbo_and_gradients(c4_model, golden):
     _, grads2 = c4_model.elbo_and_grad()
     got2 = np.array([grads2[id(p)] for p in c4_model.trainable_variables])
     np.testing.assert_allclose(got2, got, rtol=1e-9)
+
+
+def test_c4_solver_parity_with_the_oracles_kuu(cuda, golden):
+    """Block-band factorisation, per-dimension band inverses and the Kronecker trace on the oracle's K1, K2 bit for bit:
+    the bound at 1e-10 relative (625 block columns, bench hypers)."""
+    g = golden("scale_kron_c4")
+    model = _model_2d(SC.C4)[0]
+    _inject_kuu(model.inducing_features[0], g["K1"])
+    _inject_kuu(model.inducing_features[1], g["K2"])
+    want = float(g["elbo"])
+    elbo = model.elbo()
+    assert abs(elbo - want) <= 1e-10 * abs(want), (elbo, want)
 
 
 def test_c4_selected_inverse_and_alpha(c4_model, golden):
@@ -181,8 +232,22 @@ def test_c4_selected_inverse_and_alpha(c4_model, golden):
     S = SigP.cpu().numpy()[:, cols]
     want = g["sigma_cols"]
     np.testing.assert_allclose(S, want, rtol=1e-8, atol=1e-9 * np.abs(want).max())
-    a = alpha.cpu().numpy()[cols]
-    np.testing.assert_allclose(a, g["alpha_cols"], rtol=1e-8, atol=1e-9 * np.abs(g["alpha_cols"]).max())
+    # alpha solves an ill-conditioned system (Kuu spans six decades at l / delta ~ 18): single entries of the fp64 LAPACK
+    # solution and of ours differ by a few 1e-8 relative, so entries are compared at 1e-6 and the solution is pinned by
+    # its backward error instead: || P alpha sigma2 - Kuf_y || <= 1e-12 || Kuf_y || with P rebuilt from the oracle's Kuu
+    a_full = alpha.cpu().numpy()
+    np.testing.assert_allclose(a_full[cols], g["alpha_cols"], rtol=1e-6, atol=1e-7 * np.abs(g["alpha_cols"]).max())
+    import scipy.sparse as sp
+
+    c = SC.C4
+    k, ms = c["order"], list(c["m"])
+    deltas = [b.delta for b in c4_model.bases]
+    T = [O.static_bands(k, m, d) for m, d in zip(ms, deltas)]
+    Ks = [sp.csr_matrix(O.band_to_dense_sym(O.make_Kuu("Matern32", l, v, t))) for (v, l), t in zip(c["hypers"], T)]
+    P = sp.kron(Ks[0], Ks[1]) + c4_model.KufKfu_sparse / c["sigma2"]
+    b = c4_model.Kuf_y[:, 0]
+    res = P @ (a_full * c["sigma2"]) - b
+    assert np.linalg.norm(res) <= 1e-12 * np.linalg.norm(b), np.linalg.norm(res) / np.linalg.norm(b)
 
 
 def test_c5_predictions(c4_model, golden):
