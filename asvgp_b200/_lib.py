@@ -31,6 +31,8 @@ SIGNATURES = {
     "asvgp_expand_moments_2d": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp],
     "asvgp_kron_factor": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp, _vp, _vp],
     "asvgp_kron_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "asvgp_kronband_factor": [_vp, _vp, _vp, _c_int, _c_int, _c_int, _c_dbl, _vp, _vp, _vp, _vp],
+    "asvgp_kronband_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "asvgp_kron_terms": [_vp] * 11 + [_c_int, _c_int, _c_int, _vp, _vp],
     "asvgp_predict_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp],
     "asvgp_khatri_rao_csc": [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp],
@@ -48,7 +50,12 @@ VALUE_FUNCTIONS = {
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
-    "asvgp_kron_colstat_offset": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kron_plan_info": (_c_i64, [_c_int, _c_int, _c_int, _vp, _vp, _c_i64]),
+    "asvgp_kronband_band_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kronband_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kronband_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kronband_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kronband_colstat_offset": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_predict_2d_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
 }
 

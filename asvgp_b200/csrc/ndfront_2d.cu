@@ -1,0 +1,904 @@
+// Nested-dissection multifrontal factorisation and selected inverse of the 2-D (Kronecker) model's
+//     P = K1 (x) K2 + KufKfu / sigma2        (reference gpr.py:292; m1 m2 x m1 m2, a DENSE tf.linalg.cholesky there)
+//
+//   asvgp_kron_factor  <- utils.bands_to_kron_cholesky's Kronecker product, `Kuu + KufKfu / sigma2`,
+//                         tf.linalg.cholesky(P), its log-det, triangular_solve(L_P, Kuf_y)            (gpr.py:287-295)
+//   asvgp_kron_selinv  <- what TF reverse mode / cholesky_solve extract from P^-1 (gpr.py:307, 319-326): the entries of
+//                         P^-1 on the stencil pattern and P^-1 Kuf_y
+//
+// Why not the band.  In the natural order P is a band of scalar width k (m2 + 1) (gpr.py:262) and its Cholesky is ONE
+// dependency chain over all m1 m2 columns: 625 block columns of 64 at 200 x 200, 34 us each, with 98 % of the GPU idle
+// (tiledag_2d.cu, kept as asvgp_kronband_*).  The coupling graph, however, is a 2-D grid with a (2k+1) x (2k+1) stencil:
+// a strip of k grid lines separates it.  Recursive bisection by such strips (nested dissection) turns the factorisation
+// into a tree of dense FRONTS — separator unknowns + the ancestors' separator unknowns they touch — in which all fronts
+// of one tree level are independent and the dependency chain is the sum of the separator sizes along ONE root-to-leaf
+// path: 601 + 297 + 297 + 144 + 144 + 69 + 69 + 30 + 100 = 1751 columns (33 block columns) instead of 40 000 (625), for
+// 2.6x fewer flops as well.  tools/nd_prototype.py is the same algorithm in numpy (checked against LAPACK's band
+// routines in tests/test_nd_plan.py).
+//
+// Data.  Front f has ns separator unknowns (eliminated here) and nb boundary unknowns (ancestors), each padded to a
+// multiple of 64 (separator padding = unit diagonal, boundary padding = zero rows); its lower triangle is stored as
+// 64 x 64 column-major tiles packed by block column, so one TMA bulk copy fetches an operand (as in tiledag_2d.cu).
+// The right-hand side Kuf_y rides along as ONE EXTRA BOUNDARY UNKNOWN of every front ("rhs node", never eliminated):
+// row rhs of L is y^T = (L^-1 b)^T, the root's update entry (rhs, rhs) is -||y||^2, and seeding the selected inverse
+// with Sigma'(rhs, rhs) = tau gives Sigma'(s, rhs) = -tau x, x = P^-1 b, and Sigma' = P^-1 + tau x x^T on the grid
+// unknowns (inverse of [[P, b], [b^T, ||y||^2 + 1/tau]]); tau = 2^-20 / (1 + ||y||^2) keeps the correction tau x x^T a
+// 1e-6 fraction of sqrt(P^-1_ii P^-1_jj) (Cauchy-Schwarz), so subtracting it costs no digits.  No separate triangular
+// solves, no separate chains.
+//
+// Kernels, per tree level (bottom-up for the factorisation, top-down for the selected inverse):
+//   nd_assemble_kernel   entries of P (and of the children's update matrices: extend-add as a gather) into the front
+//   nd_factor_kernel     persistent tile DAG over all tiles of all fronts of the level: left-looking updates on the fp64
+//                        tensor cores, diagonal tiles factorised + inverted in registers, trailing tiles = update matrix
+//   nd_ypass_kernel      (once) L(R,C) -> Y(R,C)^T = (L(R,C) L(C,C)^-1)^T, Sigma(C,C) seeded with L(C,C)^-T L(C,C)^-1
+//   nd_gather_kernel     Sigma on the boundary of a front from its parent's Sigma
+//   nd_selinv_kernel     persistent tile DAG: blocked Takahashi recursion inside every front of the level
+//   nd_scalars_kernel / nd_x_kernel / nd_stencil_kernel   log|P|, ||y||^2, x, stencil entries of P^-1
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "tile_ops.cuh"
+#include "../../include/asvgp_b200.h"
+
+namespace asvgp {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// symbolic plan (host, built once per (m1, m2, order, device) and cached with its device copies)
+// ---------------------------------------------------------------------------------------------------------------------
+struct FrontDesc {                 // device-visible
+    long long tile_base;           // first tile of this front in the tile pools (in tiles)
+    int nT, nsT;                   // block rows in total, separator block columns
+    int ns, nb;                    // separator / boundary unknowns (unpadded; the rhs node is the last boundary unknown)
+    int idx_off;                   // into idx[]: nT * 64 node ids, -1 = padding, M = rhs node
+    int pmap_off;                  // into pmap[]: (nT - nsT) * 64 positions in the parent's padded list (-1 = none)
+    int parent;
+    int child[2];
+    int cpos_off[2];               // into cpos[]: nT * 64 boundary-local positions in child c (-1 = none)
+    int linv_base;                 // first L(C,C)^-1 tile of this front (nsT tiles)
+    int cnt_base;                  // first per-block-column counter of this front (nsT counters)
+    int level;
+};
+__host__ __device__ __forceinline__ long long front_tile(const FrontDesc& f, int R, int C) {
+    return f.tile_base + (long long)C * f.nT - (long long)C * (C - 1) / 2 + (R - C);
+}
+
+struct NdFrontHost {
+    int level = 0, parent = -1;
+    int child[2] = {-1, -1};
+    int r0 = 0, r1 = 0, c0 = 0, c1 = 0;
+    std::vector<int> sep, bnd;
+};
+
+static int nd_rec(std::vector<NdFrontHost>& F, int r0, int r1, int c0, int c1, int level, int k, int leaf, int m2) {
+    const int nr = r1 - r0, nc = c1 - c0;
+    const bool can_r = nr >= 3 * k + 2 && nr > leaf, can_c = nc >= 3 * k + 2 && nc > leaf;
+    NdFrontHost f;
+    f.level = level; f.r0 = r0; f.r1 = r1; f.c0 = c0; f.c1 = c1;
+    int a = -1, b = -1;
+    if (!(can_r || can_c)) {
+        for (int r = r0; r < r1; ++r)
+            for (int c = c0; c < c1; ++c) f.sep.push_back(r * m2 + c);
+    } else if (can_r && (nr >= nc || !can_c)) {
+        const int mid = r0 + (nr - k) / 2;
+        for (int r = mid; r < mid + k; ++r)
+            for (int c = c0; c < c1; ++c) f.sep.push_back(r * m2 + c);
+        a = nd_rec(F, r0, mid, c0, c1, level + 1, k, leaf, m2);
+        b = nd_rec(F, mid + k, r1, c0, c1, level + 1, k, leaf, m2);
+    } else {
+        const int mid = c0 + (nc - k) / 2;
+        for (int r = r0; r < r1; ++r)
+            for (int c = mid; c < mid + k; ++c) f.sep.push_back(r * m2 + c);
+        a = nd_rec(F, r0, r1, c0, mid, level + 1, k, leaf, m2);
+        b = nd_rec(F, r0, r1, mid + k, c1, level + 1, k, leaf, m2);
+    }
+    f.child[0] = a; f.child[1] = b;
+    F.push_back(f);
+    const int id = (int)F.size() - 1;
+    if (a >= 0) { F[a].parent = id; F[b].parent = id; }
+    return id;
+}
+
+struct NdPlan {
+    int m1 = 0, m2 = 0, K = 0, M = 0;
+    int n_fronts = 0, n_levels = 0, root = -1;
+    long long n_tiles = 0;         // tiles per pool
+    int n_linv = 0, n_cnt = 0;
+    std::vector<FrontDesc> fronts;
+    std::vector<int> idx, pmap, cpos;
+    std::vector<std::vector<int4>> factor_tasks, selinv_tasks, gather_tasks;    // per level
+    std::vector<int4> ypass_tasks;
+    std::vector<long long> doff, xoff, sigoff;
+    long long quad_off = 0, tau_off = 0;           // L-pool offset of the root's update entry (rhs, rhs); sig-pool offset of Sigma'(rhs, rhs)
+    // device copies
+    FrontDesc* d_fronts = nullptr;
+    int *d_idx = nullptr, *d_pmap = nullptr, *d_cpos = nullptr;
+    std::vector<int4*> d_factor_tasks, d_selinv_tasks, d_gather_tasks;
+    int4* d_ypass_tasks = nullptr;
+    long long *d_doff = nullptr, *d_xoff = nullptr, *d_sigoff = nullptr;
+};
+
+constexpr int kNdLeaf = 12;        // regions whose sides are both <= this many grid lines are eliminated as one front
+
+static void nd_build(NdPlan& P, int m1, int m2, int K) {
+    P.m1 = m1; P.m2 = m2; P.K = K; P.M = m1 * m2;
+    const int M = P.M, RHS = M;
+    std::vector<NdFrontHost> F;
+    P.root = nd_rec(F, 0, m1, 0, m2, 0, K, kNdLeaf, m2);
+    P.n_fronts = (int)F.size();
+    for (auto& f : F) {            // boundary: ancestors' separator unknowns within K grid lines of the subtree's region
+        for (int a = f.parent; a >= 0; a = F[a].parent)
+            for (int g : F[a].sep) {
+                const int s1 = g / m2, s2 = g % m2;
+                if (s1 >= f.r0 - K && s1 <= f.r1 - 1 + K && s2 >= f.c0 - K && s2 <= f.c1 - 1 + K) f.bnd.push_back(g);
+            }
+        f.bnd.push_back(RHS);
+        P.n_levels = std::max(P.n_levels, f.level + 1);
+    }
+    P.fronts.resize(P.n_fronts);
+    std::vector<std::unordered_map<int, int>> pos(P.n_fronts);      // node id -> position in the front's padded list
+    long long tiles = 0;
+    int linv = 0;
+    for (int i = 0; i < P.n_fronts; ++i) {
+        FrontDesc& d = P.fronts[i];
+        const NdFrontHost& f = F[i];
+        d.ns = (int)f.sep.size(); d.nb = (int)f.bnd.size();
+        d.nsT = (d.ns + NB - 1) / NB;
+        d.nT = d.nsT + (d.nb + NB - 1) / NB;
+        d.tile_base = tiles; tiles += (long long)d.nT * (d.nT + 1) / 2;
+        d.linv_base = linv; d.cnt_base = linv; linv += d.nsT;
+        d.parent = f.parent; d.child[0] = f.child[0]; d.child[1] = f.child[1]; d.level = f.level;
+        d.idx_off = (int)P.idx.size();
+        P.idx.resize(P.idx.size() + (size_t)d.nT * NB, -1);
+        for (int j = 0; j < d.ns; ++j) { P.idx[d.idx_off + j] = f.sep[j]; pos[i][f.sep[j]] = j; }
+        for (int j = 0; j < d.nb; ++j) { P.idx[d.idx_off + d.nsT * NB + j] = f.bnd[j]; pos[i][f.bnd[j]] = d.nsT * NB + j; }
+    }
+    P.n_tiles = tiles; P.n_linv = linv; P.n_cnt = linv;
+    for (int i = 0; i < P.n_fronts; ++i) {                          // child -> parent maps and their inverses
+        FrontDesc& d = P.fronts[i];
+        d.pmap_off = (int)P.pmap.size();
+        P.pmap.resize(P.pmap.size() + (size_t)(d.nT - d.nsT) * NB, -1);
+        if (d.parent >= 0)
+            for (int j = 0; j < d.nb; ++j) P.pmap[d.pmap_off + j] = pos[d.parent].at(F[i].bnd[j]);
+        for (int c = 0; c < 2; ++c) {
+            d.cpos_off[c] = -1;
+            if (d.child[c] < 0) continue;
+            d.cpos_off[c] = (int)P.cpos.size();
+            P.cpos.resize(P.cpos.size() + (size_t)d.nT * NB, -1);
+            const NdFrontHost& ch = F[d.child[c]];
+            for (int j = 0; j < (int)ch.bnd.size(); ++j) P.cpos[d.cpos_off[c] + pos[i].at(ch.bnd[j])] = j;
+        }
+    }
+    // task lists.  Factorisation: block column major inside a front (a topological order of its DAG), fronts interleaved so
+    // that the chains of diagonal tiles of all fronts advance together.  Selected inverse: block columns descending
+    // (counted from each front's last separator column), rows far to near.
+    P.factor_tasks.resize(P.n_levels); P.selinv_tasks.resize(P.n_levels); P.gather_tasks.resize(P.n_levels);
+    for (int lev = 0; lev < P.n_levels; ++lev) {
+        int maxT = 0, maxS = 0;
+        for (auto& d : P.fronts) if (d.level == lev) { maxT = std::max(maxT, d.nT); maxS = std::max(maxS, d.nsT); }
+        for (int C = 0; C < maxT; ++C)
+            for (int i = 0; i < P.n_fronts; ++i) {
+                const FrontDesc& d = P.fronts[i];
+                if (d.level != lev || C >= d.nT) continue;
+                for (int R = C; R < d.nT; ++R) P.factor_tasks[lev].push_back(make_int4(i, R, C, 0));
+            }
+        for (int back = 0; back < maxS; ++back)
+            for (int i = 0; i < P.n_fronts; ++i) {
+                const FrontDesc& d = P.fronts[i];
+                const int C = d.nsT - 1 - back;
+                if (d.level != lev || C < 0) continue;
+                for (int R = d.nT - 1; R > C; --R) P.selinv_tasks[lev].push_back(make_int4(i, R, C, 0));
+            }
+        for (int i = 0; i < P.n_fronts; ++i) {
+            const FrontDesc& d = P.fronts[i];
+            if (d.level != lev) continue;
+            for (int C = d.nsT; C < d.nT; ++C)
+                for (int R = C; R < d.nT; ++R) P.gather_tasks[lev].push_back(make_int4(i, R, C, 0));
+        }
+    }
+    for (int i = 0; i < P.n_fronts; ++i) {
+        const FrontDesc& d = P.fronts[i];
+        for (int C = 0; C < d.nsT; ++C)
+            for (int R = C; R < d.nT; ++R) P.ypass_tasks.push_back(make_int4(i, R, C, 0));
+    }
+    // element offsets for the scalar / extraction kernels
+    std::vector<int> owner(M), opos(M);
+    for (int i = 0; i < P.n_fronts; ++i)
+        for (int j = 0; j < P.fronts[i].ns; ++j) { owner[F[i].sep[j]] = i; opos[F[i].sep[j]] = j; }
+    auto elem = [&](const FrontDesc& d, int prow, int pcol) {       // element (prow, pcol), prow >= pcol, of the front's lower triangle
+        return front_tile(d, prow / NB, pcol / NB) * TILE + (long long)(pcol % NB) * NB + prow % NB;
+    };
+    P.doff.resize(M); P.xoff.resize(M);
+    for (int j = 0; j < M; ++j) {
+        const FrontDesc& d = P.fronts[owner[j]];
+        P.doff[j] = elem(d, opos[j], opos[j]);
+        P.xoff[j] = elem(d, d.nsT * NB + d.nb - 1, opos[j]);
+    }
+    {
+        const FrontDesc& r = P.fronts[P.root];
+        const int p = r.nsT * NB + r.nb - 1;
+        P.quad_off = elem(r, p, p);
+        P.tau_off = P.quad_off;
+    }
+    const int NS = 2 * K + 1, n_e = (K + 1) * NS;
+    P.sigoff.assign((size_t)n_e * M, -1);
+    for (int j = 0; j < M; ++j) {
+        const int j1 = j / m2, j2 = j % m2;
+        for (int d1 = 0; d1 <= K; ++d1)
+            for (int d2 = -K; d2 <= K; ++d2) {
+                if (d1 == 0 && d2 < 0) continue;
+                const int i1 = j1 + d1, i2 = j2 + d2;
+                if (i1 >= m1 || i2 < 0 || i2 >= m2) continue;
+                const int i = i1 * m2 + i2;
+                const int fi = owner[i], fj = owner[j];
+                long long off;
+                if (fi == fj) {
+                    const int hi = std::max(opos[i], opos[j]), lo = std::min(opos[i], opos[j]);
+                    off = elem(P.fronts[fi], hi, lo);
+                    if (hi / NB == lo / NB) off |= 1LL << 62;          // diagonal tile: average with the mirrored entry
+                } else {
+                    const bool j_deeper = P.fronts[fj].level > P.fronts[fi].level;
+                    const int fd = j_deeper ? fj : fi, nd = j_deeper ? j : i, na = j_deeper ? i : j;
+                    off = elem(P.fronts[fd], pos[fd].at(na), opos[nd]);
+                }
+                P.sigoff[(size_t)(d1 * NS + d2 + K) * M + j] = off;
+            }
+    }
+}
+
+template <class T>
+static int nd_upload(T** dst, const std::vector<T>& src) {
+    *dst = nullptr;
+    if (src.empty()) return kOk;
+    ASVGP_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(dst), src.size() * sizeof(T)));
+    ASVGP_CUDA_OK(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return kOk;
+}
+
+static std::mutex g_plan_mutex;
+static std::map<std::tuple<int, int, int, int>, NdPlan*> g_plans;     // (device or -1 for host-only, m1, m2, order)
+
+// host-only plan (sizes, diagnostics); no CUDA calls
+static const NdPlan* nd_plan_host(int m1, int m2, int K) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto key = std::make_tuple(-1, m1, m2, K);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) return it->second;
+    NdPlan* P = new NdPlan();
+    nd_build(*P, m1, m2, K);
+    g_plans[key] = P;
+    return P;
+}
+
+static int nd_plan_device(int m1, int m2, int K, const NdPlan** out) {
+    int dev = 0;
+    ASVGP_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto key = std::make_tuple(dev, m1, m2, K);
+    auto it = g_plans.find(key);
+    if (it != g_plans.end()) { *out = it->second; return kOk; }
+    NdPlan* P = new NdPlan();
+    nd_build(*P, m1, m2, K);
+    if (int rc = nd_upload(&P->d_fronts, P->fronts)) return rc;
+    if (int rc = nd_upload(&P->d_idx, P->idx)) return rc;
+    if (int rc = nd_upload(&P->d_pmap, P->pmap)) return rc;
+    if (int rc = nd_upload(&P->d_cpos, P->cpos)) return rc;
+    P->d_factor_tasks.resize(P->n_levels); P->d_selinv_tasks.resize(P->n_levels); P->d_gather_tasks.resize(P->n_levels);
+    for (int l = 0; l < P->n_levels; ++l) {
+        if (int rc = nd_upload(&P->d_factor_tasks[l], P->factor_tasks[l])) return rc;
+        if (int rc = nd_upload(&P->d_selinv_tasks[l], P->selinv_tasks[l])) return rc;
+        if (int rc = nd_upload(&P->d_gather_tasks[l], P->gather_tasks[l])) return rc;
+    }
+    if (int rc = nd_upload(&P->d_ypass_tasks, P->ypass_tasks)) return rc;
+    if (int rc = nd_upload(&P->d_doff, P->doff)) return rc;
+    if (int rc = nd_upload(&P->d_xoff, P->xoff)) return rc;
+    if (int rc = nd_upload(&P->d_sigoff, P->sigoff)) return rc;
+    g_plans[key] = P;
+    *out = P;
+    return kOk;
+}
+
+// Buffer layouts (doubles).  band = [ L tiles | Linv tiles | scalars(8) | flags (ints) ], sig = [ lower tiles | upper tiles ],
+// work = [ flags (ints) ]
+struct NdLayout {
+    long long linv, scal, flags, band_total, n_flag_ints;
+    long long sig_upper, sig_total;
+    long long work_total, n_work_ints;
+};
+static NdLayout nd_layout(const NdPlan& P) {
+    NdLayout L;
+    L.linv = P.n_tiles * TILE;
+    L.scal = L.linv + (long long)P.n_linv * TILE;
+    L.flags = L.scal + 8;
+    L.n_flag_ints = P.n_tiles + 8;                       // tile flags, abort, first bad pivot
+    L.band_total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
+    L.sig_upper = P.n_tiles * TILE;
+    L.sig_total = 2 * L.sig_upper;
+    L.n_work_ints = P.n_tiles + P.n_cnt + 8;             // tile flags, per-block-column counters, abort
+    L.work_total = (L.n_work_ints + 1) / 2 + 2;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// assembly: entries of P (+ right-hand side row) and the children's update matrices (extend-add as a gather)
+// ---------------------------------------------------------------------------------------------------------------------
+struct NdAssembleArgs {
+    const FrontDesc* fronts; const int4* tasks; int n_tasks;
+    const int *idx, *cpos;
+    const double *K1, *K2, *Gs, *b;
+    double sigma2;
+    int m1, m2, K, M;
+    double* Lpool;
+};
+
+__device__ __forceinline__ double nd_band_sym(const double* B, int m, int K, int i, int j) {
+    const int d = i > j ? i - j : j - i;
+    return d <= K ? __ldg(B + (long long)d * m + (i < j ? i : j)) : 0.0;
+}
+
+// A'(gi, gj): gi, gj grid unknowns or the rhs node (id M).  Same roundings as the reference's `Kuu + KufKfu / sigma2`.
+__device__ __forceinline__ double nd_entry(const NdAssembleArgs& a, int gi, int gj) {
+    if (gi == a.M || gj == a.M) return (gi == gj) ? 0.0 : __ldg(a.b + (gi == a.M ? gj : gi));
+    const int i1 = gi / a.m2, i2 = gi % a.m2, j1 = gj / a.m2, j2 = gj % a.m2;
+    int d1 = i1 - j1, d2 = i2 - j2;
+    int col = gj;
+    if (d1 < 0 || (d1 == 0 && d2 < 0)) { d1 = -d1; d2 = -d2; col = gi; }
+    if (d1 > a.K || d2 > a.K || d2 < -a.K) return 0.0;
+    const double kv = __dmul_rn(nd_band_sym(a.K1, a.m1, a.K, i1, j1), nd_band_sym(a.K2, a.m2, a.K, i2, j2));
+    const double g = __ldg(a.Gs + (long long)(d1 * (2 * a.K + 1) + d2 + a.K) * a.M + col);
+    return __dadd_rn(kv, __ddiv_rn(g, a.sigma2));
+}
+
+__global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
+    for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const int4 tk = a.tasks[t];
+        const FrontDesc f = a.fronts[tk.x];
+        const int R = tk.y, C = tk.z;
+        double* tile = a.Lpool + front_tile(f, R, C) * TILE;
+        const int* idx = a.idx + f.idx_off;
+        FrontDesc ch[2];
+        const int* cpos[2] = {nullptr, nullptr};
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (f.child[c] >= 0) { ch[c] = a.fronts[f.child[c]]; cpos[c] = a.cpos + f.cpos_off[c]; }
+        for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
+            const int r = e % NB, c = e / NB;
+            const int I = R * NB + r, J = C * NB + c;
+            const int gi = idx[I], gj = idx[J];
+            double v;
+            if (gi < 0 || gj < 0) v = (I == J && C < f.nsT) ? 1.0 : 0.0;
+            else v = (C < f.nsT) ? nd_entry(a, gi, gj) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (cpos[q] == nullptr) continue;
+                int pa = cpos[q][I], pb = cpos[q][J];
+                if (pa < 0 || pb < 0) continue;
+                if (pa < pb) { const int s = pa; pa = pb; pb = s; }     // lower triangle of the child's update matrix
+                const double* u = a.Lpool + front_tile(ch[q], ch[q].nsT + pa / NB, ch[q].nsT + pb / NB) * TILE;
+                v += __ldcg(u + (pb % NB) * NB + pa % NB);
+            }
+            tile[e] = v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// factorisation of all fronts of one level
+// ---------------------------------------------------------------------------------------------------------------------
+struct NdFactorArgs {
+    const FrontDesc* fronts; const int4* tasks; int n_tasks;
+    const int* idx;
+    double* Lpool; double* linv;
+    int* ready;         // [n_tiles] + abort at [n_tiles], first bad pivot (node id + 1) at [n_tiles + 1]
+    long long n_tiles;
+};
+
+__global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a) {
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;      // padded copies of the operands of the current product
+    double* const pB = pA + PTILE;
+    __shared__ __align__(8) uint64_t full[2];
+    __shared__ int s_bad;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    int* abort_flag = a.ready + a.n_tiles;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    fence_proxy_async();
+    __syncthreads();
+    Phases ph;
+
+    for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const int4 tk = a.tasks[t];
+        const FrontDesc f = a.fronts[tk.x];
+        const int R = tk.y, C = tk.z;
+        const bool diag = R == C;
+        double* my_tile = a.Lpool + front_tile(f, R, C) * TILE;
+        double acc[4][4];
+        regs_from_tile(acc, my_tile, tm, tn);
+        const int nJ = min(C, f.nsT);
+
+        auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
+            const long long tR = front_tile(f, R, J), tC = front_tile(f, C, J);
+            wait_flag(a.ready + tR, 1, abort_flag);
+            if (!diag) wait_flag(a.ready + tC, 1, abort_flag);
+            fence_proxy_async();
+            mbar_expect_tx(&full[s], diag ? TILE_BYTES : 2 * TILE_BYTES);
+            tma_load_tile_(sA[s], a.Lpool + tR * TILE, &full[s]);
+            if (!diag) tma_load_tile_(sB[s], a.Lpool + tC * TILE, &full[s]);
+        };
+        if (nJ > 0) {
+            double cf[8][2] = {};                    // sum_J L(R,J) L(C,J)^T as tensor-core fragments
+            if (tid == 0) issue(0, 0);
+            for (int q = 0; q < nJ; ++q) {
+                const int s = q & 1;
+                if (q + 1 < nJ && tid == 0) issue(q + 1, s ^ 1);
+                mbar_wait(&full[s], ph.get(s));
+                ph.flip(s);
+                repack_padded(pA, sA[s], tid);
+                if (!diag) repack_padded(pB, sB[s], tid);
+                __syncthreads();
+                dmma_tile(cf, pA, diag ? pA : pB, warp, lane);
+                __syncthreads();
+            }
+            frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);
+        }
+
+        if (C >= f.nsT) {
+            // ---- trailing tile: this front's update matrix (read by the parent's assembly) ----------------------------------
+            regs_to_tile(acc, my_tile, tm, tn);
+        } else if (diag) {
+            // ---- diagonal tile: Cholesky + inverse in registers ---------------------------------------------------------------
+            double V[4][4];
+            double* s11 = sA[0];                     // [16] l + [4] 1/l_cc (+ padding)
+            double* spanel = sA[0] + 32;             // [4][64] panel, transposed
+            double* swrow = sA[0] + 32 + 4 * NB;     // [4][64]
+            if (tid == 0) s_bad = -1;
+            __syncthreads();
+            potrf_regs(acc, V, tm, tn, s11, spanel, swrow, &s_bad, nullptr);
+            __syncthreads();
+            const int first_bad = s_bad;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (tm + i < tn + j) { acc[i][j] = 0.0; V[i][j] = 0.0; }
+                }
+            regs_to_tile(V, a.linv + (long long)(f.linv_base + C) * TILE, tm, tn);
+            regs_to_tile(acc, my_tile, tm, tn);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                st_release(a.ready + front_tile(f, C, C), 1);
+                if (first_bad >= 0) atomicMin(a.ready + a.n_tiles + 1, a.idx[f.idx_off + C * NB + first_bad] + 1);
+            }
+        } else {
+            // ---- sub-diagonal tile: L(R,C) = A L(C,C)^-T -------------------------------------------------------------------------
+            if (tid == 0) {
+                wait_flag(a.ready + front_tile(f, C, C), 1, abort_flag);
+                fence_proxy_async();
+                mbar_expect_tx(&full[0], TILE_BYTES);
+                tma_load_tile_(sB[0], a.linv + (long long)(f.linv_base + C) * TILE, &full[0]);
+            }
+            regs_to_tile_ld<LDT>(acc, pA, tm, tn);   // A(m, k) at [k*LDT + m]
+            __syncthreads();
+            mbar_wait(&full[0], ph.get(0));
+            ph.flip(0);
+            repack_padded(pB, sB[0], tid);
+            __syncthreads();
+            double L[4][4] = {};
+            {
+                double cf[8][2] = {};
+                dmma_tile(cf, pA, pB, warp, lane);                  // L[m][n] = sum_k A[m][k] Linv[n][k]
+                frags_subtract(L, cf, sA[1], warp, lane, tm, tn);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) L[i][j] = -L[i][j];
+            }
+            regs_to_tile(L, my_tile, tm, tn);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(a.ready + front_tile(f, R, C), 1);
+        }
+        __syncthreads();
+    }
+}
+
+// log|P| = 2 sum log L_jj (deterministic tree reduction), ||y||^2 = -(root update entry (rhs, rhs)), info, and tau
+__global__ void __launch_bounds__(1024) nd_scalars_kernel(const long long* __restrict__ doff, int M, const double* __restrict__ Lpool,
+                                                          long long quad_off, const int* __restrict__ ready, long long n_tiles,
+                                                          double* __restrict__ scal_out, double* __restrict__ scal_keep) {
+    __shared__ double s[1024];
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < M; j += blockDim.x) acc += log(Lpool[doff[j]]);
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const double quad = -Lpool[quad_off];
+        const int aborted = ready[n_tiles], bad = ready[n_tiles + 1];
+        scal_out[0] = 2.0 * s[0];
+        scal_out[1] = quad;
+        scal_out[2] = aborted ? -1.0 : (bad != kNoBadPivot ? (double)bad : 0.0);
+        scal_keep[0] = quad;
+        scal_keep[1] = 9.5367431640625e-07 / (1.0 + quad);        // tau = 2^-20 / (1 + ||y||^2)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// selected inverse
+// ---------------------------------------------------------------------------------------------------------------------
+// Pre-pass over every tile (R, C), C < nsT, of every front, fully parallel: off-diagonal tiles become Y^T
+// (Y = L(R,C) L(C,C)^-1, stored transposed so that it is a plain operand later), diagonal tiles seed
+// Sigma(C,C) = L(C,C)^-T L(C,C)^-1.
+__global__ void __launch_bounds__(kTdThreads) nd_ypass_kernel(const FrontDesc* __restrict__ fronts, const int4* __restrict__ tasks,
+                                                              int n_tasks, double* __restrict__ Lpool, const double* __restrict__ linv,
+                                                              double* __restrict__ sig_lower) {
+    constexpr int LDP = NB + 1;
+    extern __shared__ __align__(16) unsigned char yp_smem[];
+    double* sLT = reinterpret_cast<double*>(yp_smem);        // Linv transposed, padded: Linv[k][c] at [k*65 + c]
+    double* sL = sLT + NB * LDP;                             // L tile, column-major
+    const int tid = threadIdx.x, tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
+        const int4 tk = tasks[t];
+        const FrontDesc f = fronts[tk.x];
+        const int R = tk.y, C = tk.z;
+        const double* Li = linv + (long long)(f.linv_base + C) * TILE;
+        __syncthreads();
+        for (int e = tid; e < TILE; e += kTdThreads) sLT[(e % NB) * LDP + e / NB] = Li[e];
+        double* T = Lpool + front_tile(f, R, C) * TILE;
+        if (R != C)
+            for (int e = tid; e < TILE; e += kTdThreads) sL[e] = T[e];
+        __syncthreads();
+        double acc[4][4] = {};
+        if (R == C) {
+            tile_mma<LDP, LDP, false>(acc, sLT, sLT, tm, tn);        // S0[m][n] = sum_k Linv[k][m] Linv[k][n]
+            regs_to_tile(acc, sig_lower + front_tile(f, C, C) * TILE, tm, tn);
+        } else {
+            tile_mma<NB, LDP, false>(acc, sL, sLT, tm, tn);          // Y[m][n] = sum_k L[m][k] Linv[k][n]
+            regs_to_tile_t(acc, T, tm, tn);                          // in place: every read of T happened before the barrier
+        }
+    }
+}
+
+// Sigma on the boundary block of every front of a level, from the parent's Sigma (the root's boundary is the rhs node
+// alone: Sigma'(rhs, rhs) = tau).  Lower tiles and their transposes.
+struct NdGatherArgs {
+    const FrontDesc* fronts; const int4* tasks; int n_tasks;
+    const int* pmap;
+    double *sig_lower, *sig_upper;
+    const double* scal_keep;        // [1] = tau
+};
+__global__ void __launch_bounds__(256) nd_gather_kernel(NdGatherArgs a) {
+    __shared__ double s_t[NB][NB + 1];
+    for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const int4 tk = a.tasks[t];
+        const FrontDesc f = a.fronts[tk.x];
+        const int R = tk.y, C = tk.z;
+        const long long me = front_tile(f, R, C);
+        const int* pm = a.pmap + f.pmap_off;
+        FrontDesc p;
+        if (f.parent >= 0) p = a.fronts[f.parent];
+        const int rhs_pos = f.nb - 1;                                    // boundary-local position of the rhs node
+        __syncthreads();
+        for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
+            const int r = e % NB, c = e / NB;
+            const int I = (R - f.nsT) * NB + r, J = (C - f.nsT) * NB + c;
+            double v = 0.0;
+            if (f.parent < 0) {
+                v = (I == rhs_pos && J == rhs_pos) ? a.scal_keep[1] : 0.0;
+            } else {
+                int pa = pm[I], pb = pm[J];
+                if (pa >= 0 && pb >= 0) {
+                    if (pa < pb) { const int s = pa; pa = pb; pb = s; }
+                    const double* src = a.sig_lower + front_tile(p, pa / NB, pb / NB) * TILE;
+                    int rr = pa % NB, cc = pb % NB;
+                    if (pa / NB == pb / NB && rr < cc) { const int s = rr; rr = cc; cc = s; }   // diagonal tile of the parent: its lower triangle
+                    v = __ldcg(src + cc * NB + rr);
+                }
+            }
+            a.sig_lower[me * TILE + e] = v;
+            s_t[r][c] = v;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < TILE; e += blockDim.x) a.sig_upper[me * TILE + e] = s_t[e / NB][e % NB];   // (r,c) <- (c,r)
+    }
+}
+
+struct NdSelArgs {
+    const FrontDesc* fronts; const int4* tasks; int n_tasks;
+    const double* Lpool;    // Y^T tiles (off-diagonal) from the pre-pass
+    double* sig_lower;      // Sigma(R, C) tiles, R >= C
+    double* sig_upper;      // their transposes
+    int* sready;            // [n_tiles] tile flags, [n_cnt] per-block-column counters, abort
+    long long n_tiles;
+    int n_cnt;
+};
+
+__global__ void __launch_bounds__(kTdThreads, 1) nd_selinv_kernel(NdSelArgs a) {
+    extern __shared__ __align__(128) unsigned char td_smem[];
+    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
+    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;
+    double* const pB = pA + PTILE;
+    __shared__ __align__(8) uint64_t full[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    int* cnt = a.sready + a.n_tiles;
+    int* abort_flag = cnt + a.n_cnt;
+    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    fence_proxy_async();
+    __syncthreads();
+    Phases ph;
+
+    for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
+        const int4 tk = a.tasks[t];
+        const FrontDesc f = a.fronts[tk.x];
+        const int R = tk.y, C = tk.z;                // R > C, C < nsT
+        const int Kmax = f.nT - 1, nK = Kmax - C;
+        auto issue = [&](int K, int s) {             // A = Sigma(R, K), B = Y(K, C)^T
+            const double* src;
+            const int* flag = nullptr;
+            int want = 1;
+            if (K == R) {
+                src = a.sig_lower + front_tile(f, R, R) * TILE;
+                if (R < f.nsT) { flag = cnt + f.cnt_base + R; want = f.nT - 1 - R; }      // all shares in
+            } else if (K < R) {
+                src = a.sig_lower + front_tile(f, R, K) * TILE;
+                if (K < f.nsT) flag = a.sready + front_tile(f, R, K);
+            } else {
+                src = a.sig_upper + front_tile(f, K, R) * TILE;
+                if (R < f.nsT) flag = a.sready + front_tile(f, K, R);
+            }
+            // the Y^T operand is there since the pre-pass: it is requested before the wait, only Sigma(R,K) after it
+            mbar_expect_tx(&full[s], 2 * TILE_BYTES);
+            tma_load_tile_(sB[s], a.Lpool + front_tile(f, K, C) * TILE, &full[s]);
+            if (flag != nullptr) wait_flag(flag, want, abort_flag);
+            fence_proxy_async();
+            tma_load_tile_(sA[s], src, &full[s]);
+        };
+        double acc[4][4] = {};
+        double cf[8][2] = {};                        // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
+        if (tid == 0) issue(Kmax, 0);
+        for (int q = 0; q < nK; ++q) {
+            const int s = q & 1;
+            if (tid == 0) {
+                if (q + 1 < nK) {
+                    issue(Kmax - q - 1, s ^ 1);
+                } else {
+                    // last product: the idle stage already fetches this tile's own Y^T for the diagonal contribution below
+                    mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
+                    tma_load_tile_(sB[s ^ 1], a.Lpool + front_tile(f, R, C) * TILE, &full[s ^ 1]);
+                }
+            }
+            mbar_wait(&full[s], ph.get(s));
+            ph.flip(s);
+            if (Kmax - q == R) repack_padded_sym(pA, sA[s], tid);      // Sigma(R,R): enforce symmetry (see repack_padded_sym)
+            else repack_padded(pA, sA[s], tid);
+            repack_padded(pB, sB[s], tid);
+            __syncthreads();
+            dmma_tile(cf, pA, pB, warp, lane);
+            __syncthreads();
+        }
+        const int so = nK & 1;                                          // the stage holding the own tile
+        frags_subtract(acc, cf, sA[so ^ 1], warp, lane, tm, tn);       // acc = -sum_K Sigma(R,K) Y(K,C)
+        const long long me = front_tile(f, R, C);
+        regs_to_tile(acc, a.sig_lower + me * TILE, tm, tn);
+        regs_to_tile_t_ld<LDT>(acc, pA, tm, tn);         // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
+        __syncthreads();
+        {
+            double* up = a.sig_upper + me * TILE;
+#pragma unroll
+            for (int idx = tid; idx < TILE / 2; idx += kTdThreads) {
+                const int c = idx >> 5, r = (idx & 31) * 2;
+                *reinterpret_cast<double2*>(up + c * NB + r) = *reinterpret_cast<const double2*>(pA + c * LDT + r);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) st_release(a.sready + me, 1);
+        mbar_wait(&full[so], ph.get(so));
+        ph.flip(so);
+        repack_padded(pB, sB[so], tid);
+        __syncthreads();
+        {
+            // D[a][b] = sum_m T[m][a] Y[m][b]: this tile's share of Sigma(C,C), added as REDs
+            double D[8][2] = {};
+            dmma_tile(D, pA, pB, warp, lane);
+            double* Sd = a.sig_lower + front_tile(f, C, C) * TILE;
+            const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb) {
+                atomicAdd(Sd + (cb * 8 + col) * NB + row, -D[cb][0]);
+                atomicAdd(Sd + (cb * 8 + col + 1) * NB + row, -D[cb][1]);
+            }
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) red_release_add(cnt + f.cnt_base + C, 1);
+    }
+}
+
+// x_j = -Sigma'(rhs, j) / tau
+__global__ void __launch_bounds__(256) nd_x_kernel(const long long* __restrict__ xoff, int M, const double* __restrict__ sig_lower,
+                                                   const double* __restrict__ scal_keep, const int* __restrict__ abort_flag,
+                                                   double* __restrict__ x) {
+    const double inv_tau = -1.0 / scal_keep[1];
+    const bool aborted = *abort_flag != 0;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x)
+        x[j] = aborted ? nan("") : __ldcg(sig_lower + xoff[j]) * inv_tau;
+}
+
+// stencil entries of P^-1 = Sigma' - tau x x^T
+__global__ void __launch_bounds__(256) nd_stencil_kernel(const long long* __restrict__ sigoff, int m1, int m2, int K,
+                                                         const double* __restrict__ sig_lower, const double* __restrict__ x,
+                                                         const double* __restrict__ scal_keep, const int* __restrict__ abort_flag,
+                                                         double* __restrict__ out) {
+    const int NS = 2 * K + 1, n_e = (K + 1) * NS;
+    const long long M = (long long)m1 * m2, total = M * n_e;
+    const double tau = scal_keep[1];
+    const bool aborted = *abort_flag != 0;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        long long off = sigoff[t];
+        double v = 0.0;
+        if (off >= 0) {
+            const bool diag_tile = (off >> 62) & 1;
+            off &= ~(1LL << 62);
+            v = __ldcg(sig_lower + off);
+            if (diag_tile) {
+                const long long base = off & ~(long long)(TILE - 1);
+                const int e = (int)(off & (TILE - 1));
+                v = 0.5 * (v + __ldcg(sig_lower + base + (e % NB) * NB + e / NB));
+            }
+            const int ee = (int)(t / M);
+            const long long j = t % M;
+            const long long i = j + (long long)(ee / NS) * m2 + (ee % NS - K);
+            v -= tau * x[i] * x[j];
+        }
+        out[t] = aborted ? nan("") : v;
+    }
+}
+
+template <class Kernel>
+static int nd_launch_persistent(Kernel kernel, void* args, int n_tasks, cudaStream_t st) {
+    int grid = 0;
+    if (int rc = persistent_grid(kernel, kTdSmem, n_tasks, &grid)) return rc;
+    void* params[] = {args};
+    ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(kTdThreads), params, kTdSmem, st));
+    ASVGP_LAUNCHED();
+    return kOk;
+}
+
+}  // namespace asvgp
+
+using namespace asvgp;
+
+#define ND_CHECK_ARGS(name)                                                                                              \
+    ASVGP_REQUIRE(m1 > 0 && m2 > 0 && order >= 1 && order <= kMaxOrder, name ": m=%d,%d order=%d", m1, m2, order)
+
+extern "C" int64_t asvgp_kron_band_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return nd_layout(*nd_plan_host(m1, m2, order)).band_total;
+}
+extern "C" int64_t asvgp_kron_sig_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return nd_layout(*nd_plan_host(m1, m2, order)).sig_total;
+}
+extern "C" int64_t asvgp_kron_work_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return nd_layout(*nd_plan_host(m1, m2, order)).work_total;
+}
+extern "C" int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return (int64_t)m1 * m2;
+}
+
+// Diagnostics / tests: out[0..7] = fronts, levels, tiles per pool, separator block columns, sum of separator sizes along the
+// longest root-to-leaf path (the dependency chain, in columns), the same in block columns, largest front (unknowns), flops.
+// idx_out (may be NULL): for every front, level, ns, nb, then the ns + nb node ids (rhs node = m1*m2); returns the number of
+// ints that takes.
+extern "C" int64_t asvgp_kron_plan_info(int m1, int m2, int order, double* out, int32_t* idx_out, int64_t idx_capacity) {
+    if (m1 <= 0 || m2 <= 0 || order < 1 || order > kMaxOrder) return -1;
+    const NdPlan& P = *nd_plan_host(m1, m2, order);
+    std::vector<long long> chain(P.n_fronts, 0), chainT(P.n_fronts, 0);
+    double flops = 0.0;
+    long long best = 0, bestT = 0;
+    int largest = 0;
+    for (int i = P.n_fronts - 1; i >= 0; --i) {                  // parents come after children: walk from the root down
+        const FrontDesc& d = P.fronts[i];
+        chain[i] = d.ns + (d.parent >= 0 ? chain[d.parent] : 0);
+        chainT[i] = d.nsT + (d.parent >= 0 ? chainT[d.parent] : 0);
+        best = std::max(best, chain[i]); bestT = std::max(bestT, chainT[i]);
+        largest = std::max(largest, d.ns + d.nb);
+        flops += (double)d.ns * (d.ns + d.nb) * (d.ns + d.nb);
+    }
+    if (out != nullptr) {
+        out[0] = P.n_fronts; out[1] = P.n_levels; out[2] = (double)P.n_tiles; out[3] = P.n_linv;
+        out[4] = (double)best; out[5] = (double)bestT; out[6] = largest; out[7] = flops;
+    }
+    int64_t need = 0;
+    for (const FrontDesc& d : P.fronts) need += 3 + d.ns + d.nb;
+    if (idx_out != nullptr && idx_capacity >= need) {
+        int64_t w = 0;
+        for (const FrontDesc& d : P.fronts) {
+            idx_out[w++] = d.level; idx_out[w++] = d.ns; idx_out[w++] = d.nb;
+            for (int j = 0; j < d.ns; ++j) idx_out[w++] = P.idx[d.idx_off + j];
+            for (int j = 0; j < d.nb; ++j) idx_out[w++] = P.idx[d.idx_off + d.nsT * NB + j];
+        }
+    }
+    return need;
+}
+
+// Assembles and factorises P front by front.  band: asvgp_kron_band_doubles doubles (opaque).  rhs_io[m1 m2]: Kuf_y (read
+// only here; asvgp_kron_selinv overwrites it with P^-1 Kuf_y).  scal[3] = log|P|, ||L^-1 Kuf_y||^2, info.
+extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
+                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream) {
+    ND_CHECK_ARGS("kron_factor");
+    ASVGP_REQUIRE(sigma2 > 0.0, "kron_factor: sigma2=%g", sigma2);
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
+    const NdPlan& P = *Pp;
+    const NdLayout lay = nd_layout(P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* flags = reinterpret_cast<int*>(band + lay.flags);
+    ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_flag_ints * sizeof(int), st));
+    ASVGP_CUDA_OK(cudaMemsetAsync(flags + P.n_tiles + 1, 0x7f, sizeof(int), st));                       // first bad pivot = "none"
+    for (int lev = P.n_levels - 1; lev >= 0; --lev) {
+        const int n_tasks = (int)P.factor_tasks[lev].size();
+        NdAssembleArgs aa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_cpos, K1, K2, Gs, rhs_io, sigma2,
+                          m1, m2, order, P.M, band};
+        nd_assemble_kernel<<<std::min(n_tasks, 148 * 8), 256, 0, st>>>(aa); ASVGP_LAUNCHED();
+        ASVGP_CUDA_OK(cudaGetLastError());
+        NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, band, band + lay.linv, flags, P.n_tiles};
+        if (int rc = nd_launch_persistent(nd_factor_kernel, &fa, n_tasks, st)) return rc;
+    }
+    nd_scalars_kernel<<<1, 1024, 0, st>>>(P.d_doff, P.M, band, P.quad_off, flags, P.n_tiles, scal, band + lay.scal); ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+// From the factor (consumed: its off-diagonal tiles become Y^T): sigma_stencil[(order+1)(2 order+1) x M] = entries of P^-1
+// on the stencil, x_io[M] = P^-1 Kuf_y.  sig_band: asvgp_kron_sig_doubles doubles of scratch; work: asvgp_kron_work_doubles.
+// If a persistent kernel gives up waiting (abort flag), the outputs are NaN.
+extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+                                 double* sigma_stencil, double* work, void* stream) {
+    ND_CHECK_ARGS("kron_selinv");
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
+    const NdPlan& P = *Pp;
+    const NdLayout lay = nd_layout(P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int* flags = reinterpret_cast<int*>(work);
+    ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_work_ints * sizeof(int), st));
+    double* sigL = sig_band;
+    double* sigU = sig_band + lay.sig_upper;
+    const size_t yp_smem = (size_t)(NB * (NB + 1) + TILE) * sizeof(double);
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(nd_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
+    const int n_yp = (int)P.ypass_tasks.size();
+    nd_ypass_kernel<<<std::min(n_yp, 148 * 4), kTdThreads, yp_smem, st>>>(P.d_fronts, P.d_ypass_tasks, n_yp, band, band + lay.linv, sigL);
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    for (int lev = 0; lev < P.n_levels; ++lev) {
+        const int n_g = (int)P.gather_tasks[lev].size();
+        NdGatherArgs ga{P.d_fronts, P.d_gather_tasks[lev], n_g, P.d_pmap, sigL, sigU, band + lay.scal};
+        nd_gather_kernel<<<std::min(n_g, 148 * 8), 256, 0, st>>>(ga); ASVGP_LAUNCHED();
+        ASVGP_CUDA_OK(cudaGetLastError());
+        const int n_s = (int)P.selinv_tasks[lev].size();
+        if (n_s == 0) continue;
+        NdSelArgs sa{P.d_fronts, P.d_selinv_tasks[lev], n_s, band, sigL, sigU, flags, P.n_tiles, P.n_cnt};
+        if (int rc = nd_launch_persistent(nd_selinv_kernel, &sa, n_s, st)) return rc;
+    }
+    const int* abort_flag = flags + P.n_tiles + P.n_cnt;
+    nd_x_kernel<<<(P.M + 255) / 256, 256, 0, st>>>(P.d_xoff, P.M, sigL, band + lay.scal, abort_flag, x_io); ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    const int64_t total = (int64_t)P.M * (order + 1) * (2 * order + 1);
+    nd_stencil_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(P.d_sigoff, m1, m2, order, sigL, x_io,
+                                                                                          band + lay.scal, abort_flag, sigma_stencil);
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}

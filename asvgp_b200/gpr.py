@@ -251,10 +251,11 @@ class GPR_kron(_ModelBase):
         [G stencil | Kuf_y | sum y^2 | N] is all-reduced once, the factorisation is replicated.
     """
 
-    def __init__(self, data, kernels, bases, distributed="auto", check_inputs=True):
+    def __init__(self, data, kernels, bases, distributed="auto", check_inputs=True, method=None):
         X, y = data
         self.X, self.y = X, y
         self.n = X.shape[0]
+        self._method = method          # None: ops.KRON_METHOD ("nd" nested-dissection fronts; "band": tile DAG over the band)
         self.d = X.shape[1]
 
         # Check dimensionality of inputs / valid kernels (reference gpr.py:247-252)
@@ -354,7 +355,7 @@ class GPR_kron(_ModelBase):
         s2 = hyper_value(self.likelihood.variance)
         v = [hyper_value(k.variance) for k in self.kernels]
         m1, m2 = self.bases[0].m, self.bases[1].m
-        ws = ops.kron_workspace(m1, m2, self.order)
+        ws = ops.kron_workspace(m1, m2, self.order, getattr(self, "_method", None))
         Ks, dKs, Ss, dSs, scals = self._factors(want_grad)
         ops.kron_factor(Ks[0], Ks[1], self._acc, self.bases, s2, ws)
         if want_grad:
@@ -409,7 +410,7 @@ class GPR_kron(_ModelBase):
         """(alpha, SigP stencil, S1, S2) on the device: alpha = P^-1 Kuf_y / sigma2, SigP = stencil entries of P^-1,
         S_i = band(K_i^-1)."""
         s2 = hyper_value(self.likelihood.variance)
-        ws = ops.kron_workspace(self.bases[0].m, self.bases[1].m, self.order)
+        ws = ops.kron_workspace(self.bases[0].m, self.bases[1].m, self.order, getattr(self, "_method", None))
         Ks, _, Ss, _, scals = self._factors(False)
         ops.kron_factor(Ks[0], Ks[1], self._acc, self.bases, s2, ws)
         SigP, x = ops.kron_selinv(self.bases, ws)

@@ -416,18 +416,22 @@ def band_inverse_1d(A, dA, basis, chunks=0):
     return sig, dsig, scal
 
 
-class KronWorkspace:
-    """Device buffers of the block-band factorisation of P = K1 (x) K2 + G / sigma2 (cached per (device, m1, m2, k))."""
+KRON_METHODS = ("nd", "band")
+KRON_METHOD = "nd"        # default factorisation of the 2-D model: nested-dissection fronts; "band" = tile DAG over the scalar band
 
-    def __init__(self, m1, m2, order):
+
+class KronWorkspace:
+    """Device buffers of the factorisation of P = K1 (x) K2 + G / sigma2 (cached per (device, m1, m2, k, method))."""
+
+    def __init__(self, m1, m2, order, method="nd"):
         lib = _lib.load()
         dev = device()
-        self.m1, self.m2, self.order = m1, m2, order
+        if method not in KRON_METHODS:
+            raise ValueError("method must be one of %r" % (KRON_METHODS,))
+        self.m1, self.m2, self.order, self.method = m1, m2, order, method
         self.M = m1 * m2
-        nb = lib.asvgp_kron_band_doubles(m1, m2, order)
-        nw = lib.asvgp_kron_work_doubles(m1, m2, order)
-        ns = lib.asvgp_kron_sig_doubles(m1, m2, order)
-        nr = lib.asvgp_kron_rhs_doubles(m1, m2, order)
+        self.prefix = "asvgp_kron_" if method == "nd" else "asvgp_kronband_"
+        nb, nw, ns, nr = (getattr(lib, self.prefix + q)(m1, m2, order) for q in ("band_doubles", "work_doubles", "sig_doubles", "rhs_doubles"))
         if min(nb, nw, ns, nr) < 0:
             raise _lib.AsvgpNativeError("kron workspace query rejected m=%d,%d order=%d" % (m1, m2, order))
         self.band = torch.empty(nb, dtype=F64, device=dev)
@@ -443,21 +447,45 @@ class KronWorkspace:
 _KRON_WS = {}
 
 
-def kron_workspace(m1, m2, order):
-    key = (device(), m1, m2, order)
+def kron_workspace(m1, m2, order, method=None):
+    method = method or KRON_METHOD
+    key = (device(), m1, m2, order, method)
     ws = _KRON_WS.get(key)
     if ws is None:
-        ws = _KRON_WS[key] = KronWorkspace(m1, m2, order)
+        ws = _KRON_WS[key] = KronWorkspace(m1, m2, order, method)
     return ws
 
 
+def kron_plan_info(m1, m2, order, with_fronts=False):
+    """Shape of the nested-dissection elimination tree (host-side query, no GPU needed): dict of counts and, with
+    `with_fronts`, the list of fronts as (level, separator ids, boundary ids); id m1*m2 is the right-hand-side row."""
+    lib = _lib.load()
+    out = (ctypes.c_double * 8)()
+    need = lib.asvgp_kron_plan_info(m1, m2, order, ctypes.cast(out, ctypes.c_void_p), None, 0)
+    if need < 0:
+        raise _lib.AsvgpNativeError("kron_plan_info rejected m=%d,%d order=%d" % (m1, m2, order))
+    info = dict(zip(("fronts", "levels", "tiles", "separator_block_columns", "chain_columns", "chain_block_columns",
+                     "largest_front", "flops"), [float(v) for v in out]))
+    if with_fronts:
+        buf = np.zeros(need, dtype=np.int32)
+        lib.asvgp_kron_plan_info(m1, m2, order, None, buf.ctypes.data_as(ctypes.c_void_p), need)
+        fronts, w = [], 0
+        while w < need:
+            level, ns, nb = (int(v) for v in buf[w:w + 3])
+            fronts.append((level, buf[w + 3:w + 3 + ns].copy(), buf[w + 3 + ns:w + 3 + ns + nb].copy()))
+            w += 3 + ns + nb
+        info["front_list"] = fronts
+    return info
+
+
 def kron_factor(K1, K2, acc, bases, sigma2, ws):
-    """Block-band Cholesky of P, forward substitution of Kuf_y; ws.scal = {log|P|, ||L^-1 b||^2, info}."""
+    """Factorisation of P and forward substitution of Kuf_y; ws.scal = {log|P|, ||L^-1 b||^2, info}."""
     k, m1, m2 = _check_bases_2d(bases)
     Gs, b, _ = split_accum_2d(acc, bases)
-    ws.rhs.zero_()
+    if ws.method == "band":
+        ws.rhs.zero_()
     ws.rhs[: ws.M].copy_(b)
-    _lib.call("asvgp_kron_factor", _p(K1), _p(K2), _p(Gs), m1, m2, k, float(sigma2), _p(ws.band), _p(ws.rhs),
+    _lib.call(ws.prefix + "factor", _p(K1), _p(K2), _p(Gs), m1, m2, k, float(sigma2), _p(ws.band), _p(ws.rhs),
               _p(ws.scal), _stream())
     return ws
 
@@ -467,7 +495,7 @@ def kron_selinv(bases, ws):
     k, m1, m2 = _check_bases_2d(bases)
     if ws.sig_band is None:
         ws.sig_band = torch.empty(ws.n_sig, dtype=F64, device=ws.band.device)
-    _lib.call("asvgp_kron_selinv", _p(ws.band), m1, m2, k, _p(ws.sig_band), _p(ws.rhs), _p(ws.sigma_stencil),
+    _lib.call(ws.prefix + "selinv", _p(ws.band), m1, m2, k, _p(ws.sig_band), _p(ws.rhs), _p(ws.sigma_stencil),
               _p(ws.work), _stream())
     return ws.sigma_stencil, ws.rhs[: ws.M]
 

@@ -152,31 +152,50 @@ ASVGP_API int asvgp_order_probe_2d(const double* X, int64_t n, const double* mes
 ASVGP_API int asvgp_expand_moments_2d(const double* cellmom, const double* Cprod, const double* Dy, int n_knots1,
                                       int n_knots2, int order, double* Gs, double* b, void* stream);
 
-/* ---- a13 + a14: block-band factorisation of P = K1 (x) K2 + G / sigma2 -------------------------------------------------------
+/* ---- a13 + a14: factorisation of P = K1 (x) K2 + G / sigma2 and its selected inverse ---------------------------------------------
  * Replaces utils.bands_to_kron_cholesky (utils.py:45-51), tf.linalg.cholesky(P), its log-det and
- * triangular_solve(L_P, Kuf_y) (gpr.py:287-295) with a tiled band factorisation of scalar bandwidth order*(m2+1)
- * (one persistent kernel).  Buffer sizes (doubles) come from the four queries below.
- * band: receives the factor (opaque tile layout); rhs_io: in Kuf_y zero padded, out L^-1 Kuf_y;
- * scal[3] = { log|P|, ||L^-1 Kuf_y||^2, info } with info = 0 ok, j+1 first non-positive pivot, -1 internal time-out. */
+ * triangular_solve(L_P, Kuf_y) (gpr.py:287-295), and what the reference's dense cholesky_solve / TF reverse mode extract
+ * from P^-1 (gpr.py:293-307, 319-326).
+ *
+ * asvgp_kron_*: nested-dissection multifrontal method (csrc/ndfront_2d.cu).  The m1 x m2 grid of basis functions is bisected
+ * recursively by order-wide strips; every tree level is one batch of independent dense fronts (persistent tile-DAG kernels,
+ * fp64 tensor cores); the dependency chain is 1751 columns at 200 x 200, order 3, instead of 40 000.  Kuf_y rides along as
+ * an extra row of every front, so ||L^-1 Kuf_y||^2 and P^-1 Kuf_y need no separate solves.
+ * Buffer sizes (doubles) come from the four queries below.
+ *   band:   receives the factor (opaque);  rhs_io[m1 m2]: Kuf_y (input of asvgp_kron_factor; asvgp_kron_selinv overwrites it
+ *           with P^-1 Kuf_y);  scal[3] = { log|P|, ||L^-1 Kuf_y||^2, info } with info = 0 ok, j+1 = basis function whose pivot
+ *           was not positive, -1 internal time-out.
+ *   asvgp_kron_selinv: sigma_stencil = entries of P^-1 in stencil layout, x_io = P^-1 Kuf_y.  `band` is CONSUMED; sig_band:
+ *           asvgp_kron_sig_doubles of scratch; work: asvgp_kron_work_doubles.  An internal time-out poisons the outputs with NaN.
+ * asvgp_kron_plan_info: diagnostics of the elimination tree, out[8] = { fronts, levels, tiles per pool, separator block
+ *   columns, dependency chain in columns, in 64-column blocks, largest front, flops }; idx_out (may be NULL, capacity in ints):
+ *   per front { level, ns, nb, ns separator ids, nb boundary ids (m1*m2 = the right-hand-side row) }; returns the ints needed. */
 ASVGP_API int64_t asvgp_kron_band_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_sig_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_work_doubles(int m1, int m2, int order);
 ASVGP_API int64_t asvgp_kron_rhs_doubles(int m1, int m2, int order);
-/* Diagnostics: offset (doubles) inside `band` of the per-block-column record, 20 doubles per block column,
- * ceil(m1*m2/64) block columns: [0] 2 sum log L_cc, [1] ||y_C||^2, [2..7] %globaltimer stamps of the factorisation's
- * critical path, [8..11] SM-cycle split of the diagonal tile's POTRF, [12..18] stamps of the first sub-diagonal tile in
- * asvgp_kron_selinv (tools/kron_chain_times.py prints both chains). */
-ASVGP_API int64_t asvgp_kron_colstat_offset(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kron_plan_info(int m1, int m2, int order, double* out, int32_t* idx_out, int64_t idx_capacity);
 ASVGP_API int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream);
-
-/* Selected inverse on the stencil pattern (blocked Takahashi recursion, one persistent kernel) and back-substitution:
- * sigma_stencil = entries of P^-1 in stencil layout, x_io: in L^-1 b, out P^-1 b.  This is what the reference's dense
- * cholesky_solve / TF reverse mode extract from P^-1 (gpr.py:293-307, 319-326).  `band` is CONSUMED (its off-diagonal
- * tiles are overwritten); sig_band: asvgp_kron_sig_doubles of scratch; work: asvgp_kron_work_doubles.  An internal
- * time-out poisons sigma_stencil with NaN. */
 ASVGP_API int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
                                 double* sigma_stencil, double* work, void* stream);
+
+/* asvgp_kronband_*: the same two operations on the scalar band of P in the natural order (bandwidth order*(m2+1), gpr.py:262)
+ * as one tile DAG over the band (csrc/tiledag_2d.cu) — a single chain over all m1 m2 columns, 10x slower at 200 x 200; kept
+ * as an independent second implementation (the tests compare the two).  Same arguments, except that rhs_io has
+ * asvgp_kronband_rhs_doubles entries (zero padded) and holds L^-1 Kuf_y between the two calls.
+ * asvgp_kronband_colstat_offset: offset (doubles) inside `band` of the per-block-column diagnostics record, 20 doubles per
+ * block column: [0] 2 sum log L_cc, [1] ||y_C||^2, [2..7] %globaltimer stamps of the factorisation's critical path,
+ * [8..11] SM-cycle split of the diagonal tile's POTRF, [12..18] stamps of the selected inverse (tools/kron_chain_times.py). */
+ASVGP_API int64_t asvgp_kronband_band_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kronband_sig_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kronband_work_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kronband_rhs_doubles(int m1, int m2, int order);
+ASVGP_API int64_t asvgp_kronband_colstat_offset(int m1, int m2, int order);
+ASVGP_API int asvgp_kronband_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
+                                    double sigma2, double* band, double* rhs_io, double* scal, void* stream);
+ASVGP_API int asvgp_kronband_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+                                    double* sigma_stencil, double* work, void* stream);
 
 /* Scalar contractions for the ELBO gradient and the Kronecker trace term; out[11] (device):
  *   [0..3]  sum P^-1 .* Op,  [4..7]  x^T Op x   for Op = G, dK1(x)K2, K1(x)dK2, K1(x)K2

@@ -19,11 +19,11 @@ cm = ops.moment_table_2d(bases)
 ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2]); ops.expand_moments_2d(cm, bases, acc)
 kerns = [Kn.Matern32(variance=1.0, lengthscales=5.0), Kn.Matern32(variance=1.0, lengthscales=4.0)]
 Ks = [SplineFeatures1D(kerns[i], bases[i]).make_Kuu_device(kerns[i])[0] for i in range(2)]
-ws = ops.kron_workspace(m, m, k)
+ws = ops.kron_workspace(m, m, k, "band")
 for _ in range(3):
     ops.kron_factor(Ks[0], Ks[1], acc, bases, 0.01, ws)
 torch.cuda.synchronize()
-off = _lib.load().asvgp_kron_colstat_offset(m, m, k)
+off = _lib.load().asvgp_kronband_colstat_offset(m, m, k)
 nb = -(-m * m // 64)
 NS = 20
 st = ws.band[off: off + NS * nb].view(nb, NS).cpu().numpy()

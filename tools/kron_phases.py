@@ -47,7 +47,7 @@ model.kernels, model.bases, model.order = kerns, bases, k
 model.inducing_features = [SplineFeatures1D(kerns[i], bases[i]) for i in range(2)]
 out["factors_ms"] = timed(lambda: model._factors(True))
 Ks, dKs, Ss, dSs, scals = model._factors(True)
-ws = ops.kron_workspace(m, m, k)
+ws = ops.kron_workspace(m, m, k, "band")
 s2 = 0.01
 out["kron_factor_ms"] = timed(lambda: ops.kron_factor(Ks[0], Ks[1], acc, bases, s2, ws))
 M = m * m
