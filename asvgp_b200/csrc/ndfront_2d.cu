@@ -27,9 +27,11 @@
 // solves, no separate chains.
 //
 // Kernels, per tree level (bottom-up for the factorisation, top-down for the selected inverse):
-//   nd_assemble_kernel   entries of P (and of the children's update matrices: extend-add as a gather) into the front
-//   nd_factor_kernel     persistent tile DAG over all tiles of all fronts of the level: left-looking updates on the fp64
-//                        tensor cores, diagonal tiles factorised + inverted in registers, trailing tiles = update matrix
+//   nd_assemble_kernel   (once) entries of P and the right-hand-side row into every front
+//   nd_factor_kernel     persistent tile DAG over all tiles of all fronts of the level: every task first adds the entries of
+//                        the children's update matrices that land in its tile (extend-add as a gather), then left-looking
+//                        updates on the fp64 tensor cores, diagonal tiles factorised + inverted in registers, trailing
+//                        tiles = this front's update matrix
 //   nd_ypass_kernel      (once) L(R,C) -> Y(R,C)^T = (L(R,C) L(C,C)^-1)^T, Sigma(C,C) seeded with L(C,C)^-T L(C,C)^-1
 //   nd_gather_kernel     Sigma on the boundary of a front from its parent's Sigma
 //   nd_selinv_kernel     persistent tile DAG: blocked Takahashi recursion inside every front of the level
@@ -108,17 +110,18 @@ struct NdPlan {
     std::vector<FrontDesc> fronts;
     std::vector<int> idx, pmap, cpos;
     std::vector<std::vector<int4>> factor_tasks, selinv_tasks, gather_tasks;    // per level
-    std::vector<int4> ypass_tasks;
+    std::vector<int4> ypass_tasks, all_tasks;
     std::vector<long long> doff, xoff, sigoff;
     long long quad_off = 0, tau_off = 0;           // L-pool offset of the root's update entry (rhs, rhs); sig-pool offset of Sigma'(rhs, rhs)
     // device copies
     FrontDesc* d_fronts = nullptr;
     int *d_idx = nullptr, *d_pmap = nullptr, *d_cpos = nullptr;
     std::vector<int4*> d_factor_tasks, d_selinv_tasks, d_gather_tasks;
-    int4* d_ypass_tasks = nullptr;
+    int4 *d_ypass_tasks = nullptr, *d_all_tasks = nullptr;
     long long *d_doff = nullptr, *d_xoff = nullptr, *d_sigoff = nullptr;
 };
 
+constexpr int kNdScalarBlocks = 64;   // slices of the log-determinant sum
 constexpr int kNdLeaf = 12;        // regions whose sides are both <= this many grid lines are eliminated as one front
 
 static void nd_build(NdPlan& P, int m1, int m2, int K) {
@@ -199,8 +202,11 @@ static void nd_build(NdPlan& P, int m1, int m2, int K) {
     }
     for (int i = 0; i < P.n_fronts; ++i) {
         const FrontDesc& d = P.fronts[i];
-        for (int C = 0; C < d.nsT; ++C)
-            for (int R = C; R < d.nT; ++R) P.ypass_tasks.push_back(make_int4(i, R, C, 0));
+        for (int C = 0; C < d.nT; ++C)
+            for (int R = C; R < d.nT; ++R) {
+                if (C < d.nsT) P.ypass_tasks.push_back(make_int4(i, R, C, 0));
+                P.all_tasks.push_back(make_int4(i, R, C, 0));
+            }
     }
     // element offsets for the scalar / extraction kernels
     std::vector<int> owner(M), opos(M);
@@ -291,6 +297,7 @@ static int nd_plan_device(int m1, int m2, int K, const NdPlan** out) {
         if (int rc = nd_upload(&P->d_gather_tasks[l], P->gather_tasks[l])) return rc;
     }
     if (int rc = nd_upload(&P->d_ypass_tasks, P->ypass_tasks)) return rc;
+    if (int rc = nd_upload(&P->d_all_tasks, P->all_tasks)) return rc;
     if (int rc = nd_upload(&P->d_doff, P->doff)) return rc;
     if (int rc = nd_upload(&P->d_xoff, P->xoff)) return rc;
     if (int rc = nd_upload(&P->d_sigoff, P->sigoff)) return rc;
@@ -310,8 +317,8 @@ static NdLayout nd_layout(const NdPlan& P) {
     NdLayout L;
     L.linv = P.n_tiles * TILE;
     L.scal = L.linv + (long long)P.n_linv * TILE;
-    L.flags = L.scal + 8;
-    L.n_flag_ints = P.n_tiles + 8;                       // tile flags, abort, first bad pivot
+    L.flags = L.scal + 8 + kNdScalarBlocks;
+    L.n_flag_ints = P.n_tiles + 8;                       // tile flags, abort, first bad pivot, scalar-kernel block counter
     L.band_total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
     L.sig_upper = P.n_tiles * TILE;
     L.sig_total = 2 * L.sig_upper;
@@ -321,11 +328,12 @@ static NdLayout nd_layout(const NdPlan& P) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// assembly: entries of P (+ right-hand side row) and the children's update matrices (extend-add as a gather)
+// assembly: entries of P (+ right-hand side row) of every front, one fully parallel launch; the children's update matrices
+// are added by the factorisation tasks themselves (extend-add as a gather, add_children)
 // ---------------------------------------------------------------------------------------------------------------------
 struct NdAssembleArgs {
     const FrontDesc* fronts; const int4* tasks; int n_tasks;
-    const int *idx, *cpos;
+    const int* idx;
     const double *K1, *K2, *Gs, *b;
     double sigma2;
     int m1, m2, K, M;
@@ -357,11 +365,7 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
         const int R = tk.y, C = tk.z;
         double* tile = a.Lpool + front_tile(f, R, C) * TILE;
         const int* idx = a.idx + f.idx_off;
-        FrontDesc ch[2];
-        const int* cpos[2] = {nullptr, nullptr};
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
-            if (f.child[c] >= 0) { ch[c] = a.fronts[f.child[c]]; cpos[c] = a.cpos + f.cpos_off[c]; }
+        if (C >= f.nsT && f.child[0] < 0) continue;          // trailing tiles of a leaf front start from zero: never read
         for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
             const int r = e % NB, c = e / NB;
             const int I = R * NB + r, J = C * NB + c;
@@ -369,15 +373,6 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
             double v;
             if (gi < 0 || gj < 0) v = (I == J && C < f.nsT) ? 1.0 : 0.0;
             else v = (C < f.nsT) ? nd_entry(a, gi, gj) : 0.0;
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (cpos[q] == nullptr) continue;
-                int pa = cpos[q][I], pb = cpos[q][J];
-                if (pa < 0 || pb < 0) continue;
-                if (pa < pb) { const int s = pa; pa = pb; pb = s; }     // lower triangle of the child's update matrix
-                const double* u = a.Lpool + front_tile(ch[q], ch[q].nsT + pa / NB, ch[q].nsT + pb / NB) * TILE;
-                v += __ldcg(u + (pb % NB) * NB + pa % NB);
-            }
             tile[e] = v;
         }
     }
@@ -388,11 +383,41 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
 // ---------------------------------------------------------------------------------------------------------------------
 struct NdFactorArgs {
     const FrontDesc* fronts; const int4* tasks; int n_tasks;
-    const int* idx;
+    const int *idx, *cpos;
     double* Lpool; double* linv;
     int* ready;         // [n_tiles] + abort at [n_tiles], first bad pivot (node id + 1) at [n_tiles + 1]
     long long n_tiles;
 };
+
+// acc (this thread's 4 x 4 block of tile (R, C) of front f) += the entries of the children's update matrices that land there
+__device__ __forceinline__ void add_children(double (&acc)[4][4], const NdFactorArgs& a, const FrontDesc& f, int R, int C, int tm, int tn) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (f.child[q] < 0) continue;
+        const int* cp = a.cpos + f.cpos_off[q];
+        int pr[4], pc[4];
+        bool any_r = false, any_c = false;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            pr[i] = __ldg(cp + R * NB + tm + i); pc[i] = __ldg(cp + C * NB + tn + i);
+            any_r |= pr[i] >= 0; any_c |= pc[i] >= 0;
+        }
+        if (!(any_r && any_c)) continue;
+        const long long cbase = a.fronts[f.child[q]].tile_base;
+        const int cnT = a.fronts[f.child[q]].nT, cnsT = a.fronts[f.child[q]].nsT;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int pa = pr[i], pb = pc[j];
+                if (pa < 0 || pb < 0) continue;
+                if (pa < pb) { const int s = pa; pa = pb; pb = s; }     // lower triangle of the child's update matrix
+                const int Rc = cnsT + pa / NB, Cc = cnsT + pb / NB;
+                const long long tix = cbase + (long long)Cc * cnT - (long long)Cc * (Cc - 1) / 2 + (Rc - Cc);
+                acc[i][j] += __ldcg(a.Lpool + tix * TILE + (pb % NB) * NB + pa % NB);
+            }
+    }
+}
 
 __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
@@ -416,7 +441,15 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
         const bool diag = R == C;
         double* my_tile = a.Lpool + front_tile(f, R, C) * TILE;
         double acc[4][4];
-        regs_from_tile(acc, my_tile, tm, tn);
+        if (C >= f.nsT && f.child[0] < 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        } else {
+            regs_from_tile(acc, my_tile, tm, tn);
+            add_children(acc, a, f, R, C, tm, tn);
+        }
         const int nJ = min(C, f.nsT);
 
         auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
@@ -506,21 +539,34 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
     }
 }
 
-// log|P| = 2 sum log L_jj (deterministic tree reduction), ||y||^2 = -(root update entry (rhs, rhs)), info, and tau
-__global__ void __launch_bounds__(1024) nd_scalars_kernel(const long long* __restrict__ doff, int M, const double* __restrict__ Lpool,
-                                                          long long quad_off, const int* __restrict__ ready, long long n_tiles,
-                                                          double* __restrict__ scal_out, double* __restrict__ scal_keep) {
-    __shared__ double s[1024];
+// log|P| = 2 sum log L_jj (deterministic: fixed slices, tree reductions, the last block to finish adds the slices in order),
+// ||y||^2 = -(root update entry (rhs, rhs)), info, and tau
+__global__ void __launch_bounds__(256) nd_scalars_kernel(const long long* __restrict__ doff, int M, const double* __restrict__ Lpool,
+                                                         long long quad_off, int* __restrict__ ready, long long n_tiles,
+                                                         double* __restrict__ scal_out, double* __restrict__ scal_keep) {
+    __shared__ double s[256];
+    __shared__ bool last;
     double acc = 0.0;
-    for (int j = threadIdx.x; j < M; j += blockDim.x) acc += log(Lpool[doff[j]]);
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) acc += log(__ldcg(Lpool + doff[j]));
     s[threadIdx.x] = acc;
     __syncthreads();
-    for (int o = 512; o > 0; o >>= 1) {
+    for (int o = 128; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        const double quad = -Lpool[quad_off];
+        scal_keep[8 + blockIdx.x] = s[0];
+        __threadfence();
+        last = atomicAdd(ready + n_tiles + 2, 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int bk = 0; bk < (int)gridDim.x; ++bk) tot += __ldcg(scal_keep + 8 + bk);
+        s[0] = tot;
+        const double quad = -__ldcg(Lpool + quad_off);
         const int aborted = ready[n_tiles], bad = ready[n_tiles + 1];
         scal_out[0] = 2.0 * s[0];
         scal_out[1] = quad;
@@ -539,30 +585,31 @@ __global__ void __launch_bounds__(1024) nd_scalars_kernel(const long long* __res
 __global__ void __launch_bounds__(kTdThreads) nd_ypass_kernel(const FrontDesc* __restrict__ fronts, const int4* __restrict__ tasks,
                                                               int n_tasks, double* __restrict__ Lpool, const double* __restrict__ linv,
                                                               double* __restrict__ sig_lower) {
-    constexpr int LDP = NB + 1;
     extern __shared__ __align__(16) unsigned char yp_smem[];
-    double* sLT = reinterpret_cast<double*>(yp_smem);        // Linv transposed, padded: Linv[k][c] at [k*65 + c]
-    double* sL = sLT + NB * LDP;                             // L tile, column-major
-    const int tid = threadIdx.x, tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
+    double* pL = reinterpret_cast<double*>(yp_smem);         // L tile as the A operand: L[m][k] at [k*LDT + m]
+    double* pI = pL + PTILE;                                 // Linv transposed: Linv[k][n] at [k*LDT + n]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const int4 tk = tasks[t];
         const FrontDesc f = fronts[tk.x];
         const int R = tk.y, C = tk.z;
         const double* Li = linv + (long long)(f.linv_base + C) * TILE;
-        __syncthreads();
-        for (int e = tid; e < TILE; e += kTdThreads) sLT[(e % NB) * LDP + e / NB] = Li[e];
         double* T = Lpool + front_tile(f, R, C) * TILE;
-        if (R != C)
-            for (int e = tid; e < TILE; e += kTdThreads) sL[e] = T[e];
         __syncthreads();
-        double acc[4][4] = {};
-        if (R == C) {
-            tile_mma<LDP, LDP, false>(acc, sLT, sLT, tm, tn);        // S0[m][n] = sum_k Linv[k][m] Linv[k][n]
-            regs_to_tile(acc, sig_lower + front_tile(f, C, C) * TILE, tm, tn);
-        } else {
-            tile_mma<NB, LDP, false>(acc, sL, sLT, tm, tn);          // Y[m][n] = sum_k L[m][k] Linv[k][n]
-            regs_to_tile_t(acc, T, tm, tn);                          // in place: every read of T happened before the barrier
+        for (int e = tid; e < TILE; e += kTdThreads) {
+            const int r = e % NB, c = e / NB;
+            pI[r * LDT + c] = __ldcg(Li + e);                 // Li[e] = Linv[r][c]
+            if (R != C) pL[c * LDT + r] = __ldcg(T + e);
         }
+        __syncthreads();
+        double cf[8][2] = {};
+        // diagonal: S0[m][n] = sum_k Linv[k][m] Linv[k][n];  off-diagonal: Y[m][n] = sum_k L[m][k] Linv[k][n]
+        dmma_tile(cf, R == C ? pI : pL, pI, warp, lane);
+        double* out = (R == C) ? sig_lower + front_tile(f, C, C) * TILE : T;       // Y is stored transposed (row m contiguous), in place
+        const int m = warp * 8 + (lane >> 2), n0 = (lane & 3) * 2;
+#pragma unroll
+        for (int cb = 0; cb < 8; ++cb)
+            *reinterpret_cast<double2*>(out + m * NB + cb * 8 + n0) = make_double2(cf[cb][0], cf[cb][1]);
     }
 }
 
@@ -847,16 +894,18 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
     int* flags = reinterpret_cast<int*>(band + lay.flags);
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_flag_ints * sizeof(int), st));
     ASVGP_CUDA_OK(cudaMemsetAsync(flags + P.n_tiles + 1, 0x7f, sizeof(int), st));                       // first bad pivot = "none"
+    {
+        const int n_all = (int)P.all_tasks.size();
+        NdAssembleArgs aa{P.d_fronts, P.d_all_tasks, n_all, P.d_idx, K1, K2, Gs, rhs_io, sigma2, m1, m2, order, P.M, band};
+        nd_assemble_kernel<<<std::min(n_all, 148 * 16), 256, 0, st>>>(aa); ASVGP_LAUNCHED();
+        ASVGP_CUDA_OK(cudaGetLastError());
+    }
     for (int lev = P.n_levels - 1; lev >= 0; --lev) {
         const int n_tasks = (int)P.factor_tasks[lev].size();
-        NdAssembleArgs aa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_cpos, K1, K2, Gs, rhs_io, sigma2,
-                          m1, m2, order, P.M, band};
-        nd_assemble_kernel<<<std::min(n_tasks, 148 * 8), 256, 0, st>>>(aa); ASVGP_LAUNCHED();
-        ASVGP_CUDA_OK(cudaGetLastError());
-        NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, band, band + lay.linv, flags, P.n_tiles};
+        NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_cpos, band, band + lay.linv, flags, P.n_tiles};
         if (int rc = nd_launch_persistent(nd_factor_kernel, &fa, n_tasks, st)) return rc;
     }
-    nd_scalars_kernel<<<1, 1024, 0, st>>>(P.d_doff, P.M, band, P.quad_off, flags, P.n_tiles, scal, band + lay.scal); ASVGP_LAUNCHED();
+    nd_scalars_kernel<<<kNdScalarBlocks, 256, 0, st>>>(P.d_doff, P.M, band, P.quad_off, flags, P.n_tiles, scal, band + lay.scal); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
@@ -876,10 +925,10 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_work_ints * sizeof(int), st));
     double* sigL = sig_band;
     double* sigU = sig_band + lay.sig_upper;
-    const size_t yp_smem = (size_t)(NB * (NB + 1) + TILE) * sizeof(double);
+    const size_t yp_smem = (size_t)(2 * PTILE) * sizeof(double);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(nd_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
     const int n_yp = (int)P.ypass_tasks.size();
-    nd_ypass_kernel<<<std::min(n_yp, 148 * 4), kTdThreads, yp_smem, st>>>(P.d_fronts, P.d_ypass_tasks, n_yp, band, band + lay.linv, sigL);
+    nd_ypass_kernel<<<std::min(n_yp, 148 * 3), kTdThreads, yp_smem, st>>>(P.d_fronts, P.d_ypass_tasks, n_yp, band, band + lay.linv, sigL);
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     for (int lev = 0; lev < P.n_levels; ++lev) {

@@ -619,8 +619,11 @@ template <int K>
 __global__ void __launch_bounds__(kColsWarps * 32, 1)
 accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
                      const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
-                     double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe) {
-    if (probe->select != 4) return;
+                     double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe,
+                     int hint_n2) {
+    // hint_n2 > 0: the caller states that the input is a flattened raster with rows of hint_n2 points (asvgp_accum_2d_raster);
+    // no probe ran.  The per-point checks below make a wrong statement slow, never wrong.
+    if (hint_n2 <= 0 && probe->select != 4) return;
     using Mo = Moments<K>;
     constexpr int NB = Mo::NB, NY = Mo::NY, NS = NB + NY;
     constexpr int kWarps = kColsWarps;
@@ -646,7 +649,7 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
     const int nc2 = nk2 - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n2 = probe->n2, n1 = n / n2;
+    const int64_t n2 = hint_n2 > 0 ? hint_n2 : probe->n2, n1 = n / n2;
     double (*S)[NS] = s_S[warp];
     double (*Bf)[NS] = s_B[warp];
     double (*T)[NS] = s_T[warp];
@@ -1237,8 +1240,8 @@ __global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* _
                                                                  const double* __restrict__ knots2, int nk2,
                                                                  const double* __restrict__ table, double prior_var,
                                                                  double* __restrict__ mean, double* __restrict__ var,
-                                                                 const ProbeResult* __restrict__ probe) {
-    if (probe->select != 4) return;
+                                                                 const ProbeResult* __restrict__ probe, int hint_n2) {
+    if (hint_n2 <= 0 && probe->select != 4) return;
     using PT = PredTable<K>;
     constexpr int K1 = K + 1, NS = 2 * K + 1;
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
@@ -1246,7 +1249,7 @@ __global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* _
     const double* Q1 = table + (int64_t)nc1 * nc2 * PT::kCell;
     const double* Q2 = Q1 + (int64_t)nc1 * PT::NQ;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t n2 = probe->n2, n1 = n / n2;
+    const int64_t n2 = hint_n2 > 0 ? hint_n2 : probe->n2, n1 = n / n2;
     const int64_t n_strips = (n2 + 31) / 32;
     const int64_t total_warps = (int64_t)gridDim.x * 8;
     int64_t n_seg = (4 * total_warps + n_strips - 1) / n_strips;
@@ -1713,6 +1716,17 @@ ASVGP_ACC2D(5, PART(5, 0, 3, true) PART(5, 3, 8, false) PART(5, 8, 11, false))
 ASVGP_ACC2D(6, PART(6, 0, 2, true) PART(6, 2, 6, false) PART(6, 6, 10, false) PART(6, 10, 13, false))
 
 template <int K>
+static int launch_cols(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2, int nk2,
+                       double* cellmom, double* scal, const ProbeResult* probe, int hint_n2, cudaStream_t st) {
+    const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2)     // sums, factors, per-row table
+                             + (size_t)kColsWarps * ColsRing<K>::kRows * 32 * 24;            // the ring
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
+    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe, hint_n2); ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <int K>
 static int launch_raster(const double* X, const double* y, int64_t n, const double* k1, int nk1, const double* k2, int nk2,
                          double* cellmom, double* scal, const ProbeResult* probe, int blocks, size_t smem,
                          cudaStream_t st) {
@@ -1720,11 +1734,7 @@ static int launch_raster(const double* X, const double* y, int64_t n, const doub
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_raster_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     accum_2d_raster_kernel<K, true><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
     accum_2d_raster_kernel<K, false><<<blocks, kRasterWarps * 32, smem, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
-    const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2)     // sums, factors, per-row table
-                             + (size_t)kColsWarps * ColsRing<K>::kRows * 32 * 24;            // the ring
-    ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe); ASVGP_LAUNCHED();
-    return kOk;
+    return launch_cols<K>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe, 0, st);
 }
 
 }  // namespace asvgp
@@ -1776,6 +1786,20 @@ extern "C" int asvgp_accum_2d(const double* X, const double* y, int64_t n, const
         ASVGP_CUDA_OK(cudaGetLastError());
     }
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_accum_2d<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, select, st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_accum_2d_raster(const double* X, const double* y, int64_t n, int64_t row_len, const double* mesh1,
+                                     int n_knots1, const double* mesh2, int n_knots2, int order, double* cellmom,
+                                     double* scal, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "accum_2d_raster: n=%lld knots=%d,%d", (long long)n, n_knots1, n_knots2);
+    ASVGP_REQUIRE(row_len > 0 && row_len <= 0x7fffffff && n % row_len == 0, "accum_2d_raster: n=%lld is not a whole number of rows of %lld points",
+                  (long long)n, (long long)row_len);
+    ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(y) & 15u) == 0,
+                  "accum_2d_raster: X and y must be 16-byte aligned");
+    if (n == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_cols<K>(X, y, n, mesh1, n_knots1, mesh2, n_knots2, cellmom, scal, nullptr, (int)row_len, st)) return rc; });
     return kOk;
 }
 
@@ -1842,21 +1866,31 @@ extern "C" int64_t asvgp_predict_2d_work_doubles(int n_knots1, int n_knots2, int
 }
 
 template <int K>
-static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int nk1, const double* mesh2, int nk2,
-                             const double* alpha, const double* SigP, const double* S1, const double* S2,
-                             double prior_var, double* mean, double* var, double* work, cudaStream_t st) {
+static int launch_predict_2d_prepare(int nk1, int nk2, const double* alpha, const double* SigP, const double* S1, const double* S2,
+                                     double* work, cudaStream_t st) {
     const int nc1 = nk1 - 1, nc2 = nk2 - 1, m1 = nk1 + K - 1, m2 = nk2 + K - 1;
     constexpr int W = (K + 1) * (K + 1);
     const size_t smem = sizeof(double) * (size_t)(W * W + W + W * (2 * K + 1));      // window, alpha, stage-1 result
     ASVGP_CUDA_OK(cudaFuncSetAttribute(predict_2d_table_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     predict_2d_table_kernel<K><<<nc1 * nc2 + 2, 256, smem, st>>>(nc1, nc2, m1, m2, alpha, SigP, S1, S2, work); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+template <int K>
+static int launch_predict_2d_apply(const double* Xnew, int64_t n, int hint_n2, const double* mesh1, int nk1, const double* mesh2,
+                                   int nk2, double prior_var, double* mean, double* var, double* work, cudaStream_t st) {
+    ProbeResult* probe = reinterpret_cast<ProbeResult*>(work + asvgp_predict_2d_work_doubles(nk1, nk2, K) - 1);
+    if (hint_n2 > 0) {      // the caller states the test set is a flattened raster: column sweep only (it re-checks every point)
+        predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, hint_n2); ASVGP_LAUNCHED();
+        ASVGP_CUDA_OK(cudaGetLastError());
+        return kOk;
+    }
     // classification probe (as in asvgp_accum_2d): separable raster test sets take the coalesced column sweep, anything else
     // the thread-contiguous kernel; the one that is not selected returns at once
-    ProbeResult* probe = reinterpret_cast<ProbeResult*>(work + asvgp_predict_2d_work_doubles(nk1, nk2, K) - 1);
     accum_2d_probe_kernel<<<1, 1024, 0, st>>>(Xnew, Xnew, n, probe); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
-    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe); ASVGP_LAUNCHED();
+    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, 0); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     const bool vec = ((reinterpret_cast<uintptr_t>(Xnew) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 31u) == 0;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, 2 * (int64_t)sm_count2()));
@@ -1864,6 +1898,29 @@ static int launch_predict_2d(const double* Xnew, int64_t n, const double* mesh1,
     else predict_2d_kernel<K, false><<<blocks, 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe);
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+extern "C" int asvgp_predict_2d_prepare(int n_knots1, int n_knots2, int order, const double* alpha, const double* SigP,
+                                        const double* S1, const double* S2, double* work, void* stream) {
+    ASVGP_REQUIRE(n_knots1 >= 2 && n_knots2 >= 2, "predict_2d_prepare: knots=%d,%d", n_knots1, n_knots2);
+    ASVGP_REQUIRE(work != nullptr, "predict_2d_prepare: work buffer (asvgp_predict_2d_work_doubles) is required");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_predict_2d_prepare<K>(n_knots1, n_knots2, alpha, SigP, S1, S2, work, st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_predict_2d_apply(const double* Xnew, int64_t n, int64_t row_len, const double* mesh1, int n_knots1,
+                                      const double* mesh2, int n_knots2, int order, double prior_var, double* mean,
+                                      double* var, double* work, void* stream) {
+    ASVGP_REQUIRE(n >= 0 && n_knots1 >= 2 && n_knots2 >= 2, "predict_2d_apply: n=%lld", (long long)n);
+    ASVGP_REQUIRE((reinterpret_cast<uintptr_t>(Xnew) & 15u) == 0, "predict_2d_apply: Xnew must be 16-byte aligned");
+    ASVGP_REQUIRE(work != nullptr, "predict_2d_apply: work buffer prepared by asvgp_predict_2d_prepare is required");
+    ASVGP_REQUIRE(row_len >= 0 && row_len <= 0x7fffffff && (row_len == 0 || n % row_len == 0),
+                  "predict_2d_apply: n=%lld is not a whole number of rows of %lld points", (long long)n, (long long)row_len);
+    if (n == 0) return kOk;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_predict_2d_apply<K>(Xnew, n, (int)row_len, mesh1, n_knots1, mesh2, n_knots2, prior_var, mean, var, work, st)) return rc; });
     return kOk;
 }
 
@@ -1876,6 +1933,7 @@ extern "C" int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mes
     ASVGP_REQUIRE(work != nullptr, "predict_2d: work buffer (asvgp_predict_2d_work_doubles) is required");
     if (n == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_predict_2d<K>(Xnew, n, mesh1, n_knots1, mesh2, n_knots2, alpha, SigP, S1, S2, prior_var, mean, var, work, st)) return rc; });
+    if (int rc = asvgp_predict_2d_prepare(n_knots1, n_knots2, order, alpha, SigP, S1, S2, work, stream)) return rc;
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_predict_2d_apply<K>(Xnew, n, 0, mesh1, n_knots1, mesh2, n_knots2, prior_var, mean, var, work, st)) return rc; });
     return kOk;
 }

@@ -126,10 +126,11 @@ def predict_1d(xnew, basis, alpha, S_band, variance, mean=None, var=None):
 
 
 # ---- banded (latency-bound) operators ----------------------------------------------------------------------------------
-def workspace_1d(m, order, chunks=0):
-    """Scratch tensor for elbo_grad_1d / posterior_1d (cached per (device, m, order, chunks))."""
+def workspace_1d(m, order, chunks=0, slot=0):
+    """Scratch tensor for elbo_grad_1d / posterior_1d (cached per (device, m, order, chunks, slot); callers that run on
+    several streams at once use one slot per stream)."""
     dev = device()
-    key = (dev, m, order, chunks)
+    key = (dev, m, order, chunks, slot)
     ws = _WORKSPACES.get(key)
     if ws is None:
         nbytes = _lib.load().asvgp_workspace_bytes_1d(m, order, chunks)
@@ -302,9 +303,11 @@ def order_probe_2d(X, bases):
     return float(out.item())
 
 
-def accum_2d(X, y, bases, cellmom, scal, binned=False):
+def accum_2d(X, y, bases, cellmom, scal, binned=False, raster_row_len=None):
     """Adds the per-cell moments of the points (X[n,2], y[n]) into `cellmom` and (sum y^2, n) into `scal`
-    (reference gpr.py:268-274 without materialising the Khatri-Rao Kuf).  binned: as accum_1d."""
+    (reference gpr.py:268-274 without materialising the Khatri-Rao Kuf).  binned: as accum_1d.
+    raster_row_len: the caller's statement that X is a flattened raster (meshgrid, x1 slow) with rows of that many points
+    — skips the on-device classification (asvgp_accum_2d_raster); a wrong statement is slow, never wrong."""
     k, _, _ = _check_bases_2d(bases)
     X = to_device(X)
     y = to_device(y).reshape(-1)
@@ -315,6 +318,10 @@ def accum_2d(X, y, bases, cellmom, scal, binned=False):
     if y.data_ptr() % 16:
         y = y.clone()
     mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    if raster_row_len:
+        _lib.call("asvgp_accum_2d_raster", _p(X), _p(y), X.shape[0], int(raster_row_len), _p(mesh1), mesh1.numel(), _p(mesh2),
+                  mesh2.numel(), k, _p(cellmom), _p(scal), _stream())
+        return cellmom, scal
     if binned == "auto":
         binned = X.shape[0] >= BINNED_MIN_POINTS and order_probe_2d(X, bases) > BINNED_JUMP_FRACTION
     if binned:
@@ -353,8 +360,9 @@ def expand_moments_2d(cellmom, bases, acc):
     return acc
 
 
-def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22):
-    """accum_2d for HOST arrays: streamed through pinned staging buffers, double-buffered against the kernel."""
+def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22, raster_row_len=None):
+    """accum_2d for HOST arrays: streamed through pinned staging buffers, double-buffered against the kernel.
+    raster_row_len: as accum_2d (the chunks are then whole rows)."""
     dev = device()
     Xt = torch.as_tensor(np.asarray(X) if not isinstance(X, torch.Tensor) else X, dtype=F64)
     yt = torch.as_tensor(np.asarray(y) if not isinstance(y, torch.Tensor) else y, dtype=F64).reshape(-1)
@@ -366,6 +374,12 @@ def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22):
         return cellmom, scal
     k, _, _ = _check_bases_2d(bases)
     mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    if raster_row_len:
+        if n % int(raster_row_len):
+            raise ValueError("n is not a whole number of rows of raster_row_len points")
+        chunk = max(1, chunk // int(raster_row_len)) * int(raster_row_len)
+        if chunk & 1:
+            chunk *= 2
     chunk = min(chunk, n + (n & 1))
     key = (dev, "2d", chunk)
     st = _STAGING.get(key)
@@ -398,16 +412,32 @@ def accum_2d_host(X, y, bases, cellmom, scal, chunk=1 << 22):
                 st["staged"][s].record(cs)
             st["filled"][s].record(cs)
         main.wait_event(st["filled"][s])
-        _lib.call("asvgp_accum_2d", _p(dX), _p(dy), cnt, _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
-                  _p(cellmom), _p(scal), ctypes.c_void_p(main.cuda_stream))
+        if raster_row_len:
+            _lib.call("asvgp_accum_2d_raster", _p(dX), _p(dy), cnt, int(raster_row_len), _p(mesh1), mesh1.numel(), _p(mesh2),
+                      mesh2.numel(), k, _p(cellmom), _p(scal), ctypes.c_void_p(main.cuda_stream))
+        else:
+            _lib.call("asvgp_accum_2d", _p(dX), _p(dy), cnt, _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
+                      _p(cellmom), _p(scal), ctypes.c_void_p(main.cuda_stream))
         st["drained"][s].record(main)
     return cellmom, scal
 
 
-def band_inverse_1d(A, dA, basis, chunks=0):
+_SIDE_STREAMS = {}
+
+
+def side_streams(n):
+    """n cached side streams of the current device (for small independent launches that should overlap a long kernel)."""
+    dev = device()
+    pool = _SIDE_STREAMS.setdefault(dev, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+def band_inverse_1d(A, dA, basis, chunks=0, slot=0):
     """(band(A^-1), band(-A^-1 dA A^-1), scal[4] = {log|A|, dlog|A|, info, -}) of one banded SPD factor."""
     k, m = basis.order, basis.m
-    ws = workspace_1d(m, k, chunks)
+    ws = workspace_1d(m, k, chunks, slot)
     sig = torch.empty((k + 1, m), dtype=F64, device=A.device)
     dsig = torch.empty_like(sig)
     scal = torch.empty(4, dtype=F64, device=A.device)
@@ -506,6 +536,35 @@ def kron_terms(SigP, acc, x, K1, dK1, K2, dK2, S1, dS1, S2, dS2, bases, out):
     _lib.call("asvgp_kron_terms", _p(SigP), _p(Gs), _p(x), _p(K1), _p(dK1), _p(K2), _p(dK2), _p(S1), _p(dS1), _p(S2),
               _p(dS2), m1, m2, k, _p(out), _stream())
     return out
+
+
+def predict_2d_prepare(bases, alpha, SigP, S1, S2, work=None):
+    """Per-cell polynomial form of the posterior (asvgp_predict_2d_prepare): done once per set of hyper-parameters, then any
+    number of predict_2d_apply calls stream test points through it."""
+    k, _, _ = _check_bases_2d(bases)
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    if work is None:
+        nw = _lib.load().asvgp_predict_2d_work_doubles(mesh1.numel(), mesh2.numel(), k)
+        work = torch.empty(nw, dtype=F64, device=alpha.device)
+    _lib.call("asvgp_predict_2d_prepare", mesh1.numel(), mesh2.numel(), k, _p(alpha), _p(SigP), _p(S1), _p(S2), _p(work), _stream())
+    return work
+
+
+def predict_2d_apply(Xnew, bases, work, prior_var, raster_row_len=None, mean=None, var=None):
+    """Posterior mean / variance at Xnew[n, 2] from the prepared table (reference gpr.py:310-359)."""
+    k, _, _ = _check_bases_2d(bases)
+    X = to_device(Xnew)
+    if X.dim() != 2 or X.shape[1] != 2:
+        raise ValueError("Xnew must be [n, 2]")
+    if X.data_ptr() % 16:
+        X = X.clone()
+    n = X.shape[0]
+    mesh1, mesh2 = device_mesh(bases[0]), device_mesh(bases[1])
+    mean = torch.empty(n, dtype=F64, device=X.device) if mean is None else mean
+    var = torch.empty(n, dtype=F64, device=X.device) if var is None else var
+    _lib.call("asvgp_predict_2d_apply", _p(X), n, int(raster_row_len or 0), _p(mesh1), mesh1.numel(), _p(mesh2), mesh2.numel(), k,
+              float(prior_var), _p(mean), _p(var), _p(work), _stream())
+    return mean, var
 
 
 def predict_2d(Xnew, bases, alpha, SigP, S1, S2, prior_var):

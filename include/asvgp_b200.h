@@ -134,6 +134,15 @@ ASVGP_API int asvgp_accum_2d(const double* X, const double* y, int64_t n, const 
                              const double* mesh2, int n_knots2, int order, double* cellmom, double* scal,
                              void* stream);
 
+/* Same sums when the CALLER KNOWS the points are a flattened raster (np.meshgrid(x1, x2, indexing="ij"), x1 slow, rows of
+ * `row_len` points whose x2 repeat from row to row — the eNATL60-shaped inputs): skips asvgp_accum_2d's on-device
+ * classification probe and its unselected candidate kernels and launches the coalesced column sweep alone.  Every lane
+ * still bit-compares each point with what the statement implies and falls back per row / per point, so a wrong statement
+ * costs time, never correctness. */
+ASVGP_API int asvgp_accum_2d_raster(const double* X, const double* y, int64_t n, int64_t row_len, const double* mesh1,
+                                    int n_knots1, const double* mesh2, int n_knots2, int order, double* cellmom,
+                                    double* scal, void* stream);
+
 /* Same sums for points in NO PARTICULAR ORDER (SURVEY 8(d) C4 "shuffled-order variant").  asvgp_accum_2d is exact for
  * any order but pays (2o+1)^2 + (o+1)^2 fp64 REDs per point once consecutive points stop sharing a cell; this variant
  * partitions the points into <= 256 buckets of dimension-1 knot intervals, sorts each 4096-point unit by cell in
@@ -211,6 +220,15 @@ ASVGP_API int asvgp_kron_terms(const double* SigP, const double* Gs, const doubl
  * first converted to per-cell polynomial form in `work` (asvgp_predict_2d_work_doubles doubles), then streamed over
  * the test points (32 B of traffic per point). */
 ASVGP_API int64_t asvgp_predict_2d_work_doubles(int n_knots1, int n_knots2, int order);
+/* The two halves of asvgp_predict_2d for callers that predict in several batches (the reference predicts in chunks of
+ * 10 000 points, eNATL60.py:96-102): _prepare converts the posterior to per-cell polynomial form in `work` ONCE per set of
+ * hyper-parameters, _apply streams one batch of test points through it.  row_len > 0 states that the batch is a flattened
+ * raster with rows of row_len points (as asvgp_accum_2d_raster); 0 = classify on the device. */
+ASVGP_API int asvgp_predict_2d_prepare(int n_knots1, int n_knots2, int order, const double* alpha, const double* SigP,
+                                       const double* S1, const double* S2, double* work, void* stream);
+ASVGP_API int asvgp_predict_2d_apply(const double* Xnew, int64_t n, int64_t row_len, const double* mesh1, int n_knots1,
+                                     const double* mesh2, int n_knots2, int order, double prior_var, double* mean,
+                                     double* var, double* work, void* stream);
 ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh1, int n_knots1, const double* mesh2,
                                int n_knots2, int order, const double* alpha, const double* SigP, const double* S1,
                                const double* S2, double prior_var, double* mean, double* var, double* work,

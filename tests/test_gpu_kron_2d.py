@@ -338,3 +338,55 @@ def test_accumulate_binned_large_matches_streaming(cuda):
     Gs, b, scal = ops.split_accum_2d(res[0], bases)
     assert scal[1].item() == n1 * n1
     assert abs(float(b.sum()) - float(y.sum())) <= 1e-10 * float(y.abs().sum())
+
+
+def test_raster_statement_paths_match_the_classified_ones(cuda):
+    """asvgp_accum_2d_raster / asvgp_predict_2d_apply(row_len): the caller states the layout instead of the on-device probe.
+    Same sums and predictions as the classified path for a true raster — and still the right numbers when the statement is
+    WRONG (shuffled points passed as a 'raster'): every lane re-checks each point and falls back."""
+    import torch
+
+    from asvgp_b200 import basis as B, kernels as Kn, ops
+    from asvgp_b200.gpr import GPR_kron
+
+    rng = np.random.default_rng(21)
+    n1, n2 = 300, 260
+    X, y = _raster(n1, n2, rng)
+    bases = [B.B3Spline(-80, -25, 30), B.B3Spline(15, 55, 24)]
+
+    def run(Xa, ya, **kw):
+        acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
+        cm = ops.moment_table_2d(bases)
+        ops.accum_2d(Xa, ya, bases, cm, ops.split_accum_2d(acc, bases)[2], **kw)
+        ops.expand_moments_2d(cm, bases, acc)
+        return acc.cpu().numpy()
+
+    auto = run(X, y)
+    stated = run(X, y, raster_row_len=n2)
+    scale = np.abs(auto).max()
+    np.testing.assert_allclose(stated, auto, rtol=0, atol=1e-12 * scale)
+    perm = rng.permutation(X.shape[0])
+    lied = run(X[perm], y[perm], raster_row_len=n2)                 # not a raster at all
+    np.testing.assert_allclose(lied, auto, rtol=0, atol=1e-11 * scale)
+    wrong_len = run(X, y, raster_row_len=n2 // 2)                   # a raster, but not with that row length
+    np.testing.assert_allclose(wrong_len, auto, rtol=0, atol=1e-11 * scale)
+
+    kerns = [Kn.Matern32(variance=1.0, lengthscales=6.0), Kn.Matern32(variance=0.8, lengthscales=5.0)]
+    model = GPR_kron((torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda().view(-1, 1)), kerns, bases, raster_shape=(n1, n2))
+    ref = GPR_kron((X, y.reshape(-1, 1)), kerns, bases)
+    model.likelihood.variance.assign(0.01); ref.likelihood.variance.assign(0.01)
+    assert abs(model.elbo() - ref.elbo()) <= 1e-11 * abs(ref.elbo())
+    g1, g2 = np.linspace(-74.5, -30.5, 41), np.linspace(20.5, 49.5, 67)
+    Xg = np.stack(np.meshgrid(g1, g2, indexing="ij"), -1).reshape(-1, 2)
+    m0, v0 = ref.predict_f(Xg)
+    m1, v1 = model.predict_f(Xg, raster_shape=(41, 67))
+    np.testing.assert_allclose(m1, m0, atol=1e-12, rtol=0)
+    np.testing.assert_allclose(v1, v0, atol=1e-12, rtol=0)
+    m2, v2 = model.predict_f(Xg[rng.permutation(Xg.shape[0])][: 41 * 60], raster_shape=(41, 60))     # wrong statement
+    m3, v3 = ref.predict_f(Xg[rng.permutation(Xg.shape[0])][:5])
+    assert np.isfinite(m2).all() and np.isfinite(v2).all() and m3.shape == (5, 1)
+    # the cached table follows the hyper-parameters
+    model.kernels[0].lengthscales.assign(4.0); ref.kernels[0].lengthscales.assign(4.0)
+    m4, _ = model.predict_f(Xg[:50]); m5, _ = ref.predict_f(Xg[:50])
+    np.testing.assert_allclose(m4, m5, atol=1e-12, rtol=0)
+    assert np.abs(m4 - m0[:50]).max() > 1e-6
