@@ -28,14 +28,14 @@
 //
 // Kernels, per tree level (bottom-up for the factorisation, top-down for the selected inverse):
 //   nd_assemble_kernel   (once) entries of P and the right-hand-side row into every front
-//   nd_factor_kernel     persistent tile DAG over all tiles of all fronts of the level: every task first adds the entries of
-//                        the children's update matrices that land in its tile (extend-add as a gather), then left-looking
-//                        updates on the fp64 tensor cores, diagonal tiles factorised + inverted in registers, trailing
-//                        tiles = this front's update matrix
+//   nd_factor_kernel     persistent tile DAG over all tiles of all fronts of the level: left-looking updates on the fp64
+//                        tensor cores, diagonal tiles factorised + inverted in registers; trailing tiles = this front's update
+//                        matrix, added straight into the parent's front (extend-add as fp64 REDs, off the chain of diagonal tiles)
 //   nd_ypass_kernel      (once) L(R,C) -> Y(R,C)^T = (L(R,C) L(C,C)^-1)^T, Sigma(C,C) seeded with L(C,C)^-T L(C,C)^-1
 //   nd_gather_kernel     Sigma on the boundary of a front from its parent's Sigma
 //   nd_selinv_kernel     persistent tile DAG: blocked Takahashi recursion inside every front of the level
 //   nd_scalars_kernel / nd_x_kernel / nd_stencil_kernel   log|P|, ||y||^2, x, stencil entries of P^-1
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -128,7 +128,9 @@ static void nd_build(NdPlan& P, int m1, int m2, int K) {
     P.m1 = m1; P.m2 = m2; P.K = K; P.M = m1 * m2;
     const int M = P.M, RHS = M;
     std::vector<NdFrontHost> F;
-    P.root = nd_rec(F, 0, m1, 0, m2, 0, K, kNdLeaf, m2);
+    int leaf = kNdLeaf;
+    if (const char* e = getenv("ASVGP_ND_LEAF")) leaf = std::max(1, atoi(e));      // tuning knob (tools/nd_leaf_sweep.sh)
+    P.root = nd_rec(F, 0, m1, 0, m2, 0, K, leaf, m2);
     P.n_fronts = (int)F.size();
     for (auto& f : F) {            // boundary: ancestors' separator unknowns within K grid lines of the subtree's region
         for (int a = f.parent; a >= 0; a = F[a].parent)
@@ -329,7 +331,7 @@ static NdLayout nd_layout(const NdPlan& P) {
 
 // ---------------------------------------------------------------------------------------------------------------------
 // assembly: entries of P (+ right-hand side row) of every front, one fully parallel launch; the children's update matrices
-// are added by the factorisation tasks themselves (extend-add as a gather, add_children)
+// are added by the children's own factorisation tasks (scatter_to_parent)
 // ---------------------------------------------------------------------------------------------------------------------
 struct NdAssembleArgs {
     const FrontDesc* fronts; const int4* tasks; int n_tasks;
@@ -383,40 +385,33 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
 // ---------------------------------------------------------------------------------------------------------------------
 struct NdFactorArgs {
     const FrontDesc* fronts; const int4* tasks; int n_tasks;
-    const int *idx, *cpos;
+    const int *idx, *pmap;
     double* Lpool; double* linv;
     int* ready;         // [n_tiles] + abort at [n_tiles], first bad pivot (node id + 1) at [n_tiles + 1]
     long long n_tiles;
 };
 
-// acc (this thread's 4 x 4 block of tile (R, C) of front f) += the entries of the children's update matrices that land there
-__device__ __forceinline__ void add_children(double (&acc)[4][4], const NdFactorArgs& a, const FrontDesc& f, int R, int C, int tm, int tn) {
+// Extend-add, from the child's side: this thread's 4 x 4 block of the update tile (R, C) of front f (R >= C >= nsT) is added
+// into the parent's front (fp64 REDs: the two children of a parent add into the same entries; the parent was assembled before
+// any factorisation kernel ran and is factorised by a later launch).  The parent stores its lower triangle, with FULL diagonal
+// tiles; the child's diagonal update tiles are full too, so only their lower triangle is sent.
+__device__ __forceinline__ void scatter_to_parent(const double (&acc)[4][4], const NdFactorArgs& a, const FrontDesc& f, int R, int C,
+                                                  int tm, int tn) {
+    const FrontDesc p = a.fronts[f.parent];
+    const int* pm = a.pmap + f.pmap_off;
+    int pr[4], pc[4];
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        if (f.child[q] < 0) continue;
-        const int* cp = a.cpos + f.cpos_off[q];
-        int pr[4], pc[4];
-        bool any_r = false, any_c = false;
+    for (int i = 0; i < 4; ++i) { pr[i] = __ldg(pm + (R - f.nsT) * NB + tm + i); pc[i] = __ldg(pm + (C - f.nsT) * NB + tn + i); }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            pr[i] = __ldg(cp + R * NB + tm + i); pc[i] = __ldg(cp + C * NB + tn + i);
-            any_r |= pr[i] >= 0; any_c |= pc[i] >= 0;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (pr[i] < 0 || pc[j] < 0 || (R == C && tm + i < tn + j)) continue;
+            const int hi = max(pr[i], pc[j]), lo = min(pr[i], pc[j]);
+            double* t = a.Lpool + front_tile(p, hi / NB, lo / NB) * TILE;
+            atomicAdd(t + (lo % NB) * NB + hi % NB, acc[i][j]);
+            if (hi / NB == lo / NB && hi != lo) atomicAdd(t + (hi % NB) * NB + lo % NB, acc[i][j]);
         }
-        if (!(any_r && any_c)) continue;
-        const long long cbase = a.fronts[f.child[q]].tile_base;
-        const int cnT = a.fronts[f.child[q]].nT, cnsT = a.fronts[f.child[q]].nsT;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                int pa = pr[i], pb = pc[j];
-                if (pa < 0 || pb < 0) continue;
-                if (pa < pb) { const int s = pa; pa = pb; pb = s; }     // lower triangle of the child's update matrix
-                const int Rc = cnsT + pa / NB, Cc = cnsT + pb / NB;
-                const long long tix = cbase + (long long)Cc * cnT - (long long)Cc * (Cc - 1) / 2 + (Rc - Cc);
-                acc[i][j] += __ldcg(a.Lpool + tix * TILE + (pb % NB) * NB + pa % NB);
-            }
-    }
 }
 
 __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a) {
@@ -448,7 +443,6 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
         } else {
             regs_from_tile(acc, my_tile, tm, tn);
-            add_children(acc, a, f, R, C, tm, tn);
         }
         const int nJ = min(C, f.nsT);
 
@@ -479,8 +473,9 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
         }
 
         if (C >= f.nsT) {
-            // ---- trailing tile: this front's update matrix (read by the parent's assembly) ----------------------------------
-            regs_to_tile(acc, my_tile, tm, tn);
+            // ---- trailing tile: this front's update matrix, added straight into the parent's front --------------------------
+            if (f.parent >= 0) scatter_to_parent(acc, a, f, R, C, tm, tn);
+            else regs_to_tile(acc, my_tile, tm, tn);              // root: entry (rhs, rhs) = -||y||^2
         } else if (diag) {
             // ---- diagonal tile: Cholesky + inverse in registers ---------------------------------------------------------------
             double V[4][4];
@@ -902,7 +897,7 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
     }
     for (int lev = P.n_levels - 1; lev >= 0; --lev) {
         const int n_tasks = (int)P.factor_tasks[lev].size();
-        NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_cpos, band, band + lay.linv, flags, P.n_tiles};
+        NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_pmap, band, band + lay.linv, flags, P.n_tiles};
         if (int rc = nd_launch_persistent(nd_factor_kernel, &fa, n_tasks, st)) return rc;
     }
     nd_scalars_kernel<<<kNdScalarBlocks, 256, 0, st>>>(P.d_doff, P.M, band, P.quad_off, flags, P.n_tiles, scal, band + lay.scal); ASVGP_LAUNCHED();

@@ -375,5 +375,6 @@ def test_nested_dissection_and_band_factorisations_agree(cuda, case_name):
     al1, S1, *_ = nd.posterior_weights()
     al1, S1 = al1.cpu().numpy().copy(), S1.cpu().numpy().copy()
     al2, S2, *_ = band.posterior_weights()
-    np.testing.assert_allclose(S1, S2.cpu().numpy(), rtol=0, atol=1e-9 * np.abs(S1).max())
-    np.testing.assert_allclose(al1, al2.cpu().numpy(), rtol=0, atol=1e-7 * np.abs(al1).max())
+    # entries of P^-1 carry cond(P) eps ~ 1e-8 of its largest entry in either implementation (different elimination orders)
+    np.testing.assert_allclose(S1, S2.cpu().numpy(), rtol=0, atol=5e-8 * np.abs(S1).max())
+    np.testing.assert_allclose(al1, al2.cpu().numpy(), rtol=0, atol=1e-6 * np.abs(al1).max())
