@@ -66,6 +66,25 @@ __host__ __device__ __forceinline__ long long front_tile(const FrontDesc& f, int
     return f.tile_base + (long long)C * f.nT - (long long)C * (C - 1) / 2 + (R - C);
 }
 
+// Pool tiles are stored PADDED: 64 columns of LDT = 68 doubles (element (r, c) at c * LDT + r), the bank-conflict-free layout
+// the tensor-core fragment loads want (tile_ops.cuh), so that ONE bulk copy lands an operand ready for dmma_tile — no
+// repacking pass, half the shared memory (two CTAs per SM: one computes while the other waits for its operands).
+constexpr int TILE_P = NB * LDT;                       // doubles per pool tile
+constexpr uint32_t TILE_P_BYTES = TILE_P * 8;
+constexpr size_t kNdSmem = 2 * (size_t)TILE_P * sizeof(double);
+
+__device__ __forceinline__ void tma_load_ptile(double* dst_smem, const double* src_gmem, uint64_t* bar) {
+    tma_load_bulk(dst_smem, src_gmem, TILE_P_BYTES, bar);
+}
+__device__ __forceinline__ void regs_from_ptile(double (&acc)[4][4], const double* __restrict__ t, int tm, int tn) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const double2 a = *reinterpret_cast<const double2*>(t + (tn + j) * LDT + tm);
+        const double2 b = *reinterpret_cast<const double2*>(t + (tn + j) * LDT + tm + 2);
+        acc[0][j] = a.x; acc[1][j] = a.y; acc[2][j] = b.x; acc[3][j] = b.y;
+    }
+}
+
 struct NdFrontHost {
     int level = 0, parent = -1;
     int child[2] = {-1, -1};
@@ -215,7 +234,7 @@ static void nd_build(NdPlan& P, int m1, int m2, int K) {
     for (int i = 0; i < P.n_fronts; ++i)
         for (int j = 0; j < P.fronts[i].ns; ++j) { owner[F[i].sep[j]] = i; opos[F[i].sep[j]] = j; }
     auto elem = [&](const FrontDesc& d, int prow, int pcol) {       // element (prow, pcol), prow >= pcol, of the front's lower triangle
-        return front_tile(d, prow / NB, pcol / NB) * TILE + (long long)(pcol % NB) * NB + prow % NB;
+        return front_tile(d, prow / NB, pcol / NB) * TILE_P + (long long)(pcol % NB) * LDT + prow % NB;
     };
     P.doff.resize(M); P.xoff.resize(M);
     for (int j = 0; j < M; ++j) {
@@ -317,12 +336,12 @@ struct NdLayout {
 };
 static NdLayout nd_layout(const NdPlan& P) {
     NdLayout L;
-    L.linv = P.n_tiles * TILE;
-    L.scal = L.linv + (long long)P.n_linv * TILE;
+    L.linv = P.n_tiles * TILE_P;
+    L.scal = L.linv + (long long)P.n_linv * TILE_P;
     L.flags = L.scal + 8 + kNdScalarBlocks;
     L.n_flag_ints = P.n_tiles + 8;                       // tile flags, abort, first bad pivot, scalar-kernel block counter
     L.band_total = L.flags + (L.n_flag_ints + 1) / 2 + 2;
-    L.sig_upper = P.n_tiles * TILE;
+    L.sig_upper = P.n_tiles * TILE_P;
     L.sig_total = 2 * L.sig_upper;
     L.n_work_ints = P.n_tiles + P.n_cnt + 8;             // tile flags, per-block-column counters, abort
     L.work_total = (L.n_work_ints + 1) / 2 + 2;
@@ -365,7 +384,7 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
         const int4 tk = a.tasks[t];
         const FrontDesc f = a.fronts[tk.x];
         const int R = tk.y, C = tk.z;
-        double* tile = a.Lpool + front_tile(f, R, C) * TILE;
+        double* tile = a.Lpool + front_tile(f, R, C) * TILE_P;
         const int* idx = a.idx + f.idx_off;
         if (C >= f.nsT && f.child[0] < 0) continue;          // trailing tiles of a leaf front start from zero: never read
         for (int e = threadIdx.x; e < TILE; e += blockDim.x) {
@@ -375,7 +394,7 @@ __global__ void __launch_bounds__(256) nd_assemble_kernel(NdAssembleArgs a) {
             double v;
             if (gi < 0 || gj < 0) v = (I == J && C < f.nsT) ? 1.0 : 0.0;
             else v = (C < f.nsT) ? nd_entry(a, gi, gj) : 0.0;
-            tile[e] = v;
+            tile[c * LDT + r] = v;
         }
     }
 }
@@ -408,33 +427,44 @@ __device__ __forceinline__ void scatter_to_parent(const double (&acc)[4][4], con
         for (int j = 0; j < 4; ++j) {
             if (pr[i] < 0 || pc[j] < 0 || (R == C && tm + i < tn + j)) continue;
             const int hi = max(pr[i], pc[j]), lo = min(pr[i], pc[j]);
-            double* t = a.Lpool + front_tile(p, hi / NB, lo / NB) * TILE;
-            atomicAdd(t + (lo % NB) * NB + hi % NB, acc[i][j]);
-            if (hi / NB == lo / NB && hi != lo) atomicAdd(t + (hi % NB) * NB + lo % NB, acc[i][j]);
+            double* t = a.Lpool + front_tile(p, hi / NB, lo / NB) * TILE_P;
+            atomicAdd(t + (lo % NB) * LDT + hi % NB, acc[i][j]);
+            if (hi / NB == lo / NB && hi != lo) atomicAdd(t + (hi % NB) * LDT + lo % NB, acc[i][j]);
         }
 }
 
-__global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a) {
+__global__ void __launch_bounds__(kTdThreads, 2) nd_factor_kernel(NdFactorArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
-    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;      // padded copies of the operands of the current product
-    double* const pB = pA + PTILE;
-    __shared__ __align__(8) uint64_t full[2];
+    double* const pA = reinterpret_cast<double*>(td_smem);                 // landing buffers of the two operands of a product
+    double* const pB = pA + TILE_P;
+    __shared__ __align__(8) uint64_t full;
     __shared__ int s_bad;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     int* abort_flag = a.ready + a.n_tiles;
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    if (tid == 0) mbar_init(&full, 1);
     fence_proxy_async();
     __syncthreads();
-    Phases ph;
+    uint32_t phase = 0;
 
     for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
         const int4 tk = a.tasks[t];
         const FrontDesc f = a.fronts[tk.x];
         const int R = tk.y, C = tk.z;
         const bool diag = R == C;
-        double* my_tile = a.Lpool + front_tile(f, R, C) * TILE;
+        double* my_tile = a.Lpool + front_tile(f, R, C) * TILE_P;
+        const int nJ = min(C, f.nsT);
+
+        auto issue = [&](int J) {                    // thread 0: wait for the operand tiles, then fetch them by TMA
+            const long long tR = front_tile(f, R, J), tC = front_tile(f, C, J);
+            wait_flag(a.ready + tR, 1, abort_flag);
+            if (!diag) wait_flag(a.ready + tC, 1, abort_flag);
+            fence_proxy_async();
+            mbar_expect_tx(&full, diag ? TILE_P_BYTES : 2 * TILE_P_BYTES);
+            tma_load_ptile(pA, a.Lpool + tR * TILE_P, &full);
+            if (!diag) tma_load_ptile(pB, a.Lpool + tC * TILE_P, &full);
+        };
+        if (tid == 0 && nJ > 0) issue(0);
         double acc[4][4];
         if (C >= f.nsT && f.child[0] < 0) {
 #pragma unroll
@@ -442,46 +472,30 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
         } else {
-            regs_from_tile(acc, my_tile, tm, tn);
+            regs_from_ptile(acc, my_tile, tm, tn);
         }
-        const int nJ = min(C, f.nsT);
-
-        auto issue = [&](int J, int s) {             // thread 0: wait for the operand tiles, then fetch them by TMA
-            const long long tR = front_tile(f, R, J), tC = front_tile(f, C, J);
-            wait_flag(a.ready + tR, 1, abort_flag);
-            if (!diag) wait_flag(a.ready + tC, 1, abort_flag);
-            fence_proxy_async();
-            mbar_expect_tx(&full[s], diag ? TILE_BYTES : 2 * TILE_BYTES);
-            tma_load_tile_(sA[s], a.Lpool + tR * TILE, &full[s]);
-            if (!diag) tma_load_tile_(sB[s], a.Lpool + tC * TILE, &full[s]);
-        };
         if (nJ > 0) {
             double cf[8][2] = {};                    // sum_J L(R,J) L(C,J)^T as tensor-core fragments
-            if (tid == 0) issue(0, 0);
             for (int q = 0; q < nJ; ++q) {
-                const int s = q & 1;
-                if (q + 1 < nJ && tid == 0) issue(q + 1, s ^ 1);
-                mbar_wait(&full[s], ph.get(s));
-                ph.flip(s);
-                repack_padded(pA, sA[s], tid);
-                if (!diag) repack_padded(pB, sB[s], tid);
-                __syncthreads();
+                mbar_wait(&full, phase);
+                phase ^= 1u;
                 dmma_tile(cf, pA, diag ? pA : pB, warp, lane);
                 __syncthreads();
+                if (q + 1 < nJ && tid == 0) issue(q + 1);
             }
-            frags_subtract(acc, cf, sA[0], warp, lane, tm, tn);
+            frags_subtract(acc, cf, pA, warp, lane, tm, tn);
         }
 
         if (C >= f.nsT) {
             // ---- trailing tile: this front's update matrix, added straight into the parent's front --------------------------
             if (f.parent >= 0) scatter_to_parent(acc, a, f, R, C, tm, tn);
-            else regs_to_tile(acc, my_tile, tm, tn);              // root: entry (rhs, rhs) = -||y||^2
+            else regs_to_tile_ld<LDT>(acc, my_tile, tm, tn);     // root: entry (rhs, rhs) = -||y||^2
         } else if (diag) {
             // ---- diagonal tile: Cholesky + inverse in registers ---------------------------------------------------------------
             double V[4][4];
-            double* s11 = sA[0];                     // [16] l + [4] 1/l_cc (+ padding)
-            double* spanel = sA[0] + 32;             // [4][64] panel, transposed
-            double* swrow = sA[0] + 32 + 4 * NB;     // [4][64]
+            double* s11 = pA;                        // [16] l + [4] 1/l_cc (+ padding)
+            double* spanel = pA + 32;                // [4][64] panel, transposed
+            double* swrow = pA + 32 + 4 * NB;        // [4][64]
             if (tid == 0) s_bad = -1;
             __syncthreads();
             potrf_regs(acc, V, tm, tn, s11, spanel, swrow, &s_bad, nullptr);
@@ -493,8 +507,8 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
                 for (int j = 0; j < 4; ++j) {
                     if (tm + i < tn + j) { acc[i][j] = 0.0; V[i][j] = 0.0; }
                 }
-            regs_to_tile(V, a.linv + (long long)(f.linv_base + C) * TILE, tm, tn);
-            regs_to_tile(acc, my_tile, tm, tn);
+            regs_to_tile_ld<LDT>(V, a.linv + (long long)(f.linv_base + C) * TILE_P, tm, tn);
+            regs_to_tile_ld<LDT>(acc, my_tile, tm, tn);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
@@ -506,26 +520,25 @@ __global__ void __launch_bounds__(kTdThreads, 1) nd_factor_kernel(NdFactorArgs a
             if (tid == 0) {
                 wait_flag(a.ready + front_tile(f, C, C), 1, abort_flag);
                 fence_proxy_async();
-                mbar_expect_tx(&full[0], TILE_BYTES);
-                tma_load_tile_(sB[0], a.linv + (long long)(f.linv_base + C) * TILE, &full[0]);
+                mbar_expect_tx(&full, TILE_P_BYTES);
+                tma_load_ptile(pB, a.linv + (long long)(f.linv_base + C) * TILE_P, &full);
             }
             regs_to_tile_ld<LDT>(acc, pA, tm, tn);   // A(m, k) at [k*LDT + m]
             __syncthreads();
-            mbar_wait(&full[0], ph.get(0));
-            ph.flip(0);
-            repack_padded(pB, sB[0], tid);
-            __syncthreads();
+            mbar_wait(&full, phase);
+            phase ^= 1u;
             double L[4][4] = {};
             {
                 double cf[8][2] = {};
                 dmma_tile(cf, pA, pB, warp, lane);                  // L[m][n] = sum_k A[m][k] Linv[n][k]
-                frags_subtract(L, cf, sA[1], warp, lane, tm, tn);
+                __syncthreads();
+                frags_subtract(L, cf, pA, warp, lane, tm, tn);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) L[i][j] = -L[i][j];
             }
-            regs_to_tile(L, my_tile, tm, tn);
+            regs_to_tile_ld<LDT>(L, my_tile, tm, tn);
             __threadfence();
             __syncthreads();
             if (tid == 0) st_release(a.ready + front_tile(f, R, C), 1);
@@ -560,10 +573,9 @@ __global__ void __launch_bounds__(256) nd_scalars_kernel(const long long* __rest
     if (threadIdx.x == 0) {
         double tot = 0.0;
         for (int bk = 0; bk < (int)gridDim.x; ++bk) tot += __ldcg(scal_keep + 8 + bk);
-        s[0] = tot;
         const double quad = -__ldcg(Lpool + quad_off);
         const int aborted = ready[n_tiles], bad = ready[n_tiles + 1];
-        scal_out[0] = 2.0 * s[0];
+        scal_out[0] = 2.0 * tot;
         scal_out[1] = quad;
         scal_out[2] = aborted ? -1.0 : (bad != kNoBadPivot ? (double)bad : 0.0);
         scal_keep[0] = quad;
@@ -582,29 +594,29 @@ __global__ void __launch_bounds__(kTdThreads) nd_ypass_kernel(const FrontDesc* _
                                                               double* __restrict__ sig_lower) {
     extern __shared__ __align__(16) unsigned char yp_smem[];
     double* pL = reinterpret_cast<double*>(yp_smem);         // L tile as the A operand: L[m][k] at [k*LDT + m]
-    double* pI = pL + PTILE;                                 // Linv transposed: Linv[k][n] at [k*LDT + n]
+    double* pI = pL + TILE_P;                                // Linv transposed: Linv[k][n] at [k*LDT + n]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = blockIdx.x; t < n_tasks; t += gridDim.x) {
         const int4 tk = tasks[t];
         const FrontDesc f = fronts[tk.x];
         const int R = tk.y, C = tk.z;
-        const double* Li = linv + (long long)(f.linv_base + C) * TILE;
-        double* T = Lpool + front_tile(f, R, C) * TILE;
+        const double* Li = linv + (long long)(f.linv_base + C) * TILE_P;
+        double* T = Lpool + front_tile(f, R, C) * TILE_P;
         __syncthreads();
         for (int e = tid; e < TILE; e += kTdThreads) {
             const int r = e % NB, c = e / NB;
-            pI[r * LDT + c] = __ldcg(Li + e);                 // Li[e] = Linv[r][c]
-            if (R != C) pL[c * LDT + r] = __ldcg(T + e);
+            pI[r * LDT + c] = __ldcg(Li + c * LDT + r);       // Linv[r][c]
+            if (R != C) pL[c * LDT + r] = __ldcg(T + c * LDT + r);
         }
         __syncthreads();
         double cf[8][2] = {};
         // diagonal: S0[m][n] = sum_k Linv[k][m] Linv[k][n];  off-diagonal: Y[m][n] = sum_k L[m][k] Linv[k][n]
         dmma_tile(cf, R == C ? pI : pL, pI, warp, lane);
-        double* out = (R == C) ? sig_lower + front_tile(f, C, C) * TILE : T;       // Y is stored transposed (row m contiguous), in place
+        double* out = (R == C) ? sig_lower + front_tile(f, C, C) * TILE_P : T;     // Y is stored transposed (row m contiguous), in place
         const int m = warp * 8 + (lane >> 2), n0 = (lane & 3) * 2;
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb)
-            *reinterpret_cast<double2*>(out + m * NB + cb * 8 + n0) = make_double2(cf[cb][0], cf[cb][1]);
+            *reinterpret_cast<double2*>(out + m * LDT + cb * 8 + n0) = make_double2(cf[cb][0], cf[cb][1]);
     }
 }
 
@@ -638,17 +650,17 @@ __global__ void __launch_bounds__(256) nd_gather_kernel(NdGatherArgs a) {
                 int pa = pm[I], pb = pm[J];
                 if (pa >= 0 && pb >= 0) {
                     if (pa < pb) { const int s = pa; pa = pb; pb = s; }
-                    const double* src = a.sig_lower + front_tile(p, pa / NB, pb / NB) * TILE;
+                    const double* src = a.sig_lower + front_tile(p, pa / NB, pb / NB) * TILE_P;
                     int rr = pa % NB, cc = pb % NB;
                     if (pa / NB == pb / NB && rr < cc) { const int s = rr; rr = cc; cc = s; }   // diagonal tile of the parent: its lower triangle
-                    v = __ldcg(src + cc * NB + rr);
+                    v = __ldcg(src + cc * LDT + rr);
                 }
             }
-            a.sig_lower[me * TILE + e] = v;
+            a.sig_lower[me * TILE_P + c * LDT + r] = v;
             s_t[r][c] = v;
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < TILE; e += blockDim.x) a.sig_upper[me * TILE + e] = s_t[e / NB][e % NB];   // (r,c) <- (c,r)
+        for (int e = threadIdx.x; e < TILE; e += blockDim.x) a.sig_upper[me * TILE_P + (e / NB) * LDT + e % NB] = s_t[e / NB][e % NB];   // (r,c) <- (c,r)
     }
 }
 
@@ -662,101 +674,108 @@ struct NdSelArgs {
     int n_cnt;
 };
 
-__global__ void __launch_bounds__(kTdThreads, 1) nd_selinv_kernel(NdSelArgs a) {
+// A diagonal Sigma tile is symmetric only up to rounding (a sum of REDs of termwise unsymmetric products): the operand handed
+// to the tensor cores is 0.5 (S + S^T), in place in shared memory (see repack_padded_sym in tile_ops.cuh for why).
+__device__ __forceinline__ void symmetrise_ptile(double* __restrict__ s, int tid) {
+    const int c = tid & (NB - 1), g = tid >> 6;
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const int r = (c + g * 16 + j) & (NB - 1);
+        v[j] = 0.5 * (s[c * LDT + r] + s[r * LDT + c]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s[c * LDT + ((c + g * 16 + j) & (NB - 1))] = v[j];
+}
+
+__global__ void __launch_bounds__(kTdThreads, 2) nd_selinv_kernel(NdSelArgs a) {
     extern __shared__ __align__(128) unsigned char td_smem[];
-    const StageBufs sA{reinterpret_cast<double*>(td_smem)}, sB{reinterpret_cast<double*>(td_smem) + TILE};
-    double* const pA = reinterpret_cast<double*>(td_smem) + 4 * TILE;
-    double* const pB = pA + PTILE;
-    __shared__ __align__(8) uint64_t full[2];
+    double* const pA = reinterpret_cast<double*>(td_smem);
+    double* const pB = pA + TILE_P;
+    __shared__ __align__(8) uint64_t full;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tm = (tid & 15) * 4, tn = (tid >> 4) * 4;
     int* cnt = a.sready + a.n_tiles;
     int* abort_flag = cnt + a.n_cnt;
-    if (tid == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); }
+    if (tid == 0) mbar_init(&full, 1);
     fence_proxy_async();
     __syncthreads();
-    Phases ph;
+    uint32_t phase = 0;
 
     for (int t = blockIdx.x; t < a.n_tasks; t += gridDim.x) {
         const int4 tk = a.tasks[t];
         const FrontDesc f = a.fronts[tk.x];
         const int R = tk.y, C = tk.z;                // R > C, C < nsT
         const int Kmax = f.nT - 1, nK = Kmax - C;
-        auto issue = [&](int K, int s) {             // A = Sigma(R, K), B = Y(K, C)^T
+        auto issue = [&](int K) {                    // A = Sigma(R, K), B = Y(K, C)^T
             const double* src;
             const int* flag = nullptr;
             int want = 1;
             if (K == R) {
-                src = a.sig_lower + front_tile(f, R, R) * TILE;
+                src = a.sig_lower + front_tile(f, R, R) * TILE_P;
                 if (R < f.nsT) { flag = cnt + f.cnt_base + R; want = f.nT - 1 - R; }      // all shares in
             } else if (K < R) {
-                src = a.sig_lower + front_tile(f, R, K) * TILE;
+                src = a.sig_lower + front_tile(f, R, K) * TILE_P;
                 if (K < f.nsT) flag = a.sready + front_tile(f, R, K);
             } else {
-                src = a.sig_upper + front_tile(f, K, R) * TILE;
+                src = a.sig_upper + front_tile(f, K, R) * TILE_P;
                 if (R < f.nsT) flag = a.sready + front_tile(f, K, R);
             }
             // the Y^T operand is there since the pre-pass: it is requested before the wait, only Sigma(R,K) after it
-            mbar_expect_tx(&full[s], 2 * TILE_BYTES);
-            tma_load_tile_(sB[s], a.Lpool + front_tile(f, K, C) * TILE, &full[s]);
+            mbar_expect_tx(&full, 2 * TILE_P_BYTES);
+            tma_load_ptile(pB, a.Lpool + front_tile(f, K, C) * TILE_P, &full);
             if (flag != nullptr) wait_flag(flag, want, abort_flag);
             fence_proxy_async();
-            tma_load_tile_(sA[s], src, &full[s]);
+            tma_load_ptile(pA, src, &full);
         };
         double acc[4][4] = {};
         double cf[8][2] = {};                        // sum_K Sigma(R,K) Y(K,C) as tensor-core fragments
-        if (tid == 0) issue(Kmax, 0);
+        if (tid == 0) issue(Kmax);
         for (int q = 0; q < nK; ++q) {
-            const int s = q & 1;
-            if (tid == 0) {
-                if (q + 1 < nK) {
-                    issue(Kmax - q - 1, s ^ 1);
-                } else {
-                    // last product: the idle stage already fetches this tile's own Y^T for the diagonal contribution below
-                    mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
-                    tma_load_tile_(sB[s ^ 1], a.Lpool + front_tile(f, R, C) * TILE, &full[s ^ 1]);
-                }
-            }
-            mbar_wait(&full[s], ph.get(s));
-            ph.flip(s);
-            if (Kmax - q == R) repack_padded_sym(pA, sA[s], tid);      // Sigma(R,R): enforce symmetry (see repack_padded_sym)
-            else repack_padded(pA, sA[s], tid);
-            repack_padded(pB, sB[s], tid);
-            __syncthreads();
+            mbar_wait(&full, phase);
+            phase ^= 1u;
+            if (Kmax - q == R) { symmetrise_ptile(pA, tid); __syncthreads(); }
             dmma_tile(cf, pA, pB, warp, lane);
             __syncthreads();
+            if (tid == 0) {
+                if (q + 1 < nK) {
+                    issue(Kmax - q - 1);
+                } else {
+                    // after the last product: fetch this tile's own Y^T for the diagonal contribution below
+                    mbar_expect_tx(&full, TILE_P_BYTES);
+                    tma_load_ptile(pB, a.Lpool + front_tile(f, R, C) * TILE_P, &full);
+                }
+            }
         }
-        const int so = nK & 1;                                          // the stage holding the own tile
-        frags_subtract(acc, cf, sA[so ^ 1], warp, lane, tm, tn);       // acc = -sum_K Sigma(R,K) Y(K,C)
+        frags_subtract(acc, cf, pA, warp, lane, tm, tn);                // acc = -sum_K Sigma(R,K) Y(K,C)
         const long long me = front_tile(f, R, C);
-        regs_to_tile(acc, a.sig_lower + me * TILE, tm, tn);
+        regs_to_tile_ld<LDT>(acc, a.sig_lower + me * TILE_P, tm, tn);
         regs_to_tile_t_ld<LDT>(acc, pA, tm, tn);         // T[m][a] at [m*LDT + a]  ==  A'(a, k=m) at [k*LDT + a]
         __syncthreads();
         {
-            double* up = a.sig_upper + me * TILE;
+            double* up = a.sig_upper + me * TILE_P;
 #pragma unroll
             for (int idx = tid; idx < TILE / 2; idx += kTdThreads) {
                 const int c = idx >> 5, r = (idx & 31) * 2;
-                *reinterpret_cast<double2*>(up + c * NB + r) = *reinterpret_cast<const double2*>(pA + c * LDT + r);
+                *reinterpret_cast<double2*>(up + c * LDT + r) = *reinterpret_cast<const double2*>(pA + c * LDT + r);
             }
         }
         __threadfence();
         __syncthreads();
         if (tid == 0) st_release(a.sready + me, 1);
-        mbar_wait(&full[so], ph.get(so));
-        ph.flip(so);
-        repack_padded(pB, sB[so], tid);
-        __syncthreads();
+        mbar_wait(&full, phase);
+        phase ^= 1u;
         {
             // D[a][b] = sum_m T[m][a] Y[m][b]: this tile's share of Sigma(C,C), added as REDs
             double D[8][2] = {};
             dmma_tile(D, pA, pB, warp, lane);
-            double* Sd = a.sig_lower + front_tile(f, C, C) * TILE;
+            double* Sd = a.sig_lower + front_tile(f, C, C) * TILE_P;
             const int row = warp * 8 + (lane >> 2), col = (lane & 3) * 2;
 #pragma unroll
             for (int cb = 0; cb < 8; ++cb) {
-                atomicAdd(Sd + (cb * 8 + col) * NB + row, -D[cb][0]);
-                atomicAdd(Sd + (cb * 8 + col + 1) * NB + row, -D[cb][1]);
+                atomicAdd(Sd + (cb * 8 + col) * LDT + row, -D[cb][0]);
+                atomicAdd(Sd + (cb * 8 + col + 1) * LDT + row, -D[cb][1]);
             }
         }
         __threadfence();
@@ -792,9 +811,8 @@ __global__ void __launch_bounds__(256) nd_stencil_kernel(const long long* __rest
             off &= ~(1LL << 62);
             v = __ldcg(sig_lower + off);
             if (diag_tile) {
-                const long long base = off & ~(long long)(TILE - 1);
-                const int e = (int)(off & (TILE - 1));
-                v = 0.5 * (v + __ldcg(sig_lower + base + (e % NB) * NB + e / NB));
+                const int e = (int)(off % TILE_P);                      // c * LDT + r inside the tile
+                v = 0.5 * (v + __ldcg(sig_lower + (off - e) + (e % LDT) * LDT + e / LDT));
             }
             const int ee = (int)(t / M);
             const long long j = t % M;
@@ -807,10 +825,18 @@ __global__ void __launch_bounds__(256) nd_stencil_kernel(const long long* __rest
 
 template <class Kernel>
 static int nd_launch_persistent(Kernel kernel, void* args, int n_tasks, cudaStream_t st) {
-    int grid = 0;
-    if (int rc = persistent_grid(kernel, kTdSmem, n_tasks, &grid)) return rc;
+    int dev = 0, sms = 0, per_sm = 0;
+    ASVGP_CUDA_OK(cudaGetDevice(&dev));
+    ASVGP_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    ASVGP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNdSmem));
+    ASVGP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTdThreads, kNdSmem));
+    if (per_sm < 1) {
+        set_last_error("front kernel does not fit on an SM (%zu bytes of shared memory)", kNdSmem);
+        return kCudaError;
+    }
+    const int grid = std::max(1, std::min(sms * std::min(per_sm, 2), n_tasks));     // all CTAs co-resident (they wait on each other)
     void* params[] = {args};
-    ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(kTdThreads), params, kTdSmem, st));
+    ASVGP_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(kTdThreads), params, kNdSmem, st));
     ASVGP_LAUNCHED();
     return kOk;
 }
@@ -920,7 +946,7 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_work_ints * sizeof(int), st));
     double* sigL = sig_band;
     double* sigU = sig_band + lay.sig_upper;
-    const size_t yp_smem = (size_t)(2 * PTILE) * sizeof(double);
+    const size_t yp_smem = (size_t)(2 * TILE_P) * sizeof(double);
     ASVGP_CUDA_OK(cudaFuncSetAttribute(nd_ypass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)yp_smem));
     const int n_yp = (int)P.ypass_tasks.size();
     nd_ypass_kernel<<<std::min(n_yp, 148 * 3), kTdThreads, yp_smem, st>>>(P.d_fronts, P.d_ypass_tasks, n_yp, band, band + lay.linv, sigL);
