@@ -38,6 +38,15 @@ SIGNATURES = {
     "asvgp_kronband_selinv": [_vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _vp],
     "asvgp_kron_terms": [_vp] * 11 + [_c_int, _c_int, _c_int, _vp, _vp],
     "asvgp_predict_2d": [_vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp, _vp],
+    "asvgp_dense_factor": [_vp, _c_int, _vp, _vp, _vp, _vp],
+    "asvgp_dense_selinv": [_vp, _c_int, _vp, _vp, _vp, _vp, _vp],
+    "asvgp_accum_cross": [_vp, _vp, _c_i64, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp],
+    "asvgp_additive_put_band": [_vp, _c_int, _c_int, _c_int, _c_int, _c_dbl, _c_int, _vp, _vp],
+    "asvgp_additive_put_cross": [_vp, _c_int, _c_int, _c_int, _c_int, _c_int, _vp, _vp],
+    "asvgp_additive_scale": [_vp, _c_int, _c_dbl, _vp, _vp],
+    "asvgp_additive_terms": [_vp, _vp, _c_int, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp],
+    "asvgp_dense_terms": [_vp, _vp, _vp, _c_int, _vp, _vp],
+    "asvgp_predict_additive": [_vp, _c_i64, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp, _c_dbl, _vp, _vp, _vp],
     "asvgp_khatri_rao_csc": [_vp, _vp, _vp, _vp, _vp, _vp, _c_i64, _c_i64, _vp, _vp, _vp, _vp],
     "asvgp_kron_dense": [_vp, _c_int, _vp, _c_int, _vp, _vp],
     "asvgp_cholesky_dense": [_vp, _c_int, _vp, _vp, _vp],
@@ -53,6 +62,9 @@ VALUE_FUNCTIONS = {
     "asvgp_kron_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_sig_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kron_rhs_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_dense_band_doubles": (_c_i64, [_c_int]),
+    "asvgp_dense_sig_doubles": (_c_i64, [_c_int]),
+    "asvgp_dense_work_doubles": (_c_i64, [_c_int]),
     "asvgp_kron_plan_info": (_c_i64, [_c_int, _c_int, _c_int, _vp, _vp, _c_i64]),
     "asvgp_kronband_band_doubles": (_c_i64, [_c_int, _c_int, _c_int]),
     "asvgp_kronband_work_doubles": (_c_i64, [_c_int, _c_int, _c_int]),

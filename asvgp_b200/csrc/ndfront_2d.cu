@@ -149,7 +149,16 @@ static void nd_build(NdPlan& P, int m1, int m2, int K) {
     std::vector<NdFrontHost> F;
     int leaf = kNdLeaf;
     if (const char* e = getenv("ASVGP_ND_LEAF")) leaf = std::max(1, atoi(e));      // tuning knob (tools/nd_leaf_sweep.sh)
-    P.root = nd_rec(F, 0, m1, 0, m2, 0, K, leaf, m2);
+    const bool dense = K < 0;      // a dense m1 x m1 matrix (m2 = 1): ONE front holding everything (asvgp_dense_*)
+    if (dense) {
+        NdFrontHost f;
+        f.r1 = m1; f.c1 = 1;
+        for (int g = 0; g < M; ++g) f.sep.push_back(g);
+        F.push_back(f);
+        P.root = 0;
+    } else {
+        P.root = nd_rec(F, 0, m1, 0, m2, 0, K, leaf, m2);
+    }
     P.n_fronts = (int)F.size();
     for (auto& f : F) {            // boundary: ancestors' separator unknowns within K grid lines of the subtree's region
         for (int a = f.parent; a >= 0; a = F[a].parent)
@@ -248,6 +257,7 @@ static void nd_build(NdPlan& P, int m1, int m2, int K) {
         P.quad_off = elem(r, p, p);
         P.tau_off = P.quad_off;
     }
+    if (dense) return;             // the dense extraction kernel computes its offsets itself (one front)
     const int NS = 2 * K + 1, n_e = (K + 1) * NS;
     P.sigoff.assign((size_t)n_e * M, -1);
     for (int j = 0; j < M; ++j) {
@@ -359,6 +369,7 @@ struct NdAssembleArgs {
     double sigma2;
     int m1, m2, K, M;
     double* Lpool;
+    const double* dense;           // non-null: the matrix itself, M x M row-major (lower triangle read), instead of K1, K2, Gs
 };
 
 __device__ __forceinline__ double nd_band_sym(const double* B, int m, int K, int i, int j) {
@@ -369,6 +380,7 @@ __device__ __forceinline__ double nd_band_sym(const double* B, int m, int K, int
 // A'(gi, gj): gi, gj grid unknowns or the rhs node (id M).  Same roundings as the reference's `Kuu + KufKfu / sigma2`.
 __device__ __forceinline__ double nd_entry(const NdAssembleArgs& a, int gi, int gj) {
     if (gi == a.M || gj == a.M) return (gi == gj) ? 0.0 : __ldg(a.b + (gi == a.M ? gj : gi));
+    if (a.dense != nullptr) return __ldg(a.dense + (long long)max(gi, gj) * a.M + min(gi, gj));
     const int i1 = gi / a.m2, i2 = gi % a.m2, j1 = gj / a.m2, j2 = gj % a.m2;
     int d1 = i1 - j1, d2 = i2 - j2;
     int col = gj;
@@ -901,26 +913,16 @@ extern "C" int64_t asvgp_kron_plan_info(int m1, int m2, int order, double* out, 
     return need;
 }
 
-// Assembles and factorises P front by front.  band: asvgp_kron_band_doubles doubles (opaque).  rhs_io[m1 m2]: Kuf_y (read
-// only here; asvgp_kron_selinv overwrites it with P^-1 Kuf_y).  scal[3] = log|P|, ||L^-1 Kuf_y||^2, info.
-extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
-                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream) {
-    ND_CHECK_ARGS("kron_factor");
-    ASVGP_REQUIRE(sigma2 > 0.0, "kron_factor: sigma2=%g", sigma2);
-    const NdPlan* Pp = nullptr;
-    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
-    const NdPlan& P = *Pp;
+// ---- shared bodies of the Kronecker and the dense entry points -----------------------------------------------------------------
+static int nd_factor_run(const NdPlan& P, NdAssembleArgs aa, double* band, double* scal, cudaStream_t st) {
     const NdLayout lay = nd_layout(P);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     int* flags = reinterpret_cast<int*>(band + lay.flags);
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_flag_ints * sizeof(int), st));
     ASVGP_CUDA_OK(cudaMemsetAsync(flags + P.n_tiles + 1, 0x7f, sizeof(int), st));                       // first bad pivot = "none"
-    {
-        const int n_all = (int)P.all_tasks.size();
-        NdAssembleArgs aa{P.d_fronts, P.d_all_tasks, n_all, P.d_idx, K1, K2, Gs, rhs_io, sigma2, m1, m2, order, P.M, band};
-        nd_assemble_kernel<<<std::min(n_all, 148 * 16), 256, 0, st>>>(aa); ASVGP_LAUNCHED();
-        ASVGP_CUDA_OK(cudaGetLastError());
-    }
+    const int n_all = (int)P.all_tasks.size();
+    aa.fronts = P.d_fronts; aa.tasks = P.d_all_tasks; aa.n_tasks = n_all; aa.idx = P.d_idx; aa.M = P.M; aa.Lpool = band;
+    nd_assemble_kernel<<<std::min(n_all, 148 * 16), 256, 0, st>>>(aa); ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
     for (int lev = P.n_levels - 1; lev >= 0; --lev) {
         const int n_tasks = (int)P.factor_tasks[lev].size();
         NdFactorArgs fa{P.d_fronts, P.d_factor_tasks[lev], n_tasks, P.d_idx, P.d_pmap, band, band + lay.linv, flags, P.n_tiles};
@@ -931,17 +933,10 @@ extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const doubl
     return kOk;
 }
 
-// From the factor (consumed: its off-diagonal tiles become Y^T): sigma_stencil[(order+1)(2 order+1) x M] = entries of P^-1
-// on the stencil, x_io[M] = P^-1 Kuf_y.  sig_band: asvgp_kron_sig_doubles doubles of scratch; work: asvgp_kron_work_doubles.
-// If a persistent kernel gives up waiting (abort flag), the outputs are NaN.
-extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
-                                 double* sigma_stencil, double* work, void* stream) {
-    ND_CHECK_ARGS("kron_selinv");
-    const NdPlan* Pp = nullptr;
-    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
-    const NdPlan& P = *Pp;
+// selected inverse of every front + x = P^-1 b; returns the abort flag's address for the extraction kernels
+static int nd_selinv_run(const NdPlan& P, double* band, double* sig_band, double* x_out, double* work, cudaStream_t st,
+                         const int** abort_flag_out) {
     const NdLayout lay = nd_layout(P);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     int* flags = reinterpret_cast<int*>(work);
     ASVGP_CUDA_OK(cudaMemsetAsync(flags, 0, (size_t)lay.n_work_ints * sizeof(int), st));
     double* sigL = sig_band;
@@ -963,11 +958,105 @@ extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double
         if (int rc = nd_launch_persistent(nd_selinv_kernel, &sa, n_s, st)) return rc;
     }
     const int* abort_flag = flags + P.n_tiles + P.n_cnt;
-    nd_x_kernel<<<(P.M + 255) / 256, 256, 0, st>>>(P.d_xoff, P.M, sigL, band + lay.scal, abort_flag, x_io); ASVGP_LAUNCHED();
+    nd_x_kernel<<<(P.M + 255) / 256, 256, 0, st>>>(P.d_xoff, P.M, sigL, band + lay.scal, abort_flag, x_out); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
+    *abort_flag_out = abort_flag;
+    return kOk;
+}
+
+// Assembles and factorises P front by front.  band: asvgp_kron_band_doubles doubles (opaque).  rhs_io[m1 m2]: Kuf_y (read
+// only here; asvgp_kron_selinv overwrites it with P^-1 Kuf_y).  scal[3] = log|P|, ||L^-1 Kuf_y||^2, info.
+extern "C" int asvgp_kron_factor(const double* K1, const double* K2, const double* Gs, int m1, int m2, int order,
+                                 double sigma2, double* band, double* rhs_io, double* scal, void* stream) {
+    ND_CHECK_ARGS("kron_factor");
+    ASVGP_REQUIRE(sigma2 > 0.0, "kron_factor: sigma2=%g", sigma2);
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
+    NdAssembleArgs aa{};
+    aa.K1 = K1; aa.K2 = K2; aa.Gs = Gs; aa.b = rhs_io; aa.sigma2 = sigma2; aa.m1 = m1; aa.m2 = m2; aa.K = order; aa.dense = nullptr;
+    return nd_factor_run(*Pp, aa, band, scal, static_cast<cudaStream_t>(stream));
+}
+
+// From the factor (consumed: its off-diagonal tiles become Y^T): sigma_stencil[(order+1)(2 order+1) x M] = entries of P^-1
+// on the stencil, x_io[M] = P^-1 Kuf_y.  sig_band: asvgp_kron_sig_doubles doubles of scratch; work: asvgp_kron_work_doubles.
+// If a persistent kernel gives up waiting (abort flag), the outputs are NaN.
+extern "C" int asvgp_kron_selinv(double* band, int m1, int m2, int order, double* sig_band, double* x_io,
+                                 double* sigma_stencil, double* work, void* stream) {
+    ND_CHECK_ARGS("kron_selinv");
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(m1, m2, order, &Pp)) return rc;
+    const NdPlan& P = *Pp;
+    const NdLayout lay = nd_layout(P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int* abort_flag = nullptr;
+    if (int rc = nd_selinv_run(P, band, sig_band, x_io, work, st, &abort_flag)) return rc;
     const int64_t total = (int64_t)P.M * (order + 1) * (2 * order + 1);
-    nd_stencil_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(P.d_sigoff, m1, m2, order, sigL, x_io,
+    nd_stencil_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(P.d_sigoff, m1, m2, order, sig_band, x_io,
                                                                                           band + lay.scal, abort_flag, sigma_stencil);
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+// ---- dense symmetric positive definite matrices on the same kernels (one front) -----------------------------------------------------
+// What GPR_additive needs (reference gpr.py:192-195, 221-231: tf.linalg.cholesky / triangular_solve of a DENSE (sum m_d)^2
+// matrix): log|A|, b^T A^-1 b, A^-1 b and A^-1, from the tile-DAG factorisation and the blocked Takahashi recursion above.
+extern "C" int64_t asvgp_dense_band_doubles(int n) {
+    if (n <= 0 || n > 32768) return -1;
+    return nd_layout(*nd_plan_host(n, 1, -1)).band_total;
+}
+extern "C" int64_t asvgp_dense_sig_doubles(int n) {
+    if (n <= 0 || n > 32768) return -1;
+    return nd_layout(*nd_plan_host(n, 1, -1)).sig_total;
+}
+extern "C" int64_t asvgp_dense_work_doubles(int n) {
+    if (n <= 0 || n > 32768) return -1;
+    return nd_layout(*nd_plan_host(n, 1, -1)).work_total;
+}
+
+// A: n x n row-major (lower triangle read), rhs[n].  scal[3] = log|A|, rhs^T A^-1 rhs, info (0 ok, j+1 = row of the first
+// non-positive pivot, -1 internal time-out).
+extern "C" int asvgp_dense_factor(const double* A, int n, const double* rhs, double* band, double* scal, void* stream) {
+    ASVGP_REQUIRE(n > 0 && n <= 32768, "dense_factor: n=%d", n);
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(n, 1, -1, &Pp)) return rc;
+    NdAssembleArgs aa{};
+    aa.b = rhs; aa.sigma2 = 1.0; aa.m1 = n; aa.m2 = 1; aa.K = 0; aa.dense = A;
+    return nd_factor_run(*Pp, aa, band, scal, static_cast<cudaStream_t>(stream));
+}
+
+namespace asvgp {
+// inv[i * n + j] = Sigma'(i, j) - tau x_i x_j for the single front of a dense plan (diagonal tiles averaged with their mirror)
+__global__ void __launch_bounds__(256) nd_dense_extract_kernel(FrontDesc f, int n, const double* __restrict__ sig_lower,
+                                                               const double* __restrict__ x, const double* __restrict__ scal_keep,
+                                                               const int* __restrict__ abort_flag, double* __restrict__ inv) {
+    const double tau = scal_keep[1];
+    const bool aborted = *abort_flag != 0;
+    const long long total = (long long)n * n;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(t / n), j = (int)(t % n);
+        const int hi = max(i, j), lo = min(i, j);
+        const double* tile = sig_lower + front_tile(f, hi / NB, lo / NB) * TILE_P;
+        double v = __ldcg(tile + (lo % NB) * LDT + hi % NB);
+        if (hi / NB == lo / NB) v = 0.5 * (v + __ldcg(tile + (hi % NB) * LDT + lo % NB));
+        inv[t] = aborted ? nan("") : v - tau * x[i] * x[j];
+    }
+}
+}  // namespace asvgp
+
+// band is CONSUMED.  x_out[n] = A^-1 rhs, inv_out[n x n] = A^-1 (full symmetric, row-major).
+extern "C" int asvgp_dense_selinv(double* band, int n, double* sig_band, double* x_out, double* inv_out, double* work, void* stream) {
+    ASVGP_REQUIRE(n > 0 && n <= 32768, "dense_selinv: n=%d", n);
+    const NdPlan* Pp = nullptr;
+    if (int rc = nd_plan_device(n, 1, -1, &Pp)) return rc;
+    const NdPlan& P = *Pp;
+    const NdLayout lay = nd_layout(P);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int* abort_flag = nullptr;
+    if (int rc = nd_selinv_run(P, band, sig_band, x_out, work, st, &abort_flag)) return rc;
+    const int64_t total = (int64_t)n * n;
+    nd_dense_extract_kernel<<<(int)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(P.fronts[0], n, sig_band, x_out,
+                                                                                                 band + lay.scal, abort_flag, inv_out);
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;

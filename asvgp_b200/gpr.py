@@ -478,3 +478,242 @@ class GPR_kron(_ModelBase):
     def predict_f_sparse(self, Xnew, full_cov=False, full_output_cov=False):
         """Same numbers as predict_f (reference gpr.py:336-359 is its CHOLMOD twin)."""
         return self.predict_f(Xnew, full_cov=full_cov, full_output_cov=full_output_cov)
+
+
+class GPR_additive(_ModelBase):
+    """Collapsed-bound sparse GP regression with an ADDITIVE kernel, f(x) = sum_d f_d(x_d), each f_d on B-spline inducing
+    features (reference gpr.py:139-236).  Same constructor, attributes and methods; what differs is only *how*:
+
+      * the reference stacks the per-dimension Kuf and forms KufKfu by a sparse product (gpr.py:172-176).  Here the banded
+        diagonal blocks come from the fused 1-D accumulate (asvgp_accum_1d, one pass per dimension) and the dense
+        off-diagonal blocks from asvgp_accum_cross (one pass per pair); Kuf is never formed;
+      * P = Kuu + KufKfu / sigma2 is dense (sum m_d)^2 — the reference factorises it with tf.linalg.cholesky (gpr.py:192-195).
+        Here it is one dense front of the tile-DAG kernels of the Kronecker model (asvgp_dense_factor / asvgp_dense_selinv,
+        fp64 tensor cores), which also returns P^-1 Kuf_y and P^-1;
+      * trace(Kuu^-1 KufKfu) (gpr.py:209: a dense solve there) only touches the banded diagonal blocks: per dimension
+        band(K_d^-1) from asvgp_band_inverse_1d, as in GPR_kron;
+      * `elbo_and_grad()` returns the 2 D + 1 derivatives with the bound (TF reverse mode in the reference).
+    """
+
+    def __init__(self, data, kernels, bases, distributed="auto", check_inputs=True):
+        X, y = data
+        self.X, self.y = X, y
+        self.n = X.shape[0]
+        self.d = X.shape[1]
+
+        # Check dimensionality of inputs / valid kernels (reference gpr.py:146-152)
+        assert len(kernels) == len(bases) == self.d
+        if y.ndim == 1:
+            y = y.reshape(-1, 1)
+        assert y.shape[1] == 1
+        self._kinds = [kernel_kind(k) for k in kernels]
+        if self.d > 8:
+            raise NotImplementedError("GPR_additive is implemented for at most 8 input dimensions")
+        if check_inputs and self.n:
+            for i, basis in enumerate(bases):
+                col = X[:, i]
+                lo, hi = (torch.aminmax(col) if isinstance(col, torch.Tensor) else (col.min(), col.max()))
+                assert float(lo) > basis.a and float(hi) < basis.b, "inputs must lie strictly inside the basis domain"
+
+        self.kernel = kernels[-1]               # as the reference: the last loop kernel goes to GPModel (SURVEY Q8)
+        self.likelihood = Gaussian()
+        self.mean_function = None
+        self.num_latent_gps = 1
+        self.bases = list(bases)
+        self.kernels = list(kernels)
+        self.inducing_features = [SplineFeatures1D(self.kernels[i], self.bases[i]) for i in range(self.d)]
+
+        # Bandwidth (reference gpr.py:163-166)
+        bandwidths = [basis.order for basis in self.bases]
+        assert all(x == bandwidths[0] for x in bandwidths)
+        self.bandwidth = self.order = self.bases[0].order
+
+        # Precompute static quantities (reference gpr.py:169-176): D banded passes + D (D - 1) / 2 cross passes
+        Xd = ops.to_device(X)
+        yd = ops.to_device(y).reshape(-1)
+        self._offsets = np.concatenate([[0], np.cumsum([b.m for b in self.bases])]).astype(int)
+        self.M = int(self._offsets[-1])
+        self._accs = [ops.accum_1d(Xd[:, i].contiguous(), yd, self.bases[i], binned="auto") for i in range(self.d)]
+        self._cross = {}
+        for i in range(self.d):
+            for j in range(i + 1, self.d):
+                self._cross[(i, j)] = ops.accum_cross(Xd, i, j, self.bases[i], self.bases[j])
+        self._distributed = _dist.is_distributed(distributed)
+        if self._distributed:
+            for acc in self._accs:
+                _dist.allreduce_packed(acc)
+            for c in self._cross.values():
+                _dist.allreduce_packed(c)
+        # dense KufKfu and the stacked Kuf_y
+        self._G = torch.zeros((self.M, self.M), dtype=torch.float64, device=Xd.device)
+        self._b = torch.empty(self.M, dtype=torch.float64, device=Xd.device)
+        for i, (acc, basis) in enumerate(zip(self._accs, self.bases)):
+            Gi, bi, scal = ops.split_accum_1d(acc, basis)
+            o = int(self._offsets[i])
+            ops._lib.call("asvgp_additive_put_band", ops._p(Gi), basis.m, basis.order, o, self.M, 1.0, 0, ops._p(self._G), ops._stream())
+            self._b[o: o + basis.m].copy_(bi)
+        for (i, j), c in self._cross.items():
+            ops._lib.call("asvgp_additive_put_cross", ops._p(c), self.bases[i].m, self.bases[j].m, int(self._offsets[i]),
+                          int(self._offsets[j]), self.M, ops._p(self._G), ops._stream())
+        self._scal = ops.split_accum_1d(self._accs[0], self.bases[0])[2]          # {sum y^2, N}: the same in every dimension
+        self._P = torch.empty_like(self._G)
+        self._host = None
+
+    # -- the reference's cached attributes ------------------------------------------------------------------------------------
+    def _host_stats(self):
+        if self._host is None:
+            self._host = (self._G.cpu().numpy(), self._b.cpu().numpy().reshape(-1, 1), self._scal.cpu().numpy())
+        return self._host
+
+    @property
+    def KufKfu(self):
+        return self._host_stats()[0]
+
+    @property
+    def KufKfu_sparse(self):
+        import scipy.sparse as sp
+
+        return sp.csr_matrix(self.KufKfu)
+
+    @property
+    def Kuf_y(self):
+        return self._host_stats()[1]
+
+    @property
+    def tr_yTy(self):
+        return float(self._host_stats()[2][0])
+
+    @property
+    def num_data(self):
+        return int(self._host_stats()[2][1])
+
+    @property
+    def trainable_variables(self):
+        out = []
+        for k in self.kernels:
+            out += [k.variance, k.lengthscales]
+        return _unique(out + [self.likelihood.variance])
+
+    # -- objective ----------------------------------------------------------------------------------------------------------------
+    def _factor(self, want_inverse):
+        s2 = hyper_value(self.likelihood.variance)
+        main = torch.cuda.current_stream()
+        Ks, dKs, Ss, dSs, scals = [], [], [], [], []
+        for feat, kern in zip(self.inducing_features, self.kernels):
+            K, dK = feat.make_Kuu_device(kern, want_grad=True)
+            Ks.append(K); dKs.append(dK)
+        side = ops.side_streams(self.d)
+        for i, basis in enumerate(self.bases):                 # short banded chains: overlap them with the dense factorisation
+            side[i].wait_stream(main)
+            with torch.cuda.stream(side[i]):
+                S, dS, sc = ops.band_inverse_1d(Ks[i], dKs[i], basis, slot=1 + i)
+            for t in (S, dS, sc):
+                t.record_stream(main)
+            Ss.append(S); dSs.append(dS); scals.append(sc)
+        # P = KufKfu / sigma2 + Kuu  (reference gpr.py:192)
+        ops._lib.call("asvgp_additive_scale", ops._p(self._G), self.M, float(s2), ops._p(self._P), ops._stream())
+        for i, basis in enumerate(self.bases):
+            ops._lib.call("asvgp_additive_put_band", ops._p(Ks[i]), basis.m, basis.order, int(self._offsets[i]), self.M, 1.0, 1,
+                          ops._p(self._P), ops._stream())
+        ws = ops.dense_workspace(self.M)
+        ops.dense_factor(self._P, self._b, ws)
+        x, Pinv = ops.dense_selinv(ws) if want_inverse else (None, None)
+        for s in side:
+            main.wait_stream(s)
+        return Ks, dKs, Ss, dSs, scals, ws, x, Pinv
+
+    def _evaluate(self, want_grad):
+        s2 = hyper_value(self.likelihood.variance)
+        v = [hyper_value(k.variance) for k in self.kernels]
+        Ks, dKs, Ss, dSs, scals, ws, x, Pinv = self._factor(want_grad)
+        D = self.d
+        dev = self._G.device
+        # trace(Kuu^-1 KufKfu) and its lengthscale derivatives: per dimension, on the bands
+        tr = torch.zeros((D, 4), dtype=torch.float64, device=dev)         # sum S_d .* G_dd, sum dS_d .* G_dd, -, -
+        terms = torch.zeros((D, 4), dtype=torch.float64, device=dev)
+        dense = torch.zeros(2, dtype=torch.float64, device=dev)
+        zero_x = torch.zeros(self.M, dtype=torch.float64, device=dev)
+        for i, basis in enumerate(self.bases):
+            o = int(self._offsets[i])
+            # (the same contraction kernel with S := KufKfu's diagonal block and K := band(K_d^-1))
+            ops._lib.call("asvgp_additive_terms", ops._p(self._G), ops._p(zero_x), self.M, o, basis.m, basis.order, ops._p(Ss[i]),
+                          ops._p(dSs[i]), ops._p(tr[i]), ops._stream())
+            if want_grad:
+                ops._lib.call("asvgp_additive_terms", ops._p(Pinv), ops._p(x), self.M, o, basis.m, basis.order, ops._p(Ks[i]),
+                              ops._p(dKs[i]), ops._p(terms[i]), ops._stream())
+        if want_grad:
+            ops._lib.call("asvgp_dense_terms", ops._p(Pinv), ops._p(self._G), ops._p(x), self.M, ops._p(dense), ops._stream())
+        packed = torch.cat([torch.stack(scals).reshape(-1), ws.scal, tr.reshape(-1), terms.reshape(-1), dense, self._scal]).cpu().numpy()
+        sc = packed[: 4 * D].reshape(D, 4); p = 4 * D
+        scP = packed[p: p + 3]; p += 3
+        trn = packed[p: p + 4 * D].reshape(D, 4); p += 4 * D
+        T = packed[p: p + 4 * D].reshape(D, 4); p += 4 * D
+        trPG, xGx = packed[p: p + 2]; p += 2
+        yy, N = packed[p: p + 2]
+        info = scP[2] or next((s[2] for s in sc if s[2] != 0), 0.0)
+        if info != 0:
+            raise np.linalg.LinAlgError("Cholesky failed: non-positive pivot %d" % int(info))
+        logdetK = float(sc[:, 0].sum())
+        logdetP, Q = scP[0], scP[1]
+        trace = float(trn[:, 0].sum())
+        vsum = float(np.sum(v))
+        elbo = (-0.5 * N * np.log(2 * np.pi * s2) - 0.5 * logdetP + 0.5 * logdetK - 0.5 * yy / s2
+                + 0.5 * Q / s2**2 - 0.5 * N * vsum / s2 + 0.5 * trace / s2)
+        self.last_terms = dict(log_det_Kuu=logdetK, log_det_P=logdetP, quad=Q, trace=trace)
+        if not want_grad:
+            return float(elbo), None
+        pairs = []
+        for i, (kern, basis) in enumerate(zip(self.kernels, self.bases)):
+            trPK, trPdK, xKx, xdKx = T[i]
+            d_l = -0.5 * trPdK + 0.5 * sc[i, 1] - 0.5 * xdKx / s2**2 + 0.5 * trn[i, 1] / s2
+            # K_d is proportional to 1 / v_d: dK_d/dv_d = -K_d / v_d, trace(K_d^-1 G_dd) is proportional to v_d
+            d_v = (0.5 * trPK - 0.5 * basis.m + 0.5 * xKx / s2**2 + 0.5 * trn[i, 0] / s2) / v[i] - 0.5 * N / s2
+            pairs += [(kern.variance, d_v), (kern.lengthscales, d_l)]
+        d_s2 = (-0.5 * N / s2 + 0.5 * trPG / s2**2 + 0.5 * yy / s2**2 + 0.5 * xGx / s2**4 - Q / s2**3
+                + 0.5 * N * vsum / s2**2 - 0.5 * trace / s2**2)
+        pairs.append((self.likelihood.variance, d_s2))
+        return float(elbo), _grad_dict(pairs)
+
+    def elbo_and_grad(self):
+        """ELBO (reference gpr.py:181-210) and {id(param): dELBO/dparam} for (v_1, l_1, ..., v_D, l_D, sigma^2)."""
+        return self._evaluate(True)
+
+    def elbo(self):
+        return np.float64(self._evaluate(False)[0])
+
+    def maximum_log_likelihood_objective(self):
+        return self.elbo()
+
+    # -- prediction -----------------------------------------------------------------------------------------------------------------
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        """Posterior mean and variance at Xnew[n*, D], each (n*, 1) (reference gpr.py:212-236)."""
+        assert not full_output_cov
+        if full_cov:
+            raise NotImplementedError
+        s2 = hyper_value(self.likelihood.variance)
+        Ks, dKs, Ss, dSs, scals, ws, x, Pinv = self._factor(True)
+        info = torch.stack([ws.scal[2]] + [s[2] for s in scals])
+        Xs = ops.to_device(Xnew)
+        assert Xs.dim() == 2 and Xs.shape[1] == self.d
+        n = Xs.shape[0]
+        dev = Xs.device
+        meshes = torch.cat([ops.device_mesh(b) for b in self.bases])
+        meta, koff = [], 0
+        for i, b in enumerate(self.bases):
+            nk = ops.device_mesh(b).numel()
+            meta += [koff, nk, int(self._offsets[i]), b.m]
+            koff += nk
+        meta = torch.tensor(meta, dtype=torch.int32, device=dev)
+        S_all = torch.cat([S.reshape(-1) for S in Ss])
+        alpha = x / s2
+        mean = torch.empty(n, dtype=torch.float64, device=dev)
+        var = torch.empty(n, dtype=torch.float64, device=dev)
+        prior = float(sum(hyper_value(k.variance) for k in self.kernels))
+        ops._lib.call("asvgp_predict_additive", ops._p(Xs), n, self.d, ops._p(meshes), ops._p(meta), self.M, self.order, ops._p(alpha),
+                      ops._p(Pinv), ops._p(S_all), prior, ops._p(mean), ops._p(var), ops._stream())
+        if info.any().item():
+            raise np.linalg.LinAlgError("Cholesky failed in predict_f")
+        mean, var = mean.view(-1, 1), var.view(-1, 1)
+        if isinstance(Xnew, torch.Tensor) and Xnew.is_cuda:
+            return mean, var
+        return mean.cpu().numpy(), var.cpu().numpy()

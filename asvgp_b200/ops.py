@@ -588,3 +588,61 @@ def predict_2d(Xnew, bases, alpha, SigP, S1, S2, prior_var):
 
 
 _PREDICT_WORK = {}
+
+
+# =====================================================================================================================
+# dense SPD matrices (one front of the nested-dissection kernels) and the additive model's operators
+# =====================================================================================================================
+class DenseWorkspace:
+    """Device buffers of asvgp_dense_factor / asvgp_dense_selinv for n x n matrices (cached per (device, n))."""
+
+    def __init__(self, n):
+        lib = _lib.load()
+        dev = device()
+        nb, ns, nw = lib.asvgp_dense_band_doubles(n), lib.asvgp_dense_sig_doubles(n), lib.asvgp_dense_work_doubles(n)
+        if min(nb, ns, nw) < 0:
+            raise _lib.AsvgpNativeError("dense workspace query rejected n=%d" % n)
+        self.n = n
+        self.band = torch.empty(nb, dtype=F64, device=dev)
+        self.sig_band = torch.empty(ns, dtype=F64, device=dev)
+        self.work = torch.empty(nw, dtype=F64, device=dev)
+        self.scal = torch.zeros(3, dtype=F64, device=dev)
+        self.x = torch.empty(n, dtype=F64, device=dev)
+        self.inv = torch.empty((n, n), dtype=F64, device=dev)
+
+
+_DENSE_WS = {}
+
+
+def dense_workspace(n):
+    key = (device(), n)
+    ws = _DENSE_WS.get(key)
+    if ws is None:
+        ws = _DENSE_WS[key] = DenseWorkspace(n)
+    return ws
+
+
+def dense_factor(A, rhs, ws):
+    """Cholesky of the dense SPD matrix A (lower triangle read); ws.scal = {log|A|, rhs^T A^-1 rhs, info}."""
+    _lib.call("asvgp_dense_factor", _p(A), ws.n, _p(rhs), _p(ws.band), _p(ws.scal), _stream())
+    return ws
+
+
+def dense_selinv(ws):
+    """(A^-1 rhs, A^-1) from the factor held in ws (consumed)."""
+    _lib.call("asvgp_dense_selinv", _p(ws.band), ws.n, _p(ws.sig_band), _p(ws.x), _p(ws.inv), _p(ws.work), _stream())
+    return ws.x, ws.inv
+
+
+def accum_cross(X, da, db, basis_a, basis_b, out=None):
+    """out[m_a, m_b] += Kuf_a Kuf_b^T for columns da, db of the device tensor X[n, D] (reference gpr.py:174-175)."""
+    X = to_device(X)
+    if out is None:
+        out = torch.zeros((basis_a.m, basis_b.m), dtype=F64, device=X.device)
+    ma, mb = device_mesh(basis_a), device_mesh(basis_b)
+    if basis_a.order != basis_b.order:
+        raise ValueError("all bases of an additive model must have the same order (reference gpr.py:163-165)")
+    D = X.shape[1]
+    _lib.call("asvgp_accum_cross", ctypes.c_void_p(X.data_ptr() + 8 * da), ctypes.c_void_p(X.data_ptr() + 8 * db), D, X.shape[0],
+              _p(ma), ma.numel(), _p(mb), mb.numel(), basis_a.order, _p(out), _stream())
+    return out

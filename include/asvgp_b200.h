@@ -234,6 +234,44 @@ ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh
                                const double* S2, double prior_var, double* mean, double* var, double* work,
                                void* stream);
 
+/* ---- dense SPD matrices on the front kernels ----------------------------------------------------------------------------------------
+ * Replaces tf.linalg.cholesky / triangular_solve / cholesky_solve of a DENSE matrix (GPR_additive, gpr.py:192-195, 221-231):
+ * one front of the nested-dissection machinery above.  A: n x n row-major (lower triangle read), n <= 32768.
+ * asvgp_dense_factor: scal[3] = { log|A|, rhs^T A^-1 rhs, info }.  asvgp_dense_selinv (consumes band): x_out = A^-1 rhs,
+ * inv_out[n x n] = A^-1 (full, symmetric). */
+ASVGP_API int64_t asvgp_dense_band_doubles(int n);
+ASVGP_API int64_t asvgp_dense_sig_doubles(int n);
+ASVGP_API int64_t asvgp_dense_work_doubles(int n);
+ASVGP_API int asvgp_dense_factor(const double* A, int n, const double* rhs, double* band, double* scal, void* stream);
+ASVGP_API int asvgp_dense_selinv(double* band, int n, double* sig_band, double* x_out, double* inv_out, double* work,
+                                 void* stream);
+
+/* ---- GPR_additive (gpr.py:139-236): sum of 1-D models, Kuf = stacked per-dimension features ------------------------------------------
+ * asvgp_accum_cross: C[m_a x m_b] += Kuf_a Kuf_b^T for two dimensions of the same points (xa[i * stride], xb[i * stride]) — the
+ *   dense off-diagonal blocks of `Kuf @ Kuf.T` (gpr.py:174-175); the banded diagonal blocks are asvgp_accum_1d's.
+ * asvgp_additive_put_band / _put_cross: write (add != 0: add) scale * (a lower band as a symmetric block) at `offset` on the
+ *   diagonal of the dense M x M matrix `out`; write a cross block and its transpose.  asvgp_additive_scale: P = G / sigma2.
+ *   Together: KufKfu (gpr.py:175) and `Kuu.to_dense() + KufKfu / sigma2` (gpr.py:192).
+ * asvgp_additive_terms: out4 = { sum S_dd .* K_d, sum S_dd .* dK_d, x_d^T K_d x_d, x_d^T dK_d x_d } for the diagonal block of
+ *   dimension d of S = P^-1 (dense) and x = P^-1 Kuf_y;  asvgp_dense_terms: out2 = { sum S .* G, x^T G x }.  These are what the
+ *   derivatives of the bound need (TF reverse mode in the reference).
+ * asvgp_predict_additive: GPR_additive.predict_f (gpr.py:212-236).  Xnew[n, D] row-major, D <= 8; meshes = all knot arrays
+ *   concatenated; meta[4 d ..] = { knot offset, number of knots, first basis function, m_d } (device ints); S_all = the lower
+ *   bands of K_d^-1 concatenated in dimension order. */
+ASVGP_API int asvgp_accum_cross(const double* xa, const double* xb, int64_t stride, int64_t n, const double* mesh_a,
+                                int n_knots_a, const double* mesh_b, int n_knots_b, int order, double* C, void* stream);
+ASVGP_API int asvgp_additive_put_band(const double* band, int m, int order, int offset, int M, double scale, int add,
+                                      double* out, void* stream);
+ASVGP_API int asvgp_additive_put_cross(const double* C, int m_a, int m_b, int offset_a, int offset_b, int M, double* out,
+                                       void* stream);
+ASVGP_API int asvgp_additive_scale(const double* G, int M, double sigma2, double* P, void* stream);
+ASVGP_API int asvgp_additive_terms(const double* Pinv, const double* x, int M, int offset, int m, int order, const double* Kd,
+                                   const double* dKd, double* out4, void* stream);
+ASVGP_API int asvgp_dense_terms(const double* Pinv, const double* G, const double* x, int M, double* out2, void* stream);
+ASVGP_API int asvgp_predict_additive(const double* Xnew, int64_t n, int D, const double* meshes, const int* meta, int M,
+                                     int order, const double* alpha, const double* Pinv, const double* S_all,
+                                     double prior_var, double* mean, double* var, void* stream);
+
 /* ---- name-for-name counterparts of the reference's Kronecker helpers (not used by the models) -------------------------------
  * asvgp_khatri_rao_csc replaces kronecker.make_kvs_two_sparse (kronecker.py:7-27; make_kvs_sparse folds it over a list,
  * :29-33): row-wise Khatri-Rao product of two sparse feature matrices in CSC form with int64 indices, column n of the

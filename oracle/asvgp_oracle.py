@@ -663,3 +663,62 @@ def elbo_grad_1d_banded(kind, tables, G, Kuf_y, tr_yTy, n, var, ell, sigma2, blo
     g_s2 = (-0.5 * n / sigma2 + 0.5 * _band_dot(Pinv, G) / sigma2**2 + 0.5 * tr_yTy / sigma2**2 - bPb / sigma2**3
             + 0.5 * (alpha.T @ _band_matmul(G, alpha)).item() / sigma2**2 + 0.5 * n * var / sigma2**2 - 0.5 * tr / sigma2**2)
     return elbo, np.array(grads + [g_s2])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPR_additive  (asvgp/gpr.py:139-236): sum of 1-D models, Kuu block diagonal, Kuf stacked
+# ---------------------------------------------------------------------------------------------------------------------
+def precompute_additive(meshes, deltas, k, ms, X, y):
+    """Kuf = vstack of the per-dimension feature matrices; dense KufKfu, Kuf_y, tr_yTy (gpr.py:171-176)."""
+    Kuf = sp.vstack([make_Kuf(meshes[i], deltas[i], k, ms[i], X[:, i]) for i in range(X.shape[1])]).tocsr()
+    y = np.asarray(y, dtype=np.float64).reshape(-1, 1)
+    return np.asarray((Kuf @ Kuf.T).todense()), np.asarray(Kuf @ y), float(np.sum(np.square(y)))
+
+
+def elbo_additive_dense(Kuu_bands, G, Kuf_y, tr_yTy, n, variances, sigma2):
+    """GPR_additive.elbo (gpr.py:181-210) with dense algebra, as the reference does it."""
+    Kuu = sla.block_diag(*[band_to_dense_sym(b) for b in Kuu_bands])
+    P = Kuu + G / sigma2
+    L = np.linalg.cholesky(P)
+    c = sla.solve_triangular(L, Kuf_y, lower=True) / sigma2
+    elbo = -0.5 * n * np.log(2 * np.pi * sigma2) - np.sum(np.log(np.diag(L))) + 0.5 * np.linalg.slogdet(Kuu)[1]
+    elbo += -0.5 * tr_yTy / sigma2 + 0.5 * np.sum(np.square(c)) - 0.5 * n * np.sum(variances) / sigma2
+    elbo += 0.5 * np.trace(np.linalg.solve(Kuu, G)) / sigma2
+    return elbo
+
+
+def elbo_grad_additive_dense(kinds, tables, G, Kuf_y, tr_yTy, n, hypers, sigma2):
+    """The same bound and d/d(v_1, l_1, ..., v_D, l_D, sigma2) by torch-fp64 autograd (the reference gets them from TF
+    reverse mode).  hypers = [(v_i, l_i)]."""
+    import torch
+
+    flat = [h for vl in hypers for h in vl] + [sigma2]
+    th = torch.tensor(flat, dtype=torch.float64, requires_grad=True)
+    Ks = []
+    for i, kind in enumerate(kinds):
+        v, l = th[2 * i], th[2 * i + 1]
+        dense = {nme: torch.from_numpy(band_to_dense_sym(t)) for nme, t in tables[i].items()}
+        Ks.append(sum(c * dense[nme] for nme, c in _kuu_coefficients_torch(kind, l, v).items()))
+    s2 = th[-1]
+    Kuu = torch.block_diag(*Ks)
+    Gd = torch.from_numpy(np.asarray(G, dtype=np.float64))
+    b = torch.from_numpy(np.asarray(Kuf_y, dtype=np.float64).reshape(-1, 1))
+    L = torch.linalg.cholesky(Kuu + Gd / s2)
+    c = torch.linalg.solve_triangular(L, b, upper=False) / s2
+    total_var = sum(th[2 * i] for i in range(len(kinds)))
+    elbo = (-0.5 * n * torch.log(2 * np.pi * s2) - torch.log(torch.diagonal(L)).sum() + 0.5 * torch.logdet(Kuu)
+            - 0.5 * tr_yTy / s2 + 0.5 * (c**2).sum() - 0.5 * n * total_var / s2
+            + 0.5 * torch.trace(torch.linalg.solve(Kuu, Gd)) / s2)
+    elbo.backward()
+    return float(elbo.detach()), th.grad.numpy().copy()
+
+
+def predict_additive_dense(meshes, deltas, k, ms, Kuu_bands, G, Kuf_y, variances, sigma2, Xnew):
+    """GPR_additive.predict_f (gpr.py:212-236), dense."""
+    Kuu = sla.block_diag(*[band_to_dense_sym(b) for b in Kuu_bands])
+    P = G / sigma2 + Kuu
+    Kus = np.asarray(sp.vstack([make_Kuf(meshes[i], deltas[i], k, ms[i], Xnew[:, i]) for i in range(Xnew.shape[1])]).todense())
+    cP = sla.cho_factor(P, lower=True)
+    mean = Kus.T @ sla.cho_solve(cP, Kuf_y) / sigma2
+    var = np.sum(variances) + np.sum(Kus * sla.cho_solve(cP, Kus), axis=0) - np.sum(Kus * np.linalg.solve(Kuu, Kus), axis=0)
+    return mean, var.reshape(-1, 1)

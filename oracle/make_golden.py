@@ -181,10 +181,38 @@ def multi_output_1d(ns):
     print("multi_output_1d: Kuf_y", out["Kuf_y"].shape, "mean", out["mean"].shape, out["elbo_Matern52_b"])
 
 
+
+
+def additive(ns):
+    """GPR_additive (reference gpr.py:139-236) on a small 3-D synthetic set: Gram, projection, bound at two sets of
+    hyper-parameters and kernel mixes, predictions."""
+    rng = np.random.default_rng(12)
+    n, m, k = 4000, 24, 3
+    doms = [(0, 1), (0, 2), (-1, 1)]
+    X = np.stack([rng.uniform(a + 0.01, b - 0.01, n) for a, b in doms], 1)
+    y = (np.sin(5 * X[:, 0]) + np.cos(3 * X[:, 1]) + X[:, 2] ** 2 + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    Xs = np.stack([rng.uniform(a + 0.02, b - 0.02, 60) for a, b in doms], 1)
+    out = dict(X=X, y=y, Xs=Xs, m=m, order=k, doms=np.array(doms, dtype=np.float64))
+    for tag, kinds, hypers, s2 in (("a", ("Matern32",) * 3, [(1.0, 1.0)] * 3, 1.0),
+                                   ("b", ("Matern52", "Matern12", "Matern32"), [(.7, .3), (1.3, .5), (.9, .8)], .05)):
+        bases = [ns.basis.B3Spline(a, b, m) for a, b in doms]
+        kerns = [getattr(ns.gpflow.kernels, kind)() for kind in kinds]
+        model = ns.gpr.GPR_additive((X, y), kerns, bases)
+        set_hypers(ns, model, kerns, hypers, s2)
+        out["elbo_" + tag] = float(np.asarray(model.elbo()))
+        mean, var = model.predict_f(Xs)
+        out["mean_" + tag], out["var_" + tag] = np.asarray(mean), np.asarray(var)
+    out["KufKfu"] = np.asarray(model.KufKfu)
+    out["Kuf_y"] = np.asarray(model.Kuf_y)
+    out["tr_yTy"] = float(np.asarray(model.tr_yTy))
+    np.savez_compressed(os.path.join(OUT, "additive_3d.npz"), **out)
+    print("additive: elbo", out["elbo_a"], out["elbo_b"], "mean", out["mean_b"].shape, "var", out["var_b"].shape)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     ns = ref_under_shim.load()
     only = sys.argv[1:]
-    for fn in (snelson, basis_eval, synth_1d, kron_2d, multi_output_1d):
+    for fn in (snelson, basis_eval, synth_1d, kron_2d, multi_output_1d, additive):
         if not only or fn.__name__ in only:
             fn(ns)
