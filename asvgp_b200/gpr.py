@@ -108,8 +108,12 @@ class GPR_1d(_ModelBase):
                 self._accs.append(ops.accum_1d_host(X, np.ascontiguousarray(yd), basis))
         self._distributed = _dist.is_distributed(distributed)
         if self._distributed:
-            for acc in self._accs:
-                _dist.allreduce_packed(acc)
+            if len(self._accs) == 1:
+                _dist.allreduce_packed(self._accs[0])
+            else:                   # D output columns: still ONE collective, over the stacked packed buffers
+                stacked = torch.stack(self._accs)
+                _dist.allreduce_packed(stacked)
+                self._accs = list(stacked.unbind(0))
         self._acc = self._accs[0]
         self._G, self._b, self._scal = ops.split_accum_1d(self._acc, basis)
         self._host = None

@@ -4,6 +4,21 @@ import numpy as np
 import scipy.optimize
 
 
+def _same_on_every_rank(u):
+    """Data-parallel runs: every rank drives its own L-BFGS on (up to rounding) the same loss and gradient; rank 0's iterate
+    is broadcast before each evaluation so that the replicas can never drift apart by an ulp and take different line-search
+    branches (the factorisation uses fp64 REDs, whose summation order is not fixed)."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        return u
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.as_tensor(np.asarray(u, dtype=np.float64)).to(dev)
+    dist.broadcast(t, src=0)
+    return t.cpu().numpy()
+
+
 class Scipy:
     def minimize(self, closure, variables, method="L-BFGS-B", **scipy_kwargs):
         model = getattr(closure, "__self__", None)
@@ -14,6 +29,7 @@ class Scipy:
         index = [next(i for i, p in enumerate(model_vars) if p is v) for v in variables]
 
         def fun(u):
+            u = _same_on_every_rank(u)
             for v, ui in zip(variables, u):
                 v.unconstrained = float(ui)
             loss, grad = model.training_loss_and_gradients()
