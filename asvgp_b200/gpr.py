@@ -108,7 +108,11 @@ class GPR_1d(_ModelBase):
                 self._accs.append(ops.accum_1d_host(X, np.ascontiguousarray(yd), basis))
         self._distributed = _dist.is_distributed(distributed)
         if self._distributed:
-            if len(self._accs) == 1:
+            red = _dist.oneshot_reducer(self._accs[0].numel()) if (len(self._accs) == 1 and self._accs[0].is_cuda) else None
+            if red is not None:          # one kernel over NVLink peer memory (asvgp_allreduce_oneshot); else NCCL
+                red.buffer().copy_(self._accs[0])
+                red.reduce(self._accs[0])
+            elif len(self._accs) == 1:
                 _dist.allreduce_packed(self._accs[0])
             else:                   # D output columns: still ONE collective, over the stacked packed buffers
                 stacked = torch.stack(self._accs)

@@ -676,12 +676,23 @@ def main():
 
     binned = not is_sorted            # random order: bucket-partition path, the binning passes are inside the timed accumulate
 
+    # the one collective of the step: a one-shot all-reduce over NVLink peer memory (asvgp_allreduce_oneshot, the ranks
+    # accumulate straight into symmetric buffers); NCCL all_reduce when symmetric memory is unavailable
+    red = None
+    if world > 1 and os.environ.get("ASVGP_NCCL_ALLREDUCE") is None:
+        from asvgp_b200 import dist as adist
+
+        red = adist.oneshot_reducer(acc.numel())
+
     def step(timers=None):
-        acc.zero_()
+        tgt = red.buffer() if red is not None else acc
+        tgt.zero_()
         if timers: timers[0].record()
-        ops.accum_1d(x, y, basis, acc=acc, binned=binned)
+        ops.accum_1d(x, y, basis, acc=tgt, binned=binned)
         if timers: timers[1].record()
-        if world > 1:
+        if red is not None:
+            red.reduce(acc)
+        elif world > 1:
             dist.all_reduce(acc)
         if timers: timers[2].record()
         Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
@@ -740,11 +751,15 @@ def main():
         sev = [[ev() for _ in range(4)] for _ in range(args.steps)]
 
         def strong_step(t):
-            acc.zero_()
+            tgt = red.buffer() if red is not None else acc
+            tgt.zero_()
             t[0].record()
-            ops.accum_1d(xs_, ys_, basis, acc=acc, binned=binned)
+            ops.accum_1d(xs_, ys_, basis, acc=tgt, binned=binned)
             t[1].record()
-            dist.all_reduce(acc)
+            if red is not None:
+                red.reduce(acc)
+            else:
+                dist.all_reduce(acc)
             t[2].record()
             Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
             ops.elbo_grad_1d(Kuu, dKuu, acc, basis, HYPERS[0], HYPERS[2], out=out)
@@ -896,6 +911,11 @@ def main():
     }
     if strong is not None:
         line["strong_scaling"] = strong
+    if world > 1:
+        line["collective"] = ("asvgp_allreduce_oneshot: one kernel per rank over NVLink peer memory (symmetric buffers), sums in rank "
+                              "order" if red is not None else "torch.distributed.all_reduce (NCCL)")
+        if red is not None:
+            red.check()
     if e2e is not None:
         line["e2e"] = e2e
     if kron is not None:

@@ -234,6 +234,16 @@ ASVGP_API int asvgp_predict_2d(const double* Xnew, int64_t n, const double* mesh
                                const double* S2, double prior_var, double* mean, double* var, double* work,
                                void* stream);
 
+/* ---- the one collective of the data-parallel path ---------------------------------------------------------------------------
+ * One-shot all-reduce of a packed accumulator over NVLink peer memory: every rank's partial sums live in a symmetric buffer
+ * (mapped into every peer); one kernel per rank does the cross-rank barrier (signal pads, system-scope release / acquire),
+ * reads all peers' buffers and adds them in rank order (bit-identical result on every rank).  buffer_ptrs / pad_ptrs: device
+ * arrays of `world` 64-bit addresses of every rank's buffer / signal pad.  `epoch` increases by one per call, identically on all
+ * ranks; callers double-buffer the symmetric buffers (asvgp_b200/dist.py).  status[1] (device int): 1 if a peer never arrived
+ * (the output is then NaN; waits are bounded).  Replaces torch.distributed.all_reduce (NCCL) for this buffer. */
+ASVGP_API int asvgp_allreduce_oneshot(const void* buffer_ptrs, const void* pad_ptrs, int rank, int world, int64_t offset_doubles,
+                                      int64_t n, unsigned epoch, int pad_offset, double* out, int* status, void* stream);
+
 /* ---- dense SPD matrices on the front kernels ----------------------------------------------------------------------------------------
  * Replaces tf.linalg.cholesky / triangular_solve / cholesky_solve of a DENSE matrix (GPR_additive, gpr.py:192-195, 221-231):
  * one front of the nested-dissection machinery above.  A: n x n row-major (lower triangle read), n <= 32768.
