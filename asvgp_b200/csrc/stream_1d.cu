@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "partition.cuh"
@@ -528,13 +529,12 @@ __global__ void __launch_bounds__(256) order_probe_1d_kernel(const double* __res
 // instructions) and no gathers; lanes take consecutive pairs of points, loads and stores are fully coalesced 128-bit
 // accesses.  A lane whose points jump between intervals (unordered test sets) evaluates pieces and window entries
 // directly instead of refreshing its cache every time.  24 B of traffic per point.
-template <int K>
-__global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restrict__ xs, int64_t n, const double* __restrict__ knots,
+template <int K, int U, bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(256, MINB) predict_1d_kernel(const double* __restrict__ xs, int64_t n, const double* __restrict__ knots,
                                                          int n_knots, int M,
                                                          const double* __restrict__ alpha,
                                                          const double* __restrict__ S, double variance,
                                                          double* __restrict__ mean, double* __restrict__ var) {
-    constexpr int U = 4;                 // pairs of points in flight per thread (8 measured no faster)
     const Mesh mesh = load_mesh(knots, n_knots);
     const MomentCoef<K>& mc = g_moment_coef<K>;
     const bool vec = ((reinterpret_cast<uintptr_t>(xs) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 15u) == 0;
@@ -621,8 +621,8 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
         const double2* __restrict__ x2 = reinterpret_cast<const double2*>(xs);
         double2* __restrict__ m2 = reinterpret_cast<double2*>(mean);
         double2* __restrict__ v2 = reinterpret_cast<double2*>(var);
-        // the next tile's points are requested before the current tile is evaluated (the kernel was waiting on its loads:
-        // stall_long_sb 43 % of the samples with load -> evaluate -> store per tile)
+        // PREFETCH: the next tile's points are requested before the current tile is evaluated; the shipped instantiation
+        // relies on four resident CTAs per SM instead (fewer registers; see the launch-shape note at asvgp_predict_1d)
         double2 xv[U];
         const int64_t step = (int64_t)blockDim.x * U;
         int64_t base = c_begin + threadIdx.x;
@@ -632,11 +632,13 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
             xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
         }
         for (; base < c_end; base += step) {
-            double2 xn[U];
+            double2 xn[PREFETCH ? U : 1];
+            if (PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) {
-                const int64_t i = base + step + j * (int64_t)blockDim.x;
-                xn[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                for (int j = 0; j < U; ++j) {
+                    const int64_t i = base + step + j * (int64_t)blockDim.x;
+                    xn[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                }
             }
 #pragma unroll
             for (int j = 0; j < U; ++j) {
@@ -648,8 +650,16 @@ __global__ void __launch_bounds__(256) predict_1d_kernel(const double* __restric
                 __stcs(m2 + i, mo);          // written once, never read back here
                 __stcs(v2 + i, vo);
             }
+            if (PREFETCH) {
 #pragma unroll
-            for (int j = 0; j < U; ++j) xv[j] = xn[j];
+                for (int j = 0; j < U; ++j) xv[j] = xn[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < U; ++j) {
+                    const int64_t i = base + step + j * (int64_t)blockDim.x;
+                    xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                }
+            }
         }
         if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) eval(__ldg(xs + n - 1), mean[n - 1], var[n - 1]);
     } else {
@@ -783,8 +793,12 @@ extern "C" int asvgp_predict_1d(const double* xnew, int64_t n, const double* mes
     if (n == 0) return kOk;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int M = n_knots + order - 1;
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 256 * 8 - 1) / (256 * 8), (int64_t)sm_count() * 4));
-    ASVGP_DISPATCH_ORDER(order, (predict_1d_kernel<K><<<blocks, 256, 0, st>>>(xnew, n, mesh, n_knots, M, alpha, S_band, variance, mean, var))); ASVGP_LAUNCHED();
+    // Launch shape (tools/predict_1d_sweep.py, 1e8 sorted points): 64 registers / 4 CTAs per SM with two pairs in flight per
+    // thread and MANY short CTA ranges — 0.47 ms = 5.1 TB/s, the ceiling of a 1 : 2 read : write stream on this part
+    // (tools/microbench/rw12_bench.cu: 5.4 TB/s) — against 0.69 ms for 4 prefetched pairs at 80+ registers on 4 CTAs per SM.
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 4095) / 4096, (int64_t)sm_count() * 128));
+    ASVGP_DISPATCH_ORDER(order, (predict_1d_kernel<K, 2, false, 4><<<blocks, 256, 0, st>>>(xnew, n, mesh, n_knots, M, alpha, S_band, variance, mean, var)));
+    ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }

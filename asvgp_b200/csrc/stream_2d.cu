@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "async_copy.cuh"
 #include "common.cuh"
@@ -1881,8 +1882,9 @@ template <int K>
 static int launch_predict_2d_apply(const double* Xnew, int64_t n, int hint_n2, const double* mesh1, int nk1, const double* mesh2,
                                    int nk2, double prior_var, double* mean, double* var, double* work, cudaStream_t st) {
     ProbeResult* probe = reinterpret_cast<ProbeResult*>(work + asvgp_predict_2d_work_doubles(nk1, nk2, K) - 1);
+    const int cols_mult = 6;       // CTAs per SM's worth of tasks (tools/predict_2d_sweep.py: 0.69 ms at 2, 0.64 ms at 6, 0.66 ms at 8)
     if (hint_n2 > 0) {      // the caller states the test set is a flattened raster: column sweep only (it re-checks every point)
-        predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, hint_n2); ASVGP_LAUNCHED();
+        predict_2d_cols_kernel<K><<<cols_mult * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, hint_n2); ASVGP_LAUNCHED();
         ASVGP_CUDA_OK(cudaGetLastError());
         return kOk;
     }
@@ -1890,7 +1892,7 @@ static int launch_predict_2d_apply(const double* Xnew, int64_t n, int hint_n2, c
     // the thread-contiguous kernel; the one that is not selected returns at once
     accum_2d_probe_kernel<<<1, 1024, 0, st>>>(Xnew, Xnew, n, probe); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
-    predict_2d_cols_kernel<K><<<2 * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, 0); ASVGP_LAUNCHED();
+    predict_2d_cols_kernel<K><<<cols_mult * sm_count2(), 256, 0, st>>>(Xnew, n, mesh1, nk1, mesh2, nk2, work, prior_var, mean, var, probe, 0); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     const bool vec = ((reinterpret_cast<uintptr_t>(Xnew) | reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(var)) & 31u) == 0;
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 1023) / 1024, 2 * (int64_t)sm_count2()));
