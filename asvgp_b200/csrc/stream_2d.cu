@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(kColsWarps * 32, 1)
 accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t n,
                      const double* __restrict__ knots1, int nk1, const double* __restrict__ knots2, int nk2,
                      double* __restrict__ cellmom, double* __restrict__ scal, const ProbeResult* __restrict__ probe,
-                     int hint_n2) {
+                     int hint_n2, int tasks_per_warp) {
     // hint_n2 > 0: the caller states that the input is a flattened raster with rows of hint_n2 points (asvgp_accum_2d_raster);
     // no probe ran.  The per-point checks below make a wrong statement slow, never wrong.
     if (hint_n2 <= 0 && probe->select != 4) return;
@@ -662,7 +662,7 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     // tasks: 32-column strips x row segments, dealt round-robin to the warps of the grid
     const int64_t n_strips = (n2 + 31) / 32;
     const int64_t total_warps = (int64_t)gridDim.x * kWarps;
-    int64_t n_seg = (4 * total_warps + n_strips - 1) / n_strips;
+    int64_t n_seg = (tasks_per_warp * total_warps + n_strips - 1) / n_strips;
     int64_t seg_len = ((n1 + n_seg - 1) / n_seg + 31) & ~(int64_t)31;
     if (seg_len < 64) seg_len = 64;
     n_seg = (n1 + seg_len - 1) / seg_len;
@@ -1722,7 +1722,8 @@ static int launch_cols(const double* X, const double* y, int64_t n, const double
     const size_t smem_cols = sizeof(double) * 3 * kColsWarps * 32 * (3 * (size_t)K + 2)     // sums, factors, per-row table
                              + (size_t)kColsWarps * ColsRing<K>::kRows * 32 * 24;            // the ring
     ASVGP_CUDA_OK(cudaFuncSetAttribute(accum_2d_cols_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cols));
-    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe, hint_n2); ASVGP_LAUNCHED();
+    const int tpw = 8;             // row segments per warp (tools/accum_sweep.py: 0.603 ms at 4, 0.581 at 8, 0.587 at 16, 0.651 at 32)
+    accum_2d_cols_kernel<K><<<sm_count2(), kColsWarps * 32, smem_cols, st>>>(X, y, n, k1, nk1, k2, nk2, cellmom, scal, probe, hint_n2, tpw); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
