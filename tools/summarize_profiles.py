@@ -1,10 +1,12 @@
-"""Turns the ncu artefacts tools/profile_r01.sh left in gpurun_out/ into profiles/r01_ncu_summary_<tag>.md.
-   python tools/summarize_profiles.py v4   (needs `ncu` on PATH to read the .ncu-rep files)"""
+"""Turns the ncu artefacts tools/profile_r0N.sh left in gpurun_out/ into profiles/r0N_ncu_summary_<tag>.md.
+   python tools/summarize_profiles.py v1 [r02]   (needs `ncu` on PATH to read the .ncu-rep files)"""
 import collections, csv, glob, io, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 tag = sys.argv[1] if len(sys.argv) > 1 else "v4"
+rnd = sys.argv[2] if len(sys.argv) > 2 else "r01"
+PFX = "" if rnd == "r01" else "r2_"
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
@@ -44,28 +46,28 @@ def rep_row(path):
     return "| `%s` | %s |" % (os.path.basename(path)[5:-8], " | ".join(cells))
 
 
-parts = ["# r01 %s — ncu evidence (B200, `--clock-control none`)\n" % tag,
-         "Commands: `tools/profile_r01.sh a|b|c` (launch lists: `ncu --metrics gpu__time_duration.sum`; kernels: `ncu --set full`, one "
+parts = ["# %s %s — ncu evidence (B200, `--clock-control none`)\n" % (rnd, tag),
+         "Commands: `tools/profile_%s.sh a|b|c`" % rnd + " (launch lists: `ncu --metrics gpu__time_duration.sum`; kernels: `ncu --set full`, one "
          "launch each, after a plain run of the same command that exited 0); this file: `tools/summarize_profiles.py %s`.\n"
          "Per-launch times are cold-cache and serialised (compare shares, not absolutes). The bench line of the same build: "
-         "`profiles/r01_bench_v6.json`.\n" % tag]
-for f, title in (("launches_1d.csv", "1-D bench (`bench.py --steps 2 --warmup 3 --no-2d`), first 400 launches"),
-                 ("launches_2d.csv", "2-D bench (`bench.py --workload 2d --steps 1 --warmup 3`), first 600 launches"),
-                 ("launches_binned_1d.csv", "1-D accumulate, 1e8 points in random order (`tools/binned_1d_only.py`)"),
-                 ("launches_binned_2d.csv", "2-D accumulate, shuffled 1e4 x 1e4 raster (`tools/binned_2d_only.py`)")):
+         "`profiles/%s_bench_*.json`.\n" % (tag, rnd)]
+for f, title in ((PFX + "launches_1d.csv", "1-D bench (`bench.py --steps 2 --warmup 3 --no-2d`), first 400 launches"),
+                 (PFX + "launches_2d.csv", "2-D bench (`bench.py --workload 2d --steps 1 --warmup 3`), first 600 / 900 launches"),
+                 (PFX + "launches_binned_1d.csv", "1-D accumulate, 1e8 points in random order (`tools/binned_1d_only.py`)"),
+                 (PFX + "launches_binned_2d.csv", "2-D accumulate, shuffled 1e4 x 1e4 raster (`tools/binned_2d_only.py`)")):
     p = os.path.join(OUT, f)
     if os.path.exists(p):
         parts.append(launch_table(p, title))
-reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + glob.glob("/tmp/reps/prof_*.ncu-rep"))
+reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + (glob.glob("/tmp/reps/prof_*.ncu-rep") if rnd == "r01" else []))
 if reps:
     parts.append("## `--set full` captures (one launch each)\n")
     parts.append("| kernel | " + " | ".join(m.split(".")[0] for m in METRICS) + " |")
     parts.append("|" + "---|" * (len(METRICS) + 1))
     for r in reps:
         parts.append(rep_row(r))
-sass = subprocess.run("cuobjdump -sass %s | grep -oE 'UBLKCP[.A-Z0-9]*|LDGSTS[.A-Z0-9]*|SYNCS[.A-Z0-9]*|LDG\\.E\\.ENL2\\.256[.A-Z]*|REDG\\.E\\.ADD\\.F64[.A-Z]*|ATOMS\\.ADD' | sort | uniq -c"
+sass = subprocess.run("cuobjdump -sass %s | grep -oE 'UBLKCP[.A-Z0-9]*|LDGSTS[.A-Z0-9]*|SYNCS[.A-Z0-9]*|DMMA[.A-Z0-9]*|LDG\\.E\\.ENL2\\.256[.A-Z]*|REDG\\.E\\.ADD\\.F64[.A-Z]*|ATOMS\\.ADD|LD\\.E\\.[0-9]*\\.STRONG\\.SYS|ST\\.E\\.STRONG\\.SYS' | sort | uniq -c"
                       % os.path.join(ROOT, "asvgp_b200", "lib", "libasvgp_sm100a.so"), shell=True, capture_output=True, text=True).stdout
 parts.append("\n## SASS evidence (`cuobjdump -sass asvgp_b200/lib/libasvgp_sm100a.so`)\n\n```\n%s```\n" % sass)
-dst = os.path.join(ROOT, "profiles", "r01_ncu_summary_%s.md" % tag)
+dst = os.path.join(ROOT, "profiles", "%s_ncu_summary_%s.md" % (rnd, tag))
 open(dst, "w").write("\n".join(parts))
 print(dst)
