@@ -309,7 +309,7 @@ def workload_config_2d(name, n1, n2, m, k):
                         % (n, n1, n2, m, m, k),
             "name": name, "n_per_gpu": n, "m": [m, m], "order": k, "kernel": "Matern32xMatern32",
             "hypers": [list(HYPERS_2D[0]), list(HYPERS_2D[1]), HYPERS_2D[2]],
-            "l2_policy": "inputs (24 B/pt x N = %.1f GB) are larger than the 126 MB L2; a 256 MB write flushes it before every "
+            "l2_policy": "inputs (24 B/pt x N = %.1f GB) are larger than the 126 MB L2; a 512 MB write flushes it before every "
                          "step (inside the timed region)" % (24 * n / 1e9),
             "input_layout": "the caller states the raster shape (GPR_kron(..., raster_shape=(n1, n2)) / asvgp_accum_2d_raster): "
                             "no on-device classification pass; every point is still verified against the statement"}
@@ -345,14 +345,14 @@ def run_2d(args, name, torch, dist, world, rank, steps, warmup, with_e2e=True):
     ev = lambda: torch.cuda.Event(enable_timing=True)   # noqa: E731
     result = {}
 
-    flush = torch.empty(32 * 1024 * 1024, dtype=torch.float64, device="cuda")      # 256 MB > the 126 MB L2
+    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float64, device="cuda")      # 512 MB > the 126 MB L2
 
     def step(timers=None):
         # every step ends with a host read of the bound, so the host is never ahead of the GPU here; the L2 flush (the
-        # timing rules' "write a buffer larger than L2") also gives the host the ~40 us it needs to enqueue the accumulate
-        # kernel behind it, so that the accumulate phase below times the kernel and not the launch latency
-        flush.fill_(0.0)
+        # timing rules' "write a buffer larger than L2", ~80 us) also gives the host the time it needs to enqueue the
+        # accumulate kernel behind it, so that the accumulate phase below times the kernel and not the launch latency
         model._acc.zero_(); cellmom.zero_()
+        flush.fill_(0.0)
         if timers: timers[0].record()
         # the workload IS a raster (BASELINE.json configs[3]: "gridded points") and says so: no on-device classification pass
         ops.accum_2d(X, y, bases, cellmom, model._scal, raster_row_len=n2)
