@@ -23,6 +23,8 @@ SIGNATURES = {
     "asvgp_predict_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp],
     "asvgp_kuu_assemble": [_vp, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
     "asvgp_elbo_grad_1d": [_vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp],
+    "asvgp_kuu_chain_1d": [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_i64, _vp, _vp],
+    "asvgp_elbo_grad_1d_prepared": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp, _vp],
     "asvgp_posterior_1d": [_vp, _vp, _c_int, _c_int, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
     "asvgp_band_inverse_1d": [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
     "asvgp_accum_2d": [_vp, _vp, _c_i64, _vp, _c_int, _vp, _c_int, _c_int, _vp, _vp, _vp],
@@ -56,6 +58,7 @@ SIGNATURES = {
 VALUE_FUNCTIONS = {
     "asvgp_launch_count": (_c_i64, []),
     "asvgp_workspace_bytes_1d": (_c_i64, [_c_int, _c_int, _c_int]),
+    "asvgp_kuu_state_doubles": (_c_i64, [_c_int, _c_int]),
     "asvgp_accum_1d_binned_work_bytes": (_c_i64, [_c_i64]),
     "asvgp_accum_2d_binned_work_bytes": (_c_i64, [_c_i64]),
     "asvgp_accum_2d_moment_doubles": (_c_i64, [_c_int, _c_int, _c_int]),

@@ -430,6 +430,15 @@ struct CrNode {
     int info;
 };
 
+// Address of the same shared-memory object in CTA `rank` of the thread-block cluster (distributed shared memory)
+#if defined(__CUDACC__)
+template <class P> __device__ __forceinline__ P* cluster_peer(P* p, int rank) {
+    unsigned long long out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(rank));
+    return reinterpret_cast<P*>(out);
+}
+#endif
+
 template <class T, int K>
 struct ChainWork {
     ColumnStore<T, K, true> cols;              // chunk columns (global memory): kFields x n_steps x P
@@ -437,7 +446,20 @@ struct ChainWork {
     ChunkSchur<T, K>* schur;                   // [P]
     CrNode<T, K>* nodes;                       // [P-1] separator system
     T* x_red;                                  // n_red            } written by cr_export when the Schur pieces are dead:
-    T* sig_red;                                // (2K) x n_red     } they alias the schur array
+    T* sig_red;                                // (2K) x n_red     } they alias the schur array (global scratch when clustered)
+    int per_cta = 0;                           // > 0: the arrays are dealt over the CTAs of a cluster, per_cta entries each
+    ASVGP_HD ChunkSchur<T, K>& sch(int p) const {
+#if defined(__CUDA_ARCH__)
+        if (per_cta > 0) return *cluster_peer(schur + p % per_cta, p / per_cta);
+#endif
+        return schur[p];
+    }
+    ASVGP_HD CrNode<T, K>& node(int i) const {
+#if defined(__CUDA_ARCH__)
+        if (per_cta > 0) return *cluster_peer(nodes + i % per_cta, i / per_cta);
+#endif
+        return nodes[i];
+    }
 };
 
 // bytes of the small (shared-memory) part of a ChainWork and its carving; the same code sizes the host harness
@@ -466,16 +488,16 @@ struct ChainTotals { T logdet, quad; int info; };
 template <class T, int K, bool STORE, class MatFn, class RhsFn>
 ASVGP_HD void chain_phase1(const ChunkLayout& lay, int p, MatFn A, RhsFn rhs, const ChainWork<T, K>& w) {
     const int n_steps = lay.max_size();
-    if (lay.P == 1) eliminate_columns<T, K, false, STORE>(0, lay.M, n_steps, A, rhs, w.cols, 0, w.schur[0]);
-    else eliminate_columns<T, K, true, STORE>(lay.start(p), lay.size(p), n_steps, A, rhs, w.cols, p, w.schur[p]);
+    if (lay.P == 1) eliminate_columns<T, K, false, STORE>(0, lay.M, n_steps, A, rhs, w.cols, 0, w.sch(0));
+    else eliminate_columns<T, K, true, STORE>(lay.start(p), lay.size(p), n_steps, A, rhs, w.cols, p, w.sch(p));
 }
 
 // Executed by lane q < P-1: node q of the separator system from the Schur pieces of the chunks on either side of S_q.
 template <class T, int K>
 ASVGP_HD void cr_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
-    const ChunkSchur<T, K>& left = w.schur[q];        // chunk q ends at S_q
-    const ChunkSchur<T, K>& right = w.schur[q + 1];   // chunk q+1 starts after S_q
-    CrNode<T, K>& nd = w.nodes[q];
+    const ChunkSchur<T, K>& left = w.sch(q);        // chunk q ends at S_q
+    const ChunkSchur<T, K>& right = w.sch(q + 1);   // chunk q+1 starts after S_q
+    CrNode<T, K>& nd = w.node(q);
 #pragma unroll
     for (int a = 0; a < K; ++a) {
         nd.r[a] = left.rend[a] - right.rhsL[a];
@@ -494,7 +516,7 @@ ASVGP_HD void cr_assemble(const ChunkLayout& lay, int q, const ChainWork<T, K>& 
 // Cholesky of D_i, y_i, its share of log-det and quadratic form, and the factor blocks W_a, W_b.
 template <class T, int K>
 ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T, K>& w) {
-    CrNode<T, K>& nd = w.nodes[i];
+    CrNode<T, K>& nd = w.node(i);
     const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
     // work on register copies: the node lives in shared memory, where every dependent access costs a round trip
     T D[K][K], r[K], ipv[K], E[K][K], Eb[K][K];
@@ -505,7 +527,7 @@ ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T,
         for (int b = 0; b < K; ++b) {
             D[a][b] = (b <= a) ? nd.D[a][b] : zero_of<T>();
             E[a][b] = has_a ? nd.E[a][b] : zero_of<T>();
-            Eb[a][b] = has_b ? w.nodes[i + s].E[a][b] : zero_of<T>();
+            Eb[a][b] = has_b ? w.node(i + s).E[a][b] : zero_of<T>();
         }
     }
     LogAccum<T> logdet;
@@ -567,20 +589,20 @@ ASVGP_HD void cr_eliminate(int n, int s, int i, int g_offset, const ChainWork<T,
 // neighbours c + s (c is their `a`) and c - s (c is their `b`), and the new coupling with c - 2s.
 template <class T, int K>
 ASVGP_HD void cr_update(int n, int s, int c, const ChainWork<T, K>& w) {
-    CrNode<T, K>& nd = w.nodes[c];
+    CrNode<T, K>& nd = w.node(c);
     const bool has_p = c + s < n, has_m = c - s >= 0, has_a = c - 2 * s >= 0;
     T D[K][K], r[K], Wp[K][K], yp[K], Wm[K][K], Wma[K][K], ym[K];
 #pragma unroll
     for (int a = 0; a < K; ++a) {
         r[a] = nd.r[a];
-        yp[a] = has_p ? w.nodes[c + s].r[a] : zero_of<T>();
-        ym[a] = has_m ? w.nodes[c - s].r[a] : zero_of<T>();
+        yp[a] = has_p ? w.node(c + s).r[a] : zero_of<T>();
+        ym[a] = has_m ? w.node(c - s).r[a] : zero_of<T>();
 #pragma unroll
         for (int b = 0; b < K; ++b) {
             D[a][b] = (b <= a) ? nd.D[a][b] : zero_of<T>();
-            Wp[a][b] = has_p ? w.nodes[c + s].Wa[a][b] : zero_of<T>();       // c is the `a` of node c + s
-            Wm[a][b] = has_m ? w.nodes[c - s].Wb[a][b] : zero_of<T>();       // c is the `b` of node c - s
-            Wma[a][b] = (has_m && has_a) ? w.nodes[c - s].Wa[a][b] : zero_of<T>();
+            Wp[a][b] = has_p ? w.node(c + s).Wa[a][b] : zero_of<T>();       // c is the `a` of node c + s
+            Wm[a][b] = has_m ? w.node(c - s).Wb[a][b] : zero_of<T>();       // c is the `b` of node c - s
+            Wma[a][b] = (has_m && has_a) ? w.node(c - s).Wa[a][b] : zero_of<T>();
         }
     }
 #pragma unroll
@@ -611,10 +633,10 @@ ASVGP_HD void cr_update(int n, int s, int c, const ChainWork<T, K>& w) {
 // Back substitution and Takahashi recursion for node i eliminated at stride s (s = 0: the root, no neighbours).
 template <class T, int K, bool SOLVE, bool SELINV>
 ASVGP_HD void cr_back(int n, int s, int i, const ChainWork<T, K>& w) {
-    CrNode<T, K>& nd = w.nodes[i];
+    CrNode<T, K>& nd = w.node(i);
     const bool has_a = s > 0 && i - s >= 0, has_b = s > 0 && i + s < n;
-    const CrNode<T, K>& na = w.nodes[has_a ? i - s : i];
-    const CrNode<T, K>& nb = w.nodes[has_b ? i + s : i];
+    const CrNode<T, K>& na = w.node(has_a ? i - s : i);
+    const CrNode<T, K>& nb = w.node(has_b ? i + s : i);
     // register copies of everything that is read (the node lives in shared memory)
     T L[K][K], ipv[K], Wa[K][K], Wb[K][K];
 #pragma unroll
@@ -727,7 +749,7 @@ ASVGP_HD void cr_back(int n, int s, int i, const ChainWork<T, K>& w) {
 template <class T, int K, bool SOLVE, bool SELINV>
 ASVGP_HD void cr_export(const ChunkLayout& lay, int q, const ChainWork<T, K>& w) {
     const int nred = lay.n_reduced();
-    const CrNode<T, K>& nd = w.nodes[q];
+    const CrNode<T, K>& nd = w.node(q);
     if (SOLVE) {
 #pragma unroll
         for (int a = 0; a < K; ++a) w.x_red[q * K + a] = nd.r[a];
@@ -740,7 +762,7 @@ ASVGP_HD void cr_export(const ChunkLayout& lay, int q, const ChainWork<T, K>& w)
         if (q >= 1) {
             // Sigma_{q,q-1}: the odd one of (q-1, q) was eliminated at stride 1 with the other as its neighbour
             const bool q_odd = q & 1;
-            const CrNode<T, K>& prev = w.nodes[q - 1];
+            const CrNode<T, K>& prev = w.node(q - 1);
 #pragma unroll
             for (int a = 0; a < K; ++a)
 #pragma unroll
@@ -758,14 +780,14 @@ ASVGP_HD ChainTotals<T, K> chain_totals(const ChunkLayout& lay, const ChainWork<
     tot.quad = zero_of<T>();
     tot.info = 0;
     for (int p = 0; p < lay.P; ++p) {
-        tot.logdet += w.schur[p].logdet;
-        tot.quad += w.schur[p].quad;
-        if (w.schur[p].info != 0 && (tot.info == 0 || w.schur[p].info < tot.info)) tot.info = w.schur[p].info;
+        tot.logdet += w.sch(p).logdet;
+        tot.quad += w.sch(p).quad;
+        if (w.sch(p).info != 0 && (tot.info == 0 || w.sch(p).info < tot.info)) tot.info = w.sch(p).info;
     }
     for (int q = 0; q + 1 < lay.P; ++q) {
-        tot.logdet += w.nodes[q].logdet;
-        tot.quad += w.nodes[q].quad;
-        if (w.nodes[q].info != 0 && tot.info == 0) tot.info = w.nodes[q].info;   // failure inside the separator system
+        tot.logdet += w.node(q).logdet;
+        tot.quad += w.node(q).quad;
+        if (w.node(q).info != 0 && tot.info == 0) tot.info = w.node(q).info;   // failure inside the separator system
     }
     return tot;
 }

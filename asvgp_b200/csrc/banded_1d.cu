@@ -13,7 +13,11 @@
 //   posterior : [Kuu] Takahashi,  [P] solve + Takahashi
 // Derivatives ride along as Dual<1> tangents; the variance derivative follows analytically from the sigma2 one
 // because Kuu is proportional to 1/variance (see elbo_finalize_kernel).
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
 
 #include <algorithm>
 
@@ -132,24 +136,10 @@ __host__ __device__ inline size_t chain_rows_count(const ChunkLayout& lay) {
 
 template <class T> struct ChainSpec { BandMat<T> A; VecRhs<T> rhs; };
 
-// Sink of the ELBO's Kuu chain: trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G) (off-diagonals twice, reference
-// gpr.py:60-70) is accumulated entry by entry as the Takahashi recursion produces band(Kuu^-1), against a row table of
-// G in the lanes' interleaved layout — the inverse band is never stored and there is no separate trace pass.
-template <class T, int K>
-struct TraceSink {
-    const T* gtab; int g0, P, p, n_rho;
-    T acc;
-    __device__ __forceinline__ void operator()(int d, int col, const T& v) {
-        const int rho = col + d - g0;
-        const double g = (d == 0 ? 1.0 : 2.0) * gtab[((size_t)rho * (K + 1) + (K - d)) * P + p].v;
-        acc.v = fma(v.v, g, acc.v);
-        acc.d[0] = fma(v.d[0], g, acc.d[0]);
-    }
-};
-
 template <class T, int K, int NCHAINS>
 __global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainSpec<T> s0, ChainSpec<T> s1, ChainSpec<T> s2, ChainSpec<T> s3,
-                                                         T* __restrict__ out) {
+                                                         T* __restrict__ out, unsigned* __restrict__ zero_me = nullptr) {
+    if (zero_me != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0u;      // arrival counter of elbo_finalize_kernel
     const int n_rho = chain_n_rho(lay, K), P = lay.P;
     const size_t per_chain = chain_rows_count<T, K>(lay);
     const size_t total = per_chain * NCHAINS;
@@ -232,57 +222,207 @@ __device__ __forceinline__ void run_chain(const ChunkLayout& lay, const ColumnSt
     if (p == 0 && clk) clk[3] = clock64();
 }
 
+// The same chain on a thread-block CLUSTER, with MORE LANES.  A lane's per-column cost is bound by its warp's fp64 issue
+// slot (~250 fp64 instructions per column at one issue per two clocks: tools/chain_clocks.py — the per-column time does not
+// change whether 128, 64 or 32 lanes share the SM), so the only way to shorten the sweeps is fewer columns per lane:
+// P = 128 * n_cta chunks, CTA r sweeps chunks [128 r, 128 r + 128) with four full warps.  The separator system (P - 1 nodes)
+// and the per-chunk Schur pieces are dealt over the CTAs' shared memories in the same way and reached through distributed
+// shared memory (ChainWork::node / ::sch); the block cyclic reduction runs on all CTAs with cluster barriers between its
+// levels; the reduced solution phase 3 reads goes through a small global scratch.
+template <class T, int K, bool STORE, bool SOLVE, bool SELINV, class MakeMat, class MakeRhs, class MakeSink>
+__device__ __forceinline__ void run_chain_cluster(const ChunkLayout& lay, const ColumnStore<T, K, true>& cols, char* smem, T* red_scratch,
+                                                  MakeMat make_A, MakeRhs make_rhs, MakeSink make_sink, T* x_out,
+                                                  ChainTotals<T, K>* tot, long long* clk) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank(), n_cta = (int)cluster.num_blocks();
+    const int tid = threadIdx.x;
+    const int per = kChainThreads;
+    const int p = rank * per + tid;                               // this thread's chunk and separator node
+    ChainWork<T, K> w;
+    w.cols = cols;
+    ChainSmall<T, K>::carve(per + 1, smem, w);                    // every CTA holds `per` Schur pieces and `per` nodes (carve(P) lays out P - 1 nodes)
+    w.per_cta = per;
+    const size_t nred = (size_t)lay.n_reduced();
+    w.sig_red = red_scratch;
+    w.x_red = red_scratch + (size_t)(2 * K) * nred;
+#ifdef ASVGP_CHAIN_TRACE
+    __shared__ long long s_trace[64];
+    int n_trace = 0;
+#define ASVGP_STAMP() do { if (rank == 0 && tid == 0 && n_trace < 64) s_trace[n_trace++] = clock64(); } while (0)
+#else
+#define ASVGP_STAMP() do {} while (0)
+#endif
+    cluster.sync();                                               // every CTA's shared memory exists before anybody writes to it
+    ASVGP_STAMP();
+    if (rank == 0 && tid == 0 && clk) clk[0] = clock64();
+    if (p < lay.P) chain_phase1<T, K, STORE>(lay, p, make_A(p), make_rhs(p), w);
+    cluster.sync();
+    ASVGP_STAMP();
+    if (rank == 0 && tid == 0 && clk) clk[1] = clock64();
+    const int n = lay.P - 1;
+    if (p < n) cr_assemble<T, K>(lay, p, w);
+    cluster.sync();
+    ASVGP_STAMP();
+    for (int s = 1; s < n; s *= 2) {
+        if (p < n && (p & (2 * s - 1)) == s) cr_eliminate<T, K>(n, s, p, lay.M, w);
+        cluster.sync();
+        ASVGP_STAMP();
+        if (p < n && (p & (2 * s - 1)) == 0) cr_update<T, K>(n, s, p, w);
+        cluster.sync();
+        ASVGP_STAMP();
+    }
+    if (p == 0 && n > 0) cr_eliminate<T, K>(n, 0, 0, lay.M, w);
+    cluster.sync();
+    ASVGP_STAMP();
+    {
+        // totals: every lane brings its chunk's and its node's share; fixed-order tree inside the CTA, CTA partials added in rank order
+        T ld = zero_of<T>(), qd = zero_of<T>();
+        int info = 0;
+        if (p < lay.P) { const ChunkSchur<T, K>& c = w.sch(p); ld += c.logdet; qd += c.quad; info = c.info; }
+        if (p < n) { const CrNode<T, K>& nd = w.node(p); ld += nd.logdet; qd += nd.quad; if (info == 0) info = nd.info; }
+        double v[4] = {value_of(ld), tangent_of(ld, 0), value_of(qd), tangent_of(qd, 0)};
+        unsigned uinfo = info == 0 ? 0xffffffffu : (unsigned)info;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+            uinfo = min(uinfo, __shfl_xor_sync(0xffffffffu, uinfo, o));
+        }
+        __shared__ double s_tot[kChainThreads / 32][4];
+        __shared__ unsigned s_info[kChainThreads / 32];
+        __shared__ double s_cta[5];
+        if ((tid & 31) == 0) { for (int i = 0; i < 4; ++i) s_tot[tid >> 5][i] = v[i]; s_info[tid >> 5] = uinfo; }
+        __syncthreads();
+        if (tid == 0) {
+            double a[4] = {0, 0, 0, 0};
+            unsigned ui = 0xffffffffu;
+            for (int wv = 0; wv < kChainThreads / 32; ++wv) { for (int i = 0; i < 4; ++i) a[i] += s_tot[wv][i]; ui = min(ui, s_info[wv]); }
+            for (int i = 0; i < 4; ++i) s_cta[i] = a[i];
+            s_cta[4] = (double)ui;
+        }
+        cluster.sync();
+        ASVGP_STAMP();
+        if (rank == 0 && tid == 0) {
+            double a[4] = {0, 0, 0, 0};
+            double ui = 4294967295.0;
+            for (int r = 0; r < n_cta; ++r) {
+                const double* q = cluster_peer(s_cta, r);
+                for (int i = 0; i < 4; ++i) a[i] += q[i];
+                ui = q[4] < ui ? q[4] : ui;
+            }
+            tot->logdet = make_scalar<T>(a[0], a[1]);
+            tot->quad = make_scalar<T>(a[2], a[3]);
+            tot->info = ui >= 4294967295.0 ? 0 : (int)ui;
+        }
+    }
+    if ((SOLVE || SELINV) && n > 0) {
+        if (p == 0) cr_back<T, K, SOLVE, SELINV>(n, 0, 0, w);
+        cluster.sync();
+        ASVGP_STAMP();
+        for (int s = cr_top_stride(n); s >= 1; s /= 2) {
+            if (p < n && (p & (2 * s - 1)) == s) cr_back<T, K, SOLVE, SELINV>(n, s, p, w);
+            cluster.sync();
+            ASVGP_STAMP();
+        }
+        if (p < n) cr_export<T, K, SOLVE, SELINV>(lay, p, w);
+        __threadfence();
+        cluster.sync();
+        ASVGP_STAMP();
+    }
+    if (rank == 0 && tid == 0 && clk) clk[2] = clock64();
+    if ((SOLVE || SELINV) && p < lay.P) {
+        auto sink = make_sink(p);
+        chain_phase3<T, K, SOLVE, SELINV>(lay, p, w, x_out, sink);
+    }
+    cluster.sync();                                               // nobody leaves while its shared memory may still be read
+    ASVGP_STAMP();
+    if (rank == 0 && tid == 0 && clk) clk[3] = clock64();
+#ifdef ASVGP_CHAIN_TRACE
+    if (rank == 0 && tid == 0) {
+        for (int i = 1; i < n_trace; ++i) printf("trace blk=%d SELINV=%d P=%d step=%d %lld\n", (int)blockIdx.x, (int)SELINV, lay.P, i, s_trace[i] - s_trace[i - 1]);
+    }
+#endif
+#undef ASVGP_STAMP
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // ELBO + gradient
 // ------------------------------------------------------------------------------------------------------------------
+// The ELBO's work is split where its data dependencies are:
+//   Kuu chain  (chain 0: [Kuu, d/dl], factorisation + Takahashi) depends on the hyper-parameters only.  It leaves
+//              log|Kuu|, its tangent and band(Kuu^-1) (value + tangent) in a small "Kuu state" buffer — and can therefore
+//              run on a side stream WHILE the O(N) accumulate produces G (asvgp_kuu_chain_1d);
+//   P chains   (chains 1, 2: [P, d/dl], [P, d/dsigma2], forward only) need G and b;
+//   finalize   trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G) (off-diagonals twice, reference gpr.py:60-70) as a fixed-order
+//              dot product of the stored inverse band with G, then the bound and its derivatives.
 template <int K>
 struct ElboArgs {
     ChunkLayout lay;
-    ColumnStore<Dual<1>, K, true> cols[3];
-    const double* Kuu; const double* dKuu; const double* G; const double* b;
-    double sigma2;
-    double* partial;        // [3 chains][16]: logdet, dlogdet, quad, dquad, trace, dtrace, info, -, clocks[4]
-    const Dual<1>* rows;    // lane-interleaved row tables of the three chains (chain_rows_kernel)
+    int first_chain;                        // 0: the Kuu chain alone;  1: the two P chains
+    ColumnStore<Dual<1>, K, true> cols[2];  // per launched chain
+    double* partial[2];                     // per launched chain [16]: logdet, dlogdet, quad, dquad, -, -, info, -, clocks[4]
+    const Dual<1>* rows;                    // lane-interleaved row tables of the launched chains (chain_rows_kernel)
+    Dual<1>* kinv;                          // Kuu chain: where band(Kuu^-1) goes, (K+1) x M
 };
 
 template <int K>
 __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> a) {
     using T = Dual<1>;
     extern __shared__ __align__(16) char smem[];
-    const int chain = blockIdx.x, p = threadIdx.x;
+    const int slot = blockIdx.x, chain = a.first_chain + slot, p = threadIdx.x;
     const ChunkLayout lay = a.lay;
     const int M = lay.M;
     __shared__ ChainTotals<T, K> tot;
-    __shared__ double s_red[2][kChainThreads / 32];
     __shared__ long long clk[4];
-    double* out = a.partial + chain * 16;
+    double* out = a.partial[slot];
 
     const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
-    const T* tab = a.rows + (size_t)chain * chain_rows_count<T, K>(lay);
+    const T* tab = a.rows + (size_t)slot * chain_rows_count<T, K>(lay);
     const RowsMat<T, K> A{tab, g0, lay.P, pp, n_rho};
     const RowsRhs<T> rhs{tab + (size_t)n_rho * (K + 1) * lay.P, g0, lay.P, pp, n_rho};
-    BandSink<T> no_sink{nullptr, M};
     if (chain == 0) {
-        TraceSink<T, K> sink{a.rows + 3 * chain_rows_count<T, K>(lay), g0, lay.P, pp, n_rho, zero_of<T>()};
-        run_chain<T, K, true, false, true>(lay, a.cols[0], smem, A, rhs, static_cast<T*>(nullptr), sink, &tot, clk);
-        double tr = sink.acc.v, dtr = sink.acc.d[0];           // this lane's share of trace(Kuu^-1 G) and of its d/dl
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            tr += __shfl_xor_sync(0xffffffffu, tr, o);
-            dtr += __shfl_xor_sync(0xffffffffu, dtr, o);
-        }
-        if ((p & 31) == 0) { s_red[0][p >> 5] = tr; s_red[1][p >> 5] = dtr; }
-        __syncthreads();
-        if (p == 0) {
-            tr = 0.0; dtr = 0.0;
-            for (int i = 0; i < kChainThreads / 32; ++i) { tr += s_red[0][i]; dtr += s_red[1][i]; }
-            out[4] = tr; out[5] = dtr;
-        }
+        BandSink<T> sink{a.kinv, M};
+        run_chain<T, K, true, false, true>(lay, a.cols[slot], smem, A, rhs, static_cast<T*>(nullptr), sink, &tot, clk);
     } else {
-        // chain 1: P with tangent d/dl;  chain 2: P with tangent d/dsigma2 (tables built by launch_elbo)
-        run_chain<T, K, false, false, false>(lay, a.cols[chain], smem, A, rhs, static_cast<T*>(nullptr), no_sink, &tot, clk);
+        // chain 1: P with tangent d/dl;  chain 2: P with tangent d/dsigma2 (tables built by the launcher)
+        BandSink<T> no_sink{nullptr, M};
+        run_chain<T, K, false, false, false>(lay, a.cols[slot], smem, A, rhs, static_cast<T*>(nullptr), no_sink, &tot, clk);
     }
     if (p == 0) {
+        out[0] = tot.logdet.v; out[1] = tot.logdet.d[0];
+        out[2] = tot.quad.v;   out[3] = tot.quad.d[0];
+        out[6] = (double)tot.info;
+        const long long t_end = clock64();
+        out[8] = (double)(clk[1] - clk[0]); out[9] = (double)(clk[2] - clk[1]);
+        out[10] = (double)(clk[3] - clk[2]); out[11] = (double)(t_end - clk[3]);
+    }
+}
+
+// Cluster version (M large): launched chain `slot` runs on cluster `slot` of NCTA CTAs with 128 * NCTA chunks.
+template <int K, int NCTA>
+__global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(kChainThreads) elbo_chains_cluster_kernel(ElboArgs<K> a, Dual<1>* red_scratch) {
+    using T = Dual<1>;
+    extern __shared__ __align__(16) char smem[];
+    const int slot = blockIdx.x / NCTA, chain = a.first_chain + slot, rank = blockIdx.x % NCTA, tid = threadIdx.x;
+    const ChunkLayout lay = a.lay;
+    __shared__ ChainTotals<T, K> tot;
+    __shared__ long long clk[4];
+    double* out = a.partial[slot];
+    const int n_rho = chain_n_rho(lay, K);
+    const T* tab = a.rows + (size_t)slot * chain_rows_count<T, K>(lay);
+    T* scratch = red_scratch + (size_t)slot * ((size_t)(2 * K + 1) * lay.n_reduced() + 8);
+    auto g0_of = [&](int lane) { return lay.P > 1 ? lay.start(lane) : 0; };
+    auto make_A = [&](int lane) { return RowsMat<T, K>{tab, g0_of(lane), lay.P, lane, n_rho}; };
+    auto make_rhs = [&](int lane) { return RowsRhs<T>{tab + (size_t)n_rho * (K + 1) * lay.P, g0_of(lane), lay.P, lane, n_rho}; };
+    if (chain == 0) {
+        auto make_sink = [&](int) { return BandSink<T>{a.kinv, lay.M}; };
+        run_chain_cluster<T, K, true, false, true>(lay, a.cols[slot], smem, scratch, make_A, make_rhs, make_sink, static_cast<T*>(nullptr), &tot, clk);
+    } else {
+        auto make_sink = [&](int) { return BandSink<T>{nullptr, lay.M}; };
+        run_chain_cluster<T, K, false, false, false>(lay, a.cols[slot], smem, scratch, make_A, make_rhs, make_sink, static_cast<T*>(nullptr), &tot, clk);
+    }
+    if (rank == 0 && tid == 0) {
         out[0] = tot.logdet.v; out[1] = tot.logdet.d[0];
         out[2] = tot.quad.v;   out[3] = tot.quad.d[0];
         out[6] = (double)tot.info;
@@ -297,15 +437,59 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
 //   ELBO = -N/2 log(2 pi s2) - 1/2 log|P| + 1/2 log|Kuu| - yy/(2 s2) + Q/(2 s2^2) - N v/(2 s2) + tr/(2 s2)
 // Kuu = Kt(l)/v  =>  P = (Kt + (v/s2) G)/v, hence d/dv of log|P| and Q follow from d/ds2:
 //   dlog|P|/dv = -M/v - (s2/v) dlog|P|/ds2,   dQ/dv = Q/v - (s2/v) dQ/ds2,   dlog|Kuu|/dv = -M/v,   dtr/dv = tr/v.
-__global__ void elbo_finalize_kernel(const double* __restrict__ partial, const double* __restrict__ scal, int M,
-                                     double variance, double sigma2, double* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const double* cK = partial;          // Kuu chain (d/dl)
-    const double* cL = partial + 16;     // P chain (d/dl)
-    const double* cS = partial + 32;     // P chain (d/dsigma2)
+// kFinalizeBlocks CTAs: the trace and its d/dl first (every thread a fixed share of the (K+1) x M products with all its loads in
+// flight at once, fixed-order trees, per-CTA partials added in CTA order: the same bits on every run and every rank); the CTA
+// that arrives last combines.
+constexpr int kFinalizeThreads = 256, kFinalizeBlocks = 16, kFinalizeUnroll = 4;
+__global__ void __launch_bounds__(kFinalizeThreads) elbo_finalize_kernel(const double* __restrict__ kstate, double* __restrict__ partial,
+                                                                         const double* __restrict__ G, const double* __restrict__ scal,
+                                                                         int M, int K, double variance, double sigma2, double* __restrict__ out) {
+    __shared__ double s_tr[2][kFinalizeThreads / 32];
+    __shared__ bool s_last;
+    const Dual<1>* kinv = reinterpret_cast<const Dual<1>*>(kstate + 16);
+    double* tr_part = partial + 64;                                     // [kFinalizeBlocks][2]
+    unsigned* counter = reinterpret_cast<unsigned*>(partial + 32);      // zeroed by the P chains' chain_rows_kernel
+    double tr = 0.0, dtr_dl = 0.0;
+    const int band = (K + 1) * M, stride = kFinalizeThreads * kFinalizeBlocks;
+    for (int i0 = blockIdx.x * kFinalizeThreads + threadIdx.x; i0 < band; i0 += stride * kFinalizeUnroll) {
+        Dual<1> sv[kFinalizeUnroll];
+        double gv[kFinalizeUnroll];
+#pragma unroll
+        for (int u = 0; u < kFinalizeUnroll; ++u) {
+            const int i = i0 + u * stride;
+            const int d = i / M, col = i - d * M;
+            const bool ok = i < band && col + d < M;
+            sv[u] = kinv[ok ? i : 0];
+            gv[u] = ok ? (d == 0 ? 1.0 : 2.0) * G[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kFinalizeUnroll; ++u) {
+            if (gv[u] != 0.0) { tr = fma(sv[u].v, gv[u], tr); dtr_dl = fma(sv[u].d[0], gv[u], dtr_dl); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        dtr_dl += __shfl_xor_sync(0xffffffffu, dtr_dl, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_tr[0][threadIdx.x >> 5] = tr; s_tr[1][threadIdx.x >> 5] = dtr_dl; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    tr = 0.0; dtr_dl = 0.0;
+    for (int i = 0; i < kFinalizeThreads / 32; ++i) { tr += s_tr[0][i]; dtr_dl += s_tr[1][i]; }
+    tr_part[2 * blockIdx.x] = tr; tr_part[2 * blockIdx.x + 1] = dtr_dl;
+    __threadfence();
+    s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    if (!s_last) return;
+    __threadfence();
+    tr = 0.0; dtr_dl = 0.0;
+    for (int i = 0; i < (int)gridDim.x; ++i) { tr += __ldcg(tr_part + 2 * i); dtr_dl += __ldcg(tr_part + 2 * i + 1); }
+    const double* cK = kstate;           // Kuu chain (d/dl)
+    const double* cL = partial;          // P chain (d/dl)
+    const double* cS = partial + 16;     // P chain (d/dsigma2)
     const double yy = scal[0], N = scal[1];
     const double v = variance, s2 = sigma2;
-    const double logdetK = cK[0], dlogdetK_dl = cK[1], tr = cK[4], dtr_dl = cK[5];
+    const double logdetK = cK[0], dlogdetK_dl = cK[1];
     const double logdetP = cL[0], dlogdetP_dl = cL[1], Q = cL[2], dQ_dl = cL[3];
     const double dlogdetP_ds = cS[1], dQ_ds = cS[3];
     const double two_pi = 6.283185307179586476925286766559;
@@ -324,7 +508,7 @@ __global__ void elbo_finalize_kernel(const double* __restrict__ partial, const d
     if (info == 0.0) info = cL[6];
     if (info == 0.0) info = cS[6];
     out[8] = info;
-    // diagnostics: SM cycles of the Kuu chain's phases (chunk sweep, separator system, back sweep, trace)
+    // diagnostics: SM cycles of the Kuu chain's phases (chunk sweep, separator system, back sweep, tail)
     out[9] = cK[8]; out[10] = cK[9]; out[11] = cK[10]; out[12] = cK[11];
     out[13] = cL[8]; out[14] = cL[9];
     out[15] = dtr_dl;             // d trace(Kuu^-1 G) / d lengthscale (multi-output bound: trace terms count once)
@@ -442,10 +626,31 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
     return kOk;
 }
 
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per kernel and size (the call costs host time on every launch otherwise)
+template <class Kernel>
+static cudaError_t allow_smem(Kernel kernel, size_t smem) {
+    static size_t allowed = 0;          // one per kernel type = per instantiation
+    static const void* which = nullptr;
+    if (which == reinterpret_cast<const void*>(kernel) && smem <= allowed) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) { allowed = smem; which = reinterpret_cast<const void*>(kernel); }
+    return e;
+}
+// per-launch record area: [2][16] chain records, the finalize kernel's arrival counter (double slot 32), its per-CTA trace partials (from slot 64)
+constexpr size_t kPartialBytes = 1024;
+template <int K>
+static size_t red_scratch_count(const ChunkLayout& lay) { return (size_t)(2 * K + 1) * lay.n_reduced() + 8; }     // per chain (clustered layout)
+// workspace of one launch of n_chains chains: column stores, [n_chains][16] partials, row tables, reduced-solution scratch
+template <int K>
+static size_t chains_work_bytes(const ChunkLayout& lay, int n_chains) {
+    return n_chains * ChainPlan<Dual<1>, K>::bytes(lay) + kPartialBytes + align256(n_chains * chain_rows_count<Dual<1>, K>(lay) * sizeof(Dual<1>))
+           + align256(n_chains * red_scratch_count<K>(lay) * sizeof(Dual<1>));
+}
+static size_t kuu_state_doubles(int M, int K) { return 16 + 2 * (size_t)(K + 1) * M; }
 template <int K>
 static size_t elbo_work_bytes(const ChunkLayout& lay) {
-    return 3 * ChainPlan<Dual<1>, K>::bytes(lay) + (((size_t)(K + 1) * lay.M * sizeof(Dual<1>) + 255) & ~(size_t)255)
-           + 512 + 4 * chain_rows_count<Dual<1>, K>(lay) * sizeof(Dual<1>) + 256;
+    return chains_work_bytes<K>(lay, 1) + chains_work_bytes<K>(lay, 2) + align256(kuu_state_doubles(lay.M, K) * sizeof(double));
 }
 template <int K>
 static size_t posterior_work_bytes(const ChunkLayout& lay) {
@@ -453,39 +658,99 @@ static size_t posterior_work_bytes(const ChunkLayout& lay) {
            + 256 + (((size_t)lay.M * sizeof(double) + 255) & ~(size_t)255) + 2 * chain_rows_count<double, K>(lay) * sizeof(double) + 256;
 }
 
+// Row tables + chain kernel of `n_chains` chains starting at chain `first_chain` (0: Kuu; 1, 2: P with d/dl, d/dsigma2).
+// `partial0` overrides where the first chain's 16-slot record goes (the Kuu state's header); returns the partials in work.
+template <int K>
+static int launch_chain_group(const ChunkLayout& lay, int first_chain, int n_chains, const ChainSpec<Dual<1>>& s0,
+                              const ChainSpec<Dual<1>>& s1, double* partial0, Dual<1>* kinv, char* work, double** partials_out,
+                              cudaEvent_t gate, cudaStream_t st) {
+    using T = Dual<1>;
+    ElboArgs<K> a;
+    a.lay = lay;
+    a.first_chain = first_chain;
+    a.kinv = kinv;
+    char* p = work;
+    for (int c = 0; c < 2; ++c) {
+        a.cols[c] = ChainPlan<T, K>::carve(lay, c < n_chains ? p : work);
+        if (c < n_chains) p += ChainPlan<T, K>::bytes(lay);
+    }
+    double* partial = reinterpret_cast<double*>(p);
+    p += kPartialBytes;
+    a.partial[0] = partial0 != nullptr ? partial0 : partial;
+    a.partial[1] = partial + 16;
+    if (partials_out != nullptr) *partials_out = partial;
+    T* rows = reinterpret_cast<T*>(p);
+    p += align256(n_chains * chain_rows_count<T, K>(lay) * sizeof(T));
+    a.rows = rows;
+    T* scratch = reinterpret_cast<T*>(p);
+    const size_t total = n_chains * chain_rows_count<T, K>(lay);
+    const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
+    if (n_chains == 1) chain_rows_kernel<T, K, 1><<<grid, 256, 0, st>>>(lay, s0, s0, s0, s0, rows);
+    else chain_rows_kernel<T, K, 2><<<grid, 256, 0, st>>>(lay, s0, s1, s1, s1, rows, reinterpret_cast<unsigned*>(partial + 32));
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    if (gate != nullptr) ASVGP_CUDA_OK(cudaEventRecord(gate, st));          // "the chain kernel is next in line"
+    const int n_cta = (lay.P + kChainThreads - 1) / kChainThreads;          // > 1: clustered layout (pick_layout_elbo)
+    if (n_cta > 1) {
+        const size_t smem = ChainSmall<T, K>::bytes(kChainThreads + 1);
+        if (n_cta == 2) {
+            ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 2>, smem));
+            elbo_chains_cluster_kernel<K, 2><<<n_chains * 2, kChainThreads, smem, st>>>(a, scratch);
+        } else if (n_cta == 8) {
+            ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 8>, smem));
+            elbo_chains_cluster_kernel<K, 8><<<n_chains * 8, kChainThreads, smem, st>>>(a, scratch);
+        } else {
+            ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 4>, smem));
+            elbo_chains_cluster_kernel<K, 4><<<n_chains * 4, kChainThreads, smem, st>>>(a, scratch);
+        }
+    } else {
+        const size_t smem = ChainSmall<T, K>::bytes(lay.P);
+        ASVGP_CUDA_OK(allow_smem(elbo_chains_kernel<K>, smem));
+        elbo_chains_kernel<K><<<n_chains, kChainThreads, smem, st>>>(a);
+    }
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
+// The Kuu chain: log|Kuu|, its d/dl and band(Kuu^-1) with tangent into `kstate` ([16] record + (K+1) x M duals).
+template <int K>
+static int launch_kuu_chain(const ChunkLayout& lay, const double* Kuu, const double* dKuu, double* kstate, char* work, cudaEvent_t gate,
+                            cudaStream_t st) {
+    using T = Dual<1>;
+    const int M = lay.M;
+    ChainSpec<T> s0{BandMat<T>{Kuu, dKuu, nullptr, 0.0, 0.0, 1, M}, VecRhs<T>{Kuu, M, 0}};
+    return launch_chain_group<K>(lay, 0, 1, s0, s0, kstate, reinterpret_cast<T*>(kstate + 16), work, nullptr, gate, st);
+}
+
+// The two P chains and the bound, given the Kuu state.
+template <int K>
+static int launch_pchains(const ChunkLayout& lay, const double* kstate, const double* Kuu, const double* dKuu, const double* acc,
+                          double variance, double sigma2, double* out, char* work, cudaEvent_t kuu_ready, cudaStream_t st) {
+    using T = Dual<1>;
+    const int M = lay.M;
+    const double* G = acc;
+    const double* b = acc + (size_t)(K + 1) * M;
+    const double inv_s2 = 1.0 / sigma2;
+    // chain 1: P = Kuu + G/s2 with d/dl;  chain 2: P with d/dsigma2 = -G/s2^2
+    ChainSpec<T> s1{BandMat<T>{Kuu, dKuu, G, inv_s2, 0.0, 1, M}, VecRhs<T>{b, M, 1}};
+    ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{b, M, 1}};
+    double* partial = nullptr;
+    if (int rc = launch_chain_group<K>(lay, 1, 2, s1, s2, nullptr, nullptr, work, &partial, nullptr, st)) return rc;
+    if (kuu_ready != nullptr) ASVGP_CUDA_OK(cudaStreamWaitEvent(st, kuu_ready, 0));      // the Kuu state is first read here
+    elbo_finalize_kernel<<<kFinalizeBlocks, kFinalizeThreads, 0, st>>>(kstate, partial, G, acc + (size_t)(K + 2) * M, M, K, variance, sigma2, out);
+    ASVGP_LAUNCHED();
+    ASVGP_CUDA_OK(cudaGetLastError());
+    return kOk;
+}
+
 template <int K>
 static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* dKuu, const double* acc,
                        double variance, double sigma2, double* out, char* work, cudaStream_t st) {
-    ElboArgs<K> a;
-    a.lay = lay;
-    char* p = work;
-    for (int c = 0; c < 3; ++c) { a.cols[c] = ChainPlan<Dual<1>, K>::carve(lay, p); p += ChainPlan<Dual<1>, K>::bytes(lay); }
-    a.partial = reinterpret_cast<double*>(p);
-    p += 512;
-    const int M = lay.M;
-    a.Kuu = Kuu; a.dKuu = dKuu; a.G = acc; a.b = acc + (size_t)(K + 1) * M;
-    a.sigma2 = sigma2;
-    {
-        using T = Dual<1>;
-        T* rows = reinterpret_cast<T*>(p);
-        a.rows = rows;
-        const double inv_s2 = 1.0 / sigma2;
-        // chain 0: Kuu with tangent d/dl;  chain 1: P = Kuu + G/s2 with d/dl;  chain 2: P with d/dsigma2 = -G/s2^2
-        ChainSpec<T> s0{BandMat<T>{Kuu, dKuu, nullptr, 0.0, 0.0, 1, M}, VecRhs<T>{Kuu, M, 0}};
-        ChainSpec<T> s1{BandMat<T>{Kuu, dKuu, a.G, inv_s2, 0.0, 1, M}, VecRhs<T>{a.b, M, 1}};
-        ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, a.G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{a.b, M, 1}};
-        ChainSpec<T> s3{BandMat<T>{a.G, a.G, nullptr, 0.0, 0.0, 0, M}, VecRhs<T>{Kuu, M, 0}};      // G itself (for the trace)
-        const size_t total = 4 * chain_rows_count<T, K>(lay);
-        chain_rows_kernel<T, K, 4><<<(int)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(lay, s0, s1, s2, s3, rows); ASVGP_LAUNCHED();
-        ASVGP_CUDA_OK(cudaGetLastError());
-    }
-    const size_t smem = ChainSmall<Dual<1>, K>::bytes(lay.P);
-    ASVGP_CUDA_OK(cudaFuncSetAttribute(elbo_chains_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    elbo_chains_kernel<K><<<3, kChainThreads, smem, st>>>(a); ASVGP_LAUNCHED();
-    ASVGP_CUDA_OK(cudaGetLastError());
-    elbo_finalize_kernel<<<1, 32, 0, st>>>(a.partial, acc + (size_t)(K + 2) * M, M, variance, sigma2, out); ASVGP_LAUNCHED();
-    ASVGP_CUDA_OK(cudaGetLastError());
-    return kOk;
+    double* kstate = reinterpret_cast<double*>(work + chains_work_bytes<K>(lay, 1));
+    char* pwork = work + chains_work_bytes<K>(lay, 1) + align256(kuu_state_doubles(lay.M, K) * sizeof(double));
+    if (int rc = launch_kuu_chain<K>(lay, Kuu, dKuu, kstate, work, nullptr, st)) return rc;
+    return launch_pchains<K>(lay, kstate, Kuu, dKuu, acc, variance, sigma2, out, pwork, nullptr, st);
 }
 
 template <int K>
@@ -548,6 +813,20 @@ static ChunkLayout pick_layout(int M, int K, int chunks) {
     return make_layout(M, K, P);
 }
 
+// Layout of the ELBO + gradient chains: with the library default (chunks = 0) and enough columns, 128 * n_cta chunks on a
+// cluster of n_cta CTAs per chain (run_chain_cluster); n_cta = 8 (4, 2 when M is too small), ASVGP_CHAIN_CTAS overrides (1 = single CTA).
+static ChunkLayout pick_layout_elbo(int M, int K, int chunks) {
+    const ChunkLayout one = pick_layout(M, K, chunks);
+    if (chunks != 0 || one.P < kChainThreads) return one;
+    int n_cta = 8;
+    if (const char* e = getenv("ASVGP_CHAIN_CTAS")) n_cta = atoi(e);
+    if (n_cta != 2 && n_cta != 4 && n_cta != 8) return one;
+    int P = M / (2 * (K + 1) + 1);                                 // chunk interiors of at least K + 1 columns with room to spare
+    while (n_cta > 1 && P < kChainThreads * n_cta) n_cta /= 2;     // whole CTAs of 128 lanes only
+    if (n_cta <= 1) return one;
+    return make_layout(M, K, kChainThreads * n_cta);
+}
+
 }  // namespace asvgp
 
 using namespace asvgp;
@@ -582,14 +861,27 @@ extern "C" int asvgp_kuu_assemble(const double* tables, int n_terms, const doubl
 extern "C" int64_t asvgp_workspace_bytes_1d(int M, int order, int chunks) {
     if (M <= 0 || order < 1 || order > kMaxOrder) return -1;
     const ChunkLayout lay = pick_layout(M, order, chunks);
+    // the ELBO chains may run on a clustered layout (pick_layout_elbo; ASVGP_CHAIN_CTAS): size for every candidate
+    ChunkLayout cand[4] = {lay, lay, lay, lay};
+    int n_cand = 1;
+    if (chunks == 0 && lay.P >= kChainThreads) {
+        const int P = M / (2 * (order + 1) + 1);
+        if (P >= 2 * kChainThreads) cand[n_cand++] = make_layout(M, order, 2 * kChainThreads);
+        if (P >= 4 * kChainThreads) cand[n_cand++] = make_layout(M, order, 4 * kChainThreads);
+        if (P >= 8 * kChainThreads) cand[n_cand++] = make_layout(M, order, 8 * kChainThreads);
+    }
     size_t e = 0, p = 0;
-    switch (order) {
-        case 1: e = elbo_work_bytes<1>(lay); p = posterior_work_bytes<1>(lay); break;
-        case 2: e = elbo_work_bytes<2>(lay); p = posterior_work_bytes<2>(lay); break;
-        case 3: e = elbo_work_bytes<3>(lay); p = posterior_work_bytes<3>(lay); break;
-        case 4: e = elbo_work_bytes<4>(lay); p = posterior_work_bytes<4>(lay); break;
-        case 5: e = elbo_work_bytes<5>(lay); p = posterior_work_bytes<5>(lay); break;
-        case 6: e = elbo_work_bytes<6>(lay); p = posterior_work_bytes<6>(lay); break;
+    for (int c = 0; c < n_cand; ++c) {
+        size_t ec = 0;
+        switch (order) {
+            case 1: ec = elbo_work_bytes<1>(cand[c]); p = posterior_work_bytes<1>(lay); break;
+            case 2: ec = elbo_work_bytes<2>(cand[c]); p = posterior_work_bytes<2>(lay); break;
+            case 3: ec = elbo_work_bytes<3>(cand[c]); p = posterior_work_bytes<3>(lay); break;
+            case 4: ec = elbo_work_bytes<4>(cand[c]); p = posterior_work_bytes<4>(lay); break;
+            case 5: ec = elbo_work_bytes<5>(cand[c]); p = posterior_work_bytes<5>(lay); break;
+            case 6: ec = elbo_work_bytes<6>(cand[c]); p = posterior_work_bytes<6>(lay); break;
+        }
+        e = ec > e ? ec : e;
     }
     return (int64_t)(e > p ? e : p);
 }
@@ -600,10 +892,39 @@ extern "C" int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const d
     ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "elbo_grad_1d: M=%d order=%d", M, order);
     ASVGP_REQUIRE(variance > 0.0 && sigma2 > 0.0, "elbo_grad_1d: variance=%g sigma2=%g must be positive", variance, sigma2);
     ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "elbo_grad_1d: workspace too small");
-    const ChunkLayout lay = pick_layout(M, order, chunks);
+    const ChunkLayout lay = pick_layout_elbo(M, order, chunks);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_elbo<K>(lay, Kuu, dKuu, acc, variance, sigma2, out,
                                                               static_cast<char*>(work), st)) return rc; });
+    return kOk;
+}
+
+extern "C" int64_t asvgp_kuu_state_doubles(int M, int order) {
+    if (M <= 0 || order < 1 || order > kMaxOrder) return -1;
+    return (int64_t)kuu_state_doubles(M, order);
+}
+
+extern "C" int asvgp_kuu_chain_1d(const double* Kuu, const double* dKuu, int M, int order, int chunks, double* kuu_state,
+                                  void* work, int64_t work_bytes, void* gate_event, void* stream) {
+    ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "kuu_chain_1d: M=%d order=%d", M, order);
+    ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "kuu_chain_1d: workspace too small");
+    const ChunkLayout lay = pick_layout_elbo(M, order, chunks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_kuu_chain<K>(lay, Kuu, dKuu, kuu_state, static_cast<char*>(work),
+                                                                   static_cast<cudaEvent_t>(gate_event), st)) return rc; });
+    return kOk;
+}
+
+extern "C" int asvgp_elbo_grad_1d_prepared(const double* kuu_state, const double* Kuu, const double* dKuu, const double* acc,
+                                           int M, int order, double variance, double sigma2, int chunks, double* out,
+                                           void* work, int64_t work_bytes, void* kuu_ready_event, void* stream) {
+    ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "elbo_grad_1d_prepared: M=%d order=%d", M, order);
+    ASVGP_REQUIRE(variance > 0.0 && sigma2 > 0.0, "elbo_grad_1d_prepared: variance=%g sigma2=%g must be positive", variance, sigma2);
+    ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "elbo_grad_1d_prepared: workspace too small");
+    const ChunkLayout lay = pick_layout_elbo(M, order, chunks);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_pchains<K>(lay, kuu_state, Kuu, dKuu, acc, variance, sigma2, out, static_cast<char*>(work),
+                                                                 static_cast<cudaEvent_t>(kuu_ready_event), st)) return rc; });
     return kOk;
 }
 

@@ -678,6 +678,19 @@ static int sm_count() {
     return cached;
 }
 
+// CTA slots the streaming accumulate leaves free.  Its ranges are dealt statically (contiguous per CTA, so that ordered input
+// meets few interval crossings), which makes it slow by a whole second wave as soon as ANY other kernel holds a few SMs; the
+// bound's Kuu chain runs beside it on a cluster of 8 CTAs (banded_1d.cu, asvgp_kuu_chain_1d).  HBM stays saturated from 140 SMs.
+static int accum_sm_budget() {
+    static int spare = -1;
+    if (spare < 0) {
+        const char* e = getenv("ASVGP_ACCUM_SPARE_SMS");
+        spare = e ? atoi(e) : 8;
+        if (spare < 0 || spare > sm_count() / 2) spare = 8;
+    }
+    return sm_count() - spare;
+}
+
 }  // namespace asvgp
 
 using namespace asvgp;
@@ -722,7 +735,7 @@ extern "C" int asvgp_accum_1d(const double* x, const double* y, int64_t n, const
     const int64_t per_tile = 32 * kAccumUnroll * (vec ? 2 : 1);
     const int64_t n_tiles = (n + per_tile - 1) / per_tile;
     // (tools/accum_sweep.py: 2 and 4 CTAs' worth of ranges per SM both give 0.258 ms at N = 1e8; 3, 8, 16 are slower)
-    const int blocks = (int)std::min<int64_t>((n_tiles + 7) / 8, (int64_t)sm_count() * 2);
+    const int blocks = (int)std::min<int64_t>((n_tiles + 7) / 8, (int64_t)accum_sm_budget() * 2);
     if (vec) {
         ASVGP_DISPATCH_ORDER(order, (accum_1d_kernel<K, 2><<<blocks, kAccumThreads, 0, st>>>(x, y, n, mesh, n_knots, M, G, b, scal))); ASVGP_LAUNCHED();
     } else {

@@ -169,8 +169,71 @@ def kuu_assemble(basis, names, coef, dcoef=None, want_grad=True):
     return Kuu, dKuu
 
 
-def elbo_grad_1d(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None):
-    """Launches the ELBO+gradient kernels; returns the 16-slot device result (see include/asvgp_b200.h)."""
+class KuuChain:
+    """Handle of a Kuu chain in flight on the side stream (kuu_chain_1d): its state buffer, the event that marks it
+    complete, and the operands it reads (kept alive until the bound has consumed the state)."""
+    __slots__ = ("state", "event", "operands")
+
+    def __init__(self, state, event, operands):
+        self.state, self.event, self.operands = state, event, operands
+
+
+_KUU_STATES = {}
+_KUU_STREAM = {}
+_KUU_LAST = {}
+
+
+def kuu_chain_1d(Kuu, dKuu, basis, chunks=0, gate=False, timing=False):
+    """Launches the part of the bound that depends on the hyper-parameters only — log|Kuu|, band(Kuu^-1) and their
+    lengthscale tangents (reference gpr.py:56-70) — on a side stream, ordered after the current stream's work so far
+    (the Kuu assembly).  Launch it BEFORE accum_1d and the O(N) pass hides it; elbo_grad_1d(..., kuu=handle) joins.
+    gate=True: the current stream waits until the chain kernel is next in line on the side stream (its pre-pass is done), so
+    that a machine-filling kernel launched next does not take every SM before the chain's few CTAs are dispatched."""
+    k, m = basis.order, basis.m
+    dev = device()
+    side = _KUU_STREAM.get(dev)
+    if side is None:
+        # high priority: its few CTAs must get their SMs although a full-machine streaming kernel is being dispatched
+        side = _KUU_STREAM[dev] = torch.cuda.Stream(device=dev, priority=-1)
+    key = (dev, m, k)
+    state = _KUU_STATES.get(key)
+    if state is None:
+        state = _KUU_STATES[key] = torch.empty(_lib.load().asvgp_kuu_state_doubles(m, k), dtype=F64, device=dev)
+    ws = workspace_1d(m, k, chunks, slot="kuu")
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    gate_ev = torch.cuda.Event() if gate else None
+    if gate:
+        gate_ev.record(side)          # creates the underlying cudaEvent_t; the library re-records it before the chain kernel
+    _lib.call("asvgp_kuu_chain_1d", _p(Kuu), _p(dKuu), m, k, int(chunks), _p(state), _p(ws), ws.numel(),
+              ctypes.c_void_p(gate_ev.cuda_event if gate else 0), ctypes.c_void_p(side.cuda_stream))
+    done = torch.cuda.Event(enable_timing=timing)
+    done.record(side)
+    if gate:
+        main.wait_event(gate_ev)
+    # the operands stay referenced until the next chain is launched (by then this one has been joined or superseded: the
+    # side stream is in order), so the allocator cannot hand their memory out while the side stream still reads it
+    handle = _KUU_LAST[dev] = KuuChain(state, done, (Kuu, dKuu))
+    return handle
+
+
+def elbo_grad_1d(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None, kuu=None):
+    """Launches the ELBO+gradient kernels; returns the 16-slot device result (see include/asvgp_b200.h).  The Kuu chain
+    runs on a side stream next to the two P chains (`kuu`: a handle from kuu_chain_1d launched earlier, e.g. before the
+    accumulate; shared by the output columns of a multi-output model)."""
+    k, m = basis.order, basis.m
+    if kuu is None:
+        kuu = kuu_chain_1d(Kuu, dKuu, basis, chunks)
+    ws = workspace_1d(m, k, chunks)
+    if out is None:
+        out = torch.empty(16, dtype=F64, device=acc.device)
+    _lib.call("asvgp_elbo_grad_1d_prepared", _p(kuu.state), _p(Kuu), _p(dKuu), _p(acc), m, k, float(variance),
+              float(sigma2), int(chunks), _p(out), _p(ws), ws.numel(), ctypes.c_void_p(kuu.event.cuda_event), _stream())
+    return out
+
+
+def elbo_grad_1d_single_stream(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None):
+    """The same bound as ONE C call on the current stream (asvgp_elbo_grad_1d: Kuu chain, then P chains)."""
     k, m = basis.order, basis.m
     ws = workspace_1d(m, k, chunks)
     if out is None:

@@ -102,6 +102,28 @@ ASVGP_API int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const do
                                  double variance, double sigma2, int chunks, double* out, void* work,
                                  int64_t work_bytes, void* stream);
 
+/* The same bound in two calls, split where its data dependencies are.  The Kuu chain (log|Kuu|, band(Kuu^-1), both with
+ * their lengthscale tangents: gpr.py:56-70's cholesky_band(Kuu) / inverse_from_cholesky_band) depends on the
+ * hyper-parameters only, so a caller can launch it on a side stream WHILE asvgp_accum_1d streams the data, and finish with
+ * the P chains once the accumulator (and its all-reduce) is complete:
+ *   asvgp_kuu_chain_1d(Kuu, dKuu, ..., kuu_state, work_a, side_stream);
+ *   asvgp_accum_1d(..., acc, stream);  [all-reduce];
+ *   asvgp_elbo_grad_1d_prepared(kuu_state, Kuu, dKuu, acc, ..., out, work_b, kuu_ready_event, stream);
+ * `gate_event` (cudaEvent_t or NULL) is recorded on the side stream right before the chain kernel, after its parallel pre-pass:
+ * a caller about to launch a machine-filling kernel on `stream` lets `stream` wait for it, so that the chain's few CTAs are
+ * dispatched first instead of queueing behind the streaming kernel's thousands.
+ * `kuu_ready_event`: a cudaEvent_t recorded on the side stream after asvgp_kuu_chain_1d (NULL if `stream` is already ordered
+ * after it); `stream` waits for it only where the Kuu state is first read — after the P chains — so that without an
+ * accumulate in between (an optimiser iteration) the Kuu chain and the P chains still run side by side.
+ * `kuu_state`: asvgp_kuu_state_doubles(M, order) doubles on the device; the two calls need separate workspaces of
+ * asvgp_workspace_bytes_1d bytes each when they may overlap.  asvgp_elbo_grad_1d is exactly these two calls on one stream. */
+ASVGP_API int64_t asvgp_kuu_state_doubles(int M, int order);
+ASVGP_API int asvgp_kuu_chain_1d(const double* Kuu, const double* dKuu, int M, int order, int chunks, double* kuu_state,
+                                 void* work, int64_t work_bytes, void* gate_event, void* stream);
+ASVGP_API int asvgp_elbo_grad_1d_prepared(const double* kuu_state, const double* Kuu, const double* dKuu, const double* acc,
+                                          int M, int order, double variance, double sigma2, int chunks, double* out,
+                                          void* work, int64_t work_bytes, void* kuu_ready_event, void* stream);
+
 /* ---- a10 (factorisation half): posterior weights -------------------------------------------------------------------------
  * Replaces the CHOLMOD factorisations and solves of GPR_1d.predict_f (gpr.py:96-108):
  * alpha = P^-1 Kuf_y / sigma2 and S = band(P^-1) - band(Kuu^-1), P = Kuu + G / sigma2.  info[2] (device): failing

@@ -152,3 +152,45 @@ def test_snelson_notebook_known_answer(cuda, golden):
     elbo = model.elbo()
     assert abs(elbo - float(g["notebook_elbo"])) < 1e-6
     assert elbo < float(g["notebook_exact_gp"])
+
+
+@pytest.mark.parametrize("m,chunks", [(100, 0), (3000, 0), (10000, 0), (10000, 16)])
+def test_split_bound_equals_single_call(cuda, m, chunks):
+    """asvgp_kuu_chain_1d (side stream) + asvgp_elbo_grad_1d_prepared give the bits of the one-call asvgp_elbo_grad_1d, also
+    when the Kuu chain is launched before the accumulate it overlaps with (single CTA, 2/4/8-CTA cluster layouts)."""
+    import torch
+
+    from asvgp_b200 import basis as B, kernels as Kn, ops
+    from asvgp_b200.inducing_features import SplineFeatures1D
+
+    rng = np.random.default_rng(5)
+    n = 400000
+    x = np.sort(rng.uniform(0.0, m, n))
+    y = np.sin(x / 7.0) + 0.1 * rng.standard_normal(n)
+    basis = B.B3Spline(-1, m + 1, m)
+    kern = Kn.Matern52(variance=1.2, lengthscales=1.7)
+    feats = SplineFeatures1D(kern, basis)
+    xd, yd = ops.to_device(x), ops.to_device(y)
+    Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
+    acc = ops.accum_1d(xd, yd, basis)
+    one = ops.elbo_grad_1d_single_stream(Kuu, dKuu, acc, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()
+    forked = ops.elbo_grad_1d(Kuu, dKuu, acc, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()
+    # the order the bench uses: Kuu chain first, accumulate next to it, then the P chains
+    kuu = ops.kuu_chain_1d(Kuu, dKuu, basis, chunks=chunks)
+    acc2 = ops.accum_1d(xd, yd, basis)
+    early = ops.elbo_grad_1d(Kuu, dKuu, acc2, basis, 1.2, 0.3, chunks=chunks, kuu=kuu).cpu().numpy()
+    one2 = ops.elbo_grad_1d_single_stream(Kuu, dKuu, acc2, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()   # acc2 != acc bitwise (fp64 REDs)
+    torch.cuda.synchronize()
+    assert one[8] == 0
+    for got, want in ((forked, one), (early, one2)):
+        np.testing.assert_array_equal(got[:9], want[:9])
+        assert got[15] == want[15]
+    # and the trace term itself against the dense algebra
+    G, b, scal = [t.cpu().numpy() for t in ops.split_accum_1d(acc, basis)]
+    if m <= 3000:
+        from scipy.linalg import solveh_banded
+
+        Kb = Kuu.cpu().numpy()
+        dense = lambda band: sum(np.diag(band[d, : m - d], -d) + (np.diag(band[d, : m - d], d) if d else 0) for d in range(4))
+        tr = np.trace(solveh_banded(Kb, dense(G), lower=True))
+        assert abs(one[7] - tr) <= 1e-9 * abs(tr)

@@ -26,6 +26,23 @@ e0.record()
 for _ in range(20):
     ops.elbo_grad_1d(Kuu, dKuu, acc, b, 1.0, 0.1, chunks=chunks, out=out)
 e1.record(); torch.cuda.synchronize()
+kuu = ops.kuu_chain_1d(Kuu, dKuu, b, chunks=chunks)
+torch.cuda.current_stream().wait_event(kuu.event)
+torch.cuda.synchronize()
+t = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+t[0].record()
+for _ in range(20):
+    h = ops.kuu_chain_1d(Kuu, dKuu, b, chunks=chunks)
+    torch.cuda.current_stream().wait_event(h.event)
+t[1].record()
+for _ in range(20):
+    ops.elbo_grad_1d(Kuu, dKuu, acc, b, 1.0, 0.1, chunks=chunks, out=out, kuu=kuu)
+t[2].record()
+for _ in range(20):
+    ops.elbo_grad_1d_single_stream(Kuu, dKuu, acc, b, 1.0, 0.1, chunks=chunks, out=out)
+t[3].record(); torch.cuda.synchronize()
+print("  Kuu chain alone %.1f us; P chains + bound alone %.1f us; single-stream call %.1f us"
+      % (t[0].elapsed_time(t[1]) / 20 * 1e3, t[1].elapsed_time(t[2]) / 20 * 1e3, t[2].elapsed_time(t[3]) / 20 * 1e3))
 o = out.cpu().numpy()
 print("m %d chunks %d: %.1f us per call; Kuu chain cycles: sweep %.0f separators %.0f back %.0f tail %.0f; P chain: sweep %.0f separators %.0f; elbo %.6f"
       % (m, chunks, e0.elapsed_time(e1) / 20 * 1e3, o[9], o[10], o[11], o[12], o[13], o[14], o[0]))
