@@ -27,6 +27,10 @@
 namespace asvgp {
 
 constexpr int kChainThreads = 128;          // >= max chunk count P
+
+// programmatic dependent launch (see launch_dependent): no-ops when the kernel was launched the ordinary way
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 constexpr int kMaxTerms = 12;
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -136,26 +140,80 @@ __host__ __device__ inline size_t chain_rows_count(const ChunkLayout& lay) {
 
 template <class T> struct ChainSpec { BandMat<T> A; VecRhs<T> rhs; };
 
+// trace(Kuu^-1 G) = sum band(Kuu^-1) .* band(G) (off-diagonals twice, reference gpr.py:60-70) and its d/dl from the stored
+// inverse band of the Kuu chain: kTraceBlocks CTAs of 256 threads, every thread a fixed strided share with all its loads in
+// flight at once, fixed-order trees; the per-CTA partials are added in CTA order by elbo_finalize_kernel — the same bits on
+// every run and every rank, whichever kernel hosts the CTAs (the P chains' chain_rows_kernel or the finalize kernel itself).
+constexpr int kTraceBlocks = 64, kTraceThreads = 256, kTraceUnroll = 4;
+struct TraceJob {
+    const double* kstate;   // nullptr: no trace CTAs in this launch
+    const double* G;
+    double* tr_part;        // [kTraceBlocks][2]
+    int M, K, first_block;
+};
+__device__ __forceinline__ void trace_partial(const double* __restrict__ kstate, const double* __restrict__ G, int M, int K, int block,
+                                              double* __restrict__ tr_part) {
+    __shared__ double s_tr[2][kTraceThreads / 32];
+    const Dual<1>* kinv = reinterpret_cast<const Dual<1>*>(kstate + 16);
+    double tr = 0.0, dtr_dl = 0.0;
+    const int band = (K + 1) * M, stride = kTraceThreads * kTraceBlocks;
+    for (int i0 = block * kTraceThreads + threadIdx.x; i0 < band; i0 += stride * kTraceUnroll) {
+        Dual<1> sv[kTraceUnroll];
+        double gv[kTraceUnroll];
+#pragma unroll
+        for (int u = 0; u < kTraceUnroll; ++u) {
+            const int i = i0 + u * stride;
+            const int d = i / M, col = i - d * M;
+            const bool ok = i < band && col + d < M;
+            sv[u] = kinv[ok ? i : 0];
+            gv[u] = ok ? (d == 0 ? 1.0 : 2.0) * G[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kTraceUnroll; ++u) {
+            if (gv[u] != 0.0) { tr = fma(sv[u].v, gv[u], tr); dtr_dl = fma(sv[u].d[0], gv[u], dtr_dl); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+        dtr_dl += __shfl_xor_sync(0xffffffffu, dtr_dl, o);
+    }
+    if ((threadIdx.x & 31) == 0) { s_tr[0][threadIdx.x >> 5] = tr; s_tr[1][threadIdx.x >> 5] = dtr_dl; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tr = 0.0; dtr_dl = 0.0;
+        for (int i = 0; i < kTraceThreads / 32; ++i) { tr += s_tr[0][i]; dtr_dl += s_tr[1][i]; }
+        tr_part[2 * block] = tr; tr_part[2 * block + 1] = dtr_dl;
+    }
+}
+
 template <class T, int K, int NCHAINS>
 __global__ void __launch_bounds__(256) chain_rows_kernel(ChunkLayout lay, ChainSpec<T> s0, ChainSpec<T> s1, ChainSpec<T> s2, ChainSpec<T> s3,
-                                                         T* __restrict__ out, unsigned* __restrict__ zero_me = nullptr) {
+                                                         T* __restrict__ out, unsigned* __restrict__ zero_me = nullptr,
+                                                         TraceJob trace = TraceJob{nullptr, nullptr, nullptr, 0, 0, 0}) {
+    pdl_launch_dependents();
     if (zero_me != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *zero_me = 0u;      // arrival counter of elbo_finalize_kernel
-    const int n_rho = chain_n_rho(lay, K), P = lay.P;
-    const size_t per_chain = chain_rows_count<T, K>(lay);
-    const size_t total = per_chain * NCHAINS;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const int chain = (int)(t / per_chain);
-        const size_t e = t % per_chain;
+    if (trace.kstate != nullptr && (int)blockIdx.x >= trace.first_block) {              // the trailing CTAs of the launch
+        trace_partial(trace.kstate, trace.G, trace.M, trace.K, (int)blockIdx.x - trace.first_block, trace.tr_part);
+        return;
+    }
+    const unsigned n_rho = chain_n_rho(lay, K), P = lay.P;
+    const unsigned per_chain = (unsigned)chain_rows_count<T, K>(lay);          // 32-bit index arithmetic (the launchers check the range)
+    const unsigned total = per_chain * NCHAINS;
+    const unsigned n_row_blocks = trace.kstate != nullptr ? (unsigned)trace.first_block : gridDim.x;
+    for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += n_row_blocks * blockDim.x) {
+        const unsigned chain = t / per_chain;
+        const unsigned e = t - chain * per_chain;
         const ChainSpec<T>& sp = chain == 0 ? s0 : (chain == 1 ? s1 : (chain == 2 ? s2 : s3));
-        const int p = (int)(e % P);
-        const size_t q = e / P;
+        const unsigned q = e / P;
+        const int p = (int)(e - q * P);
         const int g0 = P > 1 ? lay.start(p) : 0;
-        if (q < (size_t)n_rho * (K + 1)) {
-            const int bidx = (int)(q % (K + 1)), rho = (int)(q / (K + 1));
+        if (q < n_rho * (K + 1)) {
+            const int rho = (int)(q / (K + 1)), bidx = (int)(q - (unsigned)rho * (K + 1));
             const int row = g0 + rho, col = row - K + bidx;
             out[t] = sp.A(K - bidx, col);
         } else {
-            const int rho = (int)(q - (size_t)n_rho * (K + 1));
+            const int rho = (int)(q - n_rho * (K + 1));
             out[t] = sp.rhs(g0 + rho);
         }
     }
@@ -376,6 +434,8 @@ __global__ void __launch_bounds__(kChainThreads) elbo_chains_kernel(ElboArgs<K> 
     __shared__ ChainTotals<T, K> tot;
     __shared__ long long clk[4];
     double* out = a.partial[slot];
+    pdl_launch_dependents();
+    pdl_wait();                              // the row tables are complete
 
     const int n_rho = chain_n_rho(lay, K), g0 = lay.P > 1 ? lay.start(p < lay.P ? p : 0) : 0, pp = p < lay.P ? p : 0;
     const T* tab = a.rows + (size_t)slot * chain_rows_count<T, K>(lay);
@@ -409,6 +469,8 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(kChainThreads) el
     __shared__ ChainTotals<T, K> tot;
     __shared__ long long clk[4];
     double* out = a.partial[slot];
+    pdl_launch_dependents();
+    pdl_wait();                              // the row tables are complete
     const int n_rho = chain_n_rho(lay, K);
     const T* tab = a.rows + (size_t)slot * chain_rows_count<T, K>(lay);
     T* scratch = red_scratch + (size_t)slot * ((size_t)(2 * K + 1) * lay.n_reduced() + 8);
@@ -437,53 +499,26 @@ __global__ void __cluster_dims__(NCTA, 1, 1) __launch_bounds__(kChainThreads) el
 //   ELBO = -N/2 log(2 pi s2) - 1/2 log|P| + 1/2 log|Kuu| - yy/(2 s2) + Q/(2 s2^2) - N v/(2 s2) + tr/(2 s2)
 // Kuu = Kt(l)/v  =>  P = (Kt + (v/s2) G)/v, hence d/dv of log|P| and Q follow from d/ds2:
 //   dlog|P|/dv = -M/v - (s2/v) dlog|P|/ds2,   dQ/dv = Q/v - (s2/v) dQ/ds2,   dlog|Kuu|/dv = -M/v,   dtr/dv = tr/v.
-// kFinalizeBlocks CTAs: the trace and its d/dl first (every thread a fixed share of the (K+1) x M products with all its loads in
-// flight at once, fixed-order trees, per-CTA partials added in CTA order: the same bits on every run and every rank); the CTA
-// that arrives last combines.
-constexpr int kFinalizeThreads = 256, kFinalizeBlocks = 16, kFinalizeUnroll = 4;
-__global__ void __launch_bounds__(kFinalizeThreads) elbo_finalize_kernel(const double* __restrict__ kstate, double* __restrict__ partial,
-                                                                         const double* __restrict__ G, const double* __restrict__ scal,
-                                                                         int M, int K, double variance, double sigma2, double* __restrict__ out) {
-    __shared__ double s_tr[2][kFinalizeThreads / 32];
-    __shared__ bool s_last;
-    const Dual<1>* kinv = reinterpret_cast<const Dual<1>*>(kstate + 16);
-    double* tr_part = partial + 64;                                     // [kFinalizeBlocks][2]
+// trace_done = 0: launched with kTraceBlocks CTAs that compute the trace partials first (trace_partial); the CTA that arrives
+// last combines.  trace_done = 1: the partials are there already (the P chains' chain_rows_kernel hosted the trace CTAs), one CTA.
+__global__ void __launch_bounds__(kTraceThreads) elbo_finalize_kernel(const double* __restrict__ kstate, double* __restrict__ partial,
+                                                                      const double* __restrict__ G, const double* __restrict__ scal,
+                                                                      int M, int K, double variance, double sigma2, int trace_done,
+                                                                      double* __restrict__ out) {
+    double* tr_part = partial + 64;                                     // [kTraceBlocks][2]
     unsigned* counter = reinterpret_cast<unsigned*>(partial + 32);      // zeroed by the P chains' chain_rows_kernel
+    pdl_wait();                                                         // the P chains are complete
+    if (!trace_done) {
+        trace_partial(kstate, G, M, K, (int)blockIdx.x, tr_part);
+        if (threadIdx.x != 0) return;
+        __threadfence();
+        if (atomicAdd(counter, 1u) != gridDim.x - 1) return;
+        __threadfence();
+    } else if (threadIdx.x != 0) {
+        return;
+    }
     double tr = 0.0, dtr_dl = 0.0;
-    const int band = (K + 1) * M, stride = kFinalizeThreads * kFinalizeBlocks;
-    for (int i0 = blockIdx.x * kFinalizeThreads + threadIdx.x; i0 < band; i0 += stride * kFinalizeUnroll) {
-        Dual<1> sv[kFinalizeUnroll];
-        double gv[kFinalizeUnroll];
-#pragma unroll
-        for (int u = 0; u < kFinalizeUnroll; ++u) {
-            const int i = i0 + u * stride;
-            const int d = i / M, col = i - d * M;
-            const bool ok = i < band && col + d < M;
-            sv[u] = kinv[ok ? i : 0];
-            gv[u] = ok ? (d == 0 ? 1.0 : 2.0) * G[i] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < kFinalizeUnroll; ++u) {
-            if (gv[u] != 0.0) { tr = fma(sv[u].v, gv[u], tr); dtr_dl = fma(sv[u].d[0], gv[u], dtr_dl); }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        tr += __shfl_xor_sync(0xffffffffu, tr, o);
-        dtr_dl += __shfl_xor_sync(0xffffffffu, dtr_dl, o);
-    }
-    if ((threadIdx.x & 31) == 0) { s_tr[0][threadIdx.x >> 5] = tr; s_tr[1][threadIdx.x >> 5] = dtr_dl; }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    tr = 0.0; dtr_dl = 0.0;
-    for (int i = 0; i < kFinalizeThreads / 32; ++i) { tr += s_tr[0][i]; dtr_dl += s_tr[1][i]; }
-    tr_part[2 * blockIdx.x] = tr; tr_part[2 * blockIdx.x + 1] = dtr_dl;
-    __threadfence();
-    s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
-    if (!s_last) return;
-    __threadfence();
-    tr = 0.0; dtr_dl = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) { tr += __ldcg(tr_part + 2 * i); dtr_dl += __ldcg(tr_part + 2 * i + 1); }
+    for (int i = 0; i < kTraceBlocks; ++i) { tr += __ldcg(tr_part + 2 * i); dtr_dl += __ldcg(tr_part + 2 * i + 1); }
     const double* cK = kstate;           // Kuu chain (d/dl)
     const double* cL = partial;          // P chain (d/dl)
     const double* cS = partial + 16;     // P chain (d/dsigma2)
@@ -627,6 +662,19 @@ static int launch_band_inverse(const ChunkLayout& lay, const double* A, const do
 }
 
 static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still running (its CTAs
+// park in pdl_wait() until that grid has completed and flushed), which takes the launch latency and the cluster's
+// co-scheduling off the chain of three dependent launches (row tables -> chains -> bound).
+template <class... KArgs, class... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // cudaFuncAttributeMaxDynamicSharedMemorySize, set once per kernel and size (the call costs host time on every launch otherwise)
 template <class Kernel>
 static cudaError_t allow_smem(Kernel kernel, size_t smem) {
@@ -637,8 +685,8 @@ static cudaError_t allow_smem(Kernel kernel, size_t smem) {
     if (e == cudaSuccess) { allowed = smem; which = reinterpret_cast<const void*>(kernel); }
     return e;
 }
-// per-launch record area: [2][16] chain records, the finalize kernel's arrival counter (double slot 32), its per-CTA trace partials (from slot 64)
-constexpr size_t kPartialBytes = 1024;
+// per-launch record area: [2][16] chain records, the finalize kernel's arrival counter (double slot 32), the [kTraceBlocks][2] trace partials (from slot 64)
+constexpr size_t kPartialBytes = 2048;
 template <int K>
 static size_t red_scratch_count(const ChunkLayout& lay) { return (size_t)(2 * K + 1) * lay.n_reduced() + 8; }     // per chain (clustered layout)
 // workspace of one launch of n_chains chains: column stores, [n_chains][16] partials, row tables, reduced-solution scratch
@@ -663,7 +711,7 @@ static size_t posterior_work_bytes(const ChunkLayout& lay) {
 template <int K>
 static int launch_chain_group(const ChunkLayout& lay, int first_chain, int n_chains, const ChainSpec<Dual<1>>& s0,
                               const ChainSpec<Dual<1>>& s1, double* partial0, Dual<1>* kinv, char* work, double** partials_out,
-                              cudaEvent_t gate, cudaStream_t st) {
+                              cudaEvent_t gate, TraceJob trace, cudaStream_t st) {
     using T = Dual<1>;
     ElboArgs<K> a;
     a.lay = lay;
@@ -684,29 +732,37 @@ static int launch_chain_group(const ChunkLayout& lay, int first_chain, int n_cha
     a.rows = rows;
     T* scratch = reinterpret_cast<T*>(p);
     const size_t total = n_chains * chain_rows_count<T, K>(lay);
+    ASVGP_REQUIRE(total < ((size_t)1 << 31), "banded chains: %zu row-table entries exceed the 32-bit index range", total);
     const int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 8);
-    if (n_chains == 1) chain_rows_kernel<T, K, 1><<<grid, 256, 0, st>>>(lay, s0, s0, s0, s0, rows);
-    else chain_rows_kernel<T, K, 2><<<grid, 256, 0, st>>>(lay, s0, s1, s1, s1, rows, reinterpret_cast<unsigned*>(partial + 32));
+    if (n_chains == 1) {
+        chain_rows_kernel<T, K, 1><<<grid, 256, 0, st>>>(lay, s0, s0, s0, s0, rows);
+    } else {
+        trace.first_block = grid;
+        trace.tr_part = partial + 64;
+        chain_rows_kernel<T, K, 2><<<grid + (trace.kstate != nullptr ? kTraceBlocks : 0), 256, 0, st>>>(
+            lay, s0, s1, s1, s1, rows, reinterpret_cast<unsigned*>(partial + 32), trace);
+    }
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     if (gate != nullptr) ASVGP_CUDA_OK(cudaEventRecord(gate, st));          // "the chain kernel is next in line"
     const int n_cta = (lay.P + kChainThreads - 1) / kChainThreads;          // > 1: clustered layout (pick_layout_elbo)
+    const bool pdl = gate == nullptr;        // an event record between the two launches rules the early launch out
     if (n_cta > 1) {
         const size_t smem = ChainSmall<T, K>::bytes(kChainThreads + 1);
         if (n_cta == 2) {
             ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 2>, smem));
-            elbo_chains_cluster_kernel<K, 2><<<n_chains * 2, kChainThreads, smem, st>>>(a, scratch);
+            ASVGP_CUDA_OK(launch_dependent(elbo_chains_cluster_kernel<K, 2>, n_chains * 2, kChainThreads, smem, st, pdl, a, scratch));
         } else if (n_cta == 8) {
             ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 8>, smem));
-            elbo_chains_cluster_kernel<K, 8><<<n_chains * 8, kChainThreads, smem, st>>>(a, scratch);
+            ASVGP_CUDA_OK(launch_dependent(elbo_chains_cluster_kernel<K, 8>, n_chains * 8, kChainThreads, smem, st, pdl, a, scratch));
         } else {
             ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 4>, smem));
-            elbo_chains_cluster_kernel<K, 4><<<n_chains * 4, kChainThreads, smem, st>>>(a, scratch);
+            ASVGP_CUDA_OK(launch_dependent(elbo_chains_cluster_kernel<K, 4>, n_chains * 4, kChainThreads, smem, st, pdl, a, scratch));
         }
     } else {
         const size_t smem = ChainSmall<T, K>::bytes(lay.P);
         ASVGP_CUDA_OK(allow_smem(elbo_chains_kernel<K>, smem));
-        elbo_chains_kernel<K><<<n_chains, kChainThreads, smem, st>>>(a);
+        ASVGP_CUDA_OK(launch_dependent(elbo_chains_kernel<K>, n_chains, kChainThreads, smem, st, pdl, a));
     }
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
@@ -720,13 +776,14 @@ static int launch_kuu_chain(const ChunkLayout& lay, const double* Kuu, const dou
     using T = Dual<1>;
     const int M = lay.M;
     ChainSpec<T> s0{BandMat<T>{Kuu, dKuu, nullptr, 0.0, 0.0, 1, M}, VecRhs<T>{Kuu, M, 0}};
-    return launch_chain_group<K>(lay, 0, 1, s0, s0, kstate, reinterpret_cast<T*>(kstate + 16), work, nullptr, gate, st);
+    return launch_chain_group<K>(lay, 0, 1, s0, s0, kstate, reinterpret_cast<T*>(kstate + 16), work, nullptr, gate,
+                                 TraceJob{nullptr, nullptr, nullptr, 0, 0, 0}, st);
 }
 
 // The two P chains and the bound, given the Kuu state.
 template <int K>
 static int launch_pchains(const ChunkLayout& lay, const double* kstate, const double* Kuu, const double* dKuu, const double* acc,
-                          double variance, double sigma2, double* out, char* work, cudaEvent_t kuu_ready, cudaStream_t st) {
+                          double variance, double sigma2, double* out, char* work, cudaEvent_t kuu_ready, int join_late, cudaStream_t st) {
     using T = Dual<1>;
     const int M = lay.M;
     const double* G = acc;
@@ -736,9 +793,15 @@ static int launch_pchains(const ChunkLayout& lay, const double* kstate, const do
     ChainSpec<T> s1{BandMat<T>{Kuu, dKuu, G, inv_s2, 0.0, 1, M}, VecRhs<T>{b, M, 1}};
     ChainSpec<T> s2{BandMat<T>{Kuu, dKuu, G, inv_s2, -inv_s2 * inv_s2, 0, M}, VecRhs<T>{b, M, 1}};
     double* partial = nullptr;
-    if (int rc = launch_chain_group<K>(lay, 1, 2, s1, s2, nullptr, nullptr, work, &partial, nullptr, st)) return rc;
-    if (kuu_ready != nullptr) ASVGP_CUDA_OK(cudaStreamWaitEvent(st, kuu_ready, 0));      // the Kuu state is first read here
-    elbo_finalize_kernel<<<kFinalizeBlocks, kFinalizeThreads, 0, st>>>(kstate, partial, G, acc + (size_t)(K + 2) * M, M, K, variance, sigma2, out);
+    // join_late = 0: the Kuu state is (about to be) complete — join first and let the row-table launch host the trace CTAs;
+    // join_late = 1: the Kuu chain may still be running beside us — join only where its state is first read, after the P chains.
+    if (!join_late && kuu_ready != nullptr) ASVGP_CUDA_OK(cudaStreamWaitEvent(st, kuu_ready, 0));
+    const TraceJob trace{join_late ? nullptr : kstate, G, nullptr, M, K, 0};
+    if (int rc = launch_chain_group<K>(lay, 1, 2, s1, s2, nullptr, nullptr, work, &partial, nullptr, trace, st)) return rc;
+    if (join_late && kuu_ready != nullptr) ASVGP_CUDA_OK(cudaStreamWaitEvent(st, kuu_ready, 0));
+    const bool pdl = !(join_late && kuu_ready != nullptr);       // nothing between the chain kernel and this launch
+    ASVGP_CUDA_OK(launch_dependent(elbo_finalize_kernel, join_late ? kTraceBlocks : 1, kTraceThreads, 0, st, pdl, kstate, partial, G,
+                                   acc + (size_t)(K + 2) * M, M, K, variance, sigma2, join_late ? 0 : 1, out));
     ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
@@ -750,7 +813,7 @@ static int launch_elbo(const ChunkLayout& lay, const double* Kuu, const double* 
     double* kstate = reinterpret_cast<double*>(work + chains_work_bytes<K>(lay, 1));
     char* pwork = work + chains_work_bytes<K>(lay, 1) + align256(kuu_state_doubles(lay.M, K) * sizeof(double));
     if (int rc = launch_kuu_chain<K>(lay, Kuu, dKuu, kstate, work, nullptr, st)) return rc;
-    return launch_pchains<K>(lay, kstate, Kuu, dKuu, acc, variance, sigma2, out, pwork, nullptr, st);
+    return launch_pchains<K>(lay, kstate, Kuu, dKuu, acc, variance, sigma2, out, pwork, nullptr, 0, st);
 }
 
 template <int K>
@@ -917,14 +980,14 @@ extern "C" int asvgp_kuu_chain_1d(const double* Kuu, const double* dKuu, int M, 
 
 extern "C" int asvgp_elbo_grad_1d_prepared(const double* kuu_state, const double* Kuu, const double* dKuu, const double* acc,
                                            int M, int order, double variance, double sigma2, int chunks, double* out,
-                                           void* work, int64_t work_bytes, void* kuu_ready_event, void* stream) {
+                                           void* work, int64_t work_bytes, void* kuu_ready_event, int join_late, void* stream) {
     ASVGP_REQUIRE(M > 2 * order && order >= 1 && order <= kMaxOrder, "elbo_grad_1d_prepared: M=%d order=%d", M, order);
     ASVGP_REQUIRE(variance > 0.0 && sigma2 > 0.0, "elbo_grad_1d_prepared: variance=%g sigma2=%g must be positive", variance, sigma2);
     ASVGP_REQUIRE(work_bytes >= asvgp_workspace_bytes_1d(M, order, chunks), "elbo_grad_1d_prepared: workspace too small");
     const ChunkLayout lay = pick_layout_elbo(M, order, chunks);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     ASVGP_DISPATCH_ORDER(order, { if (int rc = launch_pchains<K>(lay, kuu_state, Kuu, dKuu, acc, variance, sigma2, out, static_cast<char*>(work),
-                                                                 static_cast<cudaEvent_t>(kuu_ready_event), st)) return rc; });
+                                                                 static_cast<cudaEvent_t>(kuu_ready_event), join_late, st)) return rc; });
     return kOk;
 }
 

@@ -601,10 +601,14 @@ __device__ __noinline__ void scatter_point_2d(const Mesh mesh1, const Mesh mesh2
 // registers (3 KB per warp, 48 KB per SM) it sits at 3.3 TB/s whatever the instruction count.  So the column walk is
 // staged through shared memory instead: every lane cp.async's its own 16 B of X and 8 B of y, kColsRing rows deep
 // (18 KB per warp, ~140 KB per SM in flight, no registers, no cross-lane synchronisation because a lane only ever reads
-// what it copied itself).
+// what it copied itself).  Tried and measured slower (r02): the same ring filled by tiled TMA loads — one 4 x 512 B box of X
+// and one 4 x 256 B box of y per group of four rows, issued by one lane, completion on a per-group mbarrier — 0.640 ms
+// against 0.578 ms, with the barrier probe issued a group ahead; the 80 instructions of per-lane address arithmetic it
+// removes were not on the critical path (stall_wait/short_sb dominate, two warps per scheduler), and such small boxes do
+// not suit the TMA engine.
 constexpr int kColsWarps = 8;
 template <int K> struct ColsRing {       // rows in the ring: what fits beside the (K-dependent) tables in 227 KB
-    static constexpr int kRows = K <= 3 ? 24 : (K == 4 ? 20 : 16);
+    static constexpr int kRows = K <= 3 ? 24 : (K == 4 ? 20 : (K == 5 ? 16 : 12));   // K = 6 at 16 rows exceeded 227 KB with the static arrays
 };
 
 __device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src) {

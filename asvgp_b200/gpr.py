@@ -169,7 +169,7 @@ class GPR_1d(_ModelBase):
         Kuu, dKuu = self.inducing_features.make_Kuu_device(self.kernel, want_grad=True)
         kuu = ops.kuu_chain_1d(Kuu, dKuu, self.basis, chunks=self._chunks)     # once: it does not depend on y
         for acc, out in zip(self._accs, self._outs):
-            ops.elbo_grad_1d(Kuu, dKuu, acc, self.basis, var, s2, chunks=self._chunks, out=out, kuu=kuu)
+            ops.elbo_grad_1d(Kuu, dKuu, acc, self.basis, var, s2, chunks=self._chunks, out=out, kuu=kuu, join_late=True)
         return self._out
 
     def _combine_outputs(self):

@@ -217,18 +217,21 @@ def kuu_chain_1d(Kuu, dKuu, basis, chunks=0, gate=False, timing=False):
     return handle
 
 
-def elbo_grad_1d(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None, kuu=None):
+def elbo_grad_1d(Kuu, dKuu, acc, basis, variance, sigma2, chunks=0, out=None, kuu=None, join_late=None):
     """Launches the ELBO+gradient kernels; returns the 16-slot device result (see include/asvgp_b200.h).  The Kuu chain
     runs on a side stream next to the two P chains (`kuu`: a handle from kuu_chain_1d launched earlier, e.g. before the
     accumulate; shared by the output columns of a multi-output model)."""
     k, m = basis.order, basis.m
+    if join_late is None:
+        join_late = kuu is None      # forked right here: the P chains run beside it; a handle from earlier is joined up front
     if kuu is None:
         kuu = kuu_chain_1d(Kuu, dKuu, basis, chunks)
     ws = workspace_1d(m, k, chunks)
     if out is None:
         out = torch.empty(16, dtype=F64, device=acc.device)
     _lib.call("asvgp_elbo_grad_1d_prepared", _p(kuu.state), _p(Kuu), _p(dKuu), _p(acc), m, k, float(variance),
-              float(sigma2), int(chunks), _p(out), _p(ws), ws.numel(), ctypes.c_void_p(kuu.event.cuda_event), _stream())
+              float(sigma2), int(chunks), _p(out), _p(ws), ws.numel(), ctypes.c_void_p(kuu.event.cuda_event), int(join_late),
+              _stream())
     return out
 
 

@@ -113,8 +113,10 @@ ASVGP_API int asvgp_elbo_grad_1d(const double* Kuu, const double* dKuu, const do
  * a caller about to launch a machine-filling kernel on `stream` lets `stream` wait for it, so that the chain's few CTAs are
  * dispatched first instead of queueing behind the streaming kernel's thousands.
  * `kuu_ready_event`: a cudaEvent_t recorded on the side stream after asvgp_kuu_chain_1d (NULL if `stream` is already ordered
- * after it); `stream` waits for it only where the Kuu state is first read — after the P chains — so that without an
- * accumulate in between (an optimiser iteration) the Kuu chain and the P chains still run side by side.
+ * after it).  join_late = 0: `stream` waits for it up front and the trace(Kuu^-1 G) partial sums ride in the P chains'
+ * pre-pass launch (the Kuu chain was launched long ago, e.g. before the accumulate).  join_late = 1: `stream` waits only where
+ * the Kuu state is first read — after the P chains — so that without an accumulate in between (an optimiser iteration) the
+ * Kuu chain and the P chains still run side by side.
  * `kuu_state`: asvgp_kuu_state_doubles(M, order) doubles on the device; the two calls need separate workspaces of
  * asvgp_workspace_bytes_1d bytes each when they may overlap.  asvgp_elbo_grad_1d is exactly these two calls on one stream. */
 ASVGP_API int64_t asvgp_kuu_state_doubles(int M, int order);
@@ -122,7 +124,7 @@ ASVGP_API int asvgp_kuu_chain_1d(const double* Kuu, const double* dKuu, int M, i
                                  void* work, int64_t work_bytes, void* gate_event, void* stream);
 ASVGP_API int asvgp_elbo_grad_1d_prepared(const double* kuu_state, const double* Kuu, const double* dKuu, const double* acc,
                                           int M, int order, double variance, double sigma2, int chunks, double* out,
-                                          void* work, int64_t work_bytes, void* kuu_ready_event, void* stream);
+                                          void* work, int64_t work_bytes, void* kuu_ready_event, int join_late, void* stream);
 
 /* ---- a10 (factorisation half): posterior weights -------------------------------------------------------------------------
  * Replaces the CHOLMOD factorisations and solves of GPR_1d.predict_f (gpr.py:96-108):
