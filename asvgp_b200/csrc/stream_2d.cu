@@ -30,6 +30,9 @@ namespace asvgp {
 struct LdgLoader2 {
     __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); }
 };
+struct PlainLoader2 {         // generic load: the knots may sit in shared memory
+    __device__ __forceinline__ double operator()(const double* p) const { return *p; }
+};
 
 __device__ __forceinline__ Mesh load_mesh2(const double* knots, int n_knots) {
     Mesh m;
@@ -45,11 +48,13 @@ struct Interval {            // cached knot interval of one dimension
     double u, lo, hi;
     __device__ __forceinline__ void reset() { idx = -1; u = 0.0; lo = INFINITY; hi = -INFINITY; }
     __device__ __forceinline__ bool inside(double x) const { return x > lo && x <= hi; }
-    __device__ __forceinline__ void set(const Mesh& mesh, int i) {
+    __device__ __forceinline__ void set(const Mesh& mesh, int i) { set(mesh, i, LdgLoader2()); }
+    template <class LoadFn>
+    __device__ __forceinline__ void set(const Mesh& mesh, int i, LoadFn load) {
         idx = i;
-        u = __ldg(mesh.knots + i);
+        u = load(mesh.knots + i);
         lo = (i == 0) ? -INFINITY : u;
-        hi = (i == mesh.n_knots - 2) ? INFINITY : __ldg(mesh.knots + i + 1);
+        hi = (i == mesh.n_knots - 2) ? INFINITY : load(mesh.knots + i + 1);
     }
 };
 
@@ -545,12 +550,18 @@ __device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const d
         const unsigned grp = __ballot_sync(0xffffffffu, cell == cl) & remaining;
         const int e_lo = __ffs(grp) - 1, e_hi = 31 - __clz(grp);
         double* dst = cellmom + (int64_t)cl * Mo::kAll;
-        // GB[q] = sum over the group of the dim-2 Gram factors (lanes 0..NB-1, one q each)
+        // GB[q] = sum over the group of the dim-2 Gram factors (lanes 0..NB-1, one q each).  The sums over the group's lanes
+        // below run on four independent accumulators: a single FMA chain over up to 32 lanes was a fifth of the sweep's time.
+        auto in_grp = [&](int e) { return e <= e_hi && ((grp >> e) & 1u); };
         if (lane < NB) {
-            double acc = 0.0;
-            for (int e = e_lo; e <= e_hi; ++e)
-                if ((grp >> e) & 1u) acc += Bf[e * NS + lane];
-            GB[lane] = acc;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int e = e_lo; e <= e_hi; e += 4) {
+                a0 += Bf[e * NS + lane];                                  // e_lo itself is in the group
+                if (in_grp(e + 1)) a1 += Bf[(e + 1) * NS + lane];
+                if (in_grp(e + 2)) a2 += Bf[(e + 2) * NS + lane];
+                if (in_grp(e + 3)) a3 += Bf[(e + 3) * NS + lane];
+            }
+            GB[lane] = (a0 + a1) + (a2 + a3);
         }
         __syncwarp();
         for (int o = lane; o < Mo::kGram; o += 32) {
@@ -564,10 +575,14 @@ __device__ __noinline__ void flush_cols_2d(const double* __restrict__ S, const d
         }
         for (int o = lane; o < Mo::kProj; o += 32) {
             const int pi = NB + o / NY, qi = NB + o % NY;
-            double acc = 0.0;
-            for (int e = e_lo; e <= e_hi; ++e)
-                if ((grp >> e) & 1u) acc = fma(S[e * NS + pi], Bf[e * NS + qi], acc);
-            atomicAdd(dst + Mo::kGram + o, acc);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            for (int e = e_lo; e <= e_hi; e += 4) {
+                if (in_grp(e)) a0 = fma(S[e * NS + pi], Bf[e * NS + qi], a0);
+                if (in_grp(e + 1)) a1 = fma(S[(e + 1) * NS + pi], Bf[(e + 1) * NS + qi], a1);
+                if (in_grp(e + 2)) a2 = fma(S[(e + 2) * NS + pi], Bf[(e + 2) * NS + qi], a2);
+                if (in_grp(e + 3)) a3 = fma(S[(e + 3) * NS + pi], Bf[(e + 3) * NS + qi], a3);
+            }
+            atomicAdd(dst + Mo::kGram + o, (a0 + a1) + (a2 + a3));
         }
         __syncwarp();
         remaining &= ~grp;
@@ -651,7 +666,17 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     __shared__ __align__(16) double s_gsum[kWarps][8][NB + 1];
     __shared__ int s_gcell[kWarps][8];
     __shared__ double s_su[kWarps][NB], s_gb[kWarps][NB];      // flush: warp-uniform Gram sums, per-group factor sums
+    // the dim-1 knots in shared memory: every 32-row block looks its rows' intervals up again (a lane's rows are 32 apart), and
+    // the three dependent knot loads of a lookup cost 7 % of the sweep when they go to L1/L2 (ncu, r02)
+    constexpr int kKnotsStaged = 512;
+    __shared__ double s_knots1[kKnotsStaged];
     const Mesh mesh1 = load_mesh2(knots1, nk1), mesh2 = load_mesh2(knots2, nk2);
+    Mesh mesh1s = mesh1;
+    if (nk1 <= kKnotsStaged) {
+        for (int i = threadIdx.x; i < nk1; i += blockDim.x) s_knots1[i] = __ldg(knots1 + i);
+        mesh1s.knots = s_knots1;
+    }
+    __syncthreads();
     const int nc2 = nk2 - 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t n2 = hint_n2 > 0 ? hint_n2 : probe->n2, n1 = n / n2;
@@ -791,7 +816,7 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
                 const double x1 = x1_next;
                 if (r + 32 < r_end) x1_next = __ldg(X + 2 * ((r + 32) * n2 + strip * 32));
                 if (r < r_end) {
-                    if (!it.inside(x1)) it.set(mesh1, locate_interval(mesh1, x1, LdgLoader2()));
+                    if (!it.inside(x1)) it.set(mesh1s, locate_interval(mesh1s, x1, PlainLoader2()), PlainLoader2());
                     double tp[2 * K + 1], up[2 * K + 1];
                     powers<2 * K>((x1 - it.u) * mesh1.inv_delta, tp, up);
 #pragma unroll

@@ -764,6 +764,18 @@ def main():
     a2.record()
     torch.cuda.synchronize()
     kuu_chain_alone_ms, elbo_call_alone_ms = a0.elapsed_time(a1) / reps, a1.elapsed_time(a2) / reps
+    # the accumulate kernel with nothing beside it (in the step the Kuu chain's cluster holds 8 SMs and reads its tables next to it)
+    scratch_acc = torch.zeros_like(acc)
+    b0, b1 = ev(), ev()
+    ops.accum_1d(x, y, basis, acc=scratch_acc, binned=binned)
+    torch.cuda.synchronize()
+    b0.record()
+    for _ in range(10):
+        ops.accum_1d(x, y, basis, acc=scratch_acc, binned=binned)
+    b1.record()
+    torch.cuda.synchronize()
+    accum_alone_ms = b0.elapsed_time(b1) / 10
+    del scratch_acc
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = total_ms.item() / args.steps
@@ -924,7 +936,10 @@ def main():
                      "bound": "hbm", "achieved": achieved,
                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                      "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else "fallback",
-                     "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM * n, "launch_ms": accum_ms, "traffic": traffic},
+                     "algorithmic_bytes_per_launch": BYTES_PER_POINT_ACCUM * n, "launch_ms": accum_ms, "traffic": traffic,
+                     "launch_ms_alone": accum_alone_ms, "frac_alone": BYTES_PER_POINT_ACCUM * n / (accum_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                     "note": "launch_ms / frac: inside the timed steps, where the Kuu chain runs beside the kernel on a side stream (a "
+                             "cluster of 8 CTAs holds 8 SMs); *_alone: the same launch with nothing beside it"},
         "clocks": clocks.summary(),
         # counted by the library itself (asvgp_launch_count) over the timed region
         "gpu_launches": launches,
