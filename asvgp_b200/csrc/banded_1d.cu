@@ -747,8 +747,12 @@ static int launch_chain_group(const ChunkLayout& lay, int first_chain, int n_cha
     if (gate != nullptr) ASVGP_CUDA_OK(cudaEventRecord(gate, st));          // "the chain kernel is next in line"
     const int n_cta = (lay.P + kChainThreads - 1) / kChainThreads;          // > 1: clustered layout (pick_layout_elbo)
     const bool pdl = gate == nullptr;        // an event record between the two launches rules the early launch out
+    // A gated chain runs BESIDE a streaming kernel whose CTAs all carry the same share of the work: one of them landing on a
+    // chain SM (shared issue slots, the L1 invalidation of every cluster barrier) becomes the straggler the whole kernel waits
+    // for (+12 % on the accumulate, measured).  Asking for all of the SM's shared memory keeps the chain's SMs to itself.
+    const size_t smem_floor = gate != nullptr ? (size_t)(227 * 1024 - 2048) : 0;
     if (n_cta > 1) {
-        const size_t smem = ChainSmall<T, K>::bytes(kChainThreads + 1);
+        const size_t smem = std::max(ChainSmall<T, K>::bytes(kChainThreads + 1), smem_floor);
         if (n_cta == 2) {
             ASVGP_CUDA_OK(allow_smem(elbo_chains_cluster_kernel<K, 2>, smem));
             ASVGP_CUDA_OK(launch_dependent(elbo_chains_cluster_kernel<K, 2>, n_chains * 2, kChainThreads, smem, st, pdl, a, scratch));
@@ -760,7 +764,7 @@ static int launch_chain_group(const ChunkLayout& lay, int first_chain, int n_cha
             ASVGP_CUDA_OK(launch_dependent(elbo_chains_cluster_kernel<K, 4>, n_chains * 4, kChainThreads, smem, st, pdl, a, scratch));
         }
     } else {
-        const size_t smem = ChainSmall<T, K>::bytes(lay.P);
+        const size_t smem = std::max(ChainSmall<T, K>::bytes(lay.P), smem_floor);
         ASVGP_CUDA_OK(allow_smem(elbo_chains_kernel<K>, smem));
         ASVGP_CUDA_OK(launch_dependent(elbo_chains_kernel<K>, n_chains, kChainThreads, smem, st, pdl, a));
     }
@@ -878,10 +882,12 @@ static ChunkLayout pick_layout(int M, int K, int chunks) {
 
 // Layout of the ELBO + gradient chains: with the library default (chunks = 0) and enough columns, 128 * n_cta chunks on a
 // cluster of n_cta CTAs per chain (run_chain_cluster); n_cta = 8 (4, 2 when M is too small), ASVGP_CHAIN_CTAS overrides (1 = single CTA).
+// chunks = 256 / 512 / 1024 asks for a cluster of 2 / 4 / 8 CTAs explicitly (the Kuu chain that runs beside the accumulate takes 4).
 static ChunkLayout pick_layout_elbo(int M, int K, int chunks) {
-    const ChunkLayout one = pick_layout(M, K, chunks);
-    if (chunks != 0 || one.P < kChainThreads) return one;
-    int n_cta = 8;
+    const bool explicit_cluster = chunks == 2 * kChainThreads || chunks == 4 * kChainThreads || chunks == 8 * kChainThreads;
+    const ChunkLayout one = pick_layout(M, K, explicit_cluster ? 0 : chunks);
+    if ((chunks != 0 && !explicit_cluster) || one.P < kChainThreads) return one;
+    int n_cta = explicit_cluster ? chunks / kChainThreads : 8;
     if (const char* e = getenv("ASVGP_CHAIN_CTAS")) n_cta = atoi(e);
     if (n_cta != 2 && n_cta != 4 && n_cta != 8) return one;
     int P = M / (2 * (K + 1) + 1);                                 // chunk interiors of at least K + 1 columns with room to spare
@@ -923,11 +929,11 @@ extern "C" int asvgp_kuu_assemble(const double* tables, int n_terms, const doubl
 
 extern "C" int64_t asvgp_workspace_bytes_1d(int M, int order, int chunks) {
     if (M <= 0 || order < 1 || order > kMaxOrder) return -1;
-    const ChunkLayout lay = pick_layout(M, order, chunks);
+    const ChunkLayout lay = pick_layout(M, order, chunks > kChainThreads ? 0 : chunks);
     // the ELBO chains may run on a clustered layout (pick_layout_elbo; ASVGP_CHAIN_CTAS): size for every candidate
     ChunkLayout cand[4] = {lay, lay, lay, lay};
     int n_cand = 1;
-    if (chunks == 0 && lay.P >= kChainThreads) {
+    if ((chunks == 0 || chunks == 2 * kChainThreads || chunks == 4 * kChainThreads || chunks == 8 * kChainThreads) && lay.P >= kChainThreads) {
         const int P = M / (2 * (order + 1) + 1);
         if (P >= 2 * kChainThreads) cand[n_cand++] = make_layout(M, order, 2 * kChainThreads);
         if (P >= 4 * kChainThreads) cand[n_cand++] = make_layout(M, order, 4 * kChainThreads);

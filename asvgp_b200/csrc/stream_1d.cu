@@ -36,6 +36,19 @@ __device__ __forceinline__ Mesh load_mesh(const double* knots, int n_knots) {
 
 __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
+// Streaming loads of the points: read once, so they are marked evict-first in L2 — they must not push out what is reused (the
+// band being accumulated into, and the tables of the Kuu chain that runs beside the accumulate on a side stream).
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_stream2(const double* p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
 struct LdgLoader {
     __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); }
 };
@@ -248,6 +261,7 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
     wa.lo = INFINITY;
     wa.hi = -INFINITY;
     double yy = 0.0;
+    const uint64_t stream_policy = evict_first_policy();
 
     // within the CTA's range warp w takes the w-th contiguous share, so that (for ordered input) each warp meets as
     // few interval crossings as possible
@@ -265,8 +279,8 @@ accum_1d_kernel(const double* __restrict__ x, const double* __restrict__ y, int6
             const int64_t p = slot * VEC;
             if (VEC == 2) {
                 if (p + 1 < n) {
-                    const double2 xv = __ldg(reinterpret_cast<const double2*>(x + p));
-                    const double2 yv = __ldg(reinterpret_cast<const double2*>(y + p));
+                    const double2 xv = ldg_stream2(x + p, stream_policy);
+                    const double2 yv = ldg_stream2(y + p, stream_policy);
                     xs[j][0] = xv.x; xs[j][VEC - 1] = xv.y;
                     ys[j][0] = yv.x; ys[j][VEC - 1] = yv.y;
                 } else {
@@ -680,13 +694,14 @@ static int sm_count() {
 
 // CTA slots the streaming accumulate leaves free.  Its ranges are dealt statically (contiguous per CTA, so that ordered input
 // meets few interval crossings), which makes it slow by a whole second wave as soon as ANY other kernel holds a few SMs; the
-// bound's Kuu chain runs beside it on a cluster of 8 CTAs (banded_1d.cu, asvgp_kuu_chain_1d).  HBM stays saturated from 140 SMs.
+// bound's Kuu chain runs beside it on a cluster of 8 CTAs (banded_1d.cu, asvgp_kuu_chain_1d), each of which shares its SM with
+// one CTA of this kernel: 4 SMs' worth of slots.  (What the chain really cost the accumulate was L2: see ldg_stream2.)
 static int accum_sm_budget() {
     static int spare = -1;
     if (spare < 0) {
         const char* e = getenv("ASVGP_ACCUM_SPARE_SMS");
-        spare = e ? atoi(e) : 8;
-        if (spare < 0 || spare > sm_count() / 2) spare = 8;
+        spare = e ? atoi(e) : 4;
+        if (spare < 0 || spare > sm_count() / 2) spare = 4;
     }
     return sm_count() - spare;
 }

@@ -178,6 +178,9 @@ class KuuChain:
         self.state, self.event, self.operands = state, event, operands
 
 
+# The Kuu chain that runs BESIDE a streaming kernel (gate=True) takes a cluster of 4 CTAs (512 chunks) instead of 8: it is hidden
+# anyway, and the accumulate — which leaves exactly 4 SMs' worth of CTA slots free — runs at the rate of the SMs it keeps.
+KUU_CHUNKS_BESIDE_STREAMING = 0
 _KUU_STATES = {}
 _KUU_STREAM = {}
 _KUU_LAST = {}
@@ -190,6 +193,8 @@ def kuu_chain_1d(Kuu, dKuu, basis, chunks=0, gate=False, timing=False):
     gate=True: the current stream waits until the chain kernel is next in line on the side stream (its pre-pass is done), so
     that a machine-filling kernel launched next does not take every SM before the chain's few CTAs are dispatched."""
     k, m = basis.order, basis.m
+    if gate and chunks == 0:
+        chunks = KUU_CHUNKS_BESIDE_STREAMING
     dev = device()
     side = _KUU_STREAM.get(dev)
     if side is None:

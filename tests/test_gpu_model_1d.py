@@ -154,7 +154,7 @@ def test_snelson_notebook_known_answer(cuda, golden):
     assert elbo < float(g["notebook_exact_gp"])
 
 
-@pytest.mark.parametrize("m,chunks", [(100, 0), (3000, 0), (10000, 0), (10000, 16)])
+@pytest.mark.parametrize("m,chunks", [(100, 0), (3000, 0), (10000, 0), (10000, 16), (10000, 512), (10000, 256), (700, 512)])
 def test_split_bound_equals_single_call(cuda, m, chunks):
     """asvgp_kuu_chain_1d (side stream) + asvgp_elbo_grad_1d_prepared give the bits of the one-call asvgp_elbo_grad_1d, also
     when the Kuu chain is launched before the accumulate it overlaps with (single CTA, 2/4/8-CTA cluster layouts)."""
@@ -176,15 +176,18 @@ def test_split_bound_equals_single_call(cuda, m, chunks):
     one = ops.elbo_grad_1d_single_stream(Kuu, dKuu, acc, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()
     forked = ops.elbo_grad_1d(Kuu, dKuu, acc, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()
     # the order the bench uses: Kuu chain first, accumulate next to it, then the P chains
-    kuu = ops.kuu_chain_1d(Kuu, dKuu, basis, chunks=chunks)
+    kuu = ops.kuu_chain_1d(Kuu, dKuu, basis, chunks=chunks, gate=True)
     acc2 = ops.accum_1d(xd, yd, basis)
     early = ops.elbo_grad_1d(Kuu, dKuu, acc2, basis, 1.2, 0.3, chunks=chunks, kuu=kuu).cpu().numpy()
     one2 = ops.elbo_grad_1d_single_stream(Kuu, dKuu, acc2, basis, 1.2, 0.3, chunks=chunks).cpu().numpy()   # acc2 != acc bitwise (fp64 REDs)
     torch.cuda.synchronize()
     assert one[8] == 0
-    for got, want in ((forked, one), (early, one2)):
-        np.testing.assert_array_equal(got[:9], want[:9])
-        assert got[15] == want[15]
+    np.testing.assert_array_equal(forked[:9], one[:9])
+    assert forked[15] == one[15]
+    # beside a streaming kernel the Kuu chain takes a smaller cluster (another chunking of the same sweeps: last-bit differences)
+    np.testing.assert_allclose(early[:8], one2[:8], rtol=1e-11)
+    np.testing.assert_allclose(early[15], one2[15], rtol=1e-9)
+    assert early[8] == 0
     # and the trace term itself against the dense algebra
     G, b, scal = [t.cpu().numpy() for t in ops.split_accum_1d(acc, basis)]
     if m <= 3000:
