@@ -62,6 +62,28 @@ struct Mesh {
     double inv_delta;      // 1 / (knots[1] - knots[0])
 };
 
+#if defined(__CUDACC__)
+// Streaming loads of the points: read once, so they are marked evict-first in L2 — they must not push out what is reused (the
+// band or moment table being accumulated into, predictor tables, the tables of a Kuu chain running beside the kernel).
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ double2 ldg_stream2(const double* p, uint64_t pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+
+__device__ __forceinline__ void cp_async_16_stream(unsigned dst_smem, const void* src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cp_async_8_stream(unsigned dst_smem, const void* src, uint64_t pol) {
+    asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "l"(pol) : "memory");
+}
+#endif
+
 template <class LoadFn>
 ASVGP_HD int locate_interval(const Mesh& mesh, double x, LoadFn load) {
     // Reference semantics (basis.py:58): idx = max(searchsorted_left(mesh, x) - 1, 0), i.e. the largest idx with

@@ -36,19 +36,6 @@ __device__ __forceinline__ Mesh load_mesh(const double* knots, int n_knots) {
 
 __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
-// Streaming loads of the points: read once, so they are marked evict-first in L2 — they must not push out what is reused (the
-// band being accumulated into, and the tables of the Kuu chain that runs beside the accumulate on a side stream).
-__device__ __forceinline__ uint64_t evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ double2 ldg_stream2(const double* p, uint64_t pol) {
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-
 struct LdgLoader {
     __device__ __forceinline__ double operator()(const double* p) const { return __ldg(p); }
 };
@@ -638,12 +625,13 @@ __global__ void __launch_bounds__(256, MINB) predict_1d_kernel(const double* __r
         // PREFETCH: the next tile's points are requested before the current tile is evaluated; the shipped instantiation
         // relies on four resident CTAs per SM instead (fewer registers; see the launch-shape note at asvgp_predict_1d)
         double2 xv[U];
+        const uint64_t stream_policy = evict_first_policy();      // the test points are read once: keep alpha and the band in L2
         const int64_t step = (int64_t)blockDim.x * U;
         int64_t base = c_begin + threadIdx.x;
 #pragma unroll
         for (int j = 0; j < U; ++j) {
             const int64_t i = base + j * (int64_t)blockDim.x;
-            xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+            xv[j] = (i < c_end) ? ldg_stream2(xs + 2 * i, stream_policy) : make_double2(0.0, 0.0);
         }
         for (; base < c_end; base += step) {
             double2 xn[PREFETCH ? U : 1];
@@ -651,7 +639,7 @@ __global__ void __launch_bounds__(256, MINB) predict_1d_kernel(const double* __r
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     const int64_t i = base + step + j * (int64_t)blockDim.x;
-                    xn[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                    xn[j] = (i < c_end) ? ldg_stream2(xs + 2 * i, stream_policy) : make_double2(0.0, 0.0);
                 }
             }
 #pragma unroll
@@ -671,7 +659,7 @@ __global__ void __launch_bounds__(256, MINB) predict_1d_kernel(const double* __r
 #pragma unroll
                 for (int j = 0; j < U; ++j) {
                     const int64_t i = base + step + j * (int64_t)blockDim.x;
-                    xv[j] = (i < c_end) ? __ldg(x2 + i) : make_double2(0.0, 0.0);
+                    xv[j] = (i < c_end) ? ldg_stream2(xs + 2 * i, stream_policy) : make_double2(0.0, 0.0);
                 }
             }
         }

@@ -689,6 +689,7 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
     int* Gcell = s_gcell[warp];
 
     // tasks: 32-column strips x row segments, dealt round-robin to the warps of the grid
+    const uint64_t stream_policy = evict_first_policy();      // the points are read once: the 20 MB moment table stays in L2
     const int64_t n_strips = (n2 + 31) / 32;
     const int64_t total_warps = (int64_t)gridDim.x * kWarps;
     int64_t n_seg = (tasks_per_warp * total_warps + n_strips - 1) / n_strips;
@@ -791,8 +792,8 @@ accum_2d_cols_kernel(const double* __restrict__ X, const double* __restrict__ y,
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 if (to_request > 0) {
-                    cp_async_16(ringX + wslot * 32 + lane, xq);
-                    cp_async_8(ringY + wslot * 32 + lane, yq);
+                    cp_async_16_stream(smem_u32(ringX + wslot * 32 + lane), xq, stream_policy);
+                    cp_async_8_stream(smem_u32(ringY + wslot * 32 + lane), yq, stream_policy);
                     xq += n2;
                     yq += n2;
                     --to_request;
@@ -1344,6 +1345,7 @@ __global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* _
             vv = v;
         };
 
+        const uint64_t stream_policy = evict_first_policy();
         const double2* xp = X2 + r_begin * n2 + col;
         double* mp = mean + r_begin * n2 + col;
         double* vp = var + r_begin * n2 + col;
@@ -1351,7 +1353,7 @@ __global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* _
         double2 px[8];
         if (rows8 > 0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) px[u] = __ldg(xp + u * n2);
+            for (int u = 0; u < 8; ++u) px[u] = ldg_stream2(reinterpret_cast<const double*>(xp + u * n2), stream_policy);
         }
         for (int64_t r = 0; r < rows8; r += 8) {
             double2 cx[8];
@@ -1360,14 +1362,14 @@ __global__ void __launch_bounds__(256, 2) predict_2d_cols_kernel(const double* _
             xp += 8 * n2;
             if (r + 8 < rows8) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) px[u] = __ldg(xp + u * n2);
+                for (int u = 0; u < 8; ++u) px[u] = ldg_stream2(reinterpret_cast<const double*>(xp + u * n2), stream_policy);
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 double mu, vv;
                 eval(cx[u], mu, vv);
-                mp[u * n2] = mu;
-                vp[u * n2] = vv;
+                __stcs(mp + u * n2, mu);           // written once: streaming stores keep the per-cell tables in L2
+                __stcs(vp + u * n2, vv);
             }
             mp += 8 * n2;
             vp += 8 * n2;
