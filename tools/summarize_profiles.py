@@ -33,7 +33,11 @@ def launch_table(path, title):
 
 
 def rep_row(path):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # a capture too large to bring back from the GPU box is exported there: `ncu -i X.ncu-rep --page raw --csv > X.raw.csv`
+    if path.endswith(".raw.csv"):
+        txt = open(path).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units, vals = rows[0], rows[1], rows[-1]
     cells = []
@@ -43,7 +47,7 @@ def rep_row(path):
             cells.append("%s %s" % (vals[i], units[i]))
         else:
             cells.append("n/a")
-    return "| `%s` | %s |" % (os.path.basename(path)[5:-8], " | ".join(cells))
+    return "| `%s` | %s |" % (os.path.basename(path)[5:].replace(".ncu-rep", "").replace(".raw.csv", ""), " | ".join(cells))
 
 
 parts = ["# %s %s — ncu evidence (B200, `--clock-control none`)\n" % (rnd, tag),
@@ -58,7 +62,8 @@ for f, title in ((PFX + "launches_1d.csv", "1-D bench (`bench.py --steps 2 --war
     p = os.path.join(OUT, f)
     if os.path.exists(p):
         parts.append(launch_table(p, title))
-reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + (glob.glob("/tmp/reps/prof_*.ncu-rep") if rnd == "r01" else []))
+reps = sorted(glob.glob(os.path.join(OUT, "prof_*.ncu-rep")) + glob.glob(os.path.join(OUT, "prof_*.raw.csv"))
+              + (glob.glob("/tmp/reps/prof_*.ncu-rep") if rnd == "r01" else []))
 if reps:
     parts.append("## `--set full` captures (one launch each)\n")
     parts.append("| kernel | " + " | ".join(m.split(".")[0] for m in METRICS) + " |")
