@@ -1000,39 +1000,48 @@ __global__ void __launch_bounds__(256) expand_moments_2d_kernel(const double* __
     __shared__ double s_mom[Mo::kAll];
     __shared__ double s_C[K1 * K1 * NB];
     __shared__ double s_D[K1 * NY];
-    const int cell = blockIdx.x;
-    const int c1 = cell / nc2, c2 = cell % nc2;
-    for (int i = threadIdx.x; i < Mo::kAll; i += blockDim.x) s_mom[i] = cellmom[(int64_t)cell * Mo::kAll + i];
+    __shared__ double s_inner[K1 * K1 * NB];
     for (int i = threadIdx.x; i < K1 * K1 * NB; i += blockDim.x) s_C[i] = Cprod[i];
     for (int i = threadIdx.x; i < K1 * NY; i += blockDim.x) s_D[i] = Dy[i];
-    __syncthreads();
-    for (int o = threadIdx.x; o < K1 * K1 * K1 * K1; o += blockDim.x) {
-        const int s2 = o % K1, r2 = (o / K1) % K1, s1 = (o / (K1 * K1)) % K1, r1 = o / (K1 * K1 * K1);
-        const int d1 = r1 - s1, d2 = r2 - s2;
-        if (d1 < 0 || (d1 == 0 && d2 < 0)) continue;
-        double v = 0.0;
-#pragma unroll
-        for (int p = 0; p < NB; ++p) {
+    // persistent CTAs over the cells: one CTA per cell (38 809 launches of a few hundred instructions at 200 x 200) was bound
+    // by CTA turnover, not by its arithmetic or its REDs
+    for (int cell = blockIdx.x; cell < nc1 * nc2; cell += gridDim.x) {
+        const int c1 = cell / nc2, c2 = cell % nc2;
+        __syncthreads();                           // the previous cell's readers are done with s_mom / s_inner
+        for (int i = threadIdx.x; i < Mo::kAll; i += blockDim.x) s_mom[i] = cellmom[(int64_t)cell * Mo::kAll + i];
+        __syncthreads();
+        // stage 1: inner[(r2, s2)][p] = sum_q C[r2][s2][q] mom[p][q] — shared by every (r1, s1)
+        for (int o = threadIdx.x; o < K1 * K1 * NB; o += blockDim.x) {
+            const int p = o % NB, rs2 = o / NB;
             double inner = 0.0;
 #pragma unroll
-            for (int q = 0; q < NB; ++q) inner = fma(s_C[(r2 * K1 + s2) * NB + q], s_mom[p * NB + q], inner);
-            v = fma(s_C[(r1 * K1 + s1) * NB + p], inner, v);
+            for (int q = 0; q < NB; ++q) inner = fma(s_C[rs2 * NB + q], s_mom[p * NB + q], inner);
+            s_inner[o] = inner;
         }
-        const int e = d1 * (2 * K + 1) + (d2 + K);
-        const int64_t j = (int64_t)(c1 + s1) * m2 + (c2 + s2);
-        atomicAdd(Gs + (int64_t)e * M + j, v);
-    }
-    for (int o = threadIdx.x; o < K1 * K1; o += blockDim.x) {
-        const int r2 = o % K1, r1 = o / K1;
-        double v = 0.0;
+        __syncthreads();
+        for (int o = threadIdx.x; o < K1 * K1 * K1 * K1; o += blockDim.x) {
+            const int s2 = o % K1, r2 = (o / K1) % K1, s1 = (o / (K1 * K1)) % K1, r1 = o / (K1 * K1 * K1);
+            const int d1 = r1 - s1, d2 = r2 - s2;
+            if (d1 < 0 || (d1 == 0 && d2 < 0)) continue;
+            double v = 0.0;
 #pragma unroll
-        for (int p = 0; p < NY; ++p) {
-            double inner = 0.0;
-#pragma unroll
-            for (int q = 0; q < NY; ++q) inner = fma(s_D[r2 * NY + q], s_mom[Mo::kGram + p * NY + q], inner);
-            v = fma(s_D[r1 * NY + p], inner, v);
+            for (int p = 0; p < NB; ++p) v = fma(s_C[(r1 * K1 + s1) * NB + p], s_inner[(r2 * K1 + s2) * NB + p], v);
+            const int e = d1 * (2 * K + 1) + (d2 + K);
+            const int64_t j = (int64_t)(c1 + s1) * m2 + (c2 + s2);
+            atomicAdd(Gs + (int64_t)e * M + j, v);
         }
-        atomicAdd(b + (int64_t)(c1 + r1) * m2 + (c2 + r2), v);
+        for (int o = threadIdx.x; o < K1 * K1; o += blockDim.x) {
+            const int r2 = o % K1, r1 = o / K1;
+            double v = 0.0;
+#pragma unroll
+            for (int p = 0; p < NY; ++p) {
+                double inner = 0.0;
+#pragma unroll
+                for (int q = 0; q < NY; ++q) inner = fma(s_D[r2 * NY + q], s_mom[Mo::kGram + p * NY + q], inner);
+                v = fma(s_D[r1 * NY + p], inner, v);
+            }
+            atomicAdd(b + (int64_t)(c1 + r1) * m2 + (c2 + r2), v);
+        }
     }
 }
 
@@ -1886,7 +1895,8 @@ extern "C" int asvgp_expand_moments_2d(const double* cellmom, const double* Cpro
     const int m2 = n_knots2 + order - 1;
     const int64_t M = (int64_t)(n_knots1 + order - 1) * m2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    ASVGP_DISPATCH_ORDER(order, (expand_moments_2d_kernel<K><<<nc1 * nc2, 256, 0, st>>>(cellmom, Cprod, Dy, nc1, nc2, m2, M, Gs, b))); ASVGP_LAUNCHED();
+    const int blocks = std::min(nc1 * nc2, sm_count2() * 8);
+    ASVGP_DISPATCH_ORDER(order, (expand_moments_2d_kernel<K><<<blocks, 256, 0, st>>>(cellmom, Cprod, Dy, nc1, nc2, m2, M, Gs, b))); ASVGP_LAUNCHED();
     ASVGP_CUDA_OK(cudaGetLastError());
     return kOk;
 }
