@@ -841,6 +841,11 @@ def main():
         e2e = {"value": world * n / dt.item(), "unit": "datapoints/s", "h2d_bytes_per_step": 16 * n,
                "d2h_bytes_per_step": 16 * 8, "ms_per_step": dt.item() * 1e3, "steps": k_e2e,
                "host_buffers": "pinned", "pcie_gb_per_s_per_rank": 16 * n / dt.item() / 1e9,
+               # all ranks read pinned host memory at once: the aggregate is what the box's host DRAM / PCIe root complexes give
+               "aggregate_h2d_gb_per_s": world * 16 * n / dt.item() / 1e9,
+               "host": {"cpus_visible": len(os.sched_getaffinity(0)),
+                        "numa_nodes": len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+                        if os.path.isdir("/sys/devices/system/node") else None},
                "api": "GPR_1d((X_host, y_host), kernel, basis).training_loss_and_gradients()"}
         if world == 1:
             # the same call with ordinary (pageable) numpy arrays: staged through the library's pinned buffers

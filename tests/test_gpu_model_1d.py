@@ -197,3 +197,28 @@ def test_split_bound_equals_single_call(cuda, m, chunks):
         dense = lambda band: sum(np.diag(band[d, : m - d], -d) + (np.diag(band[d, : m - d], d) if d else 0) for d in range(4))
         tr = np.trace(solveh_banded(Kb, dense(G), lower=True))
         assert abs(one[7] - tr) <= 1e-9 * abs(tr)
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("m", [300, 3000, 30000])
+def test_bound_layouts_agree(cuda, k, m):
+    """The default layout of the chains (single CTA, or 2/4/8-CTA clusters where 128 separator nodes per CTA fit in shared
+    memory) against a 7-chunk single-CTA evaluation of the same bound, for every spline order."""
+    from asvgp_b200 import basis as B, kernels as Kn, ops
+    from asvgp_b200.inducing_features import SplineFeatures1D
+
+    rng = np.random.default_rng(11 * k + m)
+    n = 200000
+    x = np.sort(rng.uniform(0.0, m, n))
+    y = np.cos(x / 9.0) + 0.2 * rng.standard_normal(n)
+    basis = getattr(B, "B%dSpline" % k)(-1, m + 1, m)
+    kind = {1: "Matern12", 2: "Matern32"}.get(k, "Matern52")
+    kern = getattr(Kn, kind)(variance=0.9, lengthscales=2.2)
+    feats = SplineFeatures1D(kern, basis)
+    Kuu, dKuu = feats.make_Kuu_device(kern, want_grad=True)
+    acc = ops.accum_1d(ops.to_device(x), ops.to_device(y), basis)
+    a = ops.elbo_grad_1d(Kuu, dKuu, acc, basis, 0.9, 0.4).cpu().numpy()
+    b = ops.elbo_grad_1d(Kuu, dKuu, acc, basis, 0.9, 0.4, chunks=7).cpu().numpy()
+    assert a[8] == 0 and b[8] == 0
+    np.testing.assert_allclose(a[:8], b[:8], rtol=1e-9)
+    np.testing.assert_allclose(a[15], b[15], rtol=1e-7, atol=1e-7 * abs(a[7]))

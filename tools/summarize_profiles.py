@@ -70,9 +70,31 @@ if reps:
     parts.append("|" + "---|" * (len(METRICS) + 1))
     for r in reps:
         parts.append(rep_row(r))
-sass = subprocess.run("cuobjdump -sass %s | grep -oE 'UBLKCP[.A-Z0-9]*|LDGSTS[.A-Z0-9]*|SYNCS[.A-Z0-9]*|DMMA[.A-Z0-9]*|LDG\\.E\\.ENL2\\.256[.A-Z]*|REDG\\.E\\.ADD\\.F64[.A-Z]*|ATOMS\\.ADD|LD\\.E\\.[0-9]*\\.STRONG\\.SYS|ST\\.E\\.STRONG\\.SYS' | sort | uniq -c"
-                      % os.path.join(ROOT, "asvgp_b200", "lib", "libasvgp_sm100a.so"), shell=True, capture_output=True, text=True).stdout
+LIBSO = os.path.join(ROOT, "asvgp_b200", "lib", "libasvgp_sm100a.so")
+PAT = r"UBLKCP[.A-Z0-9]*|UTMALDG[.A-Z0-9]*|LDGSTS[.A-Z0-9]*|SYNCS[.A-Z0-9]*|DMMA[.A-Z0-9]*|LDG\.E\.ENL2\.256[.A-Z]*|REDG\.E\.ADD\.F64[.A-Z]*|ATOMS\.ADD|LD\.E\.[0-9]*\.STRONG\.SYS|ST\.E\.STRONG\.SYS|UCGABAR_[A-Z]*|ACQBULK|MAPA[.A-Z0-9]*"
+sass = subprocess.run("cuobjdump -sass %s | grep -oE '%s' | sort | uniq -c" % (LIBSO, PAT), shell=True, capture_output=True, text=True).stdout
 parts.append("\n## SASS evidence (`cuobjdump -sass asvgp_b200/lib/libasvgp_sm100a.so`)\n\n```\n%s```\n" % sass)
+# the same mnemonics per kernel (only kernels that have any): tensor-core fp64 (DMMA), TMA bulk copies (UBLKCP) and their mbarriers
+# (SYNCS), cp.async (LDGSTS), cluster barriers (UCGABAR_*), fp64 REDs
+import re
+dump = subprocess.run("cuobjdump -sass %s | c++filt" % LIBSO, shell=True, capture_output=True, text=True).stdout
+per, cur = collections.OrderedDict(), None
+for line in dump.splitlines():
+    m = re.match(r"\s*Function : (.*)", line)
+    if m:
+        cur = m.group(1).split("(")[0].replace("void ", "").replace("asvgp::", "")
+        continue
+    if cur is None:
+        continue
+    for tok in re.findall(PAT, line):
+        key = tok.split(".")[0] if not tok.startswith("REDG") else "REDG.F64"
+        per.setdefault(cur, collections.Counter())[key] += 1
+keys = ["DMMA", "UBLKCP", "SYNCS", "LDGSTS", "UCGABAR_ARV", "UCGABAR_WAIT", "REDG.F64", "ATOMS"]
+rows = ["| kernel | " + " | ".join(keys) + " |", "|---|" + "---|" * len(keys)]
+for name, c in per.items():
+    if any(c.get(k, 0) for k in keys[:6]):
+        rows.append("| `%s` | %s |" % (name[:90], " | ".join(str(c.get(k, 0)) for k in keys)))
+parts.append("Per kernel (kernels with tensor-core, TMA, cp.async or cluster-barrier instructions):\n\n" + "\n".join(rows) + "\n")
 dst = os.path.join(ROOT, "profiles", "%s_ncu_summary_%s.md" % (rnd, tag))
 open(dst, "w").write("\n".join(parts))
 print(dst)
