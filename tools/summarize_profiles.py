@@ -54,7 +54,11 @@ parts = ["# %s %s — ncu evidence (B200, `--clock-control none`)\n" % (rnd, tag
          "Commands: `tools/profile_%s.sh a|b|c`" % rnd + " (launch lists: `ncu --metrics gpu__time_duration.sum`; kernels: `ncu --set full`, one "
          "launch each, after a plain run of the same command that exited 0); this file: `tools/summarize_profiles.py %s`.\n"
          "Per-launch times are cold-cache and serialised (compare shares, not absolutes). The bench line of the same build: "
-         "`profiles/%s_bench_*.json`.\n" % (tag, rnd)]
+         "`profiles/%s_bench_*.json`.\n" % (tag, rnd),
+         "ncu serialises the launches: in a real 1-D step the Kuu chain (the 8-CTA launch of each `elbo_chains_cluster_kernel` pair, "
+         "94 us here) runs on a side stream BESIDE `accum_1d_kernel`, so the step's critical path is accumulate + `chain_rows_kernel<.., 2>` "
+         "+ the 16-CTA P-chain launch (51 us here) + `elbo_finalize_kernel`: accumulate share 267 / (267 + 10 + 51 + 8) = 79 % of that "
+         "path against 0.262 / 0.339 = 77 % of the step in the bench's CUDA-event phases.\n"]
 for f, title in ((PFX + "launches_1d.csv", "1-D bench (`bench.py --steps 2 --warmup 3 --no-2d`), first 400 launches"),
                  (PFX + "launches_2d.csv", "2-D bench (`bench.py --workload 2d --steps 1 --warmup 3`), first 600 / 900 launches"),
                  (PFX + "launches_binned_1d.csv", "1-D accumulate, 1e8 points in random order (`tools/binned_1d_only.py`)"),
