@@ -23,6 +23,7 @@ SIGNATURES = {
     "asvgp_predict_1d": [_vp, _c_i64, _vp, _c_int, _c_int, _vp, _vp, _c_dbl, _vp, _vp, _vp],
     "asvgp_kuu_assemble": [_vp, _c_int, _vp, _vp, _c_int, _c_int, _vp, _vp, _vp],
     "asvgp_elbo_grad_1d": [_vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp],
+    "asvgp_debug_poison_smem": [_vp],
     "asvgp_kuu_chain_1d": [_vp, _vp, _c_int, _c_int, _c_int, _vp, _vp, _c_i64, _vp, _vp],
     "asvgp_elbo_grad_1d_prepared": [_vp, _vp, _vp, _vp, _c_int, _c_int, _c_dbl, _c_dbl, _c_int, _vp, _vp, _c_i64, _vp, _c_int, _vp],
     "asvgp_posterior_1d": [_vp, _vp, _c_int, _c_int, _c_dbl, _c_int, _vp, _vp, _vp, _vp, _c_i64, _vp],
@@ -110,8 +111,13 @@ def load():
     return lib
 
 
+_POISON_EVERY_CALL = os.environ.get("ASVGP_POISON_SMEM") is not None      # test aid: NaN-fill shared memory before EVERY native call
+
+
 def call(name, *args):
     lib = load()
+    if _POISON_EVERY_CALL and name != "asvgp_debug_poison_smem":
+        lib.asvgp_debug_poison_smem(args[-1] if isinstance(args[-1], ctypes.c_void_p) else None)    # the call's own stream (always last)
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise AsvgpNativeError("%s failed (%d): %s" % (name, rc, lib.asvgp_last_error().decode()))

@@ -1626,8 +1626,12 @@ accum_2d_units_kernel(PartWork w, int64_t n, const double* __restrict__ knots1, 
                     const int left = end - begin - base;              // points of this batch that exist (may be <= 0)
 #pragma unroll
                     for (int i = 0; i < GL; ++i) {
-                        const int pt = begin + base + (i < left ? i : 0);      // past the run: any valid slot, its column of A is zero
-                        const double t2 = s_t2[pt < kUnitPoints2 ? pt : 0], yv = s_y[pt < kUnitPoints2 ? pt : 0];
+                        // past the run: slot 0, whose column of A is zero.  It must be a slot that HOLDS A FINITE NUMBER (slot 0 does:
+                        // zeroed at kernel start, a real point afterwards) — a slot past the unit's count holds whatever the
+                        // previous kernel left in shared memory, and 0 * NaN poisoned the cell (r02: seen once the suite's other
+                        // kernels started leaving NaN bit patterns there)
+                        const int pt = i < left ? begin + base + i : 0;
+                        const double t2 = s_t2[pt], yv = s_y[pt];
                         double tp[2 * K + 1], up[2 * K + 1];
                         powers<2 * K>(t2, tp, up);
                         const double ayv = ay[i] * yv;

@@ -44,6 +44,9 @@ ASVGP_API int asvgp_abi_version(void);
 ASVGP_API const char* asvgp_last_error(void);
 /* Number of CUDA kernels this library has launched in this process so far (all streams, all entry points). */
 ASVGP_API int64_t asvgp_launch_count(void);
+/* Test aid: fills every SM's shared memory with a NaN bit pattern (kernels inherit the previous kernel's shared memory; the GPU
+ * test suite calls this before every test so that a read of a never-written slot fails deterministically). */
+ASVGP_API int asvgp_debug_poison_smem(void* stream);
 
 /* ---- a2/a6: basis evaluation = the non-zeros of Kuf -------------------------------------------------------------
  * Replaces SplineBasis.evaluate_basis (basis.py:51-80) / SplineFeatures1D.make_Kuf (inducing_features.py:47-48).

@@ -282,7 +282,9 @@ def test_accumulate_binned_matches_oracle(cuda, k, m1, m2, n, dist):
     acc = torch.zeros(ops.accum_size_2d(bases), dtype=torch.float64, device="cuda")
     cm = ops.moment_table_2d(bases)
     ops.accum_2d(X, y, bases, cm, ops.split_accum_2d(acc, bases)[2], binned=True)
+    assert bool(torch.isfinite(cm).all()), "moment table has %d non-finite entries" % int((~torch.isfinite(cm)).sum())
     ops.expand_moments_2d(cm, bases, acc)
+    assert bool(torch.isfinite(acc).all()), "expand_moments_2d produced %d non-finite entries" % int((~torch.isfinite(acc)).sum())
     Gs, b, scal = [t.cpu().numpy() for t in ops.split_accum_2d(acc, bases)]
     G0, b0, yy0 = O.precompute_kron([bb.mesh for bb in bases], [bb.delta for bb in bases], k, [m1, m2], X, y)
     scale = abs(G0).max()
