@@ -53,3 +53,30 @@ def _poison_shared_memory(request):
     if torch.cuda.is_available():
         _lib.call("asvgp_debug_poison_smem", ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     yield
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _poison_device_allocations():
+    """ASVGP_POISON_SMEM=1 also NaN-fills (0xFF bytes for integer types) every CUDA tensor that torch.empty / empty_like hands
+    out for the duration of the run: scratch and output buffers must not be read before the kernels write them."""
+    if os.environ.get("ASVGP_POISON_SMEM") is None:
+        yield
+        return
+    import torch
+
+    orig_empty, orig_like = torch.empty, torch.empty_like
+
+    def poison(t):
+        if isinstance(t, torch.Tensor) and t.is_cuda and t.numel() > 0:
+            if t.dtype.is_floating_point:
+                t.fill_(float("nan"))
+            elif t.dtype in (torch.uint8, torch.int8, torch.int16, torch.int32, torch.int64):
+                t.fill_(-1 if t.dtype != torch.uint8 else 255)
+        return t
+
+    torch.empty = lambda *a, **k: poison(orig_empty(*a, **k))
+    torch.empty_like = lambda *a, **k: poison(orig_like(*a, **k))
+    try:
+        yield
+    finally:
+        torch.empty, torch.empty_like = orig_empty, orig_like
