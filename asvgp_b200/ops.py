@@ -11,15 +11,28 @@ from . import _lib
 F64 = torch.float64
 
 
+_HAVE_CUDA = None
+_DEVICES = {}
+
+
 def device():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:                      # asked once: torch.cuda.is_available() costs microseconds on every call
+        _HAVE_CUDA = bool(torch.cuda.is_available())
+    if not _HAVE_CUDA:
         raise _lib.AsvgpNativeError("asvgp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-    return torch.device("cuda", torch.cuda.current_device())
+    i = torch.cuda.current_device()
+    d = _DEVICES.get(i)
+    if d is None:
+        d = _DEVICES[i] = torch.device("cuda", i)
+    return d
 
 
 def to_device(a, dtype=F64):
     """numpy / torch / DLPack object -> contiguous CUDA tensor of `dtype` on the current device."""
     if isinstance(a, torch.Tensor):
+        if a.is_cuda and a.dtype == dtype and a.is_contiguous() and a.device.index == torch.cuda.current_device():
+            return a                            # the hot path's inputs are already where they belong
         t = a
     elif isinstance(a, np.ndarray):
         t = torch.from_numpy(np.ascontiguousarray(a))
@@ -35,7 +48,8 @@ def _p(t):
 
 
 def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw cudaStream_t of torch's current stream (torch.cuda.current_stream() builds a Python Stream object every call)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def device_mesh(basis):
